@@ -1,0 +1,436 @@
+// dwgpu_engine.cu — host side of the B200 batched subproblem engine behind include/dwgpu.h.
+//
+// Owns every device allocation (one pooled arena per kind, per-block offsets), builds the
+// per-block descriptors, picks the kernel path per block and launches the rounds.  The
+// reference's equivalent state is the per-thread glp_prob plus the subprob_struct mailbox
+// (/root/reference/src/dw_subprob.h:44-94); here it is the (T, beta, head, nbv, vstat)
+// arrays that stay resident in HBM between rounds.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dwgpu.h"
+#include "simplex_cta.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(DWGPU_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+constexpr int NT_SMEM = 256;
+constexpr int NT_GMEM = 1024;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        n = count;
+        return cudaMalloc((void **)&p, sizeof(T) * std::max<size_t>(count, 1));
+    }
+    cudaError_t upload(const std::vector<T> &h)
+    {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpy(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice);
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
+};
+
+inline double norm_bound(double v, bool upper)
+{
+    if (std::isnan(v)) return upper ? INFINITY : -INFINITY;
+    if (v >= DWGPU_INF) return INFINITY;
+    if (v <= -DWGPU_INF) return -INFINITY;
+    return v;
+}
+
+}  // namespace
+
+struct dwgpu_engine {
+    int K = 0, L = 0, device = 0;
+    dwgpu_options opt{};
+    cudaStream_t stream = nullptr;
+    std::vector<int> m, n;
+    std::vector<long long> xoff;   // prefix sums of n
+    long long ntot = 0;
+    std::vector<int> path;         // 1 smem, 2 gmem
+    std::vector<int> list_smem, list_gmem;
+    size_t smem_dyn = 0;
+    int max_smem_optin = 0;
+    // device arenas
+    DevBuf<double> T, beta, lo, up, a_v, dc_val, dr_val, c_file, c_master, x, ws;
+    DevBuf<int> head, nbv, a_rp, a_ci, dc_ptr, dc_row, dr_ptr, dr_col;
+    DevBuf<signed char> vstat;
+    DevBuf<dwk::BlockDev> blocks;
+    DevBuf<int> d_list_smem, d_list_gmem;
+    // round inputs / outputs
+    DevBuf<double> pi, obj, cost, val;
+    DevBuf<int> status, len, ind;
+    DevBuf<unsigned long long> counters;
+    DevBuf<long long> last_iters;
+    // pinned staging
+    double *h_pi = nullptr;
+    long long solves = 0;
+    int last_launches = 0;
+    bool initialised = false;
+};
+
+extern "C" {
+
+const char *dwgpu_last_error(void) { return g_err.c_str(); }
+const char *dwgpu_version(void) { return "dwgpu 0.1 (sm_100a)"; }
+
+void dwgpu_options_init(dwgpu_options *o)
+{
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->device = 0;
+    o->clamp_lo_cols = 1;
+    o->force_path = 0;
+    o->max_iter_mult = 50;
+    o->tol_dj = 1e-9;
+    o->tol_bnd = 1e-9;
+    o->tol_piv = 1e-9;
+}
+
+void dwgpu_destroy(dwgpu_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    e->T.release(); e->beta.release(); e->lo.release(); e->up.release(); e->a_v.release();
+    e->dc_val.release(); e->dr_val.release(); e->c_file.release(); e->c_master.release();
+    e->x.release(); e->ws.release(); e->head.release(); e->nbv.release(); e->a_rp.release();
+    e->a_ci.release(); e->dc_ptr.release(); e->dc_row.release(); e->dr_ptr.release();
+    e->dr_col.release(); e->vstat.release(); e->blocks.release(); e->d_list_smem.release();
+    e->d_list_gmem.release(); e->pi.release(); e->obj.release(); e->cost.release();
+    e->val.release(); e->status.release(); e->len.release(); e->ind.release();
+    e->counters.release(); e->last_iters.release();
+    if (e->h_pi) cudaFreeHost(e->h_pi);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *opt_in, dwgpu_engine **out)
+{
+    if (!out) return fail(DWGPU_E_ARGS, "out is NULL");
+    *out = nullptr;
+    if (K < 1 || L < 0 || !bd) return fail(DWGPU_E_ARGS, "bad K/L/blocks");
+    dwgpu_options opt;
+    if (opt_in) opt = *opt_in; else dwgpu_options_init(&opt);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev < 1)
+        return fail(DWGPU_E_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(ce));
+    if (opt.device < 0 || opt.device >= ndev) return fail(DWGPU_E_ARGS, "device ordinal out of range");
+    CU(cudaSetDevice(opt.device));
+
+    dwgpu_engine *e = new dwgpu_engine();
+    e->K = K; e->L = L; e->device = opt.device; e->opt = opt;
+    int rc = 0;
+    auto bail = [&](int code) { dwgpu_destroy(e); return code; };
+#define CUE(call)                                                                             \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            fail(DWGPU_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+            return bail(DWGPU_E_CUDA);                                                        \
+        }                                                                                     \
+    } while (0)
+
+    CUE(cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, opt.device));
+    CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+
+    // ---- sizes and offsets
+    e->m.resize(K); e->n.resize(K); e->xoff.resize(K + 1); e->path.resize(K);
+    std::vector<long long> t_off(K + 1, 0), r_off(K + 1, 0), v_off(K + 1, 0), a_off(K + 1, 0),
+        arp_off(K + 1, 0), d_off(K + 1, 0), dcp_off(K + 1, 0), drp_off(K + 1, 0), ws_off(K + 1, 0);
+    std::vector<int> ldg(K);
+    e->xoff[0] = 0;
+    const size_t smem_cap = (size_t)e->max_smem_optin - 2048;   // static scratch + reserve
+    for (int k = 0; k < K; ++k) {
+        const dwgpu_block_desc &b = bd[k];
+        if (b.m < 0 || b.n < 0 || b.d_nnz < 0 || (b.m > 0 && !b.a_rowptr))
+            { fail(DWGPU_E_ARGS, "bad block descriptor"); return bail(DWGPU_E_ARGS); }
+        e->m[k] = b.m; e->n[k] = b.n;
+        ldg[k] = (b.n + 3) & ~3;
+        const int nnz = b.m > 0 ? b.a_rowptr[b.m] : 0;
+        t_off[k + 1] = t_off[k] + (long long)b.m * ldg[k];
+        r_off[k + 1] = r_off[k] + b.m;
+        e->xoff[k + 1] = e->xoff[k] + b.n;
+        v_off[k + 1] = v_off[k] + b.m + b.n;
+        a_off[k + 1] = a_off[k] + nnz;
+        arp_off[k + 1] = arp_off[k] + b.m + 1;
+        d_off[k + 1] = d_off[k] + b.d_nnz;
+        dcp_off[k + 1] = dcp_off[k] + b.n + 1;
+        drp_off[k + 1] = drp_off[k] + L + 1;
+        const bool fits = dwk::smem_bytes(b.m, b.n) <= smem_cap;
+        int path = fits ? 1 : 2;
+        if (opt.force_path == 2) path = 2;
+        if (opt.force_path == 1 && !fits)
+            { fail(DWGPU_E_ARGS, "force_path=1 but a block does not fit shared memory"); return bail(DWGPU_E_ARGS); }
+        e->path[k] = path;
+        if (path == 1) { e->list_smem.push_back(k); e->smem_dyn = std::max(e->smem_dyn, dwk::smem_bytes(b.m, b.n)); }
+        else e->list_gmem.push_back(k);
+        ws_off[k + 1] = ws_off[k] + (path == 2 ? (long long)((dwk::vec_bytes(b.m, b.n) + 15) / 16 * 2) : 0);
+    }
+    e->ntot = e->xoff[K];
+
+    // ---- host staging of the static data
+    std::vector<double> h_lo(v_off[K]), h_up(v_off[K]), h_av(a_off[K]), h_dcv(d_off[K]), h_drv(d_off[K]),
+        h_cf(e->ntot), h_cm(e->ntot);
+    std::vector<int> h_arp(arp_off[K]), h_aci(a_off[K]), h_dcp(dcp_off[K]), h_dcr(d_off[K]), h_drp(drp_off[K]),
+        h_drc(d_off[K]);
+    for (int k = 0; k < K; ++k) {
+        const dwgpu_block_desc &b = bd[k];
+        const int m = b.m, n = b.n;
+        double *lo = h_lo.data() + v_off[k], *up = h_up.data() + v_off[k];
+        for (int i = 0; i < m; ++i) { lo[i] = norm_bound(b.row_lb[i], false); up[i] = norm_bound(b.row_ub[i], true); }
+        for (int j = 0; j < n; ++j) {
+            double l = norm_bound(b.col_lb[j], false), u = norm_bound(b.col_ub[j], true);
+            // dw_subprob.c:116-120 — GLP_LO column (finite lb, no ub) becomes GLP_DB [lb, 3000]
+            if (opt.clamp_lo_cols && std::isfinite(l) && std::isinf(u) && u > 0) u = 3000.0;
+            lo[m + j] = l; up[m + j] = u;
+            h_cf[e->xoff[k] + j] = b.c_file ? b.c_file[j] : 0.0;
+            h_cm[e->xoff[k] + j] = b.c_master ? b.c_master[j] : 0.0;
+        }
+        const int nnz = m > 0 ? b.a_rowptr[m] : 0;
+        for (int i = 0; i <= m; ++i) h_arp[arp_off[k] + i] = m > 0 ? b.a_rowptr[i] : 0;
+        for (int p = 0; p < nnz; ++p) {
+            if (b.a_col[p] < 0 || b.a_col[p] >= n) { fail(DWGPU_E_ARGS, "A column index out of range"); return bail(DWGPU_E_ARGS); }
+            h_aci[a_off[k] + p] = b.a_col[p];
+            h_av[a_off[k] + p] = b.a_val[p];
+        }
+        // D_k by column and by row, both keeping the reference's COO order inside a bucket
+        int *cp = h_dcp.data() + dcp_off[k], *rp = h_drp.data() + drp_off[k];
+        std::fill(cp, cp + n + 1, 0); std::fill(rp, rp + L + 1, 0);
+        for (int t = 0; t < b.d_nnz; ++t) {
+            if (b.d_row[t] < 0 || b.d_row[t] >= L || b.d_col[t] < 0 || b.d_col[t] >= n)
+                { fail(DWGPU_E_ARGS, "D index out of range"); return bail(DWGPU_E_ARGS); }
+            cp[b.d_col[t] + 1]++; rp[b.d_row[t] + 1]++;
+        }
+        for (int j = 0; j < n; ++j) cp[j + 1] += cp[j];
+        for (int i = 0; i < L; ++i) rp[i + 1] += rp[i];
+        std::vector<int> cpos(cp, cp + n), rpos(rp, rp + L);
+        for (int t = 0; t < b.d_nnz; ++t) {
+            int a = cpos[b.d_col[t]]++, r = rpos[b.d_row[t]]++;
+            h_dcr[d_off[k] + a] = b.d_row[t]; h_dcv[d_off[k] + a] = b.d_val[t];
+            h_drc[d_off[k] + r] = b.d_col[t]; h_drv[d_off[k] + r] = b.d_val[t];
+        }
+    }
+
+    // ---- device arenas
+    CUE(e->T.alloc(t_off[K]));
+    CUE(e->beta.alloc(r_off[K])); CUE(e->head.alloc(r_off[K]));
+    CUE(e->nbv.alloc(e->ntot)); CUE(e->vstat.alloc(v_off[K]));
+    CUE(e->lo.upload(h_lo)); CUE(e->up.upload(h_up));
+    CUE(e->a_rp.upload(h_arp)); CUE(e->a_ci.upload(h_aci)); CUE(e->a_v.upload(h_av));
+    CUE(e->dc_ptr.upload(h_dcp)); CUE(e->dc_row.upload(h_dcr)); CUE(e->dc_val.upload(h_dcv));
+    CUE(e->dr_ptr.upload(h_drp)); CUE(e->dr_col.upload(h_drc)); CUE(e->dr_val.upload(h_drv));
+    CUE(e->c_file.upload(h_cf)); CUE(e->c_master.upload(h_cm));
+    CUE(e->x.alloc(e->ntot));
+    CUE(e->ws.alloc(ws_off[K]));
+    CUE(e->pi.alloc(L)); CUE(e->obj.alloc(K)); CUE(e->cost.alloc(K));
+    CUE(e->status.alloc(K)); CUE(e->len.alloc(K));
+    CUE(e->ind.alloc((size_t)K * L)); CUE(e->val.alloc((size_t)K * L));
+    CUE(e->counters.alloc((size_t)K * 4)); CUE(e->last_iters.alloc(K));
+    CUE(cudaMemset(e->counters.p, 0, sizeof(unsigned long long) * (size_t)K * 4));
+    CUE(cudaMemset(e->x.p, 0, sizeof(double) * std::max<long long>(e->ntot, 1)));
+    CUE(cudaMallocHost((void **)&e->h_pi, sizeof(double) * std::max(L, 1)));
+
+    std::vector<dwk::BlockDev> hb(K);
+    for (int k = 0; k < K; ++k) {
+        dwk::BlockDev &B = hb[k];
+        std::memset(&B, 0, sizeof(B));
+        B.m = e->m[k]; B.n = e->n[k]; B.L = L; B.ldg = ldg[k];
+        B.T = e->T.p + t_off[k];
+        B.beta = e->beta.p + r_off[k]; B.head = e->head.p + r_off[k];
+        B.nbv = e->nbv.p + e->xoff[k]; B.vstat = e->vstat.p + v_off[k];
+        B.lo = e->lo.p + v_off[k]; B.up = e->up.p + v_off[k];
+        B.a_rp = e->a_rp.p + arp_off[k]; B.a_ci = e->a_ci.p + a_off[k]; B.a_v = e->a_v.p + a_off[k];
+        B.dc_ptr = e->dc_ptr.p + dcp_off[k]; B.dc_row = e->dc_row.p + d_off[k]; B.dc_val = e->dc_val.p + d_off[k];
+        B.dr_ptr = e->dr_ptr.p + drp_off[k]; B.dr_col = e->dr_col.p + d_off[k]; B.dr_val = e->dr_val.p + d_off[k];
+        B.c_file = e->c_file.p + e->xoff[k]; B.c_master = e->c_master.p + e->xoff[k];
+        B.x = e->x.p + e->xoff[k];
+        B.ws = e->ws.p + ws_off[k];
+    }
+    CUE(e->blocks.upload(hb));
+    CUE(e->d_list_smem.upload(e->list_smem));
+    CUE(e->d_list_gmem.upload(e->list_gmem));
+
+    if (!e->list_smem.empty())
+        CUE(cudaFuncSetAttribute(dwk::solve_kernel<true, NT_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)e->smem_dyn));
+
+    dwk::init_kernel<256><<<K, 256, 0, e->stream>>>(e->blocks.p, K);
+    CUE(cudaGetLastError());
+    CUE(cudaStreamSynchronize(e->stream));
+    e->initialised = true;
+    (void)rc;
+    *out = e;
+    return 0;
+#undef CUE
+}
+
+static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int initial, cudaStream_t st)
+{
+    dwk::SolveParams P;
+    P.pi = d_pi; P.phase_one = phase_one; P.initial = initial;
+    P.max_iter_mult = e->opt.max_iter_mult;
+    P.tol_dj = e->opt.tol_dj; P.tol_bnd = e->opt.tol_bnd; P.tol_piv = e->opt.tol_piv;
+    P.obj = e->obj.p; P.cost = e->cost.p; P.status = e->status.p; P.len = e->len.p;
+    P.ind = e->ind.p; P.val = e->val.p; P.counters = e->counters.p; P.last_iters = e->last_iters.p;
+    e->last_launches = 0;
+    // large blocks first: they are the long poles
+    if (!e->list_gmem.empty()) {
+        dwk::solve_kernel<false, NT_GMEM><<<(unsigned)e->list_gmem.size(), NT_GMEM, 0, st>>>(
+            e->blocks.p, e->d_list_gmem.p, (int)e->list_gmem.size(), P);
+        CU(cudaGetLastError());
+        e->last_launches++;
+    }
+    if (!e->list_smem.empty()) {
+        dwk::solve_kernel<true, NT_SMEM><<<(unsigned)e->list_smem.size(), NT_SMEM, e->smem_dyn, st>>>(
+            e->blocks.p, e->d_list_smem.p, (int)e->list_smem.size(), P);
+        CU(cudaGetLastError());
+        e->last_launches++;
+    }
+    e->solves += e->K;
+    return 0;
+}
+
+int dwgpu_fetch_results(dwgpu_engine *e, dwgpu_proposals *o)
+{
+    if (!e) return fail(DWGPU_E_ARGS, "engine is NULL");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    if (o) {
+        const size_t K = e->K, KL = (size_t)e->K * e->L;
+        if (o->obj) CU(cudaMemcpyAsync(o->obj, e->obj.p, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
+        if (o->cost) CU(cudaMemcpyAsync(o->cost, e->cost.p, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
+        if (o->status) CU(cudaMemcpyAsync(o->status, e->status.p, sizeof(int) * K, cudaMemcpyDeviceToHost, st));
+        if (o->len) CU(cudaMemcpyAsync(o->len, e->len.p, sizeof(int) * K, cudaMemcpyDeviceToHost, st));
+        if (o->ind && KL) CU(cudaMemcpyAsync(o->ind, e->ind.p, sizeof(int) * KL, cudaMemcpyDeviceToHost, st));
+        if (o->val && KL) CU(cudaMemcpyAsync(o->val, e->val.p, sizeof(double) * KL, cudaMemcpyDeviceToHost, st));
+        if (o->x && e->ntot) CU(cudaMemcpyAsync(o->x, e->x.p, sizeof(double) * e->ntot, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int dwgpu_initial_solve(dwgpu_engine *e, dwgpu_proposals *out)
+{
+    if (!e || !e->initialised) return fail(DWGPU_E_STATE, "engine not initialised");
+    CU(cudaSetDevice(e->device));
+    int rc = launch_round(e, nullptr, 0, 1, e->stream);
+    if (rc) return rc;
+    return dwgpu_fetch_results(e, out);
+}
+
+int dwgpu_iterate(dwgpu_engine *e, const double *pi, int phase_one, dwgpu_proposals *out)
+{
+    if (!e || !e->initialised) return fail(DWGPU_E_STATE, "engine not initialised");
+    if (!pi && e->L > 0) return fail(DWGPU_E_ARGS, "pi is NULL");
+    CU(cudaSetDevice(e->device));
+    if (e->L > 0) {
+        std::memcpy(e->h_pi, pi, sizeof(double) * e->L);
+        CU(cudaMemcpyAsync(e->pi.p, e->h_pi, sizeof(double) * e->L, cudaMemcpyHostToDevice, e->stream));
+    }
+    int rc = launch_round(e, e->pi.p, phase_one ? 1 : 0, 0, e->stream);
+    if (rc) return rc;
+    return dwgpu_fetch_results(e, out);
+}
+
+int dwgpu_iterate_device(dwgpu_engine *e, const double *d_pi, int phase_one, void *stream)
+{
+    if (!e || !e->initialised) return fail(DWGPU_E_STATE, "engine not initialised");
+    if (!d_pi && e->L > 0) return fail(DWGPU_E_ARGS, "d_pi is NULL");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    return launch_round(e, d_pi, phase_one ? 1 : 0, 0, st);
+}
+
+int dwgpu_device_results(dwgpu_engine *e, dwgpu_proposals *d)
+{
+    if (!e || !d) return fail(DWGPU_E_ARGS, "NULL argument");
+    d->obj = e->obj.p; d->cost = e->cost.p; d->status = e->status.p; d->len = e->len.p;
+    d->ind = e->ind.p; d->val = e->val.p; d->x = e->x.p;
+    return 0;
+}
+
+int dwgpu_fetch_x(dwgpu_engine *e, int k, double *x)
+{
+    if (!e || !x || k < 0 || k >= e->K) return fail(DWGPU_E_ARGS, "bad arguments");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->n[k] > 0)
+        CU(cudaMemcpy(x, e->x.p + e->xoff[k], sizeof(double) * e->n[k], cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dwgpu_get_counters(dwgpu_engine *e, dwgpu_counters *t)
+{
+    if (!e || !t) return fail(DWGPU_E_ARGS, "NULL argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    std::vector<unsigned long long> h((size_t)e->K * 4);
+    CU(cudaMemcpy(h.data(), e->counters.p, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
+    std::memset(t, 0, sizeof(*t));
+    for (int k = 0; k < e->K; ++k) {
+        t->pivots += (long long)h[4 * (size_t)k]; t->flips += (long long)h[4 * (size_t)k + 1];
+        t->rebuilds += (long long)h[4 * (size_t)k + 2]; t->phase1_iter += (long long)h[4 * (size_t)k + 3];
+    }
+    t->solves = e->solves;
+    return 0;
+}
+
+int dwgpu_get_block_iterations(dwgpu_engine *e, long long *iters)
+{
+    if (!e || !iters) return fail(DWGPU_E_ARGS, "NULL argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(iters, e->last_iters.p, sizeof(long long) * e->K, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dwgpu_last_launch_count(dwgpu_engine *e) { return e ? e->last_launches : 0; }
+
+int dwgpu_get_block_paths(dwgpu_engine *e, int *paths)
+{
+    if (!e || !paths) return fail(DWGPU_E_ARGS, "NULL argument");
+    for (int k = 0; k < e->K; ++k) paths[k] = e->path[k];
+    return 0;
+}
+
+int dwgpu_sync(dwgpu_engine *e)
+{
+    if (!e) return fail(DWGPU_E_ARGS, "engine is NULL");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+"""ctypes mirror of the engine's C ABI (include/dwgpu.h -> dwsolver_b200/lib/libdwgpu.so).
+
+The names, argument meaning and error behaviour follow the C header one to one; the Python
+layer only marshals numpy arrays.  There is NO fallback: if the shared library is missing or
+no CUDA device is usable this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdwgpu.so")
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+DWGPU_UNDEF, DWGPU_NOFEAS, DWGPU_OPT, DWGPU_UNBND = 1, 4, 5, 6
+
+#: every symbol include/dwgpu.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    "dwgpu_options_init", "dwgpu_create", "dwgpu_destroy", "dwgpu_initial_solve", "dwgpu_iterate",
+    "dwgpu_iterate_device", "dwgpu_device_results", "dwgpu_fetch_results", "dwgpu_fetch_x",
+    "dwgpu_get_counters", "dwgpu_get_block_iterations", "dwgpu_last_launch_count", "dwgpu_get_block_paths",
+    "dwgpu_sync", "dwgpu_last_error", "dwgpu_version",
+]
+
+
+class BlockDesc(C.Structure):
+    _fields_ = [("m", C.c_int), ("n", C.c_int),
+                ("a_rowptr", c_ip), ("a_col", c_ip), ("a_val", c_dp),
+                ("row_lb", c_dp), ("row_ub", c_dp), ("col_lb", c_dp), ("col_ub", c_dp),
+                ("c_file", c_dp), ("c_master", c_dp),
+                ("d_nnz", C.c_int), ("d_row", c_ip), ("d_col", c_ip), ("d_val", c_dp)]
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int), ("clamp_lo_cols", C.c_int), ("force_path", C.c_int),
+                ("max_iter_mult", C.c_int), ("tol_dj", C.c_double), ("tol_bnd", C.c_double),
+                ("tol_piv", C.c_double), ("reserved", C.c_int * 8)]
+
+
+class Proposals(C.Structure):
+    _fields_ = [("obj", c_dp), ("cost", c_dp), ("status", c_ip), ("len", c_ip), ("ind", c_ip),
+                ("val", c_dp), ("x", c_dp)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("pivots", C.c_longlong), ("flips", C.c_longlong), ("rebuilds", C.c_longlong),
+                ("phase1_iter", C.c_longlong), ("solves", C.c_longlong)]
+
+
+_LIB = None
+
+
+def load_library():
+    """Load libdwgpu.so (raises if it has not been built: there is no CPU fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing — build it with `make -C dwsolver_b200/csrc` "
+                               "(or __graft_entry__.build()); the engine has no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.dwgpu_options_init.argtypes = [C.POINTER(Options)]
+        L.dwgpu_options_init.restype = None
+        L.dwgpu_create.argtypes = [C.c_int, C.c_int, C.POINTER(BlockDesc), C.POINTER(Options), C.POINTER(C.c_void_p)]
+        L.dwgpu_destroy.argtypes = [C.c_void_p]
+        L.dwgpu_destroy.restype = None
+        L.dwgpu_initial_solve.argtypes = [C.c_void_p, C.POINTER(Proposals)]
+        L.dwgpu_iterate.argtypes = [C.c_void_p, c_dp, C.c_int, C.POINTER(Proposals)]
+        L.dwgpu_iterate_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.dwgpu_device_results.argtypes = [C.c_void_p, C.POINTER(Proposals)]
+        L.dwgpu_fetch_results.argtypes = [C.c_void_p, C.POINTER(Proposals)]
+        L.dwgpu_fetch_x.argtypes = [C.c_void_p, C.c_int, c_dp]
+        L.dwgpu_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+        L.dwgpu_get_block_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        L.dwgpu_last_launch_count.argtypes = [C.c_void_p]
+        L.dwgpu_get_block_paths.argtypes = [C.c_void_p, c_ip]
+        L.dwgpu_sync.argtypes = [C.c_void_p]
+        L.dwgpu_last_error.restype = C.c_char_p
+        L.dwgpu_version.restype = C.c_char_p
+        _LIB = L
+    return _LIB
+
+
+class DwGpuError(RuntimeError):
+    pass
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load_library().dwgpu_last_error().decode()
+        raise DwGpuError(f"{what} failed (code {rc}): {msg}")
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _bnd(a):
+    a = _f64(a).copy()
+    a[np.isposinf(a)] = 1e30
+    a[np.isneginf(a)] = -1e30
+    return a
+
+
+class Engine:
+    """Batched subproblem engine for one BlockAngularLP shard on one GPU."""
+
+    def __init__(self, prob, device: int = 0, block_range: Optional[range] = None, **opts):
+        lib = load_library()
+        blocks = prob.blocks if block_range is None else [prob.blocks[k] for k in block_range]
+        self.K, self.L = len(blocks), prob.L
+        self.n = np.asarray([b.n for b in blocks], np.int64)
+        self.m = np.asarray([b.m for b in blocks], np.int64)
+        self.xoff = np.concatenate([[0], np.cumsum(self.n)])
+        keep = []
+        descs = (BlockDesc * self.K)()
+        for k, b in enumerate(blocks):
+            arrs = dict(a_rowptr=_i32(b.a_rowptr), a_col=_i32(b.a_col), a_val=_f64(b.a_val),
+                        row_lb=_bnd(b.row_lb), row_ub=_bnd(b.row_ub), col_lb=_bnd(b.col_lb), col_ub=_bnd(b.col_ub),
+                        c_file=_f64(b.c_file), c_master=_f64(b.c_master),
+                        d_row=_i32(b.d_row), d_col=_i32(b.d_col), d_val=_f64(b.d_val))
+            keep.append(arrs)
+            d = descs[k]
+            d.m, d.n, d.d_nnz = int(b.m), int(b.n), int(len(arrs["d_val"]))
+            for name, arr in arrs.items():
+                ptr_t = c_ip if arr.dtype == np.int32 else c_dp
+                setattr(d, name, arr.ctypes.data_as(ptr_t))
+        o = Options()
+        lib.dwgpu_options_init(C.byref(o))
+        o.device = device
+        for key, v in opts.items():
+            if not hasattr(o, key):
+                raise TypeError(f"unknown engine option {key!r}")
+            setattr(o, key, v)
+        h = C.c_void_p()
+        _check(lib.dwgpu_create(self.K, self.L, descs, C.byref(o), C.byref(h)), "dwgpu_create")
+        self._h = h
+        self._lib = lib
+        KL = max(self.K * self.L, 1)
+        self.obj = np.zeros(self.K)
+        self.cost = np.zeros(self.K)
+        self.status = np.zeros(self.K, np.int32)
+        self.len = np.zeros(self.K, np.int32)
+        self.ind = np.zeros(KL, np.int32)
+        self.val = np.zeros(KL)
+        self.x = np.zeros(max(int(self.xoff[-1]), 1))
+        self._out = Proposals(self.obj.ctypes.data_as(c_dp), self.cost.ctypes.data_as(c_dp),
+                              self.status.ctypes.data_as(c_ip), self.len.ctypes.data_as(c_ip),
+                              self.ind.ctypes.data_as(c_ip), self.val.ctypes.data_as(c_dp),
+                              self.x.ctypes.data_as(c_dp))
+
+    # ---- rounds (host buffers; arrays self.obj/... are overwritten in place) -------------
+    def initial_solve(self):
+        _check(self._lib.dwgpu_initial_solve(self._h, C.byref(self._out)), "dwgpu_initial_solve")
+
+    def iterate_arrays(self, pi, phase_one: bool):
+        pi = _f64(pi)
+        _check(self._lib.dwgpu_iterate(self._h, pi.ctypes.data_as(c_dp), int(bool(phase_one)), C.byref(self._out)),
+               "dwgpu_iterate")
+
+    def iterate_device(self, d_pi_ptr: int, phase_one: bool, stream: int = 0):
+        _check(self._lib.dwgpu_iterate_device(self._h, C.c_void_p(d_pi_ptr), int(bool(phase_one)),
+                                              C.c_void_p(stream) if stream else None), "dwgpu_iterate_device")
+
+    def fetch_results(self):
+        _check(self._lib.dwgpu_fetch_results(self._h, C.byref(self._out)), "dwgpu_fetch_results")
+
+    def device_results(self) -> Proposals:
+        p = Proposals()
+        _check(self._lib.dwgpu_device_results(self._h, C.byref(p)), "dwgpu_device_results")
+        return p
+
+    def sync(self):
+        _check(self._lib.dwgpu_sync(self._h), "dwgpu_sync")
+
+    # ---- proposal dicts for the test-harness DW loop ----------------------------------------
+    def _collect(self) -> List[dict]:
+        out = []
+        for k in range(self.K):
+            ln = int(self.len[k])
+            s = k * self.L
+            out.append(dict(status=int(self.status[k]), obj=float(self.obj[k]), cost=float(self.cost[k]), len=ln,
+                            ind=self.ind[s:s + ln].copy(), val=self.val[s:s + ln].copy(),
+                            x=self.x[self.xoff[k]:self.xoff[k + 1]].copy()))
+        return out
+
+    def initial(self):
+        self.initial_solve()
+        return self._collect()
+
+    def iterate(self, pi, phase_one: bool):
+        self.iterate_arrays(pi, phase_one)
+        return self._collect()
+
+    # ---- diagnostics --------------------------------------------------------------------------
+    def counters(self) -> dict:
+        c = Counters()
+        _check(self._lib.dwgpu_get_counters(self._h, C.byref(c)), "dwgpu_get_counters")
+        return dict(pivots=c.pivots, flips=c.flips, rebuilds=c.rebuilds, phase1_iter=c.phase1_iter, solves=c.solves)
+
+    def block_iterations(self) -> np.ndarray:
+        it = np.zeros(self.K, np.int64)
+        _check(self._lib.dwgpu_get_block_iterations(self._h, it.ctypes.data_as(C.POINTER(C.c_longlong))),
+               "dwgpu_get_block_iterations")
+        return it
+
+    def block_paths(self) -> np.ndarray:
+        p = np.zeros(self.K, np.int32)
+        _check(self._lib.dwgpu_get_block_paths(self._h, p.ctypes.data_as(c_ip)), "dwgpu_get_block_paths")
+        return p
+
+    def last_launch_count(self) -> int:
+        return int(self._lib.dwgpu_last_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dwgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,141 @@
+/*
+ * dwgpu.h — C ABI of the B200 batched subproblem engine.
+ *
+ * This is the seam that replaces the reference's pthread/semaphore hand-off between the
+ * master thread and the K subproblem threads (all paths relative to /root/reference):
+ *
+ *   reference (what exists)                                   replacement entry point
+ *   ---------------------------------------------------------------------------------------
+ *   pthread_create(subproblem_thread, &sub_data[k])           dwgpu_create()
+ *     src/dw_solver.c:154-184; block set-up
+ *     src/dw_subprob.c:100-120 (bounds clamp), :203-258 (c_k, COO D_k)
+ *   first proposal: cold glp_simplex with the file objective  dwgpu_initial_solve()
+ *     src/dw_subprob.c:121-122, 262-269
+ *   one round: md->row_duals / phase_one published, cond      dwgpu_iterate()  (host buffers)
+ *     broadcast, K x { D_k'pi, d = c_k - y, glp_simplex,      dwgpu_iterate_device() (device
+ *     x_k, D_k x_k compaction, c_k.x_k }, K x sem_post          buffers, caller's stream)
+ *     src/dw_phases.c:526-548 (down-link), src/dw_subprob.c:291-373 (worker),
+ *     src/dw_phases.c:338-350 (up-link)
+ *   mailbox fields obj / unbounded / new_obj_coeff / len /    struct dwgpu_proposals
+ *     ind / val / current_solution  src/dw_subprob.h:44-94
+ *   COMMAND_STOP + pthread_join, free_sub_data                dwgpu_destroy()
+ *     src/dw_solver.c:681-688, 757-772; src/dw_support.c:925-960
+ *
+ * Conventions: plain C, plain pointers and sizes.  Every function returns 0 on success and
+ * a negative DWGPU_E_* code otherwise (the host library maps any failure to
+ * DW_STATUS_ERR_INTERNAL = 99); nothing in this layer calls exit().  One host thread drives
+ * one engine (like dw_solve(), the engine is not re-entrant).  There is no CPU fallback: if
+ * no CUDA device is usable, dwgpu_create() fails with DWGPU_E_CUDA.
+ */
+#ifndef DWGPU_H_
+#define DWGPU_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DWGPU_INF 1e30 /* |bound| >= DWGPU_INF (or IEEE inf) means "no bound" */
+
+/* per-block solution status: numerically equal to GLPK's glp_get_status() values, which is
+ * what the reference stores in subprob_struct.unbounded (src/dw_subprob.c:340) */
+#define DWGPU_UNDEF  1 /* iteration limit / numerical failure */
+#define DWGPU_NOFEAS 4
+#define DWGPU_OPT    5
+#define DWGPU_UNBND  6
+
+#define DWGPU_E_ARGS   (-1)
+#define DWGPU_E_CUDA   (-2)
+#define DWGPU_E_NOMEM  (-3)
+#define DWGPU_E_STATE  (-4)
+
+/* One block k, as the reference's worker assembles it.  Indices 0-based. */
+typedef struct dwgpu_block_desc {
+    int m, n;                /* rows / columns of A_k */
+    const int    *a_rowptr;  /* CSR of A_k: m+1 */
+    const int    *a_col;
+    const double *a_val;
+    const double *row_lb, *row_ub; /* m  (FX rows: lb == ub) */
+    const double *col_lb, *col_ub; /* n */
+    const double *c_file;    /* n: objective of the block's own LP file (cold solve) */
+    const double *c_master;  /* n: master cost of each block column (c_k) */
+    int d_nnz;               /* COO of D_k in the reference's append order */
+    const int    *d_row;     /* master row   (0-based) */
+    const int    *d_col;     /* local column (0-based) */
+    const double *d_val;
+} dwgpu_block_desc;
+
+typedef struct dwgpu_options {
+    int    device;        /* CUDA device ordinal (default 0) */
+    int    clamp_lo_cols; /* 1: finite-lb/no-ub columns get ub = 3000 (dw_subprob.c:116-120) */
+    int    force_path;    /* 0 auto; 1 shared-memory CTA path; 2 global-memory CTA path */
+    int    max_iter_mult; /* iteration limit = max_iter_mult*(m+n) + 1000 (default 50) */
+    double tol_dj;        /* dual feasibility   (default 1e-9) */
+    double tol_bnd;       /* primal feasibility, scaled by 1+|bound| (default 1e-9) */
+    double tol_piv;       /* minimum |pivot|    (default 1e-9) */
+    int    reserved[8];
+} dwgpu_options;
+
+/* Host-side result buffers for one round; any pointer may be NULL (that field is skipped).
+ * ind/val rows have stride L: block k's compacted column is ind[k*L .. k*L+len[k]).
+ * x is the concatenation of all blocks' solutions (offsets = prefix sums of n_k). */
+typedef struct dwgpu_proposals {
+    double *obj;    /* K: optimum of the priced LP, d_k . x_k          (mailbox: obj) */
+    double *cost;   /* K: c_k . x_k                                    (new_obj_coeff) */
+    int    *status; /* K: DWGPU_OPT / NOFEAS / UNBND / UNDEF           (unbounded) */
+    int    *len;    /* K: exact nonzeros of D_k x_k                    (len) */
+    int    *ind;    /* K*L: 1-based master rows                        (ind[1..len]) */
+    double *val;    /* K*L                                             (val[1..len]) */
+    double *x;      /* sum n_k                                         (current_solution) */
+} dwgpu_proposals;
+
+typedef struct dwgpu_counters {
+    long long pivots;      /* basis changes (a rank-1 tableau update happened) */
+    long long flips;       /* bound flips (no update) */
+    long long rebuilds;    /* tableau rebuilt from A_k after a residual check */
+    long long phase1_iter; /* iterations spent restoring primal feasibility */
+    long long solves;      /* block solves */
+} dwgpu_counters;
+
+typedef struct dwgpu_engine dwgpu_engine;
+
+void dwgpu_options_init(dwgpu_options *opt);
+
+/* Copies everything it needs; the descriptors may be freed after the call. */
+int  dwgpu_create(int K, int L, const dwgpu_block_desc *blocks, const dwgpu_options *opt,
+                  dwgpu_engine **out);
+void dwgpu_destroy(dwgpu_engine *e);
+
+/* Cold solve of every block with its file objective; fills *out (may be NULL). */
+int  dwgpu_initial_solve(dwgpu_engine *e, dwgpu_proposals *out);
+
+/* One round with HOST buffers: pi (L doubles) is copied to the device, every block is priced
+ * and re-solved from its stored basis, and the proposals are copied back into *out. */
+int  dwgpu_iterate(dwgpu_engine *e, const double *pi, int phase_one, dwgpu_proposals *out);
+
+/* One round with DEVICE buffers on the caller's stream (cudaStream_t passed as void*; NULL =
+ * the engine's own stream).  Asynchronous; results stay on the device, see
+ * dwgpu_device_results().  d_pi must stay valid until the stream reaches the end of the call. */
+int  dwgpu_iterate_device(dwgpu_engine *e, const double *d_pi, int phase_one, void *stream);
+
+/* Device-resident result arrays of the last round (same layout as dwgpu_proposals). */
+int  dwgpu_device_results(dwgpu_engine *e, dwgpu_proposals *dev_ptrs);
+/* Copy the last round's results to host buffers (synchronises the engine stream). */
+int  dwgpu_fetch_results(dwgpu_engine *e, dwgpu_proposals *out);
+/* x_k of the last round for one block (n_k doubles). */
+int  dwgpu_fetch_x(dwgpu_engine *e, int k, double *x);
+
+int  dwgpu_get_counters(dwgpu_engine *e, dwgpu_counters *total);
+/* per-block pivots+flips of the LAST round (K long longs) — load-balance diagnostics */
+int  dwgpu_get_block_iterations(dwgpu_engine *e, long long *iters);
+/* kernels launched by the last iterate / initial_solve call */
+int  dwgpu_last_launch_count(dwgpu_engine *e);
+/* 1 = shared-memory CTA path, 2 = global-memory CTA path, per block */
+int  dwgpu_get_block_paths(dwgpu_engine *e, int *paths);
+int  dwgpu_sync(dwgpu_engine *e);
+const char *dwgpu_last_error(void);
+const char *dwgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DWGPU_H_ */

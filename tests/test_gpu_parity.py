@@ -1,0 +1,170 @@
+"""GPU parity tests: the CUDA engine (through the C ABI, dwsolver_b200/engine.py) against the CPU
+oracle on the same seeded inputs, and against the committed goldens.
+
+Tolerances (BASELINE.json north_star): block optimum |z_gpu - z_ref| <= 1e-9 (1+|z_ref|) at identical
+(k, pi, phase); primal residuals <= 1e-9 scaled; master objective 1e-7 relative.  Vertex identity is
+not required.  Pricing (D'pi, D x) is compared bit-for-bit."""
+import zlib
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import EXAMPLES, load_example
+from dw_loop import run_dw
+from dwsolver_b200 import problem as P
+
+pytestmark = pytest.mark.gpu
+
+OPT = 5
+
+
+def engine(prob, **kw):
+    from dwsolver_b200.engine import Engine
+    return Engine(prob, **kw)
+
+
+def residual(block, x):
+    """max scaled violation of rows and column bounds."""
+    A = sp.csr_matrix((block.a_val, block.a_col, block.a_rowptr), shape=(block.m, block.n))
+    act = A @ x
+    ub = P.effective_col_ub(block)
+    worst = 0.0
+    for v, lo, up in ((act, block.row_lb, block.row_ub), (x, block.col_lb, ub)):
+        flo, fup = np.isfinite(lo), np.isfinite(up)
+        if flo.any():
+            worst = max(worst, float(np.max((lo[flo] - v[flo]) / (1 + np.abs(lo[flo])), initial=0.0)))
+        if fup.any():
+            worst = max(worst, float(np.max((v[fup] - up[fup]) / (1 + np.abs(up[fup])), initial=0.0)))
+    return worst
+
+
+def compare_round(prob, gp, op, pi, phase_one, initial=False):
+    for k, b in enumerate(prob.blocks):
+        g, o = gp[k], op[k]
+        assert g["status"] == OPT and o["status"] == OPT, (k, g["status"], o["status"])
+        assert abs(g["obj"] - o["obj"]) <= 1e-9 * (1 + abs(o["obj"])), (k, g["obj"], o["obj"])
+        x = g["x"]
+        assert residual(b, x) <= 1e-9, (k, residual(b, x))
+        # the proposal is self-consistent with the reference's formulas, bit for bit
+        if initial:
+            d = b.c_file
+        else:
+            y = np.zeros(b.n)
+            for r, c, v in zip(b.d_row, b.d_col, b.d_val):      # dw_dcoogemv order
+                y[c] += pi[r] * v
+            d = (0.0 if phase_one else b.c_master) + (-1.0 * y)
+        assert abs(d @ x - g["obj"]) <= 1e-9 * (1 + abs(g["obj"]))
+        yc = np.zeros(prob.L)
+        for r, c, v in zip(b.d_row, b.d_col, b.d_val):
+            yc[r] += x[c] * v
+        nz = np.nonzero(yc != 0.0)[0]
+        assert np.array_equal(g["ind"], nz + 1)
+        assert np.array_equal(g["val"], yc[nz])                 # exact: same order, no FMA
+        assert abs(g["cost"] - b.c_master @ x) <= 1e-12 * (1 + abs(g["cost"]))
+
+
+@pytest.mark.parametrize("force_path", [0, 2])
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_examples_fixed_pi_parity(name, force_path):
+    from oracle import oracle as O
+    prob = load_example(name)
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    eng = engine(prob, force_path=force_path)
+    orc = O.OracleBlocks(prob)
+    compare_round(prob, eng.initial(), orc.initial(), None, False, initial=True)
+    for trial in range(4):
+        pi = rng.standard_normal(prob.L) * (1 + trial)
+        phase_one = trial == 0
+        compare_round(prob, eng.iterate(pi, phase_one), orc.iterate(pi, phase_one), pi, phase_one)
+    # warm start invariant: same prices again -> zero pivots
+    before = eng.counters()
+    eng.iterate(pi, False)
+    after = eng.counters()
+    assert after["pivots"] == before["pivots"] and after["flips"] == before["flips"]
+    eng.close()
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_examples_dw_objective(name, golden):
+    prob = load_example(name)
+    eng = engine(prob)
+    res = run_dw(prob, eng)
+    exp = golden["objective"][name]
+    assert res["status"] == "optimal"
+    assert abs(res["objective"] - exp) <= 1e-7 * (1 + abs(exp))
+    if name in golden["objective_literal"]:
+        assert "%e" % res["objective"] == golden["objective_literal"][name]
+    if name in golden["relaxed_solution"]:
+        sol = golden["relaxed_solution"][name]
+        for k, b in enumerate(prob.blocks):
+            for j, nm in enumerate(b.col_names):
+                assert "%f" % (res["x"][k][j] + 0.0) == "%f" % sol[nm]
+    eng.close()
+
+
+@pytest.mark.parametrize("K,nodes,cols,L,seed", [(64, 16, 40, 8, 7), (96, 64, 128, 32, 1024001)])
+def test_mcf_parity_and_dw(K, nodes, cols, L, seed):
+    from oracle import oracle as O
+    prob = P.gen_mcf(K, nodes, cols, L, seed)
+    eng = engine(prob)
+    assert set(eng.block_paths()) == {1}
+    orc = O.OracleBlocks(prob)
+    compare_round(prob, eng.initial(), orc.initial(8), None, False, initial=True)
+    rng = np.random.default_rng(seed)
+    for trial in range(3):
+        pi = -rng.random(L) * 10.0 * (trial + 1)
+        compare_round(prob, eng.iterate(pi, trial == 0), orc.iterate(pi, trial == 0, 8), pi, trial == 0)
+    eng.close()
+    eng = engine(prob)
+    res = run_dw(prob, eng)
+    from highs_util import solve_monolithic
+    ref = solve_monolithic(prob)["objective"]
+    assert res["status"] == "optimal"
+    assert abs(res["objective"] - ref) <= 1e-7 * (1 + abs(ref))
+    eng.close()
+
+
+def test_dense_blocks_global_path():
+    from oracle import oracle as O
+    prob = P.gen_dense(6, 150, 300, 12, 64001, dens_a=0.05)
+    eng = engine(prob, force_path=2)
+    orc = O.OracleBlocks(prob)
+    compare_round(prob, eng.initial(), orc.initial(6), None, False, initial=True)
+    rng = np.random.default_rng(5)
+    for trial in range(2):
+        pi = -rng.random(prob.L)
+        compare_round(prob, eng.iterate(pi, False), orc.iterate(pi, False, 6), pi, False)
+    eng.close()
+
+
+def test_edge_cases():
+    """empty D_k, a block without rows, fixed columns, infeasible and unbounded blocks"""
+    z = np.zeros(0)
+    zi = np.zeros(0, np.int32)
+    mk = lambda **kw: P.Block(**kw)
+    b0 = mk(m=0, n=3, a_rowptr=np.zeros(1, np.int32), a_col=zi, a_val=z, row_lb=z, row_ub=z,
+            col_lb=np.array([0.0, -1.0, 2.0]), col_ub=np.array([1.0, 1.0, 2.0]),
+            c_file=np.array([1.0, -1.0, 5.0]), c_master=np.array([1.0, -1.0, 5.0]), d_row=zi, d_col=zi, d_val=z)
+    # infeasible: x1 + x2 <= 1 and >= 2
+    b1 = mk(m=2, n=2, a_rowptr=np.array([0, 2, 4], np.int32), a_col=np.array([0, 1, 0, 1], np.int32),
+            a_val=np.ones(4), row_lb=np.array([-np.inf, 2.0]), row_ub=np.array([1.0, np.inf]),
+            col_lb=np.zeros(2), col_ub=np.full(2, np.inf), c_file=np.ones(2), c_master=np.ones(2),
+            d_row=np.array([0], np.int32), d_col=np.array([0], np.int32), d_val=np.array([1.0]))
+    # unbounded: min -x1 with x1 free of an upper bound only through the clamp -> bounded at 3000
+    b2 = mk(m=1, n=2, a_rowptr=np.array([0, 2], np.int32), a_col=np.array([0, 1], np.int32),
+            a_val=np.array([1.0, -1.0]), row_lb=np.array([-np.inf]), row_ub=np.array([1.0]),
+            col_lb=np.zeros(2), col_ub=np.full(2, np.inf), c_file=np.array([-1.0, 0.0]),
+            c_master=np.array([-1.0, 0.0]), d_row=zi, d_col=zi, d_val=z)
+    prob = P.BlockAngularLP(K=3, L=1, blocks=[b0, b1, b2], link_lb=np.array([-np.inf]), link_ub=np.array([1.0]))
+    eng = engine(prob)
+    props = eng.initial()
+    assert props[0]["status"] == OPT and np.allclose(props[0]["x"], [0, 1, 2]) and props[0]["obj"] == 9.0
+    assert props[0]["len"] == 0
+    assert props[1]["status"] == 4
+    assert props[2]["status"] == OPT and props[2]["obj"] == -3000.0          # the 3000 clamp
+    eng.close()
+    eng = engine(prob, clamp_lo_cols=0)
+    props = eng.initial()
+    assert props[2]["status"] == 6                                             # truly unbounded
+    eng.close()
