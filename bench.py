@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py — subproblem pivots/s of the B200 engine on BASELINE.json's synthetic configurations.
+
+One "step" = the hot-path work of ONE COMPLETE Dantzig-Wolfe solve of the instance: reset every block
+to its all-logical basis, cold-solve every block with its file objective (first proposals), then R
+priced rounds — price every block with the round's master duals pi_r (D_k' pi, d = c_k - y or -y in
+Phase I), re-solve it from its stored basis, build its proposal column (x_k, D_k x_k compacted,
+c_k.x_k).  The R dual vectors (and Phase-I flags) are the recorded trajectory of a real DW run of the
+same instance (tests/golden/traj_<config>.npz, made by tests/golden/make_trajectory.py with a HiGHS
+master): exactly what the reference's master publishes to its workers each round
+(src/dw_phases.c:271-275, 526-530).  Every step therefore does identical, fully warm-start-dependent
+work.  The master LP itself is outside the hot path.
+
+  value     device-only: all pi_r already in HBM, results left in HBM
+  e2e       through the C ABI with host buffers: per round H2D of pi_r, kernels, D2H of the proposals
+  roofline  dominant kernel: algorithmic bytes of its basis changes (+ state load/store) divided by
+            its CUDA-event time, summed over the timed region
+  cpu_baseline   the CPU oracle ("port": pthreads + our restatement, NOT GLPK — GLPK is neither in the
+            reference tree nor on the box) replaying the same trajectory on a bounded sample of blocks
+
+`--impl reference` times that CPU arm alone with all host threads and prints the same line shape.
+Launch:  python bench.py [--gpus N --steps K --warmup W]   (N>1: via torch.distributed.run)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from dwsolver_b200 import problem as P  # noqa: E402
+
+METRIC = "subproblem_pivots_per_sec"
+UNIT = "pivots/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=os.environ.get("DWBENCH_CONFIG", "A"), choices=list(P.CONFIGS))
+    ap.add_argument("--cpu-blocks", type=int, default=0, help="blocks in the CPU arm's sample (0 = auto)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_trajectory(tag):
+    path = os.path.join(ROOT, "tests", "golden", f"traj_{tag}.npz")
+    if not os.path.exists(path):
+        raise SystemExit(f"bench.py: {path} is missing (run tests/golden/make_trajectory.py {tag})")
+    z = np.load(path)
+    return np.ascontiguousarray(z["pis"], dtype=np.float64), [bool(v) for v in z["phase_one"]], float(z["objective"])
+
+
+def algorithmic_bytes_per_pivot(m, n):
+    """condensed (Tucker) tableau: every entry of the (m+1) x (n+1) array [T d; beta .] is read and
+    written once per basis change.  The survey's canonical full-tableau figure
+    16(m+1)(n+m+1) would be larger; we charge only what this representation must move."""
+    return 16.0 * (m + 1) * (n + 1)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm (oracle): used for cpu_baseline and for --impl reference
+# ------------------------------------------------------------------------------------------
+def cpu_replay(prob_sample, pis, phases, threads):
+    """One full replay (cold solve + R rounds) on the sample with a pool of pthreads.
+    Returns (pivots+flips, seconds)."""
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    blocks = O.OracleBlocks(prob_sample)       # fresh all-logical bases (the reset)
+    t_setup = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    blocks.initial(threads)
+    for pi, ph in zip(pis, phases):
+        blocks.iterate(pi, ph, threads, collect=False)
+    dt = time.perf_counter() - t0
+    c = blocks.counters()
+    del blocks
+    return c[0] + c[1], dt, t_setup
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        args.gpus = world
+    cfg = dict(P.CONFIGS[args.config])
+    K_total = cfg["K"]
+    m, n, L = cfg["m"], cfg["n"], cfg["L"]
+    pis, phases, dw_objective = load_trajectory(args.config)
+    R = len(phases)
+    workload = (f"synthetic {'multicommodity flow' if cfg['kind'] == 'mcf' else 'dense'} config {args.config}: "
+                f"{K_total} blocks x {m} rows x {n} cols, {L} linking rows (seed {cfg['seed']}); "
+                f"step = cold solve + {R} priced rounds of a recorded DW run")
+    W, S = args.warmup, args.steps
+    cores = os.cpu_count() or 1
+    cpu_note = ("pthreads + this repo's CPU restatement (oracle/), NOT GLPK: GLPK is absent from the reference "
+                "tree and from the box")
+
+    # ---------------- reference arm: CPU only, rank 0 only ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample_k = min(K_total, args.cpu_blocks or (32 * cores if m <= 64 else 2 * cores))
+        prob = P.make_config(args.config, block_range=range(sample_k))
+        piv_total, t_total = 0, 0.0
+        for step in range(W + S):
+            piv, dt, _ = cpu_replay(prob, pis, phases, cores)
+            if step >= W:
+                piv_total += piv
+                t_total += dt
+        v = piv_total / t_total if t_total > 0 else 0.0
+        sample = f"first {sample_k} of {K_total} blocks per step, full trajectory ({R} rounds), {cores} pthreads"
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": S,
+            "warmup": W, "ms_per_step": 1e3 * t_total / max(S, 1), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": cpu_note},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    # ---------------- our arm ----------------
+    import torch
+    from dwsolver_b200 import engine as E
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    if K_total % world:
+        raise SystemExit("block count must divide evenly over the ranks")
+    K_loc = K_total // world
+    my_range = range(rank * K_loc, (rank + 1) * K_loc)
+    prob = P.make_config(args.config, block_range=my_range)
+    bpp = algorithmic_bytes_per_pivot(m, n)
+
+    class Cai:   # zero-copy torch view of an engine-owned device array
+        def __init__(self, ptr, shape, typestr):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+    eng = E.Engine(prob, device=local_rank, fetch_x=False)
+
+    def dev_views():
+        import ctypes as C
+        d = eng.device_results()
+        addr = lambda p: C.cast(p, C.c_void_p).value
+        return {
+            "obj": torch.as_tensor(Cai(addr(d.obj), (K_loc,), "<f8"), device=dev),
+            "cost": torch.as_tensor(Cai(addr(d.cost), (K_loc,), "<f8"), device=dev),
+            "status": torch.as_tensor(Cai(addr(d.status), (K_loc,), "<i4"), device=dev),
+            "len": torch.as_tensor(Cai(addr(d.len), (K_loc,), "<i4"), device=dev),
+            "ind": torch.as_tensor(Cai(addr(d.ind), (K_loc, L), "<i4"), device=dev),
+            "val": torch.as_tensor(Cai(addr(d.val), (K_loc, L), "<f8"), device=dev),
+        }
+
+    views = dev_views()
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gat = None
+    if dist is not None:   # every rank receives every shard's proposals; rank 0 is the consumer
+        gat = {"len": torch.empty(K_total, dtype=torch.int32, device=dev),
+               "ind": torch.empty((K_total, L), dtype=torch.int32, device=dev),
+               "val": torch.empty((K_total, L), dtype=torch.float64, device=dev),
+               "obj": torch.empty(K_total, dtype=torch.float64, device=dev),
+               "cost": torch.empty(K_total, dtype=torch.float64, device=dev),
+               "status": torch.empty(K_total, dtype=torch.int32, device=dev)}
+        h_pin = {k_: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k_, v in gat.items()}
+    pi_pin = torch.zeros(L, dtype=torch.float64).pin_memory()
+    pi_dev = torch.zeros(L, dtype=torch.float64, device=dev)
+    pis_dev = torch.from_numpy(pis).to(dev)
+
+    def exchange_up():
+        for key, g in gat.items():
+            dist.all_gather_into_tensor(g.view(-1), views[key].reshape(-1))
+
+    def up_to_host():
+        if rank == 0:
+            for key in h_pin:
+                h_pin[key].copy_(gat[key], non_blocking=True)
+        torch.cuda.synchronize()
+
+    launches = [0]
+
+    # ---- one step, end to end: host buffers in, host buffers out, every round
+    def step_e2e():
+        eng.reset(sptr if dist is not None else 0)
+        launches[0] = 1
+        if dist is None:
+            eng.initial_solve()                                    # kernels + D2H of the first proposals
+            launches[0] += eng.last_launch_count()
+            for r in range(R):
+                eng.iterate_arrays(pis[r], phases[r])              # H2D pi_r, kernels, D2H proposals
+                launches[0] += eng.last_launch_count()
+        else:
+            eng.initial_solve_device(sptr)
+            exchange_up(); up_to_host()
+            for r in range(R):
+                if rank == 0:
+                    pi_pin.copy_(torch.from_numpy(pis[r]))
+                    pi_dev.copy_(pi_pin, non_blocking=True)
+                dist.broadcast(pi_dev, src=0)                      # duals down (NCCL)
+                eng.iterate_device(pi_dev.data_ptr(), phases[r], sptr)
+                exchange_up(); up_to_host()                        # proposals up (NCCL) + D2H on rank 0
+
+    # ---- one step, device only: duals already in HBM, results stay in HBM
+    def step_dev(kern_acc=None):
+        eng.reset(sptr)
+        eng.initial_solve_device(sptr)
+        if kern_acc is not None:
+            kern_acc.append(eng.last_kernel_ms())
+        if dist is not None:
+            exchange_up()
+        for r in range(R):
+            if dist is not None:
+                pi_dev.copy_(pis_dev[r])
+                dist.broadcast(pi_dev, src=0)
+                eng.iterate_device(pi_dev.data_ptr(), phases[r], sptr)
+                exchange_up()
+            else:
+                eng.iterate_device(pis_dev[r].data_ptr(), phases[r], sptr)
+            if kern_acc is not None:
+                kern_acc.append(eng.last_kernel_ms())
+
+    def count():
+        c = eng.counters()
+        return np.array([c["pivots"], c["flips"], c["rebuilds"]], dtype=np.float64)
+
+    # =========================== e2e ===========================
+    e2e_time, e2e_cnt = 0.0, np.zeros(3)
+    for step in range(W + S):
+        flush_buf.fill_(1)
+        barrier()
+        c0 = count()
+        t0 = time.perf_counter()
+        step_e2e()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if step >= W:
+            e2e_time += dt
+            e2e_cnt += count() - c0
+    status_ok = bool((eng.status == 5).all()) if dist is None else bool((h_pin["status"].numpy() == 5).all()) if rank == 0 else True
+
+    # =========================== device only ===========================
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + S)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + S)]
+    dev_cnt = np.zeros(3)
+    kern = []
+    clocks = ClockSampler(local_rank)
+    for step in range(W + S):
+        flush_buf.fill_(1)
+        barrier()
+        if step == W:
+            clocks.start()
+        c0 = count()
+        ev0[step].record(stream)
+        step_dev()
+        ev1[step].record(stream)
+        torch.cuda.synchronize()
+        if step >= W:
+            dev_cnt += count() - c0
+    clk = clocks.stop()
+    t_dev = sum(ev0[i].elapsed_time(ev1[i]) for i in range(W, W + S)) * 1e-3
+    # kernel-only time of the dominant kernel: separate pass with a sync after every launch (the
+    # per-launch events live inside the engine), same work, not part of `value`
+    for step in range(2):
+        kern = []
+        flush_buf.fill_(1)
+        barrier()
+        c0 = count()
+        step_dev(kern)
+        torch.cuda.synchronize()
+        kcnt = count() - c0
+    kern = np.array(kern)
+    dom = 0 if kern[:, 0].sum() >= kern[:, 1].sum() else 1
+    k_time = float(kern[:, dom].sum()) * 1e-3
+    k_share = float(kern[:, dom].sum() / max(kern.sum(), 1e-30))
+
+    if dist is not None:
+        tt = torch.tensor([t_dev, e2e_time, k_time], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        pv = torch.tensor(np.concatenate([dev_cnt, e2e_cnt, kcnt]), dtype=torch.float64, device=dev)
+        dist.all_reduce(pv, op=dist.ReduceOp.SUM)
+        t_dev, e2e_time, k_time = (float(v) for v in tt.tolist())
+        pv = pv.cpu().numpy()
+        dev_cnt, e2e_cnt, kcnt = pv[0:3], pv[3:6], pv[6:9]
+    eng.close()
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (one replay, per-launch events) ----------------
+    on_smem = dom == 0
+    n_launch = R + 1
+    state_bytes = n_launch * K_total * 2.0 * 8.0 * m * n       # T loaded + stored once per launch per block
+    alg_bytes = kcnt[0] * bpp + state_bytes
+    if on_smem:
+        peak = E.measure_smem_bandwidth(local_rank)
+        peak_src = "measured live: dwgpu_measure_smem_bandwidth (FP64 read+write of a 100 KB tile, 2 CTAs/SM)"
+        bound = "smem"
+    else:
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peak = float(json.load(fh)["hbm_gbs"])
+            peak_src = "of measured (MEASURED_PEAKS.json hbm_gbs)"
+        except (OSError, KeyError, ValueError):
+            peak = 6650.0
+            peak_src = "of fallback (B200_PROFILING.md)"
+        bound = "hbm"
+    achieved = alg_bytes / k_time / 1e9 if k_time > 0 else 0.0
+    roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if peak else None, "traffic": None,
+                "kernel": "dwk::solve_kernel<%s>" % ("true,256" if on_smem else "false,1024"),
+                "kernel_ms_per_launch": 1e3 * k_time / n_launch, "launches_per_step": n_launch,
+                "kernel_share_of_solve_kernels": k_share,
+                "bytes_per_basis_change": bpp, "basis_changes_per_step": float(kcnt[0]),
+                "state_bytes_per_step": state_bytes, "peak_source": peak_src,
+                "hbm_state_GBps": state_bytes / k_time / 1e9 if k_time > 0 else None}
+
+    # ---------------- CPU baseline: same trajectory on a bounded sample of the blocks ----------------
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        sample_k = min(K_loc, args.cpu_blocks or (32 * cores if m <= 64 else 2 * cores))
+        sub = P.BlockAngularLP(K=sample_k, L=L, blocks=prob.blocks[:sample_k], link_lb=prob.link_lb,
+                               link_ub=prob.link_ub)
+        piv, secs, reps = 0, 0.0, 0
+        cpu_replay(sub, pis, phases, cores)                       # warm-up
+        while secs < args.cpu_seconds and reps < 50:
+            p_, dt, _ = cpu_replay(sub, pis, phases, cores)
+            piv += p_; secs += dt; reps += 1
+        cpu = {"value": piv / secs if secs > 0 else None, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {sample_k} of {K_total} blocks, full trajectory ({R} rounds) x {reps} replays, "
+                         f"{cores} pthreads", "seconds": secs, "note": cpu_note}
+
+    out = {
+        "metric": METRIC, "value": (dev_cnt[0] + dev_cnt[1]) / t_dev if t_dev > 0 else 0.0, "unit": UNIT,
+        "n_gpus": world, "steps": S, "warmup": W, "ms_per_step": 1e3 * t_dev / S, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "l2": "flushed between steps (256 MiB write)",
+                   "parallelism": f"blocks sharded over {world} GPU(s)" +
+                   ("; pi broadcast + proposal all-gather over NCCL every round" if world > 1 else ""),
+                   "dw_objective_of_trajectory": dw_objective},
+        "e2e": {"value": (e2e_cnt[0] + e2e_cnt[1]) / e2e_time if e2e_time > 0 else 0.0, "unit": UNIT,
+                "h2d_bytes_per_step": 8 * L * R,
+                "d2h_bytes_per_step": (R + 1) * (K_total * (8 + 8 + 4 + 4) + K_total * L * 12),
+                "ms_per_step": 1e3 * e2e_time / S},
+        "gpu_launches": launches[0] * S,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+        "pivots": {"basis_changes_per_step": dev_cnt[0] / S, "bound_flips_per_step": dev_cnt[1] / S,
+                   "rebuilds_per_step": dev_cnt[2] / S, "all_optimal": status_ok},
+    }
+    print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -96,6 +96,8 @@ struct dwgpu_engine {
     double *h_pi = nullptr;
     long long solves = 0;
     int last_launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // gmem start/end, smem start/end
+    bool ev_used[2] = {false, false};
     bool initialised = false;
 };
 
@@ -131,6 +133,7 @@ void dwgpu_destroy(dwgpu_engine *e)
     e->val.release(); e->status.release(); e->len.release(); e->ind.release();
     e->counters.release(); e->last_iters.release();
     if (e->h_pi) cudaFreeHost(e->h_pi);
+    for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -164,6 +167,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
 
     CUE(cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, opt.device));
     CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    for (auto &ev : e->ev) CUE(cudaEventCreate(&ev));
 
     // ---- sizes and offsets
     e->m.resize(K); e->n.resize(K); e->xoff.resize(K + 1); e->path.resize(K);
@@ -306,16 +310,23 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
     P.ind = e->ind.p; P.val = e->val.p; P.counters = e->counters.p; P.last_iters = e->last_iters.p;
     e->last_launches = 0;
     // large blocks first: they are the long poles
+    e->ev_used[0] = e->ev_used[1] = false;
     if (!e->list_gmem.empty()) {
+        CU(cudaEventRecord(e->ev[0], st));
         dwk::solve_kernel<false, NT_GMEM><<<(unsigned)e->list_gmem.size(), NT_GMEM, 0, st>>>(
             e->blocks.p, e->d_list_gmem.p, (int)e->list_gmem.size(), P);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(e->ev[1], st));
+        e->ev_used[1] = true;
         e->last_launches++;
     }
     if (!e->list_smem.empty()) {
+        CU(cudaEventRecord(e->ev[2], st));
         dwk::solve_kernel<true, NT_SMEM><<<(unsigned)e->list_smem.size(), NT_SMEM, e->smem_dyn, st>>>(
             e->blocks.p, e->d_list_smem.p, (int)e->list_smem.size(), P);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(e->ev[3], st));
+        e->ev_used[0] = true;
         e->last_launches++;
     }
     e->solves += e->K;
@@ -339,6 +350,23 @@ int dwgpu_fetch_results(dwgpu_engine *e, dwgpu_proposals *o)
     }
     CU(cudaStreamSynchronize(st));
     return 0;
+}
+
+int dwgpu_reset(dwgpu_engine *e, void *stream)
+{
+    if (!e || !e->initialised) return fail(DWGPU_E_STATE, "engine not initialised");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    dwk::init_kernel<256><<<e->K, 256, 0, st>>>(e->blocks.p, e->K);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int dwgpu_initial_solve_device(dwgpu_engine *e, void *stream)
+{
+    if (!e || !e->initialised) return fail(DWGPU_E_STATE, "engine not initialised");
+    CU(cudaSetDevice(e->device));
+    return launch_round(e, nullptr, 0, 1, stream ? (cudaStream_t)stream : e->stream);
 }
 
 int dwgpu_initial_solve(dwgpu_engine *e, dwgpu_proposals *out)
@@ -422,6 +450,60 @@ int dwgpu_get_block_paths(dwgpu_engine *e, int *paths)
 {
     if (!e || !paths) return fail(DWGPU_E_ARGS, "NULL argument");
     for (int k = 0; k < e->K; ++k) paths[k] = e->path[k];
+    return 0;
+}
+
+int dwgpu_last_kernel_ms(dwgpu_engine *e, float ms[2])
+{
+    if (!e || !ms) return fail(DWGPU_E_ARGS, "NULL argument");
+    CU(cudaSetDevice(e->device));
+    ms[0] = ms[1] = 0.f;
+    if (e->ev_used[0]) { CU(cudaEventSynchronize(e->ev[3])); CU(cudaEventElapsedTime(&ms[0], e->ev[2], e->ev[3])); }
+    if (e->ev_used[1]) { CU(cudaEventSynchronize(e->ev[1])); CU(cudaEventElapsedTime(&ms[1], e->ev[0], e->ev[1])); }
+    return 0;
+}
+
+namespace {
+// FP64 read-modify-write sweep over a shared-memory tile: the access pattern of the pivot update
+__global__ void __launch_bounds__(256) smem_rw_kernel(double *sink, int n_elems, int iters)
+{
+    extern __shared__ __align__(16) double tile[];
+    for (int e = threadIdx.x; e < n_elems; e += 256) tile[e] = (double)e;
+    __syncthreads();
+    const double a = 1.0000001, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+        for (int e = threadIdx.x; e < n_elems; e += 256) tile[e] = fma(tile[e], a, b);
+        __syncthreads();
+    }
+    if (sink) sink[blockIdx.x * 256 + threadIdx.x] = tile[threadIdx.x];
+}
+}  // namespace
+
+int dwgpu_measure_smem_bandwidth(int device, double *gbps)
+{
+    if (!gbps) return fail(DWGPU_E_ARGS, "NULL argument");
+    CU(cudaSetDevice(device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int n_elems = 12800, iters = 2000;             // 100 KB tile, 2 CTAs per SM
+    const size_t bytes = sizeof(double) * n_elems;
+    CU(cudaFuncSetAttribute(smem_rw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    double *sink = nullptr;
+    CU(cudaMalloc((void **)&sink, sizeof(double) * 256 * (size_t)sms * 2));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(a, 0));
+        smem_rw_kernel<<<sms * 2, 256, bytes, 0>>>(sink, n_elems, iters);
+        CU(cudaEventRecord(b, 0));
+        CU(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+    *gbps = 16.0 * n_elems * (double)iters * sms * 2 / (best * 1e-3) / 1e9;
     return 0;
 }
 

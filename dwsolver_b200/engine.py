@@ -25,7 +25,8 @@ ABI_SYMBOLS = [
     "dwgpu_options_init", "dwgpu_create", "dwgpu_destroy", "dwgpu_initial_solve", "dwgpu_iterate",
     "dwgpu_iterate_device", "dwgpu_device_results", "dwgpu_fetch_results", "dwgpu_fetch_x",
     "dwgpu_get_counters", "dwgpu_get_block_iterations", "dwgpu_last_launch_count", "dwgpu_get_block_paths",
-    "dwgpu_sync", "dwgpu_last_error", "dwgpu_version",
+    "dwgpu_sync", "dwgpu_last_error", "dwgpu_version", "dwgpu_last_kernel_ms", "dwgpu_measure_smem_bandwidth",
+    "dwgpu_reset", "dwgpu_initial_solve_device",
 ]
 
 
@@ -80,6 +81,10 @@ def load_library():
         L.dwgpu_last_launch_count.argtypes = [C.c_void_p]
         L.dwgpu_get_block_paths.argtypes = [C.c_void_p, c_ip]
         L.dwgpu_sync.argtypes = [C.c_void_p]
+        L.dwgpu_reset.argtypes = [C.c_void_p, C.c_void_p]
+        L.dwgpu_initial_solve_device.argtypes = [C.c_void_p, C.c_void_p]
+        L.dwgpu_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.dwgpu_measure_smem_bandwidth.argtypes = [C.c_int, c_dp]
         L.dwgpu_last_error.restype = C.c_char_p
         L.dwgpu_version.restype = C.c_char_p
         _LIB = L
@@ -88,6 +93,15 @@ def load_library():
 
 class DwGpuError(RuntimeError):
     pass
+
+
+def measure_smem_bandwidth(device: int = 0) -> float:
+    """GB/s, read+write, see dwgpu_measure_smem_bandwidth in include/dwgpu.h."""
+    g = C.c_double(0.0)
+    rc = load_library().dwgpu_measure_smem_bandwidth(device, C.byref(g))
+    if rc != 0:
+        raise DwGpuError(f"dwgpu_measure_smem_bandwidth failed: {load_library().dwgpu_last_error().decode()}")
+    return g.value
 
 
 def _check(rc: int, what: str):
@@ -114,7 +128,7 @@ def _bnd(a):
 class Engine:
     """Batched subproblem engine for one BlockAngularLP shard on one GPU."""
 
-    def __init__(self, prob, device: int = 0, block_range: Optional[range] = None, **opts):
+    def __init__(self, prob, device: int = 0, block_range: Optional[range] = None, fetch_x: bool = True, **opts):
         lib = load_library()
         blocks = prob.blocks if block_range is None else [prob.blocks[k] for k in block_range]
         self.K, self.L = len(blocks), prob.L
@@ -156,7 +170,7 @@ class Engine:
         self._out = Proposals(self.obj.ctypes.data_as(c_dp), self.cost.ctypes.data_as(c_dp),
                               self.status.ctypes.data_as(c_ip), self.len.ctypes.data_as(c_ip),
                               self.ind.ctypes.data_as(c_ip), self.val.ctypes.data_as(c_dp),
-                              self.x.ctypes.data_as(c_dp))
+                              self.x.ctypes.data_as(c_dp) if fetch_x else None)
 
     # ---- rounds (host buffers; arrays self.obj/... are overwritten in place) -------------
     def initial_solve(self):
@@ -170,6 +184,13 @@ class Engine:
     def iterate_device(self, d_pi_ptr: int, phase_one: bool, stream: int = 0):
         _check(self._lib.dwgpu_iterate_device(self._h, C.c_void_p(d_pi_ptr), int(bool(phase_one)),
                                               C.c_void_p(stream) if stream else None), "dwgpu_iterate_device")
+
+    def reset(self, stream: int = 0):
+        _check(self._lib.dwgpu_reset(self._h, C.c_void_p(stream) if stream else None), "dwgpu_reset")
+
+    def initial_solve_device(self, stream: int = 0):
+        _check(self._lib.dwgpu_initial_solve_device(self._h, C.c_void_p(stream) if stream else None),
+               "dwgpu_initial_solve_device")
 
     def fetch_results(self):
         _check(self._lib.dwgpu_fetch_results(self._h, C.byref(self._out)), "dwgpu_fetch_results")
@@ -217,6 +238,12 @@ class Engine:
         p = np.zeros(self.K, np.int32)
         _check(self._lib.dwgpu_get_block_paths(self._h, p.ctypes.data_as(c_ip)), "dwgpu_get_block_paths")
         return p
+
+    def last_kernel_ms(self):
+        """(shared-memory path ms, global-memory path ms) of the last round's kernels."""
+        ms = (C.c_float * 2)()
+        _check(self._lib.dwgpu_last_kernel_ms(self._h, ms), "dwgpu_last_kernel_ms")
+        return float(ms[0]), float(ms[1])
 
     def last_launch_count(self) -> int:
         return int(self._lib.dwgpu_last_launch_count(self._h))

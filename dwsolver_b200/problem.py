@@ -598,11 +598,15 @@ def load_npz(path: str) -> BlockAngularLP:
 # --------------------------------------------------------------------------------------
 # Synthetic generators
 # --------------------------------------------------------------------------------------
-def gen_mcf(K: int, nodes: int, cols: int, L: int, seed: int, name: str = "mcf") -> BlockAngularLP:
+def gen_mcf(K: int, nodes: int, cols: int, L: int, seed: int, name: str = "mcf",
+            block_range: Optional[range] = None) -> BlockAngularLP:
     """Multicommodity flow: one shared digraph (ring + random chords, ``cols-1`` arcs) plus one
     per-commodity overflow arc; block k = commodity k with flow-conservation rows (FX) and
-    per-commodity arc capacities; linking rows = joint capacity on the first L (ring) arcs.
-    All data are small integers (capacities of linking rows are multiples of 0.5)."""
+    per-commodity arc capacities; linking rows = joint capacity on the first L (ring) arcs,
+    set to 0.6 x the load of independent shortest-path routing so that they bind.
+    All data are small integers (linking capacities are multiples of 0.5), so every basic
+    solution is exactly representable.  ``block_range`` builds only a shard of the blocks (the
+    instance itself — graph, costs, capacities, linking rhs — never depends on the shard)."""
     rng = np.random.default_rng(seed)
     n_arcs = cols - 1
     if n_arcs < nodes or L > nodes:
@@ -617,77 +621,70 @@ def gen_mcf(K: int, nodes: int, cols: int, L: int, seed: int, name: str = "mcf")
             if u != v and (v - u) % nodes != 1:
                 break
         tail[a], head[a] = u, v
-    # CSR of the node-arc incidence (+1 leaves, -1 enters), shared by all commodities,
-    # extended per commodity with the overflow arc s->t in the last column.
     src = rng.integers(0, nodes, K)
     dst = (src + 1 + rng.integers(0, nodes - 1, K)) % nodes
     dem = rng.integers(1, 11, K).astype(np.float64)
     cap = rng.integers(5, 16, (K, n_arcs)).astype(np.float64)
     cost = rng.integers(1, 21, (K, n_arcs)).astype(np.float64)
 
-    # unconstrained load: per-commodity shortest path by cost (Bellman-Ford on dense arcs)
+    # unconstrained load: per-commodity shortest path by cost (Bellman-Ford, all commodities at once)
+    dist = np.full((K, nodes), np.inf)
+    dist[np.arange(K), src] = 0.0
+    for _ in range(nodes):
+        nd = dist[:, tail] + cost                      # K x arcs
+        best = np.full((K, nodes), np.inf)
+        np.minimum.at(best, (np.arange(K)[:, None], head[None, :]), nd)
+        if not (best < dist).any():
+            break
+        dist = np.minimum(dist, best)
+    tight = (dist[:, tail] + cost) == dist[:, head]    # K x arcs; costs are integers: exact
     load = np.zeros(n_arcs)
-    for k in range(K):
-        dist = np.full(nodes, np.inf)
-        pred = np.full(nodes, -1, np.int64)
-        dist[src[k]] = 0.0
-        for _ in range(nodes):
-            nd = dist[tail] + cost[k]
-            order = np.lexsort((nd, head))           # by head, then by tentative distance
-            ho = head[order]
-            first = np.ones(n_arcs, bool)
-            first[1:] = ho[1:] != ho[:-1]
-            cand_a = order[first]
-            cand_v = head[cand_a]
-            cand_d = nd[cand_a]
-            upd = cand_d < dist[cand_v]
-            if not upd.any():
-                break
-            dist[cand_v[upd]] = cand_d[upd]
-            pred[cand_v[upd]] = cand_a[upd]
-        v = dst[k]
-        guard = 0
-        while v != src[k] and pred[v] >= 0 and guard <= nodes:
-            a = pred[v]
-            load[a] += dem[k]
-            v = tail[a]
-            guard += 1
+    cur = dst.copy()
+    alive = cur != src
+    ks = np.arange(K)
+    for _ in range(nodes):
+        if not alive.any():
+            break
+        cand = tight & (head[None, :] == cur[:, None]) & alive[:, None]
+        arc = np.argmax(cand, axis=1)                  # first tight incoming arc
+        ok = cand[ks, arc]
+        np.add.at(load, arc[ok], dem[ok])
+        cur = np.where(ok, tail[arc], cur)
+        alive = ok & (cur != src)
     link_ub = np.maximum(1.0, np.floor(0.6 * load[:L] * 2.0) / 2.0)
 
-    blocks = []
-    base_rows = [[] for _ in range(nodes)]
-    for a in range(n_arcs):
-        base_rows[tail[a]].append((a, 1.0))
-        base_rows[head[a]].append((a, -1.0))
+    # shared incidence CSR (+1 leaves, -1 enters), columns sorted inside each row
+    rows_b = np.concatenate([tail, head])
+    cols_b = np.concatenate([np.arange(n_arcs), np.arange(n_arcs)])
+    vals_b = np.concatenate([np.ones(n_arcs), -np.ones(n_arcs)])
+    order = np.lexsort((cols_b, rows_b))
+    rows_b, cols_b, vals_b = rows_b[order], cols_b[order].astype(np.int32), vals_b[order]
+    rp_b = np.zeros(nodes + 1, np.int64)
+    np.add.at(rp_b, rows_b + 1, 1)
+    rp_b = np.cumsum(rp_b)
     d_row = np.arange(L, dtype=np.int32)
-    d_col = np.arange(L, dtype=np.int32)
     d_val = np.ones(L)
-    for k in range(K):
-        rowptr = [0]
-        ci: List[int] = []
-        cv: List[float] = []
-        for v in range(nodes):
-            ent = list(base_rows[v])
-            if v == src[k]:
-                ent.append((n_arcs, 1.0))
-            if v == dst[k]:
-                ent.append((n_arcs, -1.0))
-            ent.sort()
-            ci.extend(e[0] for e in ent)
-            cv.extend(e[1] for e in ent)
-            rowptr.append(len(ci))
+    blocks = []
+    vidx = np.arange(nodes + 1)
+    for k in (range(K) if block_range is None else block_range):
+        s, t = int(src[k]), int(dst[k])
+        # the overflow arc (last column) is appended to the rows of its two end nodes
+        ins = np.array([rp_b[s + 1], rp_b[t + 1]]) if s < t else np.array([rp_b[t + 1], rp_b[s + 1]])
+        insv = np.array([1.0, -1.0]) if s < t else np.array([-1.0, 1.0])
+        ci = np.insert(cols_b, ins, n_arcs).astype(np.int32)
+        cv = np.insert(vals_b, ins, insv)
+        rowptr = (rp_b + (vidx > s) + (vidx > t)).astype(np.int32)
         b = np.zeros(nodes)
-        b[src[k]] = dem[k]
-        b[dst[k]] = -dem[k]
+        b[s] = dem[k]
+        b[t] = -dem[k]
         c = np.concatenate([cost[k], [1000.0]])
         ub = np.concatenate([cap[k], [dem[k]]])
         blocks.append(Block(
-            m=nodes, n=cols, a_rowptr=np.asarray(rowptr, np.int32), a_col=np.asarray(ci, np.int32),
-            a_val=np.asarray(cv, np.float64), row_lb=b.copy(), row_ub=b.copy(),
-            col_lb=np.zeros(cols), col_ub=ub, c_file=c.copy(), c_master=c.copy(),
-            d_row=d_row.copy(), d_col=d_col.copy(), d_val=d_val.copy()))
-    return BlockAngularLP(K=K, L=L, blocks=blocks, link_lb=np.full(L, -INF), link_ub=link_ub,
-                          name=name, meta={"kind": "mcf", "seed": seed, "nodes": nodes, "cols": cols})
+            m=nodes, n=cols, a_rowptr=rowptr, a_col=ci, a_val=cv, row_lb=b, row_ub=b.copy(),
+            col_lb=np.zeros(cols), col_ub=ub, c_file=c, c_master=c.copy(),
+            d_row=d_row, d_col=d_row, d_val=d_val))
+    return BlockAngularLP(K=len(blocks), L=L, blocks=blocks, link_lb=np.full(L, -INF), link_ub=link_ub,
+                          name=name, meta={"kind": "mcf", "seed": seed, "nodes": nodes, "cols": cols, "K_total": K})
 
 
 def gen_dense(K: int, m: int, n: int, L: int, seed: int, dens_a: float = 0.02, dens_d: float = 0.25,
@@ -730,10 +727,16 @@ CONFIGS = {
 }
 
 
-def make_config(tag: str, K: Optional[int] = None) -> BlockAngularLP:
+def make_config(tag: str, K: Optional[int] = None, block_range: Optional[range] = None) -> BlockAngularLP:
+    """The named synthetic instance; ``K`` overrides the block count (a different, smaller
+    instance), ``block_range`` builds only that shard of the SAME instance."""
     cfg = dict(CONFIGS[tag])
     if K is not None:
         cfg["K"] = K
     if cfg["kind"] == "mcf":
-        return gen_mcf(cfg["K"], cfg["m"], cfg["n"], cfg["L"], cfg["seed"], name=f"mcf{tag}")
-    return gen_dense(cfg["K"], cfg["m"], cfg["n"], cfg["L"], cfg["seed"], name=f"dense{tag}")
+        return gen_mcf(cfg["K"], cfg["m"], cfg["n"], cfg["L"], cfg["seed"], name=f"mcf{tag}", block_range=block_range)
+    p = gen_dense(cfg["K"], cfg["m"], cfg["n"], cfg["L"], cfg["seed"], name=f"dense{tag}")
+    if block_range is not None:
+        p.blocks = [p.blocks[k] for k in block_range]
+        p.K = len(p.blocks)
+    return p

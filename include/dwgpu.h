@@ -105,12 +105,20 @@ int  dwgpu_create(int K, int L, const dwgpu_block_desc *blocks, const dwgpu_opti
                   dwgpu_engine **out);
 void dwgpu_destroy(dwgpu_engine *e);
 
+/* Back to the state right after dwgpu_create(): all-logical basis, T = A_k (what a fresh
+ * glp_read_lp gives the reference, src/dw_subprob.c:105-111).  Asynchronous on `stream`
+ * (NULL = the engine's stream).  Counters are kept. */
+int  dwgpu_reset(dwgpu_engine *e, void *stream);
+
 /* Cold solve of every block with its file objective; fills *out (may be NULL). */
 int  dwgpu_initial_solve(dwgpu_engine *e, dwgpu_proposals *out);
 
 /* One round with HOST buffers: pi (L doubles) is copied to the device, every block is priced
  * and re-solved from its stored basis, and the proposals are copied back into *out. */
 int  dwgpu_iterate(dwgpu_engine *e, const double *pi, int phase_one, dwgpu_proposals *out);
+
+/* Cold solve on the caller's stream, results left on the device (see dwgpu_iterate_device). */
+int  dwgpu_initial_solve_device(dwgpu_engine *e, void *stream);
 
 /* One round with DEVICE buffers on the caller's stream (cudaStream_t passed as void*; NULL =
  * the engine's own stream).  Asynchronous; results stay on the device, see
@@ -131,6 +139,14 @@ int  dwgpu_get_block_iterations(dwgpu_engine *e, long long *iters);
 int  dwgpu_last_launch_count(dwgpu_engine *e);
 /* 1 = shared-memory CTA path, 2 = global-memory CTA path, per block */
 int  dwgpu_get_block_paths(dwgpu_engine *e, int *paths);
+/* device time (CUDA events on the launching stream) of the last round's solve kernels:
+ * ms[0] = shared-memory path launch, ms[1] = global-memory path launch (0 when not launched).
+ * Synchronises on the end events. */
+int  dwgpu_last_kernel_ms(dwgpu_engine *e, float ms[2]);
+/* Shared-memory read+write bandwidth of the device in GB/s (FP64 read-modify-write of a
+ * ~100 KB tile per CTA, 2 CTAs per SM, all SMs) — the roofline denominator for the
+ * shared-memory path, which MEASURED_PEAKS.json does not carry. */
+int  dwgpu_measure_smem_bandwidth(int device, double *gbps);
 int  dwgpu_sync(dwgpu_engine *e);
 const char *dwgpu_last_error(void);
 const char *dwgpu_version(void);
