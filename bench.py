@@ -225,8 +225,12 @@ def main():
 
     views = dev_views()
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the C ABI treats a NULL stream as "the engine's own stream",
+    # and all timing events must sit on the stream the kernels are launched on
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
 
     def barrier():
         if dist is not None:
@@ -260,7 +264,7 @@ def main():
 
     # ---- one step, end to end: host buffers in, host buffers out, every round
     def step_e2e():
-        eng.reset(sptr if dist is not None else 0)
+        eng.reset(sptr if dist is not None else 0)    # single GPU: the engine's own stream end to end
         launches[0] = 1
         if dist is None:
             eng.initial_solve()                                    # kernels + D2H of the first proposals
@@ -391,6 +395,7 @@ def main():
                 "kernel": "dwk::solve_kernel<%s>" % ("true,256" if on_smem else "false,1024"),
                 "kernel_ms_per_launch": 1e3 * k_time / n_launch, "launches_per_step": n_launch,
                 "kernel_share_of_solve_kernels": k_share,
+                "kernel_ms_by_launch": [round(float(v), 4) for v in kern[:, dom]],
                 "bytes_per_basis_change": bpp, "basis_changes_per_step": float(kcnt[0]),
                 "state_bytes_per_step": state_bytes, "peak_source": peak_src,
                 "hbm_state_GBps": state_bytes / k_time / 1e9 if k_time > 0 else None}

@@ -17,6 +17,7 @@
 
 #include "../../include/dwgpu.h"
 #include "simplex_cta.cuh"
+#include "simplex_smem.cuh"
 
 namespace {
 
@@ -82,9 +83,9 @@ struct dwgpu_engine {
     size_t smem_dyn = 0;
     int max_smem_optin = 0;
     // device arenas
-    DevBuf<double> T, beta, lo, up, a_v, dc_val, dr_val, c_file, c_master, x, ws;
-    DevBuf<int> head, nbv, a_rp, a_ci, dc_ptr, dc_row, dr_ptr, dr_col;
-    DevBuf<signed char> vstat;
+    DevBuf<double> T, bnd, a_v, dc_val, dr_val, c_file, c_master, x, ws;
+    DevBuf<int> a_rp, a_ci, dc_ptr, dc_row, dr_ptr, dr_col;
+    DevBuf<char> pst;
     DevBuf<dwk::BlockDev> blocks;
     DevBuf<int> d_list_smem, d_list_gmem;
     // round inputs / outputs
@@ -124,11 +125,11 @@ void dwgpu_destroy(dwgpu_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    e->T.release(); e->beta.release(); e->lo.release(); e->up.release(); e->a_v.release();
+    e->T.release(); e->bnd.release(); e->pst.release(); e->a_v.release();
     e->dc_val.release(); e->dr_val.release(); e->c_file.release(); e->c_master.release();
-    e->x.release(); e->ws.release(); e->head.release(); e->nbv.release(); e->a_rp.release();
+    e->x.release(); e->ws.release(); e->a_rp.release();
     e->a_ci.release(); e->dc_ptr.release(); e->dc_row.release(); e->dr_ptr.release();
-    e->dr_col.release(); e->vstat.release(); e->blocks.release(); e->d_list_smem.release();
+    e->dr_col.release(); e->blocks.release(); e->d_list_smem.release();
     e->d_list_gmem.release(); e->pi.release(); e->obj.release(); e->cost.release();
     e->val.release(); e->status.release(); e->len.release(); e->ind.release();
     e->counters.release(); e->last_iters.release();
@@ -172,7 +173,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     // ---- sizes and offsets
     e->m.resize(K); e->n.resize(K); e->xoff.resize(K + 1); e->path.resize(K);
     std::vector<long long> t_off(K + 1, 0), r_off(K + 1, 0), v_off(K + 1, 0), a_off(K + 1, 0),
-        arp_off(K + 1, 0), d_off(K + 1, 0), dcp_off(K + 1, 0), drp_off(K + 1, 0), ws_off(K + 1, 0);
+        arp_off(K + 1, 0), d_off(K + 1, 0), dcp_off(K + 1, 0), drp_off(K + 1, 0), ws_off(K + 1, 0), pst_off(K + 1, 0);
     std::vector<int> ldg(K);
     e->xoff[0] = 0;
     const size_t smem_cap = (size_t)e->max_smem_optin - 2048;   // static scratch + reserve
@@ -181,9 +182,17 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         if (b.m < 0 || b.n < 0 || b.d_nnz < 0 || (b.m > 0 && !b.a_rowptr))
             { fail(DWGPU_E_ARGS, "bad block descriptor"); return bail(DWGPU_E_ARGS); }
         e->m[k] = b.m; e->n[k] = b.n;
-        ldg[k] = (b.n + 3) & ~3;
+        const bool fits = dwk::smem2_bytes(b.m, b.n) <= smem_cap;
+        int path = fits ? 1 : 2;
+        if (opt.force_path == 2) path = 2;
+        if (opt.force_path == 1 && !fits)
+            { fail(DWGPU_E_ARGS, "force_path=1 but a block does not fit shared memory"); return bail(DWGPU_E_ARGS); }
+        e->path[k] = path;
+        // shared-memory path: the HBM image of T has the shared layout (even ld), one bulk copy
+        ldg[k] = path == 1 ? dwk::smem2_ld(b.n) : ((b.n + 3) & ~3);
         const int nnz = b.m > 0 ? b.a_rowptr[b.m] : 0;
         t_off[k + 1] = t_off[k] + (long long)b.m * ldg[k];
+        pst_off[k + 1] = pst_off[k] + (long long)dwk::pst_bytes(b.m, b.n);
         r_off[k + 1] = r_off[k] + b.m;
         e->xoff[k + 1] = e->xoff[k] + b.n;
         v_off[k + 1] = v_off[k] + b.m + b.n;
@@ -192,27 +201,21 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         d_off[k + 1] = d_off[k] + b.d_nnz;
         dcp_off[k + 1] = dcp_off[k] + b.n + 1;
         drp_off[k + 1] = drp_off[k] + L + 1;
-        const bool fits = dwk::smem_bytes(b.m, b.n) <= smem_cap;
-        int path = fits ? 1 : 2;
-        if (opt.force_path == 2) path = 2;
-        if (opt.force_path == 1 && !fits)
-            { fail(DWGPU_E_ARGS, "force_path=1 but a block does not fit shared memory"); return bail(DWGPU_E_ARGS); }
-        e->path[k] = path;
-        if (path == 1) { e->list_smem.push_back(k); e->smem_dyn = std::max(e->smem_dyn, dwk::smem_bytes(b.m, b.n)); }
+        if (path == 1) { e->list_smem.push_back(k); e->smem_dyn = std::max(e->smem_dyn, dwk::smem2_bytes(b.m, b.n)); }
         else e->list_gmem.push_back(k);
         ws_off[k + 1] = ws_off[k] + (path == 2 ? (long long)((dwk::vec_bytes(b.m, b.n) + 15) / 16 * 2) : 0);
     }
     e->ntot = e->xoff[K];
 
     // ---- host staging of the static data
-    std::vector<double> h_lo(v_off[K]), h_up(v_off[K]), h_av(a_off[K]), h_dcv(d_off[K]), h_drv(d_off[K]),
+    std::vector<double> h_bnd(2 * v_off[K]), h_av(a_off[K]), h_dcv(d_off[K]), h_drv(d_off[K]),
         h_cf(e->ntot), h_cm(e->ntot);
     std::vector<int> h_arp(arp_off[K]), h_aci(a_off[K]), h_dcp(dcp_off[K]), h_dcr(d_off[K]), h_drp(drp_off[K]),
         h_drc(d_off[K]);
     for (int k = 0; k < K; ++k) {
         const dwgpu_block_desc &b = bd[k];
         const int m = b.m, n = b.n;
-        double *lo = h_lo.data() + v_off[k], *up = h_up.data() + v_off[k];
+        double *lo = h_bnd.data() + 2 * v_off[k], *up = lo + (m + n);
         for (int i = 0; i < m; ++i) { lo[i] = norm_bound(b.row_lb[i], false); up[i] = norm_bound(b.row_ub[i], true); }
         for (int j = 0; j < n; ++j) {
             double l = norm_bound(b.col_lb[j], false), u = norm_bound(b.col_ub[j], true);
@@ -249,9 +252,9 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
 
     // ---- device arenas
     CUE(e->T.alloc(t_off[K]));
-    CUE(e->beta.alloc(r_off[K])); CUE(e->head.alloc(r_off[K]));
-    CUE(e->nbv.alloc(e->ntot)); CUE(e->vstat.alloc(v_off[K]));
-    CUE(e->lo.upload(h_lo)); CUE(e->up.upload(h_up));
+    CUE(e->pst.alloc(pst_off[K]));
+    CUE(cudaMemset(e->pst.p, 0, std::max<long long>(pst_off[K], 1)));
+    CUE(e->bnd.upload(h_bnd));
     CUE(e->a_rp.upload(h_arp)); CUE(e->a_ci.upload(h_aci)); CUE(e->a_v.upload(h_av));
     CUE(e->dc_ptr.upload(h_dcp)); CUE(e->dc_row.upload(h_dcr)); CUE(e->dc_val.upload(h_dcv));
     CUE(e->dr_ptr.upload(h_drp)); CUE(e->dr_col.upload(h_drc)); CUE(e->dr_val.upload(h_drv));
@@ -272,9 +275,10 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         std::memset(&B, 0, sizeof(B));
         B.m = e->m[k]; B.n = e->n[k]; B.L = L; B.ldg = ldg[k];
         B.T = e->T.p + t_off[k];
-        B.beta = e->beta.p + r_off[k]; B.head = e->head.p + r_off[k];
-        B.nbv = e->nbv.p + e->xoff[k]; B.vstat = e->vstat.p + v_off[k];
-        B.lo = e->lo.p + v_off[k]; B.up = e->up.p + v_off[k];
+        char *ps = e->pst.p + pst_off[k];        // beta[m] | head[m] | nbv[n] | vstat[m+n]
+        B.beta = (double *)ps; B.head = (int *)(ps + sizeof(double) * (size_t)B.m);
+        B.nbv = B.head + B.m; B.vstat = (signed char *)(B.nbv + B.n);
+        B.lo = e->bnd.p + 2 * v_off[k]; B.up = B.lo + (B.m + B.n);
         B.a_rp = e->a_rp.p + arp_off[k]; B.a_ci = e->a_ci.p + a_off[k]; B.a_v = e->a_v.p + a_off[k];
         B.dc_ptr = e->dc_ptr.p + dcp_off[k]; B.dc_row = e->dc_row.p + d_off[k]; B.dc_val = e->dc_val.p + d_off[k];
         B.dr_ptr = e->dr_ptr.p + drp_off[k]; B.dr_col = e->dr_col.p + d_off[k]; B.dr_val = e->dr_val.p + d_off[k];
@@ -287,7 +291,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(e->d_list_gmem.upload(e->list_gmem));
 
     if (!e->list_smem.empty())
-        CUE(cudaFuncSetAttribute(dwk::solve_kernel<true, NT_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)e->smem_dyn));
 
     dwk::init_kernel<256><<<K, 256, 0, e->stream>>>(e->blocks.p, K);
@@ -322,7 +326,7 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
     }
     if (!e->list_smem.empty()) {
         CU(cudaEventRecord(e->ev[2], st));
-        dwk::solve_kernel<true, NT_SMEM><<<(unsigned)e->list_smem.size(), NT_SMEM, e->smem_dyn, st>>>(
+        dwk::solve_smem_kernel<NT_SMEM><<<(unsigned)e->list_smem.size(), NT_SMEM, e->smem_dyn, st>>>(
             e->blocks.p, e->d_list_smem.p, (int)e->list_smem.size(), P);
         CU(cudaGetLastError());
         CU(cudaEventRecord(e->ev[3], st));
