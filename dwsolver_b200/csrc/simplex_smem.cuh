@@ -1,17 +1,22 @@
 // simplex_smem.cuh — shared-memory-resident CTA-per-block simplex (config A class blocks).
 //
 // Same algorithm and tolerances as simplex_cta.cuh (the generic kernel), specialised for blocks
-// whose whole working set fits one CTA's shared memory:
-//   * the block's state image [T | beta head nbv vstat] and its bounds are moved HBM<->SMEM with
-//     TMA bulk copies (cp.async.bulk + mbarrier): one elected thread issues three copies, nobody
-//     spins on LDG latency, and T is written back only if the basis changed;
+// whose whole working set fits one CTA's shared memory (three CTAs per SM at 64 x 128):
+//   * the block's state image [T | beta head nbv vstat] moves HBM<->SMEM with TMA bulk copies
+//     (cp.async.bulk + mbarrier): one elected thread issues them, nobody spins on LDG latency; T
+//     is written back only if the basis changed, and nothing at all is written back (not even the
+//     proposal) when the block was already optimal under the new prices;
 //   * the reduced-cost row d is row m of the shared tableau, so one rank-1 sweep updates both;
-//   * pricing (argmax |d_j|) and the two-pass Harris ratio test run inside warp 0 with shuffle
-//     reductions only; bound flips loop inside warp 0 without any block barrier; a basis change
-//     costs two __syncthreads (decision -> update -> next decision);
-//   * the rank-1 update is row-per-warp, 16-byte (double2) shared accesses, four rows in flight
-//     per warp, and rows whose pivot-column entry is exactly zero are skipped (network LPs have
-//     very sparse tableau columns).
+//   * bounds are kept per ROW (basic variable of row i) and per COLUMN (nonbasic variable of
+//     column j) and swapped at a basis change, so pricing and the ratio test have no dependent
+//     gathers;
+//   * pricing (argmax |d_j|) and the two-pass Harris ratio test run inside warp 0: one reciprocal
+//     per blocking row, exact ratios cached for pass 2, `redux.sync` max/min on the two 32-bit
+//     halves of the (non-negative) keys instead of 64-bit shuffle trees; bound flips loop inside
+//     warp 0 without any block barrier; a basis change costs two __syncthreads;
+//   * while it reads the pivot column, warp 0 builds the list of rows whose entry is non-zero
+//     (ballot + popc); the rank-1 sweep only visits those rows (network LPs: ~10 % of the rows),
+//     one row per warp at a time, 16-byte (double2) shared accesses.
 // Reference being replaced: one warm-started glp_simplex call per block and round
 // (/root/reference/src/dw_subprob.c:329) plus the pricing / column code around it (:291-321,
 // :453-540).
@@ -75,147 +80,192 @@ __host__ __device__ inline size_t smem2_bytes(int m, int n)
 {
     const size_t ld = smem2_ld(n);
     return align16(sizeof(double) * (size_t)(m + 1) * ld)     // T and the d row
-         + align16(sizeof(double) * 2 * (size_t)(m + n))      // lo | up
          + pst_bytes(m, n)
-         + align16(sizeof(double) * ld)                       // rowp
-         + align16(sizeof(double) * (size_t)n) * 2            // cs, d1
+         + align16(sizeof(double) * 2 * (size_t)(m + n))      // rlo rup clo cup
+         + align16(sizeof(double) * ld)                       // rowp (also phase-1 prices, x staging)
+         + align16(sizeof(double) * (size_t)n)                // cs
          + align16(sizeof(double) * (size_t)(m + 1))          // colq
-         + align16(sizeof(double) * (size_t)m);               // w
+         + align16(sizeof(double) * (size_t)m)                // w (phase-1 weights / cached ratios)
+         + align16((size_t)n)                                 // cstat
+         + align16(sizeof(unsigned short) * (size_t)(m + 1)); // active rows
 }
 
 enum { K_NONE = 0, K_PIVOT = 1, K_FAIL = 2, K_REDO = 3 };
 
 struct Decision {
-    int kind, p, q, fail_status;
+    int p, q, na, fail_status;
     double inv;
 };
 
-struct Smem2 {
+struct Sm3 {
     int m, n, ld;
-    double *T;       // (m+1) x ld, row m = reduced costs d
-    double *lo, *up;
+    double *T, *drow;
     double *beta;
     int *head, *nbv;
     signed char *vstat;
-    double *rowp, *cs, *d1, *colq, *w;
+    double *rlo, *rup, *clo, *cup;
+    double *rowp, *cs, *colq, *w;
+    signed char *cstat;
+    unsigned short *arow;
 };
 
-__device__ __forceinline__ double warp_min(double v)
+// lane holding the maximum of non-negative keys (ties: lowest lane); -1 if no lane is valid
+__device__ __forceinline__ int warp_argmax_nonneg(double key, bool valid)
 {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+    const unsigned hi = valid ? (unsigned)__double2hiint(key) : 0u;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const bool c1 = valid && hi == mh;
+    const unsigned lo = c1 ? (unsigned)__double2loint(key) : 0u;
+    const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+    const unsigned b = __ballot_sync(0xffffffffu, c1 && lo == ml);
+    return b ? (__ffs(b) - 1) : -1;
 }
-
-__device__ __forceinline__ RowLim row_limit2(const Smem2 &c, int i, double s, double tiq, bool infeasible,
-                                             double tol_bnd, double tol_piv)
+// minimum of non-negative doubles (+inf allowed)
+__device__ __forceinline__ double warp_min_nonneg(double v)
 {
-    RowLim r; r.a = s * tiq; r.blocks = false; r.target = 0.0;
-    const int v = c.head[i];
-    double lo = c.lo[v], up = c.up[v];
-    if (infeasible) {
-        const double b = c.beta[i];
-        if (b < lo - tol_bnd * (1.0 + fabs(lo))) { up = lo; lo = -CUDART_INF; }
-        else if (b > up + tol_bnd * (1.0 + fabs(up))) { lo = up; up = CUDART_INF; }
-    }
-    if (r.a > tol_piv) { if (up < BIG) { r.blocks = true; r.target = up; } }
-    else if (r.a < -tol_piv) { if (lo > -BIG) { r.blocks = true; r.target = lo; } }
-    return r;
+    const unsigned hi = (unsigned)__double2hiint(v);
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned lo = hi == mh ? (unsigned)__double2loint(v) : 0xffffffffu;
+    const unsigned ml = __reduce_min_sync(0xffffffffu, lo);
+    return __hiloint2double((int)mh, (int)ml);
 }
 
 // Executed by warp 0 only.  Chooses the entering column and the leaving row, applies bound flips
-// on the spot, and for a basis change stages everything the rank-1 sweep needs (colq, rowp, beta,
-// head/nbv/vstat).  dd = reduced costs to price with (row m of T in phase 2, d1 in phase 1).
-__device__ int decide_warp0(Smem2 &c, const double *dd, bool infeasible, bool d_live, bool &bland, int &degen,
-                            int degen_limit, double tol_dj, double tol_bnd, double tol_piv,
+// on the spot, and for a basis change stages everything the rank-1 sweep needs (colq, rowp,
+// active rows, beta, head/nbv/vstat/bounds).  dd = prices (row m of T in phase 2; phase-1 prices
+// live in rowp and are consumed before rowp is overwritten).
+template <bool INF>
+__device__ int decide_warp0(Sm3 &c, const double *dd, bool d_live, bool &bland, int &degen, int degen_limit,
+                            double tol_dj, double tol_bnd, double tol_piv,
                             unsigned long long &n_piv, unsigned long long &n_flip, Decision *dec)
 {
     const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int m = c.m, n = c.n, ld = c.ld;
     const double harris = 0.5 * tol_bnd;
     for (;;) {
-        double key = -CUDART_INF; int q = INT_MAX;
+        // ---- pricing
+        double key = 0.0; int q = -1;
         for (int j = lane; j < n; j += 32) {
             const double dj = dd[j];
-            const int v = c.nbv[j];
-            const signed char st = c.vstat[v];
+            const signed char st = c.cstat[j];
             const bool ok = (st == ST_LO && dj < -tol_dj) || (st == ST_UP && dj > tol_dj) ||
                             (st == ST_FREE && fabs(dj) > tol_dj);
-            if (ok) {
-                const double kj = bland ? -(double)v : fabs(dj);
-                if (kj > key) { key = kj; q = j; }
-            }
+            const double kj = bland ? 2147483648.0 - (double)c.nbv[j] : fabs(dj);
+            if (ok && kj > key) { key = kj; q = j; }
         }
-        warp_argmax(key, q);
-        if (q == INT_MAX) return K_NONE;
+        {
+            const int src = warp_argmax_nonneg(key, q >= 0);
+            if (src < 0) return K_NONE;
+            q = __shfl_sync(0xffffffffu, q, src);
+        }
         const double dq = dd[q];
         const double s = dq < 0.0 ? 1.0 : -1.0;
-        const int vq = c.nbv[q];
-        const signed char stq = c.vstat[vq];
-        // pass 1: Harris bound on the step
+        const signed char stq = c.cstat[q];
+        const double loq = c.clo[q], upq = c.cup[q];
+        // ---- ratio test, pass 1: Harris bound; caches exact ratios in w, builds the active-row list
         double tmax = CUDART_INF;
-        for (int i = lane; i < m; i += 32) {
-            const double tiq = c.T[(size_t)i * ld + q];
-            c.colq[i] = tiq;
-            const RowLim r = row_limit2(c, i, s, tiq, infeasible, tol_bnd, tol_piv);
-            if (r.blocks) {
-                const double delta = bland ? 0.0 : harris * (1.0 + fabs(r.target));
-                const double t = fmax((r.target - c.beta[i]) / r.a + delta / fabs(r.a), 0.0);
-                tmax = fmin(tmax, t);
+        int na = 0;
+        for (int i0 = 0; i0 < m; i0 += 32) {
+            const int i = i0 + lane;
+            const bool in = i < m;
+            double tiq = 0.0, tex = CUDART_INF;
+            if (in) {
+                tiq = c.T[(size_t)i * ld + q];
+                c.colq[i] = tiq;
+                const double a = s * tiq;
+                double lo = c.rlo[i], up = c.rup[i];
+                const double b = c.beta[i];
+                if (INF) {
+                    if (b < lo - tol_bnd * (1.0 + fabs(lo))) { up = lo; lo = -CUDART_INF; }
+                    else if (b > up + tol_bnd * (1.0 + fabs(up))) { lo = up; up = CUDART_INF; }
+                }
+                bool blocks = false; double slack = 0.0, target = 0.0;
+                if (a > tol_piv) { if (up < BIG) { blocks = true; slack = up - b; target = up; } }
+                else if (a < -tol_piv) { if (lo > -BIG) { blocks = true; slack = b - lo; target = lo; } }
+                if (blocks) {
+                    const double r = __drcp_rn(fabs(a));
+                    tex = slack * r;
+                    const double delta = bland ? 0.0 : harris * (1.0 + fabs(target));
+                    tmax = fmin(tmax, fmax((slack + delta) * r, 0.0));
+                }
+                c.w[i] = tex;
             }
+            const unsigned bal = __ballot_sync(0xffffffffu, in && tiq != 0.0);
+            if (in && tiq != 0.0) c.arow[na + __popc(bal & lt_mask)] = (unsigned short)i;
+            na += __popc(bal);
         }
-        tmax = warp_min(tmax);
-        // pass 2: largest |pivot| among rows whose exact ratio is within the bound
-        double pk = -CUDART_INF; int p = INT_MAX;
+        tmax = warp_min_nonneg(tmax);
+        // ---- pass 2: largest |pivot| among rows whose exact ratio is within the bound
+        int p = -1;
         if (tmax < CUDART_INF) {
-            const double slack = bland ? 1e-12 * (1.0 + tmax) : 0.0;
+            const double lim = bland ? tmax + 1e-12 * (1.0 + tmax) : tmax;
+            double pk = 0.0;
+            __syncwarp();
             for (int i = lane; i < m; i += 32) {
-                const RowLim r = row_limit2(c, i, s, c.colq[i], infeasible, tol_bnd, tol_piv);
-                if (r.blocks) {
-                    const double t = (r.target - c.beta[i]) / r.a;
-                    if (t <= tmax + slack) {
-                        const double kk = bland ? -(double)c.head[i] : fabs(r.a);
-                        if (kk > pk) { pk = kk; p = i; }
-                    }
+                if (c.w[i] <= lim) {
+                    const double kk = bland ? 2147483648.0 - (double)c.head[i] : fabs(c.colq[i]);
+                    if (kk > pk) { pk = kk; p = i; }
                 }
             }
-            warp_argmax(pk, p);
+            const int src = warp_argmax_nonneg(pk, p >= 0);
+            p = src >= 0 ? __shfl_sync(0xffffffffu, p, src) : -1;
         }
         __syncwarp();
-        double theta = CUDART_INF, target = 0.0;
-        if (p != INT_MAX) {
-            const RowLim r = row_limit2(c, p, s, c.colq[p], infeasible, tol_bnd, tol_piv);
-            target = r.target;
-            theta = fmax(0.0, (r.target - c.beta[p]) / r.a);
-        }
-        const double range = (stq == ST_FREE) ? CUDART_INF : c.up[vq] - c.lo[vq];
+        const double theta = p >= 0 ? fmax(0.0, c.w[p]) : CUDART_INF;
+        const double range = (stq == ST_FREE) ? CUDART_INF : upq - loq;
         if (range <= theta) {
-            if (!(range < BIG)) { if (lane == 0) dec->fail_status = infeasible ? 1 : 6; return K_FAIL; }
+            if (!(range < BIG)) { if (lane == 0) dec->fail_status = INF ? 1 : 6; return K_FAIL; }
             for (int i = lane; i < m; i += 32) c.beta[i] = fma(s * range, c.colq[i], c.beta[i]);
-            if (lane == 0) c.vstat[vq] = (stq == ST_LO) ? ST_UP : ST_LO;
+            if (lane == 0) {
+                const signed char ns = (stq == ST_LO) ? ST_UP : ST_LO;
+                c.cstat[q] = ns;
+                c.vstat[c.nbv[q]] = ns;
+            }
             ++n_flip;
             degen = 0; bland = false;
             __syncwarp();
-            if (infeasible) return K_REDO;     // phase-1 prices depend on beta
+            if (INF) return K_REDO;     // phase-1 prices depend on beta
             continue;
         }
-        if (p == INT_MAX) { if (lane == 0) dec->fail_status = infeasible ? 1 : 6; return K_FAIL; }
+        if (p < 0) { if (lane == 0) dec->fail_status = INF ? 1 : 6; return K_FAIL; }
         // ---- basis change: stage the sweep
-        const double xq_new = nb_value(stq, c.lo[vq], c.up[vq]) + s * theta;
-        const int vleave = c.head[p];
-        const double inv = 1.0 / c.colq[p];
+        const double piv = c.colq[p];
+        const double inv = __drcp_rn(piv);
+        const double xq_new = nb_value(stq, loq, upq) + s * theta;
+        const double lov = c.rlo[p], upv = c.rup[p];
+        double target;      // the bound the leaving variable was heading for
+        {
+            double lo = lov, up = upv;
+            if (INF) {
+                const double bp = c.beta[p];
+                if (bp < lo - tol_bnd * (1.0 + fabs(lo))) up = lo;          // rises to its lower bound
+                else if (bp > up + tol_bnd * (1.0 + fabs(up))) lo = up;     // falls to its upper bound
+            }
+            target = (s * piv > 0.0) ? up : lo;
+        }
         __syncwarp();
         for (int i = lane; i < m; i += 32)
             c.beta[i] = (i == p) ? xq_new : fma(s * theta, c.colq[i], c.beta[i]);
-        for (int j = lane; j < ld; j += 32) c.rowp[j] = c.T[(size_t)p * ld + j] * inv;
+        {
+            const double2 *prow = reinterpret_cast<const double2 *>(c.T + (size_t)p * ld);
+            double2 *rp2 = reinterpret_cast<double2 *>(c.rowp);
+            for (int j2 = lane; j2 < (ld >> 1); j2 += 32) {
+                double2 v = prow[j2];
+                v.x *= inv; v.y *= inv;
+                rp2[j2] = v;
+            }
+        }
         if (lane == 0) {
-            c.colq[m] = d_live ? dq : 0.0;
-            const double lov = c.lo[vleave], upv = c.up[vleave];
-            c.vstat[vleave] = (lov == upv) ? ST_FIX : (target == lov ? ST_LO : ST_UP);
-            c.vstat[vq] = ST_BASIC;
-            c.head[p] = vq;
-            c.nbv[q] = vleave;
-            dec->p = p; dec->q = q; dec->inv = inv;
+            const signed char ns = (lov == upv) ? ST_FIX : (target == lov ? ST_LO : ST_UP);
+            const int vleave = c.head[p], vq = c.nbv[q];
+            c.rlo[p] = loq; c.rup[p] = upq; c.clo[q] = lov; c.cup[q] = upv;
+            c.cstat[q] = ns; c.vstat[vleave] = ns; c.vstat[vq] = ST_BASIC;
+            c.head[p] = vq; c.nbv[q] = vleave;
+            const bool with_d = d_live && dq != 0.0;
+            c.colq[m] = with_d ? dq : 0.0;
+            if (with_d) c.arow[na] = (unsigned short)m;      // the reduced-cost row rides along
+            dec->p = p; dec->q = q; dec->inv = inv; dec->na = na + (with_d ? 1 : 0);
         }
         ++n_piv;
         if (theta <= 1e-11) { if (++degen > degen_limit) bland = true; }
@@ -224,48 +274,62 @@ __device__ int decide_warp0(Smem2 &c, const double *dd, bool infeasible, bool d_
     }
 }
 
-// rank-1 sweep over rows [0, rows) of T (row m = d): row-per-warp, double2, 4 rows in flight,
-// rows with a zero multiplier are skipped
+// rank-1 sweep over the active rows only (row m = reduced costs when it is in the list)
 template <int NT>
-__device__ __forceinline__ void sweep(Smem2 &c, int p, int q, double inv, int rows)
+__device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, int na)
 {
     constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nc2 = c.ld >> 1;
+    const int nc2 = c.ld >> 1;              // row pitch in double2
+    const int nc2a = (c.n + 1) >> 1;        // double2 columns that can be non-zero
     double2 *T2 = reinterpret_cast<double2 *>(c.T);
     const double2 *rowp2 = reinterpret_cast<const double2 *>(c.rowp);
-    for (int c0 = 0; c0 < nc2; c0 += 32) {
-        const int j2 = c0 + lane;
-        const bool act = j2 < nc2;
-        const double2 rp = act ? rowp2[j2] : make_double2(0.0, 0.0);
-        const int jq = q - 2 * j2;               // 0: .x is column q, 1: .y is column q
-        for (int i0 = warp; i0 < rows; i0 += 4 * NW) {
-            double ci[4]; double2 v[4]; bool on[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * NW;
-                const bool in = i < rows;
-                ci[u] = in ? c.colq[i] : 0.0;
-                on[u] = in && act && (ci[u] != 0.0 || i == p);
-                if (on[u]) v[u] = T2[(size_t)i * nc2 + j2];
+    for (int a = warp; a < na; a += NW) {
+        const int i = c.arow[a];
+        const double ci = c.colq[i];
+        const double cq = ci * inv;
+        double2 *row = T2 + (size_t)i * nc2;
+        const bool is_p = i == p;
+        for (int j0 = 0; j0 < nc2a; j0 += 64) {
+            const int ja = j0 + lane, jb = j0 + 32 + lane;
+            const bool oa = ja < nc2a, ob = jb < nc2a;
+            double2 va, vb, ra, rb;
+            if (oa) { va = row[ja]; ra = rowp2[ja]; }
+            if (ob) { vb = row[jb]; rb = rowp2[jb]; }
+            if (oa) {
+                const int jq = q - 2 * ja;
+                double2 r;
+                r.x = is_p ? -ra.x : fma(-ci, ra.x, va.x);
+                r.y = is_p ? -ra.y : fma(-ci, ra.y, va.y);
+                if (jq == 0) r.x = is_p ? inv : cq;
+                if (jq == 1) r.y = is_p ? inv : cq;
+                row[ja] = r;
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * NW;
-                if (on[u]) {
-                    double2 r;
-                    if (i == p) {
-                        r.x = jq == 0 ? inv : -rp.x;
-                        r.y = jq == 1 ? inv : -rp.y;
-                    } else {
-                        const double cq = ci[u] * inv;
-                        r.x = jq == 0 ? cq : fma(-ci[u], rp.x, v[u].x);
-                        r.y = jq == 1 ? cq : fma(-ci[u], rp.y, v[u].y);
-                    }
-                    T2[(size_t)i * nc2 + j2] = r;
-                }
+            if (ob) {
+                const int jq = q - 2 * jb;
+                double2 r;
+                r.x = is_p ? -rb.x : fma(-ci, rb.x, vb.x);
+                r.y = is_p ? -rb.y : fma(-ci, rb.y, vb.y);
+                if (jq == 0) r.x = is_p ? inv : cq;
+                if (jq == 1) r.y = is_p ? inv : cq;
+                row[jb] = r;
             }
         }
+    }
+}
+
+// per-row / per-column bounds and column status from the by-variable arrays in HBM
+template <int NT>
+__device__ __forceinline__ void gather_bounds(const BlockDev &B, Sm3 &c)
+{
+    for (int i = threadIdx.x; i < c.m; i += NT) {
+        const int v = c.head[i];
+        c.rlo[i] = __ldg(B.lo + v); c.rup[i] = __ldg(B.up + v);
+    }
+    for (int j = threadIdx.x; j < c.n; j += NT) {
+        const int v = c.nbv[j];
+        c.clo[j] = __ldg(B.lo + v); c.cup[j] = __ldg(B.up + v);
+        c.cstat[j] = c.vstat[v];
     }
 }
 
@@ -277,41 +341,42 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
     __shared__ Scratch<NT> scr;
     __shared__ Decision dec;
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int s_kind;
+    __shared__ int s_kind, s_changed;
     if ((int)blockIdx.x >= count) return;
     const int k = list[blockIdx.x];
     const BlockDev B = blocks[k];
     const int m = B.m, n = B.n, L = B.L, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double tol_dj = P.tol_dj, tol_bnd = P.tol_bnd, tol_piv = P.tol_piv;
 
-    Smem2 c;
+    Sm3 c;
     c.m = m; c.n = n; c.ld = smem2_ld(n);
     const int ld = c.ld;
     char *sp = smem_raw;
     c.T = (double *)sp;            sp += align16(sizeof(double) * (size_t)(m + 1) * ld);
-    c.lo = (double *)sp; c.up = c.lo + (m + n);  sp += align16(sizeof(double) * 2 * (size_t)(m + n));
+    c.drow = c.T + (size_t)m * ld;
     char *pst = sp;                sp += pst_bytes(m, n);
     c.beta = (double *)pst;
     c.head = (int *)(pst + sizeof(double) * (size_t)m);
     c.nbv = c.head + m;
     c.vstat = (signed char *)(c.nbv + n);
+    c.rlo = (double *)sp; c.rup = c.rlo + m; c.clo = c.rup + m; c.cup = c.clo + n;
+    sp += align16(sizeof(double) * 2 * (size_t)(m + n));
     c.rowp = (double *)sp;         sp += align16(sizeof(double) * ld);
     c.cs = (double *)sp;           sp += align16(sizeof(double) * (size_t)n);
-    c.d1 = (double *)sp;           sp += align16(sizeof(double) * (size_t)n);
     c.colq = (double *)sp;         sp += align16(sizeof(double) * (size_t)(m + 1));
-    c.w = (double *)sp;
-    double *drow = c.T + (size_t)m * ld;
+    c.w = (double *)sp;            sp += align16(sizeof(double) * (size_t)m);
+    c.cstat = (signed char *)sp;   sp += align16((size_t)n);
+    c.arow = (unsigned short *)sp;
 
-    // ---- state in: three bulk copies, one mbarrier
+    // ---- state in: two bulk copies, one mbarrier
     const uint32_t t_bytes = (uint32_t)(sizeof(double) * (size_t)m * ld);
-    const uint32_t b_bytes = (uint32_t)(sizeof(double) * 2 * (size_t)(m + n));
     const uint32_t p_bytes = (uint32_t)pst_bytes(m, n);
     if (tid == 0) {
         mbar_init(&bar, 1);
-        mbar_expect_tx(&bar, t_bytes + b_bytes + p_bytes);
+        mbar_expect_tx(&bar, t_bytes + p_bytes);
         if (t_bytes) bulk_g2s(c.T, B.T, t_bytes, &bar);
-        if (b_bytes) bulk_g2s(c.lo, B.lo, b_bytes, &bar);
         bulk_g2s(pst, B.beta, p_bytes, &bar);
+        s_changed = 0;
     }
     // priced objective while the copies fly (same arithmetic as the generic kernel / reference)
     for (int j = tid; j < n; j += NT) {
@@ -328,11 +393,13 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
     }
     __syncthreads();            // mbarrier init + cs visible
     mbar_wait(&bar, 0);
+    gather_bounds<NT>(B, c);
+    __syncthreads();
 
     int status = 0;
     long long iter = 0;
     const long long max_iter = (long long)P.max_iter_mult * (m + n) + 1000;
-    unsigned long long n_piv = 0, n_flip = 0, n_reb = 0, n_p1 = 0;   // live in warp 0, lane-uniform
+    unsigned long long n_piv = 0, n_flip = 0, n_reb = 0, n_p1 = 0;   // n_piv/n_flip live in warp 0
     bool need_check = true, infeasible = false, d_valid = false, bland = false;
     int degen = 0;
     const int degen_limit = 100 + (m + n) / 2;
@@ -343,8 +410,7 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
         if (need_check || infeasible) {
             int viol = 0;
             for (int i = tid; i < m; i += NT) {
-                const int v = c.head[i];
-                const double b = c.beta[i], lo = c.lo[v], up = c.up[v];
+                const double b = c.beta[i], lo = c.rlo[i], up = c.rup[i];
                 double wi = 0.0;
                 if (b < lo - tol_bnd * (1.0 + fabs(lo))) wi = -1.0;
                 else if (b > up + tol_bnd * (1.0 + fabs(up))) wi = 1.0;
@@ -356,13 +422,11 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
             if (infeasible) d_valid = false;
         }
         if (infeasible) {
+            // phase-1 prices T'w into rowp (consumed by the pricing loop before rowp is restaged)
             for (int j = tid; j < n; j += NT) {
                 double s = 0.0;
-                for (int i = 0; i < m; ++i) {
-                    const double wi = c.w[i];
-                    if (wi != 0.0) s += wi * c.T[(size_t)i * ld + j];
-                }
-                c.d1[j] = s;
+                for (int i = 0; i < m; ++i) s = fma(c.w[i], c.T[(size_t)i * ld + j], s);
+                c.rowp[j] = s;
             }
             ++n_p1;
             __syncthreads();
@@ -377,26 +441,28 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
                 if (j < n) {
                     const int v = c.nbv[j];
                     s = v >= m ? c.cs[v - m] : 0.0;
-                    for (int i = 0; i < m; ++i) {
-                        const double cb = c.colq[i];
-                        if (cb != 0.0) s = fma(cb, c.T[(size_t)i * ld + j], s);
-                    }
+                    for (int i = 0; i < m; ++i) s = fma(c.colq[i], c.T[(size_t)i * ld + j], s);
                 }
-                drow[j] = s;
+                c.drow[j] = s;
             }
             d_valid = true;
             __syncthreads();
         }
         // ---- B. decision (warp 0)
         if (warp == 0) {
-            const int kind = decide_warp0(c, infeasible ? c.d1 : drow, infeasible, d_valid && !infeasible, bland, degen,
-                                          degen_limit, tol_dj, tol_bnd, tol_piv, n_piv, n_flip, &dec);
-            if (lane == 0) s_kind = kind;
+            int kind;
+            if (infeasible)
+                kind = decide_warp0<true>(c, c.rowp, false, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
+                                          n_piv, n_flip, &dec);
+            else
+                kind = decide_warp0<false>(c, c.drow, true, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
+                                           n_piv, n_flip, &dec);
+            if (lane == 0) { s_kind = kind; if (n_piv + n_flip) s_changed = 1; }
         }
         __syncthreads();
         const int kind = s_kind;
         if (kind == K_PIVOT) {
-            sweep<NT>(c, dec.p, dec.q, dec.inv, m + 1);
+            sweep_active<NT>(c, dec.p, dec.q, dec.inv, dec.na);
             __syncthreads();
             continue;
         }
@@ -404,10 +470,10 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
         if (kind == K_FAIL) { status = dec.fail_status; break; }
         // ---- K_NONE
         if (infeasible) { status = 4; break; }
-        // claimed optimal: extract x, check the residual against the original rows
+        // claimed optimal: x into rowp, auxiliary values into colq
         for (int j = tid; j < n; j += NT) {
             const int v = c.nbv[j];
-            const double xv = nb_value(c.vstat[v], c.lo[v], c.up[v]);
+            const double xv = nb_value(c.cstat[j], c.clo[j], c.cup[j]);
             if (v >= m) c.rowp[v - m] = xv; else c.colq[v] = xv;
         }
         for (int i = tid; i < m; i += NT) {
@@ -415,10 +481,12 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
             if (v >= m) c.rowp[v - m] = c.beta[i]; else c.colq[v] = c.beta[i];
         }
         __syncthreads();
+        if (!s_changed && n_reb == 0 && !P.initial) { status = 5; break; }   // nothing moved: already verified
+        // residual of the state against the original rows
         double worst = 0.0;
         for (int i = tid; i < m; i += NT) {
             double s = 0.0;
-            for (int p = B.a_rp[i]; p < B.a_rp[i + 1]; ++p) s = fma(B.a_v[p], c.rowp[B.a_ci[p]], s);
+            for (int e = B.a_rp[i]; e < B.a_rp[i + 1]; ++e) s = fma(B.a_v[e], c.rowp[B.a_ci[e]], s);
             worst = fmax(worst, fabs(s - c.colq[i]) / (1.0 + fabs(s)));
         }
         worst = block_max<NT>(worst, scr);
@@ -428,7 +496,7 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
             for (int e = tid; e < m * ld; e += NT) c.T[e] = 0.0;
             __syncthreads();
             for (int i = tid; i < m; i += NT) {
-                for (int p = B.a_rp[i]; p < B.a_rp[i + 1]; ++p) c.T[(size_t)i * ld + B.a_ci[p]] += B.a_v[p];
+                for (int e = B.a_rp[i]; e < B.a_rp[i + 1]; ++e) c.T[(size_t)i * ld + B.a_ci[e]] += B.a_v[e];
                 c.head[i] = i;
             }
             for (int j = tid; j < n; j += NT) c.nbv[j] = m + j;
@@ -450,20 +518,21 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
                 if (pr == INT_MAX || pk < 1e-11) { singular = true; break; }
                 const double inv = 1.0 / c.colq[pr];
                 for (int jj = tid; jj < ld; jj += NT) c.rowp[jj] = c.T[(size_t)pr * ld + jj] * inv;
+                for (int i = tid; i < m; i += NT) c.arow[i] = (unsigned short)i;
                 __syncthreads();
-                sweep<NT>(c, pr, j, inv, m);
+                sweep_active<NT>(c, pr, j, inv, m);
                 if (tid == 0) { const int t = c.head[pr]; c.head[pr] = c.nbv[j]; c.nbv[j] = t; }
                 __syncthreads();
             }
             if (singular) { status = 1; break; }
+            gather_bounds<NT>(B, c);
+            __syncthreads();
             {   // beta = T x_N, one warp per row
                 constexpr int NW = NT / 32;
                 for (int i = warp; i < m; i += NW) {
                     double s = 0.0;
-                    for (int j = lane; j < n; j += 32) {
-                        const int v = c.nbv[j];
-                        s += c.T[(size_t)i * ld + j] * nb_value(c.vstat[v], c.lo[v], c.up[v]);
-                    }
+                    for (int j = lane; j < n; j += 32)
+                        s += c.T[(size_t)i * ld + j] * nb_value(c.cstat[j], c.clo[j], c.cup[j]);
 #pragma unroll
                     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                     if (lane == 0) c.beta[i] = s;
@@ -478,11 +547,12 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
     }
 
     // ---- epilogue
+    __syncthreads();
+    const bool changed = s_changed != 0 || n_reb != 0 || P.initial != 0 || status != 5;
     if (status != 5) {
-        __syncthreads();
         for (int j = tid; j < n; j += NT) {
             const int v = c.nbv[j];
-            if (v >= m) c.rowp[v - m] = nb_value(c.vstat[v], c.lo[v], c.up[v]);
+            if (v >= m) c.rowp[v - m] = nb_value(c.cstat[j], c.clo[j], c.cup[j]);
         }
         for (int i = tid; i < m; i += NT) {
             const int v = c.head[i];
@@ -490,8 +560,16 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
         }
         __syncthreads();
     }
+    if (!changed) {
+        // the block was already optimal under the new prices: x_k, D_k x_k, c_k.x_k and the whole
+        // state in HBM are still those of the previous round; only the priced optimum moves
+        double zo = 0.0;
+        for (int j = tid; j < n; j += NT) zo = fma(c.cs[j], c.rowp[j], zo);
+        zo = block_sum<NT>(zo, scr);
+        if (tid == 0) { P.obj[k] = zo; P.status[k] = 5; P.last_iters[k] = 0; }
+        return;
+    }
     // state out first (async), then the proposal while the copies fly
-    __syncthreads();
     if (tid == 0) {
         const bool t_dirty = (n_piv + n_reb) != 0;        // thread 0 sits in warp 0, which owns n_piv
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
