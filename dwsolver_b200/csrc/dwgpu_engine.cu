@@ -79,7 +79,7 @@ struct dwgpu_engine {
     std::vector<long long> xoff;   // prefix sums of n
     long long ntot = 0;
     std::vector<int> path;         // 1 smem, 2 gmem
-    std::vector<int> list_smem, list_gmem;
+    std::vector<int> list_smem, list_gmem, list_a;   // list_a: blocks of the specialised 64x128 shape
     size_t smem_dyn = 0;
     int max_smem_optin = 0;
     // device arenas
@@ -87,7 +87,7 @@ struct dwgpu_engine {
     DevBuf<int> a_rp, a_ci, dc_ptr, dc_row, dr_ptr, dr_col;
     DevBuf<char> pst;
     DevBuf<dwk::BlockDev> blocks;
-    DevBuf<int> d_list_smem, d_list_gmem;
+    DevBuf<int> d_list_smem, d_list_gmem, d_list_a;
     // round inputs / outputs
     DevBuf<double> pi, obj, cost, val;
     DevBuf<int> status, len, ind;
@@ -130,7 +130,7 @@ void dwgpu_destroy(dwgpu_engine *e)
     e->x.release(); e->ws.release(); e->a_rp.release();
     e->a_ci.release(); e->dc_ptr.release(); e->dc_row.release(); e->dr_ptr.release();
     e->dr_col.release(); e->blocks.release(); e->d_list_smem.release();
-    e->d_list_gmem.release(); e->pi.release(); e->obj.release(); e->cost.release();
+    e->d_list_gmem.release(); e->d_list_a.release(); e->pi.release(); e->obj.release(); e->cost.release();
     e->val.release(); e->status.release(); e->len.release(); e->ind.release();
     e->counters.release(); e->last_iters.release();
     if (e->h_pi) cudaFreeHost(e->h_pi);
@@ -201,7 +201,8 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         d_off[k + 1] = d_off[k] + b.d_nnz;
         dcp_off[k + 1] = dcp_off[k] + b.n + 1;
         drp_off[k + 1] = drp_off[k] + L + 1;
-        if (path == 1) { e->list_smem.push_back(k); e->smem_dyn = std::max(e->smem_dyn, dwk::smem2_bytes(b.m, b.n)); }
+        if (path == 1 && b.m == 64 && b.n == 128) e->list_a.push_back(k);
+        else if (path == 1) { e->list_smem.push_back(k); e->smem_dyn = std::max(e->smem_dyn, dwk::smem2_bytes(b.m, b.n)); }
         else e->list_gmem.push_back(k);
         ws_off[k + 1] = ws_off[k] + (path == 2 ? (long long)((dwk::vec_bytes(b.m, b.n) + 15) / 16 * 2) : 0);
     }
@@ -289,10 +290,14 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(e->blocks.upload(hb));
     CUE(e->d_list_smem.upload(e->list_smem));
     CUE(e->d_list_gmem.upload(e->list_gmem));
+    CUE(e->d_list_a.upload(e->list_a));
 
     if (!e->list_smem.empty())
-        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)e->smem_dyn));
+    if (!e->list_a.empty())
+        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)dwk::smem2_bytes(64, 128)));
 
     dwk::init_kernel<256><<<K, 256, 0, e->stream>>>(e->blocks.p, K);
     CUE(cudaGetLastError());
@@ -324,14 +329,22 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         e->ev_used[1] = true;
         e->last_launches++;
     }
-    if (!e->list_smem.empty()) {
+    if (!e->list_smem.empty() || !e->list_a.empty()) {
         CU(cudaEventRecord(e->ev[2], st));
-        dwk::solve_smem_kernel<NT_SMEM><<<(unsigned)e->list_smem.size(), NT_SMEM, e->smem_dyn, st>>>(
-            e->blocks.p, e->d_list_smem.p, (int)e->list_smem.size(), P);
-        CU(cudaGetLastError());
+        if (!e->list_a.empty()) {
+            dwk::solve_smem_kernel<NT_SMEM, 64, 128><<<(unsigned)e->list_a.size(), NT_SMEM, dwk::smem2_bytes(64, 128), st>>>(
+                e->blocks.p, e->d_list_a.p, (int)e->list_a.size(), P);
+            CU(cudaGetLastError());
+            e->last_launches++;
+        }
+        if (!e->list_smem.empty()) {
+            dwk::solve_smem_kernel<NT_SMEM, 0, 0><<<(unsigned)e->list_smem.size(), NT_SMEM, e->smem_dyn, st>>>(
+                e->blocks.p, e->d_list_smem.p, (int)e->list_smem.size(), P);
+            CU(cudaGetLastError());
+            e->last_launches++;
+        }
         CU(cudaEventRecord(e->ev[3], st));
         e->ev_used[0] = true;
-        e->last_launches++;
     }
     e->solves += e->K;
     return 0;

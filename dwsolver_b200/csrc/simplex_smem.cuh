@@ -134,14 +134,14 @@ __device__ __forceinline__ double warp_min_nonneg(double v)
 // on the spot, and for a basis change stages everything the rank-1 sweep needs (colq, rowp,
 // active rows, beta, head/nbv/vstat/bounds).  dd = prices (row m of T in phase 2; phase-1 prices
 // live in rowp and are consumed before rowp is overwritten).
-template <bool INF>
-__device__ int decide_warp0(Sm3 &c, const double *dd, bool d_live, bool &bland, int &degen, int degen_limit,
+template <bool INF, int MC, int NC>
+__device__ __forceinline__ int decide_warp0(Sm3 &c, const double *dd, bool d_live, bool &bland, int &degen, int degen_limit,
                             double tol_dj, double tol_bnd, double tol_piv,
                             unsigned long long &n_piv, unsigned long long &n_flip, Decision *dec)
 {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int m = c.m, n = c.n, ld = c.ld;
+    const int m = MC ? MC : c.m, n = NC ? NC : c.n, ld = NC ? smem2_ld(NC) : c.ld;
     const double harris = 0.5 * tol_bnd;
     for (;;) {
         // ---- pricing
@@ -275,13 +275,13 @@ __device__ int decide_warp0(Sm3 &c, const double *dd, bool d_live, bool &bland, 
 }
 
 // rank-1 sweep over the active rows only (row m = reduced costs when it is in the list)
-template <int NT>
+template <int NT, int NC>
 __device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, int na)
 {
     constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nc2 = c.ld >> 1;              // row pitch in double2
-    const int nc2a = (c.n + 1) >> 1;        // double2 columns that can be non-zero
+    const int nc2 = (NC ? smem2_ld(NC) : c.ld) >> 1;      // row pitch in double2
+    const int nc2a = ((NC ? NC : c.n) + 1) >> 1;          // double2 columns that can be non-zero
     double2 *T2 = reinterpret_cast<double2 *>(c.T);
     const double2 *rowp2 = reinterpret_cast<const double2 *>(c.rowp);
     for (int a = warp; a < na; a += NW) {
@@ -333,7 +333,9 @@ __device__ __forceinline__ void gather_bounds(const BlockDev &B, Sm3 &c)
     }
 }
 
-template <int NT>
+// MC/NC != 0: block shape known at compile time (all shared-memory offsets and trip counts are
+// constants); MC = NC = 0: any shape that fits.
+template <int NT, int MC, int NC>
 __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
                                                           SolveParams P)
 {
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
     if ((int)blockIdx.x >= count) return;
     const int k = list[blockIdx.x];
     const BlockDev B = blocks[k];
-    const int m = B.m, n = B.n, L = B.L, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = MC ? MC : B.m, n = NC ? NC : B.n, L = B.L, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double tol_dj = P.tol_dj, tol_bnd = P.tol_bnd, tol_piv = P.tol_piv;
 
     Sm3 c;
@@ -452,17 +454,17 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
         if (warp == 0) {
             int kind;
             if (infeasible)
-                kind = decide_warp0<true>(c, c.rowp, false, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
+                kind = decide_warp0<true, MC, NC>(c, c.rowp, false, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
                                           n_piv, n_flip, &dec);
             else
-                kind = decide_warp0<false>(c, c.drow, true, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
+                kind = decide_warp0<false, MC, NC>(c, c.drow, true, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
                                            n_piv, n_flip, &dec);
             if (lane == 0) { s_kind = kind; if (n_piv + n_flip) s_changed = 1; }
         }
         __syncthreads();
         const int kind = s_kind;
         if (kind == K_PIVOT) {
-            sweep_active<NT>(c, dec.p, dec.q, dec.inv, dec.na);
+            sweep_active<NT, NC>(c, dec.p, dec.q, dec.inv, dec.na);
             __syncthreads();
             continue;
         }
@@ -520,7 +522,7 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
                 for (int jj = tid; jj < ld; jj += NT) c.rowp[jj] = c.T[(size_t)pr * ld + jj] * inv;
                 for (int i = tid; i < m; i += NT) c.arow[i] = (unsigned short)i;
                 __syncthreads();
-                sweep_active<NT>(c, pr, j, inv, m);
+                sweep_active<NT, NC>(c, pr, j, inv, m);
                 if (tid == 0) { const int t = c.head[pr]; c.head[pr] = c.nbv[j]; c.nbv[j] = t; }
                 __syncthreads();
             }

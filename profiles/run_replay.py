@@ -22,8 +22,14 @@ pis_dev = torch.from_numpy(pis).cuda()
 for rep in range(reps):
     eng.reset()
     eng.initial_solve_device()
+    if rep == 0:
+        it = eng.block_iterations()
+        print("cold iterations/block: mean %.1f max %d p90 %d" % (it.mean(), it.max(), np.percentile(it, 90)))
     for r in range(len(phases)):
         eng.iterate_device(pis_dev[r].data_ptr(), phases[r])
+        if rep == 0:
+            it = eng.block_iterations()
+            print("round %d iterations/block: mean %.2f max %d zero-blocks %d" % (r, it.mean(), it.max(), (it == 0).sum()))
     eng.sync()
 c = eng.counters()
 print("replays", reps, c)
