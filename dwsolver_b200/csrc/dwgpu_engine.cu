@@ -79,7 +79,9 @@ struct dwgpu_engine {
     std::vector<long long> xoff;   // prefix sums of n
     long long ntot = 0;
     std::vector<int> path;         // 1 smem, 2 gmem
-    std::vector<int> list_smem, list_gmem, list_a;   // list_a: blocks of the specialised 64x128 shape
+    // kernel lists: smem-generic, legacy global, specialised 64x128 (A), global-T generic (g), global-T 256x512 (B)
+    std::vector<int> list_smem, list_gmem, list_a, list_g, list_b;
+    size_t smem_dyn_g = 0;
     size_t smem_dyn = 0;
     int max_smem_optin = 0;
     // device arenas
@@ -87,7 +89,7 @@ struct dwgpu_engine {
     DevBuf<int> a_rp, a_ci, dc_ptr, dc_row, dr_ptr, dr_col;
     DevBuf<char> pst;
     DevBuf<dwk::BlockDev> blocks;
-    DevBuf<int> d_list_smem, d_list_gmem, d_list_a;
+    DevBuf<int> d_list_smem, d_list_gmem, d_list_a, d_list_g, d_list_b;
     // round inputs / outputs
     DevBuf<double> pi, obj, cost, val;
     DevBuf<int> status, len, ind;
@@ -130,7 +132,7 @@ void dwgpu_destroy(dwgpu_engine *e)
     e->x.release(); e->ws.release(); e->a_rp.release();
     e->a_ci.release(); e->dc_ptr.release(); e->dc_row.release(); e->dr_ptr.release();
     e->dr_col.release(); e->blocks.release(); e->d_list_smem.release();
-    e->d_list_gmem.release(); e->d_list_a.release(); e->pi.release(); e->obj.release(); e->cost.release();
+    e->d_list_gmem.release(); e->d_list_a.release(); e->d_list_g.release(); e->d_list_b.release(); e->pi.release(); e->obj.release(); e->cost.release();
     e->val.release(); e->status.release(); e->len.release(); e->ind.release();
     e->counters.release(); e->last_iters.release();
     if (e->h_pi) cudaFreeHost(e->h_pi);
@@ -183,8 +185,10 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
             { fail(DWGPU_E_ARGS, "bad block descriptor"); return bail(DWGPU_E_ARGS); }
         e->m[k] = b.m; e->n[k] = b.n;
         const bool fits = dwk::smem2_bytes(b.m, b.n) <= smem_cap;
-        int path = fits ? 1 : 2;
+        const bool fits_g = dwk::smem2_bytes(b.m, b.n, true) <= smem_cap / 2;   // at least 2 CTAs per SM
+        int path = fits ? 1 : (fits_g ? 3 : 2);
         if (opt.force_path == 2) path = 2;
+        if (opt.force_path == 3 && fits_g) path = 3;
         if (opt.force_path == 1 && !fits)
             { fail(DWGPU_E_ARGS, "force_path=1 but a block does not fit shared memory"); return bail(DWGPU_E_ARGS); }
         e->path[k] = path;
@@ -203,6 +207,8 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         drp_off[k + 1] = drp_off[k] + L + 1;
         if (path == 1 && b.m == 64 && b.n == 128) e->list_a.push_back(k);
         else if (path == 1) { e->list_smem.push_back(k); e->smem_dyn = std::max(e->smem_dyn, dwk::smem2_bytes(b.m, b.n)); }
+        else if (path == 3 && b.m == 256 && b.n == 512) e->list_b.push_back(k);
+        else if (path == 3) { e->list_g.push_back(k); e->smem_dyn_g = std::max(e->smem_dyn_g, dwk::smem2_bytes(b.m, b.n, true)); }
         else e->list_gmem.push_back(k);
         ws_off[k + 1] = ws_off[k] + (path == 2 ? (long long)((dwk::vec_bytes(b.m, b.n) + 15) / 16 * 2) : 0);
     }
@@ -291,13 +297,21 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(e->d_list_smem.upload(e->list_smem));
     CUE(e->d_list_gmem.upload(e->list_gmem));
     CUE(e->d_list_a.upload(e->list_a));
+    CUE(e->d_list_g.upload(e->list_g));
+    CUE(e->d_list_b.upload(e->list_b));
 
     if (!e->list_smem.empty())
-        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)e->smem_dyn));
     if (!e->list_a.empty())
-        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 64, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)dwk::smem2_bytes(64, 128)));
+    if (!e->list_g.empty())
+        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)e->smem_dyn_g));
+    if (!e->list_b.empty())
+        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 256, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)dwk::smem2_bytes(256, 512, true)));
 
     dwk::init_kernel<256><<<K, 256, 0, e->stream>>>(e->blocks.p, K);
     CUE(cudaGetLastError());
@@ -329,16 +343,34 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         e->ev_used[1] = true;
         e->last_launches++;
     }
+    if (!e->list_g.empty() || !e->list_b.empty()) {
+        const bool own_events = !e->ev_used[1];
+        if (own_events) CU(cudaEventRecord(e->ev[0], st));
+        if (!e->list_b.empty()) {
+            dwk::solve_smem_kernel<NT_SMEM, 256, 512, true><<<(unsigned)e->list_b.size(), NT_SMEM, dwk::smem2_bytes(256, 512, true), st>>>(
+                e->blocks.p, e->d_list_b.p, (int)e->list_b.size(), P);
+            CU(cudaGetLastError());
+            e->last_launches++;
+        }
+        if (!e->list_g.empty()) {
+            dwk::solve_smem_kernel<NT_SMEM, 0, 0, true><<<(unsigned)e->list_g.size(), NT_SMEM, e->smem_dyn_g, st>>>(
+                e->blocks.p, e->d_list_g.p, (int)e->list_g.size(), P);
+            CU(cudaGetLastError());
+            e->last_launches++;
+        }
+        CU(cudaEventRecord(e->ev[1], st));
+        e->ev_used[1] = true;
+    }
     if (!e->list_smem.empty() || !e->list_a.empty()) {
         CU(cudaEventRecord(e->ev[2], st));
         if (!e->list_a.empty()) {
-            dwk::solve_smem_kernel<NT_SMEM, 64, 128><<<(unsigned)e->list_a.size(), NT_SMEM, dwk::smem2_bytes(64, 128), st>>>(
+            dwk::solve_smem_kernel<NT_SMEM, 64, 128, false><<<(unsigned)e->list_a.size(), NT_SMEM, dwk::smem2_bytes(64, 128), st>>>(
                 e->blocks.p, e->d_list_a.p, (int)e->list_a.size(), P);
             CU(cudaGetLastError());
             e->last_launches++;
         }
         if (!e->list_smem.empty()) {
-            dwk::solve_smem_kernel<NT_SMEM, 0, 0><<<(unsigned)e->list_smem.size(), NT_SMEM, e->smem_dyn, st>>>(
+            dwk::solve_smem_kernel<NT_SMEM, 0, 0, false><<<(unsigned)e->list_smem.size(), NT_SMEM, e->smem_dyn, st>>>(
                 e->blocks.p, e->d_list_smem.p, (int)e->list_smem.size(), P);
             CU(cudaGetLastError());
             e->last_launches++;

@@ -76,10 +76,12 @@ __host__ __device__ inline size_t pst_bytes(int m, int n)
 {
     return align16(sizeof(double) * (size_t)m + sizeof(int) * (size_t)(m + n) + (size_t)(m + n));
 }
-__host__ __device__ inline size_t smem2_bytes(int m, int n)
+// leading dimension of the tableau: shared (TG = false) or global-memory resident (TG = true)
+__host__ __device__ inline int tab_ld(int n, bool tg) { return tg ? ((n + 3) & ~3) : smem2_ld(n); }
+__host__ __device__ inline size_t smem2_bytes(int m, int n, bool tg = false)
 {
-    const size_t ld = smem2_ld(n);
-    return align16(sizeof(double) * (size_t)(m + 1) * ld)     // T and the d row
+    const size_t ld = tab_ld(n, tg);
+    return align16(sizeof(double) * (size_t)(tg ? 1 : m + 1) * ld)     // (T and) the d row
          + pst_bytes(m, n)
          + align16(sizeof(double) * 2 * (size_t)(m + n))      // rlo rup clo cup
          + align16(sizeof(double) * ld)                       // rowp (also phase-1 prices, x staging)
@@ -134,14 +136,14 @@ __device__ __forceinline__ double warp_min_nonneg(double v)
 // on the spot, and for a basis change stages everything the rank-1 sweep needs (colq, rowp,
 // active rows, beta, head/nbv/vstat/bounds).  dd = prices (row m of T in phase 2; phase-1 prices
 // live in rowp and are consumed before rowp is overwritten).
-template <bool INF, int MC, int NC>
+template <bool INF, int MC, int NC, bool TG>
 __device__ __forceinline__ int decide_warp0(Sm3 &c, const double *dd, bool d_live, bool &bland, int &degen, int degen_limit,
                             double tol_dj, double tol_bnd, double tol_piv,
                             unsigned long long &n_piv, unsigned long long &n_flip, Decision *dec)
 {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int m = MC ? MC : c.m, n = NC ? NC : c.n, ld = NC ? smem2_ld(NC) : c.ld;
+    const int m = MC ? MC : c.m, n = NC ? NC : c.n, ld = NC ? tab_ld(NC, TG) : c.ld;
     const double harris = 0.5 * tol_bnd;
     for (;;) {
         // ---- pricing
@@ -275,20 +277,21 @@ __device__ __forceinline__ int decide_warp0(Sm3 &c, const double *dd, bool d_liv
 }
 
 // rank-1 sweep over the active rows only (row m = reduced costs when it is in the list)
-template <int NT, int NC>
+template <int NT, int NC, bool TG>
 __device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, int na)
 {
     constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nc2 = (NC ? smem2_ld(NC) : c.ld) >> 1;      // row pitch in double2
+    const int nc2 = (NC ? tab_ld(NC, TG) : c.ld) >> 1;    // row pitch in double2
     const int nc2a = ((NC ? NC : c.n) + 1) >> 1;          // double2 columns that can be non-zero
     double2 *T2 = reinterpret_cast<double2 *>(c.T);
+    double2 *d2 = reinterpret_cast<double2 *>(c.drow);
     const double2 *rowp2 = reinterpret_cast<const double2 *>(c.rowp);
     for (int a = warp; a < na; a += NW) {
         const int i = c.arow[a];
         const double ci = c.colq[i];
         const double cq = ci * inv;
-        double2 *row = T2 + (size_t)i * nc2;
+        double2 *row = (i == c.m) ? d2 : T2 + (size_t)i * nc2;
         const bool is_p = i == p;
         for (int j0 = 0; j0 < nc2a; j0 += 64) {
             const int ja = j0 + lane, jb = j0 + 32 + lane;
@@ -335,8 +338,10 @@ __device__ __forceinline__ void gather_bounds(const BlockDev &B, Sm3 &c)
 
 // MC/NC != 0: block shape known at compile time (all shared-memory offsets and trip counts are
 // constants); MC = NC = 0: any shape that fits.
-template <int NT, int MC, int NC>
-__global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
+// TG = true: the tableau stays in global memory (L2/HBM) and only the vectors live in shared memory
+// (blocks too large for one CTA's shared memory, config B class); the decision/sweep code is shared.
+template <int NT, int MC, int NC, bool TG>
+__global__ void __launch_bounds__(NT, TG ? 4 : 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
                                                           SolveParams P)
 {
     extern __shared__ __align__(16) char smem_raw[];
@@ -351,11 +356,16 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
     const double tol_dj = P.tol_dj, tol_bnd = P.tol_bnd, tol_piv = P.tol_piv;
 
     Sm3 c;
-    c.m = m; c.n = n; c.ld = smem2_ld(n);
+    c.m = m; c.n = n; c.ld = tab_ld(n, TG);
     const int ld = c.ld;
     char *sp = smem_raw;
-    c.T = (double *)sp;            sp += align16(sizeof(double) * (size_t)(m + 1) * ld);
-    c.drow = c.T + (size_t)m * ld;
+    if (TG) {
+        c.T = B.T;
+        c.drow = (double *)sp;     sp += align16(sizeof(double) * (size_t)ld);
+    } else {
+        c.T = (double *)sp;        sp += align16(sizeof(double) * (size_t)(m + 1) * ld);
+        c.drow = c.T + (size_t)m * ld;
+    }
     char *pst = sp;                sp += pst_bytes(m, n);
     c.beta = (double *)pst;
     c.head = (int *)(pst + sizeof(double) * (size_t)m);
@@ -371,7 +381,7 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
     c.arow = (unsigned short *)sp;
 
     // ---- state in: two bulk copies, one mbarrier
-    const uint32_t t_bytes = (uint32_t)(sizeof(double) * (size_t)m * ld);
+    const uint32_t t_bytes = TG ? 0u : (uint32_t)(sizeof(double) * (size_t)m * ld);
     const uint32_t p_bytes = (uint32_t)pst_bytes(m, n);
     if (tid == 0) {
         mbar_init(&bar, 1);
@@ -427,7 +437,10 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
             // phase-1 prices T'w into rowp (consumed by the pricing loop before rowp is restaged)
             for (int j = tid; j < n; j += NT) {
                 double s = 0.0;
-                for (int i = 0; i < m; ++i) s = fma(c.w[i], c.T[(size_t)i * ld + j], s);
+                for (int i = 0; i < m; ++i) {
+                    const double wi = c.w[i];
+                    if (wi != 0.0) s = fma(wi, c.T[(size_t)i * ld + j], s);      // block-uniform branch
+                }
                 c.rowp[j] = s;
             }
             ++n_p1;
@@ -443,7 +456,10 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
                 if (j < n) {
                     const int v = c.nbv[j];
                     s = v >= m ? c.cs[v - m] : 0.0;
-                    for (int i = 0; i < m; ++i) s = fma(c.colq[i], c.T[(size_t)i * ld + j], s);
+                    for (int i = 0; i < m; ++i) {
+                        const double cb = c.colq[i];
+                        if (cb != 0.0) s = fma(cb, c.T[(size_t)i * ld + j], s);  // block-uniform branch
+                    }
                 }
                 c.drow[j] = s;
             }
@@ -454,17 +470,17 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
         if (warp == 0) {
             int kind;
             if (infeasible)
-                kind = decide_warp0<true, MC, NC>(c, c.rowp, false, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
+                kind = decide_warp0<true, MC, NC, TG>(c, c.rowp, false, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
                                           n_piv, n_flip, &dec);
             else
-                kind = decide_warp0<false, MC, NC>(c, c.drow, true, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
+                kind = decide_warp0<false, MC, NC, TG>(c, c.drow, true, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
                                            n_piv, n_flip, &dec);
             if (lane == 0) { s_kind = kind; if (n_piv + n_flip) s_changed = 1; }
         }
         __syncthreads();
         const int kind = s_kind;
         if (kind == K_PIVOT) {
-            sweep_active<NT, NC>(c, dec.p, dec.q, dec.inv, dec.na);
+            sweep_active<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na);
             __syncthreads();
             continue;
         }
@@ -522,7 +538,7 @@ __global__ void __launch_bounds__(NT, 3) solve_smem_kernel(const BlockDev *block
                 for (int jj = tid; jj < ld; jj += NT) c.rowp[jj] = c.T[(size_t)pr * ld + jj] * inv;
                 for (int i = tid; i < m; i += NT) c.arow[i] = (unsigned short)i;
                 __syncthreads();
-                sweep_active<NT, NC>(c, pr, j, inv, m);
+                sweep_active<NT, NC, TG>(c, pr, j, inv, m);
                 if (tid == 0) { const int t = c.head[pr]; c.head[pr] = c.nbv[j]; c.nbv[j] = t; }
                 __syncthreads();
             }

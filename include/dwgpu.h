@@ -67,7 +67,8 @@ typedef struct dwgpu_block_desc {
 typedef struct dwgpu_options {
     int    device;        /* CUDA device ordinal (default 0) */
     int    clamp_lo_cols; /* 1: finite-lb/no-ub columns get ub = 3000 (dw_subprob.c:116-120) */
-    int    force_path;    /* 0 auto; 1 shared-memory CTA path; 2 global-memory CTA path */
+    int    force_path;    /* 0 auto; 1 shared-memory tableau; 2 legacy all-global kernel;
+                             3 global-memory tableau + shared-memory vectors */
     int    max_iter_mult; /* iteration limit = max_iter_mult*(m+n) + 1000 (default 50) */
     double tol_dj;        /* dual feasibility   (default 1e-9) */
     double tol_bnd;       /* primal feasibility, scaled by 1+|bound| (default 1e-9) */
@@ -137,7 +138,8 @@ int  dwgpu_get_counters(dwgpu_engine *e, dwgpu_counters *total);
 int  dwgpu_get_block_iterations(dwgpu_engine *e, long long *iters);
 /* kernels launched by the last iterate / initial_solve call */
 int  dwgpu_last_launch_count(dwgpu_engine *e);
-/* 1 = shared-memory CTA path, 2 = global-memory CTA path, per block */
+/* per block: 1 = shared-memory tableau, 3 = global-memory tableau with shared-memory vectors,
+ * 2 = legacy kernel with everything in global memory */
 int  dwgpu_get_block_paths(dwgpu_engine *e, int *paths);
 /* device time (CUDA events on the launching stream) of the last round's solve kernels:
  * ms[0] = shared-memory path launch, ms[1] = global-memory path launch (0 when not launched).

@@ -64,7 +64,7 @@ def compare_round(prob, gp, op, pi, phase_one, initial=False):
         assert abs(g["cost"] - b.c_master @ x) <= 1e-12 * (1 + abs(g["cost"]))
 
 
-@pytest.mark.parametrize("force_path", [0, 2])
+@pytest.mark.parametrize("force_path", [0, 2, 3])
 @pytest.mark.parametrize("name", EXAMPLES)
 def test_examples_fixed_pi_parity(name, force_path):
     from oracle import oracle as O
@@ -125,16 +125,33 @@ def test_mcf_parity_and_dw(K, nodes, cols, L, seed):
     eng.close()
 
 
-def test_dense_blocks_global_path():
+@pytest.mark.parametrize("force_path", [2, 3])
+def test_dense_blocks_global_path(force_path):
     from oracle import oracle as O
     prob = P.gen_dense(6, 150, 300, 12, 64001, dens_a=0.05)
-    eng = engine(prob, force_path=2)
+    eng = engine(prob, force_path=force_path)
+    assert set(eng.block_paths()) == {force_path}
     orc = O.OracleBlocks(prob)
     compare_round(prob, eng.initial(), orc.initial(6), None, False, initial=True)
     rng = np.random.default_rng(5)
     for trial in range(2):
         pi = -rng.random(prob.L)
         compare_round(prob, eng.iterate(pi, False), orc.iterate(pi, False, 6), pi, False)
+    eng.close()
+
+
+def test_mcf_config_b_shape_global_tableau_kernel():
+    """256 x 512 blocks take the specialised global-tableau kernel (path 3)."""
+    from oracle import oracle as O
+    prob = P.gen_mcf(48, 256, 512, 256, 8192001)
+    eng = engine(prob)
+    assert set(eng.block_paths()) == {3}
+    orc = O.OracleBlocks(prob)
+    compare_round(prob, eng.initial(), orc.initial(8), None, False, initial=True)
+    rng = np.random.default_rng(3)
+    for trial in range(3):
+        pi = -rng.random(prob.L) * 20.0 * (trial + 1)
+        compare_round(prob, eng.iterate(pi, trial == 0), orc.iterate(pi, trial == 0, 8), pi, trial == 0)
     eng.close()
 
 
