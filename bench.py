@@ -187,6 +187,7 @@ def main():
     # ---------------- our arm ----------------
     import torch
     from dwsolver_b200 import engine as E
+    from dwsolver_b200 import sharding as S
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
@@ -197,10 +198,8 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
-    if K_total % world:
-        raise SystemExit("block count must divide evenly over the ranks")
-    K_loc = K_total // world
-    my_range = range(rank * K_loc, (rank + 1) * K_loc)
+    my_range = S.shard_range(K_total, world, rank)
+    K_loc = len(my_range)
     prob = P.make_config(args.config, block_range=my_range)
     bpp = algorithmic_bytes_per_pivot(m, n)
 
@@ -239,20 +238,14 @@ def main():
 
     gat = None
     if dist is not None:   # every rank receives every shard's proposals; rank 0 is the consumer
-        gat = {"len": torch.empty(K_total, dtype=torch.int32, device=dev),
-               "ind": torch.empty((K_total, L), dtype=torch.int32, device=dev),
-               "val": torch.empty((K_total, L), dtype=torch.float64, device=dev),
-               "obj": torch.empty(K_total, dtype=torch.float64, device=dev),
-               "cost": torch.empty(K_total, dtype=torch.float64, device=dev),
-               "status": torch.empty(K_total, dtype=torch.int32, device=dev)}
+        gat = S.alloc_gathered(torch, K_total, L, dev)
         h_pin = {k_: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k_, v in gat.items()}
     pi_pin = torch.zeros(L, dtype=torch.float64).pin_memory()
     pi_dev = torch.zeros(L, dtype=torch.float64, device=dev)
     pis_dev = torch.from_numpy(pis).to(dev)
 
     def exchange_up():
-        for key, g in gat.items():
-            dist.all_gather_into_tensor(g.view(-1), views[key].reshape(-1))
+        S.proposals_up(dist, views, gat)
 
     def up_to_host():
         if rank == 0:
@@ -279,7 +272,7 @@ def main():
                 if rank == 0:
                     pi_pin.copy_(torch.from_numpy(pis[r]))
                     pi_dev.copy_(pi_pin, non_blocking=True)
-                dist.broadcast(pi_dev, src=0)                      # duals down (NCCL)
+                S.duals_down(dist, pi_dev, src=0)                  # duals down (NCCL)
                 eng.iterate_device(pi_dev.data_ptr(), phases[r], sptr)
                 exchange_up(); up_to_host()                        # proposals up (NCCL) + D2H on rank 0
 
@@ -294,7 +287,7 @@ def main():
         for r in range(R):
             if dist is not None:
                 pi_dev.copy_(pis_dev[r])
-                dist.broadcast(pi_dev, src=0)
+                S.duals_down(dist, pi_dev, src=0)
                 eng.iterate_device(pi_dev.data_ptr(), phases[r], sptr)
                 exchange_up()
             else:
@@ -304,10 +297,10 @@ def main():
 
     def count():
         c = eng.counters()
-        return np.array([c["pivots"], c["flips"], c["rebuilds"]], dtype=np.float64)
+        return np.array([c["pivots"], c["flips"], c["rebuilds"], c["rows_swept"]], dtype=np.float64)
 
     # =========================== e2e ===========================
-    e2e_time, e2e_cnt = 0.0, np.zeros(3)
+    e2e_time, e2e_cnt = 0.0, np.zeros(4)
     for step in range(W + S):
         flush_buf.fill_(1)
         barrier()
@@ -324,7 +317,7 @@ def main():
     # =========================== device only ===========================
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + S)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + S)]
-    dev_cnt = np.zeros(3)
+    dev_cnt = np.zeros(4)
     kern = []
     clocks = ClockSampler(local_rank)
     for step in range(W + S):
@@ -363,7 +356,7 @@ def main():
         dist.all_reduce(pv, op=dist.ReduceOp.SUM)
         t_dev, e2e_time, k_time = (float(v) for v in tt.tolist())
         pv = pv.cpu().numpy()
-        dev_cnt, e2e_cnt, kcnt = pv[0:3], pv[3:6], pv[6:9]
+        dev_cnt, e2e_cnt, kcnt = pv[0:4], pv[4:8], pv[8:12]
     eng.close()
     if rank != 0:
         if dist is not None:
@@ -372,10 +365,18 @@ def main():
         return
 
     # ---------------- roofline of the dominant kernel (one replay, per-launch events) ----------------
+    # Bytes the kernel's algorithm must move:
+    #   per basis change   8(m+n)                 pivot column + pivot row read
+    #   per swept row      16(n+1)                row read + written (rows whose pivot-column entry is
+    #                                             exactly zero are not touched; the device counts rows)
+    #   per launch & block 16 m n (shared-memory path only): tableau image loaded + stored
+    # The survey's dense figure 16(m+1)(n+1) per basis change is reported next to it.
     on_smem = dom == 0
     n_launch = R + 1
-    state_bytes = n_launch * K_total * 2.0 * 8.0 * m * n       # T loaded + stored once per launch per block
-    alg_bytes = kcnt[0] * bpp + state_bytes
+    state_bytes = n_launch * K_total * 2.0 * 8.0 * m * n if on_smem else 0.0
+    touched = kcnt[3] * 16.0 * (n + 1) + kcnt[0] * 8.0 * (m + n)
+    alg_bytes = touched + state_bytes
+    dense_bytes = kcnt[0] * bpp + state_bytes
     if on_smem:
         peak = E.measure_smem_bandwidth(local_rank)
         peak_src = "measured live: dwgpu_measure_smem_bandwidth (FP64 read+write of a 100 KB tile, 2 CTAs/SM)"
@@ -390,15 +391,20 @@ def main():
             peak_src = "of fallback (B200_PROFILING.md)"
         bound = "hbm"
     achieved = alg_bytes / k_time / 1e9 if k_time > 0 else 0.0
+    kname = {("A", True): "dwk::solve_smem_kernel<256,64,128,false>", ("B", False): "dwk::solve_smem_kernel<256,256,512,true>"}
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if peak else None, "traffic": None,
-                "kernel": "dwk::solve_kernel<%s>" % ("true,256" if on_smem else "false,1024"),
+                "kernel": kname.get((args.config, on_smem), "dwk::solve_kernel<false,1024>"),
+                "bytes_definition": "touched: 16(n+1) per swept row + 8(m+n) per basis change"
+                                    + (" + 16mn state image per block-launch" if on_smem else ""),
+                "dense_equivalent_GBps": dense_bytes / k_time / 1e9 if k_time > 0 else None,
+                "dense_equivalent_frac": dense_bytes / k_time / 1e9 / peak if k_time > 0 and peak else None,
                 "kernel_ms_per_launch": 1e3 * k_time / n_launch, "launches_per_step": n_launch,
                 "kernel_share_of_solve_kernels": k_share,
                 "kernel_ms_by_launch": [round(float(v), 4) for v in kern[:, dom]],
-                "bytes_per_basis_change": bpp, "basis_changes_per_step": float(kcnt[0]),
-                "state_bytes_per_step": state_bytes, "peak_source": peak_src,
-                "hbm_state_GBps": state_bytes / k_time / 1e9 if k_time > 0 else None}
+                "bytes_per_basis_change_dense": bpp, "basis_changes_per_step": float(kcnt[0]),
+                "rows_swept_per_basis_change": float(kcnt[3] / max(kcnt[0], 1.0)),
+                "state_bytes_per_step": state_bytes, "peak_source": peak_src}
 
     # ---------------- CPU baseline: same trajectory on a bounded sample of the blocks ----------------
     cpu = None

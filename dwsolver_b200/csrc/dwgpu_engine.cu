@@ -271,8 +271,8 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(e->pi.alloc(L)); CUE(e->obj.alloc(K)); CUE(e->cost.alloc(K));
     CUE(e->status.alloc(K)); CUE(e->len.alloc(K));
     CUE(e->ind.alloc((size_t)K * L)); CUE(e->val.alloc((size_t)K * L));
-    CUE(e->counters.alloc((size_t)K * 4)); CUE(e->last_iters.alloc(K));
-    CUE(cudaMemset(e->counters.p, 0, sizeof(unsigned long long) * (size_t)K * 4));
+    CUE(e->counters.alloc((size_t)K * 8)); CUE(e->last_iters.alloc(K));
+    CUE(cudaMemset(e->counters.p, 0, sizeof(unsigned long long) * (size_t)K * 8));
     CUE(cudaMemset(e->x.p, 0, sizeof(double) * std::max<long long>(e->ntot, 1)));
     CUE(cudaMallocHost((void **)&e->h_pi, sizeof(double) * std::max(L, 1)));
 
@@ -473,12 +473,13 @@ int dwgpu_get_counters(dwgpu_engine *e, dwgpu_counters *t)
     if (!e || !t) return fail(DWGPU_E_ARGS, "NULL argument");
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream));
-    std::vector<unsigned long long> h((size_t)e->K * 4);
+    std::vector<unsigned long long> h((size_t)e->K * 8);
     CU(cudaMemcpy(h.data(), e->counters.p, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
     std::memset(t, 0, sizeof(*t));
     for (int k = 0; k < e->K; ++k) {
-        t->pivots += (long long)h[4 * (size_t)k]; t->flips += (long long)h[4 * (size_t)k + 1];
-        t->rebuilds += (long long)h[4 * (size_t)k + 2]; t->phase1_iter += (long long)h[4 * (size_t)k + 3];
+        t->pivots += (long long)h[8 * (size_t)k]; t->flips += (long long)h[8 * (size_t)k + 1];
+        t->rebuilds += (long long)h[8 * (size_t)k + 2]; t->phase1_iter += (long long)h[8 * (size_t)k + 3];
+        t->rows_swept += (long long)h[8 * (size_t)k + 4];
     }
     t->solves = e->solves;
     return 0;

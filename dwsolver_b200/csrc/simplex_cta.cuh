@@ -56,7 +56,7 @@ struct SolveParams {
     int *status, *len;  // K
     int *ind;           // K*L
     double *val;        // K*L
-    unsigned long long *counters;  // K*4: pivots, flips, rebuilds, phase-1 iterations
+    unsigned long long *counters;  // K*8: pivots, flips, rebuilds, phase-1 iterations, rows swept, 3 spare
     long long *last_iters;         // K
 };
 
@@ -525,10 +525,11 @@ __device__ void solve_block(const BlockDev &B, const SolveParams &P, int k, Ctx 
             P.obj[k] = zo;
             P.cost[k] = zc;
             P.status[k] = status;
-            P.counters[4 * (size_t)k + 0] += n_piv;
-            P.counters[4 * (size_t)k + 1] += n_flip;
-            P.counters[4 * (size_t)k + 2] += n_reb;
-            P.counters[4 * (size_t)k + 3] += n_p1;
+            P.counters[8 * (size_t)k + 0] += n_piv;
+            P.counters[8 * (size_t)k + 1] += n_flip;
+            P.counters[8 * (size_t)k + 2] += n_reb;
+            P.counters[8 * (size_t)k + 3] += n_p1;
+            P.counters[8 * (size_t)k + 4] += n_piv * (unsigned long long)(m + 1);   // dense sweep bound
             P.last_iters[k] = (long long)(n_piv + n_flip);
         }
     }

@@ -139,7 +139,8 @@ __device__ __forceinline__ double warp_min_nonneg(double v)
 template <bool INF, int MC, int NC, bool TG>
 __device__ __forceinline__ int decide_warp0(Sm3 &c, const double *dd, bool d_live, bool &bland, int &degen, int degen_limit,
                             double tol_dj, double tol_bnd, double tol_piv,
-                            unsigned long long &n_piv, unsigned long long &n_flip, Decision *dec)
+                            unsigned long long &n_piv, unsigned long long &n_flip, unsigned long long &n_rows,
+                            Decision *dec)
 {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -270,6 +271,7 @@ __device__ __forceinline__ int decide_warp0(Sm3 &c, const double *dd, bool d_liv
             dec->p = p; dec->q = q; dec->inv = inv; dec->na = na + (with_d ? 1 : 0);
         }
         ++n_piv;
+        n_rows += (unsigned long long)na;
         if (theta <= 1e-11) { if (++degen > degen_limit) bland = true; }
         else { degen = 0; bland = false; }
         return K_PIVOT;
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(NT, TG ? 4 : 3) solve_smem_kernel(const BlockD
     int status = 0;
     long long iter = 0;
     const long long max_iter = (long long)P.max_iter_mult * (m + n) + 1000;
-    unsigned long long n_piv = 0, n_flip = 0, n_reb = 0, n_p1 = 0;   // n_piv/n_flip live in warp 0
+    unsigned long long n_piv = 0, n_flip = 0, n_reb = 0, n_p1 = 0, n_rows = 0;   // n_piv/n_flip/n_rows live in warp 0
     bool need_check = true, infeasible = false, d_valid = false, bland = false;
     int degen = 0;
     const int degen_limit = 100 + (m + n) / 2;
@@ -471,10 +473,10 @@ __global__ void __launch_bounds__(NT, TG ? 4 : 3) solve_smem_kernel(const BlockD
             int kind;
             if (infeasible)
                 kind = decide_warp0<true, MC, NC, TG>(c, c.rowp, false, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
-                                          n_piv, n_flip, &dec);
+                                          n_piv, n_flip, n_rows, &dec);
             else
                 kind = decide_warp0<false, MC, NC, TG>(c, c.drow, true, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
-                                           n_piv, n_flip, &dec);
+                                           n_piv, n_flip, n_rows, &dec);
             if (lane == 0) { s_kind = kind; if (n_piv + n_flip) s_changed = 1; }
         }
         __syncthreads();
@@ -634,10 +636,11 @@ __global__ void __launch_bounds__(NT, TG ? 4 : 3) solve_smem_kernel(const BlockD
             P.obj[k] = zo;
             P.cost[k] = zc;
             P.status[k] = status;
-            P.counters[4 * (size_t)k + 0] += n_piv;
-            P.counters[4 * (size_t)k + 1] += n_flip;
-            P.counters[4 * (size_t)k + 2] += n_reb;
-            P.counters[4 * (size_t)k + 3] += n_p1;
+            P.counters[8 * (size_t)k + 0] += n_piv;
+            P.counters[8 * (size_t)k + 1] += n_flip;
+            P.counters[8 * (size_t)k + 2] += n_reb;
+            P.counters[8 * (size_t)k + 3] += n_p1;
+            P.counters[8 * (size_t)k + 4] += n_rows;
             P.last_iters[k] = (long long)(n_piv + n_flip);
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }

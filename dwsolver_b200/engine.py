@@ -51,7 +51,7 @@ class Proposals(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("pivots", C.c_longlong), ("flips", C.c_longlong), ("rebuilds", C.c_longlong),
-                ("phase1_iter", C.c_longlong), ("solves", C.c_longlong)]
+                ("phase1_iter", C.c_longlong), ("solves", C.c_longlong), ("rows_swept", C.c_longlong)]
 
 
 _LIB = None
@@ -226,7 +226,8 @@ class Engine:
     def counters(self) -> dict:
         c = Counters()
         _check(self._lib.dwgpu_get_counters(self._h, C.byref(c)), "dwgpu_get_counters")
-        return dict(pivots=c.pivots, flips=c.flips, rebuilds=c.rebuilds, phase1_iter=c.phase1_iter, solves=c.solves)
+        return dict(pivots=c.pivots, flips=c.flips, rebuilds=c.rebuilds, phase1_iter=c.phase1_iter, solves=c.solves,
+                    rows_swept=c.rows_swept)
 
     def block_iterations(self) -> np.ndarray:
         it = np.zeros(self.K, np.int64)

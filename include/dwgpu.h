@@ -95,6 +95,7 @@ typedef struct dwgpu_counters {
     long long rebuilds;    /* tableau rebuilt from A_k after a residual check */
     long long phase1_iter; /* iterations spent restoring primal feasibility */
     long long solves;      /* block solves */
+    long long rows_swept;  /* tableau rows (incl. the reduced-cost row) rewritten by basis changes */
 } dwgpu_counters;
 
 typedef struct dwgpu_engine dwgpu_engine;
