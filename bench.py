@@ -45,10 +45,10 @@ UNIT = "pivots/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default=os.environ.get("DWBENCH_CONFIG", "A"), choices=list(P.CONFIGS))
+    ap.add_argument("--config", default=os.environ.get("DWBENCH_CONFIG", "B"), choices=list(P.CONFIGS))
     ap.add_argument("--cpu-blocks", type=int, default=0, help="blocks in the CPU arm's sample (0 = auto)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -187,7 +187,7 @@ def main():
     # ---------------- our arm ----------------
     import torch
     from dwsolver_b200 import engine as E
-    from dwsolver_b200 import sharding as S
+    from dwsolver_b200 import sharding as SH
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
@@ -198,7 +198,7 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
-    my_range = S.shard_range(K_total, world, rank)
+    my_range = SH.shard_range(K_total, world, rank)
     K_loc = len(my_range)
     prob = P.make_config(args.config, block_range=my_range)
     bpp = algorithmic_bytes_per_pivot(m, n)
@@ -238,14 +238,14 @@ def main():
 
     gat = None
     if dist is not None:   # every rank receives every shard's proposals; rank 0 is the consumer
-        gat = S.alloc_gathered(torch, K_total, L, dev)
+        gat = SH.alloc_gathered(torch, K_total, L, dev)
         h_pin = {k_: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k_, v in gat.items()}
     pi_pin = torch.zeros(L, dtype=torch.float64).pin_memory()
     pi_dev = torch.zeros(L, dtype=torch.float64, device=dev)
     pis_dev = torch.from_numpy(pis).to(dev)
 
     def exchange_up():
-        S.proposals_up(dist, views, gat)
+        SH.proposals_up(dist, views, gat)
 
     def up_to_host():
         if rank == 0:
@@ -267,13 +267,15 @@ def main():
                 launches[0] += eng.last_launch_count()
         else:
             eng.initial_solve_device(sptr)
+            launches[0] += eng.last_launch_count()
             exchange_up(); up_to_host()
             for r in range(R):
                 if rank == 0:
                     pi_pin.copy_(torch.from_numpy(pis[r]))
                     pi_dev.copy_(pi_pin, non_blocking=True)
-                S.duals_down(dist, pi_dev, src=0)                  # duals down (NCCL)
+                SH.duals_down(dist, pi_dev, src=0)                  # duals down (NCCL)
                 eng.iterate_device(pi_dev.data_ptr(), phases[r], sptr)
+                launches[0] += eng.last_launch_count()
                 exchange_up(); up_to_host()                        # proposals up (NCCL) + D2H on rank 0
 
     # ---- one step, device only: duals already in HBM, results stay in HBM
@@ -287,7 +289,7 @@ def main():
         for r in range(R):
             if dist is not None:
                 pi_dev.copy_(pis_dev[r])
-                S.duals_down(dist, pi_dev, src=0)
+                SH.duals_down(dist, pi_dev, src=0)
                 eng.iterate_device(pi_dev.data_ptr(), phases[r], sptr)
                 exchange_up()
             else:

@@ -38,6 +38,7 @@ int fail(int code, const std::string &msg)
 
 constexpr int NT_SMEM = 256;
 constexpr int NT_GMEM = 1024;
+constexpr int NT_TG = 128;     // global-tableau kernel: 128-thread CTAs, 6 per SM (DWGPU_TG_THREADS=256: 4 per SM)
 
 template <typename T>
 struct DevBuf {
@@ -82,17 +83,26 @@ struct dwgpu_engine {
     // kernel lists: smem-generic, legacy global, specialised 64x128 (A), global-T generic (g), global-T 256x512 (B)
     std::vector<int> list_smem, list_gmem, list_a, list_g, list_b;
     size_t smem_dyn_g = 0;
+    int tg_threads = NT_TG;
     size_t smem_dyn = 0;
     int max_smem_optin = 0;
     // device arenas
-    DevBuf<double> T, bnd, a_v, dc_val, dr_val, c_file, c_master, x, ws;
+    DevBuf<double> T, bnd, dsave, cssave, a_v, dc_val, dr_val, c_file, c_master, x, ws;
     DevBuf<int> a_rp, a_ci, dc_ptr, dc_row, dr_ptr, dr_col;
     DevBuf<char> pst;
+    DevBuf<int> dflag;
     DevBuf<dwk::BlockDev> blocks;
     DevBuf<int> d_list_smem, d_list_gmem, d_list_a, d_list_g, d_list_b;
     // round inputs / outputs
-    DevBuf<double> pi, obj, cost, val;
-    DevBuf<int> status, len, ind;
+    DevBuf<double> pi;
+    DevBuf<char> rec;                  // [obj K | cost K | val K*L] doubles, then [status K | len K | ind K*L] ints
+    size_t rec_bytes = 0;
+    struct View { double *p = nullptr; } obj, cost, val;
+    struct IView { int *p = nullptr; } status, len, ind;
+    DevBuf<int> colptr;                // K+1, device scratch of the pack kernel
+    // mapped pinned host mirror written by the pack kernel: header + packed columns
+    char *h_pack = nullptr, *d_pack = nullptr;
+    size_t pack_bytes = 0;
     DevBuf<unsigned long long> counters;
     DevBuf<long long> last_iters;
     // pinned staging
@@ -127,13 +137,13 @@ void dwgpu_destroy(dwgpu_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    e->T.release(); e->bnd.release(); e->pst.release(); e->a_v.release();
+    e->T.release(); e->bnd.release(); e->pst.release(); e->a_v.release(); e->dsave.release(); e->cssave.release(); e->dflag.release();
     e->dc_val.release(); e->dr_val.release(); e->c_file.release(); e->c_master.release();
     e->x.release(); e->ws.release(); e->a_rp.release();
     e->a_ci.release(); e->dc_ptr.release(); e->dc_row.release(); e->dr_ptr.release();
     e->dr_col.release(); e->blocks.release(); e->d_list_smem.release();
-    e->d_list_gmem.release(); e->d_list_a.release(); e->d_list_g.release(); e->d_list_b.release(); e->pi.release(); e->obj.release(); e->cost.release();
-    e->val.release(); e->status.release(); e->len.release(); e->ind.release();
+    e->d_list_gmem.release(); e->d_list_a.release(); e->d_list_g.release(); e->d_list_b.release(); e->pi.release(); e->rec.release(); e->colptr.release();
+    if (e->h_pack) cudaFreeHost(e->h_pack);
     e->counters.release(); e->last_iters.release();
     if (e->h_pi) cudaFreeHost(e->h_pi);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -267,10 +277,27 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(e->dr_ptr.upload(h_drp)); CUE(e->dr_col.upload(h_drc)); CUE(e->dr_val.upload(h_drv));
     CUE(e->c_file.upload(h_cf)); CUE(e->c_master.upload(h_cm));
     CUE(e->x.alloc(e->ntot));
+    CUE(e->dsave.alloc(e->ntot)); CUE(e->cssave.alloc(e->ntot)); CUE(e->dflag.alloc(K));
+    CUE(cudaMemset(e->dflag.p, 0, sizeof(int) * (size_t)K));
     CUE(e->ws.alloc(ws_off[K]));
-    CUE(e->pi.alloc(L)); CUE(e->obj.alloc(K)); CUE(e->cost.alloc(K));
-    CUE(e->status.alloc(K)); CUE(e->len.alloc(K));
-    CUE(e->ind.alloc((size_t)K * L)); CUE(e->val.alloc((size_t)K * L));
+    CUE(e->pi.alloc(L));
+    {
+        const size_t KL = (size_t)K * L;
+        const size_t nd = 2 * (size_t)K + KL, ni = 2 * (size_t)K + KL;
+        e->rec_bytes = sizeof(double) * nd + sizeof(int) * ni;
+        CUE(e->rec.alloc(e->rec_bytes));
+        CUE(cudaMemset(e->rec.p, 0, e->rec_bytes));
+        double *dp = (double *)e->rec.p;
+        e->obj.p = dp; e->cost.p = dp + K; e->val.p = dp + 2 * (size_t)K;
+        int *ip = (int *)(dp + nd);
+        e->status.p = ip; e->len.p = ip + K; e->ind.p = ip + 2 * (size_t)K;
+        CUE(e->colptr.alloc((size_t)K + 1));
+        // host mirror: obj K, cost K, val nnz<=KL (doubles) | status K, len K, colptr K+1, ind nnz<=KL (ints)
+        e->pack_bytes = sizeof(double) * (2 * (size_t)K + KL) + sizeof(int) * (3 * (size_t)K + 1 + KL) + 64;
+        CUE(cudaHostAlloc((void **)&e->h_pack, e->pack_bytes, cudaHostAllocMapped));
+        CUE(cudaHostGetDevicePointer((void **)&e->d_pack, e->h_pack, 0));
+        std::memset(e->h_pack, 0, e->pack_bytes);
+    }
     CUE(e->counters.alloc((size_t)K * 8)); CUE(e->last_iters.alloc(K));
     CUE(cudaMemset(e->counters.p, 0, sizeof(unsigned long long) * (size_t)K * 8));
     CUE(cudaMemset(e->x.p, 0, sizeof(double) * std::max<long long>(e->ntot, 1)));
@@ -291,6 +318,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         B.dr_ptr = e->dr_ptr.p + drp_off[k]; B.dr_col = e->dr_col.p + d_off[k]; B.dr_val = e->dr_val.p + d_off[k];
         B.c_file = e->c_file.p + e->xoff[k]; B.c_master = e->c_master.p + e->xoff[k];
         B.x = e->x.p + e->xoff[k];
+        B.dsave = e->dsave.p + e->xoff[k]; B.cssave = e->cssave.p + e->xoff[k]; B.dflag = e->dflag.p + k;
         B.ws = e->ws.p + ws_off[k];
     }
     CUE(e->blocks.upload(hb));
@@ -306,12 +334,19 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     if (!e->list_a.empty())
         CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 64, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)dwk::smem2_bytes(64, 128)));
-    if (!e->list_g.empty())
+    if (const char *tg = std::getenv("DWGPU_TG_THREADS")) e->tg_threads = std::atoi(tg) == 256 ? 256 : 128;
+    if (!e->list_g.empty()) {
         CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)e->smem_dyn_g));
-    if (!e->list_b.empty())
+        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_TG, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)e->smem_dyn_g));
+    }
+    if (!e->list_b.empty()) {
         CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 256, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)dwk::smem2_bytes(256, 512, true)));
+        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_TG, 256, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)dwk::smem2_bytes(256, 512, true)));
+    }
 
     dwk::init_kernel<256><<<K, 256, 0, e->stream>>>(e->blocks.p, K);
     CUE(cudaGetLastError());
@@ -347,14 +382,22 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         const bool own_events = !e->ev_used[1];
         if (own_events) CU(cudaEventRecord(e->ev[0], st));
         if (!e->list_b.empty()) {
-            dwk::solve_smem_kernel<NT_SMEM, 256, 512, true><<<(unsigned)e->list_b.size(), NT_SMEM, dwk::smem2_bytes(256, 512, true), st>>>(
-                e->blocks.p, e->d_list_b.p, (int)e->list_b.size(), P);
+            if (e->tg_threads == 256)
+                dwk::solve_smem_kernel<NT_SMEM, 256, 512, true><<<(unsigned)e->list_b.size(), NT_SMEM, dwk::smem2_bytes(256, 512, true), st>>>(
+                    e->blocks.p, e->d_list_b.p, (int)e->list_b.size(), P);
+            else
+                dwk::solve_smem_kernel<NT_TG, 256, 512, true><<<(unsigned)e->list_b.size(), NT_TG, dwk::smem2_bytes(256, 512, true), st>>>(
+                    e->blocks.p, e->d_list_b.p, (int)e->list_b.size(), P);
             CU(cudaGetLastError());
             e->last_launches++;
         }
         if (!e->list_g.empty()) {
-            dwk::solve_smem_kernel<NT_SMEM, 0, 0, true><<<(unsigned)e->list_g.size(), NT_SMEM, e->smem_dyn_g, st>>>(
-                e->blocks.p, e->d_list_g.p, (int)e->list_g.size(), P);
+            if (e->tg_threads == 256)
+                dwk::solve_smem_kernel<NT_SMEM, 0, 0, true><<<(unsigned)e->list_g.size(), NT_SMEM, e->smem_dyn_g, st>>>(
+                    e->blocks.p, e->d_list_g.p, (int)e->list_g.size(), P);
+            else
+                dwk::solve_smem_kernel<NT_TG, 0, 0, true><<<(unsigned)e->list_g.size(), NT_TG, e->smem_dyn_g, st>>>(
+                    e->blocks.p, e->d_list_g.p, (int)e->list_g.size(), P);
             CU(cudaGetLastError());
             e->last_launches++;
         }

@@ -44,6 +44,9 @@ struct BlockDev {
     const double *c_file, *c_master;
     double *x;              // n (output of the last round)
     double *ws;             // global workspace for the vectors (TSMEM=false)
+    double *dsave;          // n: reduced costs by column position at the end of the last optimal solve
+    double *cssave;         // n: priced structural costs they were computed with
+    int *dflag;             // solves since dsave was last recomputed in full (0 = dsave invalid)
 };
 
 struct SolveParams {
@@ -612,6 +615,7 @@ __global__ void __launch_bounds__(NT) init_kernel(const BlockDev *blocks, int K)
     c.d = c.d1 = c.rowp = c.cs = c.colq = c.w = nullptr;
     for (int v = threadIdx.x; v < B.m + B.n; v += NT)
         B.vstat[v] = v < B.m ? ST_BASIC : initial_stat(B.lo[v], B.up[v]);
+    if (threadIdx.x == 0) B.dflag[0] = 0;
     __syncthreads();
     reset_tableau<NT>(B, c);
     recompute_beta<NT>(c);

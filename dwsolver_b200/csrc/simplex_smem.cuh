@@ -278,6 +278,16 @@ __device__ __forceinline__ int decide_warp0(Sm3 &c, const double *dd, bool d_liv
     }
 }
 
+// Change of a priced cost that the saved reduced costs still have to absorb.  Differences at the
+// noise level of the master's duals (<= 1e-11 relative) are NOT applied and the saved cost is left
+// as it is, so they keep accumulating until they matter; the reduced costs used for pricing are
+// then off by at most ~1e-11 |T|_1, two orders below tol_dj.
+__device__ __forceinline__ double cost_delta(double cs_new, double cs_saved)
+{
+    const double d = cs_new - cs_saved;
+    return fabs(d) > 1e-11 * (1.0 + fabs(cs_new)) ? d : 0.0;
+}
+
 // rank-1 sweep over the active rows only (row m = reduced costs when it is in the list)
 template <int NT, int NC, bool TG>
 __device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, int na)
@@ -343,7 +353,7 @@ __device__ __forceinline__ void gather_bounds(const BlockDev &B, Sm3 &c)
 // TG = true: the tableau stays in global memory (L2/HBM) and only the vectors live in shared memory
 // (blocks too large for one CTA's shared memory, config B class); the decision/sweep code is shared.
 template <int NT, int MC, int NC, bool TG>
-__global__ void __launch_bounds__(NT, TG ? 4 : 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
+__global__ void __launch_bounds__(NT, TG ? (NT <= 128 ? 6 : 4) : 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
                                                           SolveParams P)
 {
     extern __shared__ __align__(16) char smem_raw[];
@@ -414,9 +424,11 @@ __global__ void __launch_bounds__(NT, TG ? 4 : 3) solve_smem_kernel(const BlockD
     long long iter = 0;
     const long long max_iter = (long long)P.max_iter_mult * (m + n) + 1000;
     unsigned long long n_piv = 0, n_flip = 0, n_reb = 0, n_p1 = 0, n_rows = 0;   // n_piv/n_flip/n_rows live in warp 0
-    bool need_check = true, infeasible = false, d_valid = false, bland = false;
+    bool need_check = true, infeasible = false, d_valid = false, bland = false, d_full = false;
     int degen = 0;
     const int degen_limit = 100 + (m + n) / 2;
+    const int dflag_in = B.dflag[0];
+    const bool use_saved = dflag_in > 0 && dflag_in < 32;
 
     for (;;) {
         if (++iter > max_iter) { status = 1; break; }
@@ -448,16 +460,24 @@ __global__ void __launch_bounds__(NT, TG ? 4 : 3) solve_smem_kernel(const BlockD
             ++n_p1;
             __syncthreads();
         } else if (!d_valid) {
+            // reduced costs.  If the basis has not moved since the last optimal solve of this block,
+            // update the saved row incrementally: d = d_saved + dc_N + T' dc_B with dc = cs - cs_saved,
+            // which only touches the rows of T whose basic cost changed (late rounds: a handful);
+            // otherwise (and every 32nd solve, to stop drift) recompute d = c_N + T' c_B in full.
+            const bool inc = use_saved && !s_changed && n_reb == 0;
             for (int i = tid; i < m; i += NT) {
                 const int v = c.head[i];
-                c.colq[i] = v >= m ? c.cs[v - m] : 0.0;
+                double cb = 0.0;
+                if (v >= m) cb = inc ? cost_delta(c.cs[v - m], B.cssave[v - m]) : c.cs[v - m];
+                c.colq[i] = cb;
             }
             __syncthreads();
             for (int j = tid; j < ld; j += NT) {
                 double s = 0.0;
                 if (j < n) {
                     const int v = c.nbv[j];
-                    s = v >= m ? c.cs[v - m] : 0.0;
+                    if (v >= m) s = inc ? cost_delta(c.cs[v - m], B.cssave[v - m]) : c.cs[v - m];
+                    if (inc) s += B.dsave[j];
                     for (int i = 0; i < m; ++i) {
                         const double cb = c.colq[i];
                         if (cb != 0.0) s = fma(cb, c.T[(size_t)i * ld + j], s);  // block-uniform branch
@@ -466,6 +486,7 @@ __global__ void __launch_bounds__(NT, TG ? 4 : 3) solve_smem_kernel(const BlockD
                 c.drow[j] = s;
             }
             d_valid = true;
+            d_full = !inc;
             __syncthreads();
         }
         // ---- B. decision (warp 0)
@@ -584,11 +605,25 @@ __global__ void __launch_bounds__(NT, TG ? 4 : 3) solve_smem_kernel(const BlockD
         // the block was already optimal under the new prices: x_k, D_k x_k, c_k.x_k and the whole
         // state in HBM are still those of the previous round; only the priced optimum moves
         double zo = 0.0;
-        for (int j = tid; j < n; j += NT) zo = fma(c.cs[j], c.rowp[j], zo);
+        for (int j = tid; j < n; j += NT) {
+            zo = fma(c.cs[j], c.rowp[j], zo);
+            B.dsave[j] = c.drow[j];
+            if (d_full || cost_delta(c.cs[j], B.cssave[j]) != 0.0) B.cssave[j] = c.cs[j];
+        }
         zo = block_sum<NT>(zo, scr);
-        if (tid == 0) { P.obj[k] = zo; P.status[k] = 5; P.last_iters[k] = 0; }
+        if (tid == 0) {
+            P.obj[k] = zo; P.status[k] = 5; P.last_iters[k] = 0;
+            B.dflag[0] = d_full ? 1 : dflag_in + 1;
+        }
         return;
     }
+    if (status == 5 && d_valid) {
+        for (int j = tid; j < n; j += NT) {
+            B.dsave[j] = c.drow[j];
+            if (d_full || cost_delta(c.cs[j], B.cssave[j]) != 0.0) B.cssave[j] = c.cs[j];
+        }
+        if (tid == 0) B.dflag[0] = d_full ? 1 : dflag_in + 1;
+    } else if (tid == 0) B.dflag[0] = 0;
     // state out first (async), then the proposal while the copies fly
     if (tid == 0) {
         const bool t_dirty = (n_piv + n_reb) != 0;        // thread 0 sits in warp 0, which owns n_piv
