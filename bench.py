@@ -71,52 +71,59 @@ def algorithmic_bytes_per_pivot(m, n):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region: NVML every 5 ms from a thread
+    (nvidia-smi -lms cannot go below ~100 ms, too coarse for millisecond steps)."""
 
     def __init__(self, device):
         self.device = device
-        self.proc = None
-        self.lines = []
+        self.sm, self.reasons, self.smax = [], set(), None
+        self._stop = threading.Event()
+        self.th = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except OSError:
-            self.proc = None
+            import pynvml as N
+            N.nvmlInit()
+            idx = self.device
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.device])
+                except (ValueError, IndexError):
+                    pass
+            h = N.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            names = {"hw_slowdown": N.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": N.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": N.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": N.nvmlClocksThrottleReasonSwPowerCap}
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                        r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for nm, bit in names.items():
+                            if r & bit:
+                                self.reasons.add(nm)
+                    except N.NVMLError as exc:      # keep sampling
+                        self.err = str(exc)
+                    time.sleep(0.005)
+            self.th = threading.Thread(target=loop, daemon=True)
+            self.th.start()
+        except Exception as exc:                    # no NVML: report it, never fake a clock
+            self.err = f"NVML unavailable: {exc}"
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        if self.th:
+            self.th.join(timeout=1.0)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax,
+               "samples": len(self.sm), "reasons": sorted(self.reasons)}
+        if self.err:
+            out["note"] = self.err
+        return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -163,7 +170,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sample_k = min(K_total, args.cpu_blocks or (32 * cores if m <= 64 else 2 * cores))
+        sample_k = min(K_total, args.cpu_blocks or (32 * cores if m <= 64 else 8 * cores))
         prob = P.make_config(args.config, block_range=range(sample_k))
         piv_total, t_total = 0, 0.0
         for step in range(W + S):
@@ -254,17 +261,26 @@ def main():
         torch.cuda.synchronize()
 
     launches = [0]
+    d2h = [0]
+    last_status = [None]
+
+    def packed_bytes(pk):      # what the GPU wrote into the pinned record this round
+        return 8 + K_loc * (8 + 8 + 4) + (K_loc + 1) * 4 + pk["nnz"] * 12
 
     # ---- one step, end to end: host buffers in, host buffers out, every round
     def step_e2e():
         eng.reset(sptr if dist is not None else 0)    # single GPU: the engine's own stream end to end
         launches[0] = 1
+        d2h[0] = 0
         if dist is None:
-            eng.initial_solve()                                    # kernels + D2H of the first proposals
+            pk = eng.initial_solve_packed()                        # kernels + packed proposals to pinned host
             launches[0] += eng.last_launch_count()
+            d2h[0] += packed_bytes(pk)
             for r in range(R):
-                eng.iterate_arrays(pis[r], phases[r])              # H2D pi_r, kernels, D2H proposals
+                pk = eng.iterate_packed(pis[r], phases[r])         # H2D pi_r, kernels, packed proposals back
                 launches[0] += eng.last_launch_count()
+                d2h[0] += packed_bytes(pk)
+            last_status[0] = np.array(pk["status"])
         else:
             eng.initial_solve_device(sptr)
             launches[0] += eng.last_launch_count()
@@ -299,10 +315,10 @@ def main():
 
     def count():
         c = eng.counters()
-        return np.array([c["pivots"], c["flips"], c["rebuilds"], c["rows_swept"]], dtype=np.float64)
+        return np.array([c["pivots"], c["flips"], c["rebuilds"], c["rows_swept"], c["cells_swept"]], dtype=np.float64)
 
     # =========================== e2e ===========================
-    e2e_time, e2e_cnt = 0.0, np.zeros(4)
+    e2e_time, e2e_cnt = 0.0, np.zeros(5)
     for step in range(W + S):
         flush_buf.fill_(1)
         barrier()
@@ -314,12 +330,12 @@ def main():
         if step >= W:
             e2e_time += dt
             e2e_cnt += count() - c0
-    status_ok = bool((eng.status == 5).all()) if dist is None else bool((h_pin["status"].numpy() == 5).all()) if rank == 0 else True
+    status_ok = bool((last_status[0] == 5).all()) if dist is None else bool((h_pin["status"].numpy() == 5).all()) if rank == 0 else True
 
     # =========================== device only ===========================
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + S)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + S)]
-    dev_cnt = np.zeros(4)
+    dev_cnt = np.zeros(5)
     kern = []
     clocks = ClockSampler(local_rank)
     for step in range(W + S):
@@ -358,7 +374,7 @@ def main():
         dist.all_reduce(pv, op=dist.ReduceOp.SUM)
         t_dev, e2e_time, k_time = (float(v) for v in tt.tolist())
         pv = pv.cpu().numpy()
-        dev_cnt, e2e_cnt, kcnt = pv[0:4], pv[4:8], pv[8:12]
+        dev_cnt, e2e_cnt, kcnt = pv[0:5], pv[5:10], pv[10:15]
     eng.close()
     if rank != 0:
         if dist is not None:
@@ -368,15 +384,16 @@ def main():
 
     # ---------------- roofline of the dominant kernel (one replay, per-launch events) ----------------
     # Bytes the kernel's algorithm must move:
-    #   per basis change   8(m+n)                 pivot column + pivot row read
-    #   per swept row      16(n+1)                row read + written (rows whose pivot-column entry is
-    #                                             exactly zero are not touched; the device counts rows)
-    #   per launch & block 16 m n (shared-memory path only): tableau image loaded + stored
+    #   per basis change   8(m+n)   pivot column + pivot row read
+    #   per rewritten cell 16       read + write of every tableau double that changes: only
+    #                               (rows with a non-zero pivot-column entry) x (non-zero items of the
+    #                               pivot row) move; the device counts them (dwgpu_counters.cells_swept)
+    #   per launch & block 16 m n   (shared-memory path only): tableau image loaded + stored
     # The survey's dense figure 16(m+1)(n+1) per basis change is reported next to it.
     on_smem = dom == 0
     n_launch = R + 1
     state_bytes = n_launch * K_total * 2.0 * 8.0 * m * n if on_smem else 0.0
-    touched = kcnt[3] * 16.0 * (n + 1) + kcnt[0] * 8.0 * (m + n)
+    touched = kcnt[4] * 16.0 + kcnt[0] * 8.0 * (m + n)
     alg_bytes = touched + state_bytes
     dense_bytes = kcnt[0] * bpp + state_bytes
     if on_smem:
@@ -393,11 +410,12 @@ def main():
             peak_src = "of fallback (B200_PROFILING.md)"
         bound = "hbm"
     achieved = alg_bytes / k_time / 1e9 if k_time > 0 else 0.0
-    kname = {("A", True): "dwk::solve_smem_kernel<256,64,128,false>", ("B", False): "dwk::solve_smem_kernel<256,256,512,true>"}
+    kname = {("A", True): "dwk::solve_smem_kernel<256,64,128,false>", ("B", False): "dwk::solve_smem_kernel<128,256,512,true>",
+             ("C", False): "dwk::solve_cluster_kernel<512>"}
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if peak else None, "traffic": None,
                 "kernel": kname.get((args.config, on_smem), "dwk::solve_kernel<false,1024>"),
-                "bytes_definition": "touched: 16(n+1) per swept row + 8(m+n) per basis change"
+                "bytes_definition": "touched: 16 B per rewritten tableau double + 8(m+n) per basis change"
                                     + (" + 16mn state image per block-launch" if on_smem else ""),
                 "dense_equivalent_GBps": dense_bytes / k_time / 1e9 if k_time > 0 else None,
                 "dense_equivalent_frac": dense_bytes / k_time / 1e9 / peak if k_time > 0 and peak else None,
@@ -406,17 +424,18 @@ def main():
                 "kernel_ms_by_launch": [round(float(v), 4) for v in kern[:, dom]],
                 "bytes_per_basis_change_dense": bpp, "basis_changes_per_step": float(kcnt[0]),
                 "rows_swept_per_basis_change": float(kcnt[3] / max(kcnt[0], 1.0)),
+                "cells_rewritten_per_basis_change": float(kcnt[4] / max(kcnt[0], 1.0)),
                 "state_bytes_per_step": state_bytes, "peak_source": peak_src}
 
     # ---------------- CPU baseline: same trajectory on a bounded sample of the blocks ----------------
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        sample_k = min(K_loc, args.cpu_blocks or (32 * cores if m <= 64 else 2 * cores))
+        sample_k = min(K_loc, args.cpu_blocks or (32 * cores if m <= 64 else 8 * cores))
         sub = P.BlockAngularLP(K=sample_k, L=L, blocks=prob.blocks[:sample_k], link_lb=prob.link_lb,
                                link_ub=prob.link_ub)
         piv, secs, reps = 0, 0.0, 0
         cpu_replay(sub, pis, phases, cores)                       # warm-up
-        while secs < args.cpu_seconds and reps < 50:
+        while secs < args.cpu_seconds and reps < 100000:
             p_, dt, _ = cpu_replay(sub, pis, phases, cores)
             piv += p_; secs += dt; reps += 1
         cpu = {"value": piv / secs if secs > 0 else None, "unit": UNIT, "cores": cores, "kind": "port",
@@ -433,7 +452,9 @@ def main():
                    "dw_objective_of_trajectory": dw_objective},
         "e2e": {"value": (e2e_cnt[0] + e2e_cnt[1]) / e2e_time if e2e_time > 0 else 0.0, "unit": UNIT,
                 "h2d_bytes_per_step": 8 * L * R,
-                "d2h_bytes_per_step": (R + 1) * (K_total * (8 + 8 + 4 + 4) + K_total * L * 12),
+                "d2h_bytes_per_step": d2h[0] if world == 1 else (R + 1) * (K_total * (8 + 8 + 4 + 4) + K_total * L * 12),
+                "api": "dwgpu_initial_solve_packed + dwgpu_iterate_packed (host pi in, pinned packed record out)"
+                       if world == 1 else "dwgpu_iterate_device + NCCL broadcast/all-gather + D2H on rank 0",
                 "ms_per_step": 1e3 * e2e_time / S},
         "gpu_launches": launches[0] * S,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,

@@ -18,6 +18,8 @@
 #include "../../include/dwgpu.h"
 #include "simplex_cta.cuh"
 #include "simplex_smem.cuh"
+#include "pack.cuh"
+#include "simplex_cluster.cuh"
 
 namespace {
 
@@ -38,7 +40,7 @@ int fail(int code, const std::string &msg)
 
 constexpr int NT_SMEM = 256;
 constexpr int NT_GMEM = 1024;
-constexpr int NT_TG = 128;     // global-tableau kernel: 128-thread CTAs, 6 per SM (DWGPU_TG_THREADS=256: 4 per SM)
+constexpr int NT_TG = 64;      // global-tableau kernel: 64-thread CTAs, 9 per SM (DWGPU_TG_THREADS=256: 4 per SM)
 
 template <typename T>
 struct DevBuf {
@@ -81,7 +83,9 @@ struct dwgpu_engine {
     long long ntot = 0;
     std::vector<int> path;         // 1 smem, 2 gmem
     // kernel lists: smem-generic, legacy global, specialised 64x128 (A), global-T generic (g), global-T 256x512 (B)
-    std::vector<int> list_smem, list_gmem, list_a, list_g, list_b;
+    std::vector<int> list_smem, list_gmem, list_a, list_g, list_b, list_c;
+    int cluster_size = 1;              // CTAs per block on the cluster path (list_c)
+    size_t smem_dyn_c = 0;
     size_t smem_dyn_g = 0;
     int tg_threads = NT_TG;
     size_t smem_dyn = 0;
@@ -92,7 +96,7 @@ struct dwgpu_engine {
     DevBuf<char> pst;
     DevBuf<int> dflag;
     DevBuf<dwk::BlockDev> blocks;
-    DevBuf<int> d_list_smem, d_list_gmem, d_list_a, d_list_g, d_list_b;
+    DevBuf<int> d_list_smem, d_list_gmem, d_list_a, d_list_g, d_list_b, d_list_c;
     // round inputs / outputs
     DevBuf<double> pi;
     DevBuf<char> rec;                  // [obj K | cost K | val K*L] doubles, then [status K | len K | ind K*L] ints
@@ -103,6 +107,9 @@ struct dwgpu_engine {
     // mapped pinned host mirror written by the pack kernel: header + packed columns
     char *h_pack = nullptr, *d_pack = nullptr;
     size_t pack_bytes = 0;
+    dwk::PackDst pk_dev{}, pk_host{};  // the same mirror through its device alias / its host address
+    DevBuf<double> r_dev;              // K convexity duals of the packed call
+    double *h_r = nullptr;
     DevBuf<unsigned long long> counters;
     DevBuf<long long> last_iters;
     // pinned staging
@@ -142,8 +149,10 @@ void dwgpu_destroy(dwgpu_engine *e)
     e->x.release(); e->ws.release(); e->a_rp.release();
     e->a_ci.release(); e->dc_ptr.release(); e->dc_row.release(); e->dr_ptr.release();
     e->dr_col.release(); e->blocks.release(); e->d_list_smem.release();
-    e->d_list_gmem.release(); e->d_list_a.release(); e->d_list_g.release(); e->d_list_b.release(); e->pi.release(); e->rec.release(); e->colptr.release();
+    e->d_list_gmem.release(); e->d_list_a.release(); e->d_list_g.release(); e->d_list_b.release(); e->d_list_c.release(); e->pi.release(); e->rec.release(); e->colptr.release();
     if (e->h_pack) cudaFreeHost(e->h_pack);
+    if (e->h_r) cudaFreeHost(e->h_r);
+    e->r_dev.release();
     e->counters.release(); e->last_iters.release();
     if (e->h_pi) cudaFreeHost(e->h_pi);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -188,6 +197,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         arp_off(K + 1, 0), d_off(K + 1, 0), dcp_off(K + 1, 0), drp_off(K + 1, 0), ws_off(K + 1, 0), pst_off(K + 1, 0);
     std::vector<int> ldg(K);
     e->xoff[0] = 0;
+    int n_cluster_blocks = 0;
     const size_t smem_cap = (size_t)e->max_smem_optin - 2048;   // static scratch + reserve
     for (int k = 0; k < K; ++k) {
         const dwgpu_block_desc &b = bd[k];
@@ -196,14 +206,17 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         e->m[k] = b.m; e->n[k] = b.n;
         const bool fits = dwk::smem2_bytes(b.m, b.n) <= smem_cap;
         const bool fits_g = dwk::smem2_bytes(b.m, b.n, true) <= smem_cap / 2;   // at least 2 CTAs per SM
-        int path = fits ? 1 : (fits_g ? 3 : 2);
+        const bool fits_c = dwk::cl_smem_bytes(b.m, b.n) <= smem_cap && b.m >= 1 && b.m < 65535 && b.n < 65535;
+        int path = fits ? 1 : (fits_g ? 3 : (fits_c ? 4 : 2));
         if (opt.force_path == 2) path = 2;
         if (opt.force_path == 3 && fits_g) path = 3;
+        if (opt.force_path == 4 && fits_c) path = 4;
         if (opt.force_path == 1 && !fits)
             { fail(DWGPU_E_ARGS, "force_path=1 but a block does not fit shared memory"); return bail(DWGPU_E_ARGS); }
         e->path[k] = path;
         // shared-memory path: the HBM image of T has the shared layout (even ld), one bulk copy
         ldg[k] = path == 1 ? dwk::smem2_ld(b.n) : ((b.n + 3) & ~3);
+        if (path == 4) n_cluster_blocks++;
         const int nnz = b.m > 0 ? b.a_rowptr[b.m] : 0;
         t_off[k + 1] = t_off[k] + (long long)b.m * ldg[k];
         pst_off[k + 1] = pst_off[k] + (long long)dwk::pst_bytes(b.m, b.n);
@@ -219,8 +232,26 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         else if (path == 1) { e->list_smem.push_back(k); e->smem_dyn = std::max(e->smem_dyn, dwk::smem2_bytes(b.m, b.n)); }
         else if (path == 3 && b.m == 256 && b.n == 512) e->list_b.push_back(k);
         else if (path == 3) { e->list_g.push_back(k); e->smem_dyn_g = std::max(e->smem_dyn_g, dwk::smem2_bytes(b.m, b.n, true)); }
+        else if (path == 4) { e->list_c.push_back(k); e->smem_dyn_c = std::max(e->smem_dyn_c, dwk::cl_smem_bytes(b.m, b.n)); }
         else e->list_gmem.push_back(k);
-        ws_off[k + 1] = ws_off[k] + (path == 2 ? (long long)((dwk::vec_bytes(b.m, b.n) + 15) / 16 * 2) : 0);
+    }
+    // cluster path: G CTAs (one per SM) per block, the largest power of two that keeps every block of
+    // the shard co-resident (148 SMs / blocks), 16 at most (non-portable size); reserved[0] overrides
+    if (n_cluster_blocks > 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, opt.device);
+        int G = 1;
+        while (G * 2 <= 16 && G * 2 * n_cluster_blocks <= sms) G *= 2;
+        if (opt.cluster_size > 0) { G = 1; while (G * 2 <= 16 && G * 2 <= opt.cluster_size) G *= 2; }
+        e->cluster_size = G;
+    }
+    for (int k = 0; k < K; ++k) {
+        const dwgpu_block_desc &b = bd[k];
+        long long w = 0;
+        if (e->path[k] == 2) w = (long long)((dwk::vec_bytes(b.m, b.n) + 15) / 16 * 2);
+        if (e->path[k] == 3) w = (long long)((b.n + 1) & ~1);      // priced costs cs[n]
+        if (e->path[k] == 4) w = (long long)dwk::cl_ws_doubles(b.n, e->cluster_size);
+        ws_off[k + 1] = ws_off[k] + w;
     }
     e->ntot = e->xoff[K];
 
@@ -293,10 +324,22 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         e->status.p = ip; e->len.p = ip + K; e->ind.p = ip + 2 * (size_t)K;
         CUE(e->colptr.alloc((size_t)K + 1));
         // host mirror: obj K, cost K, val nnz<=KL (doubles) | status K, len K, colptr K+1, ind nnz<=KL (ints)
-        e->pack_bytes = sizeof(double) * (2 * (size_t)K + KL) + sizeof(int) * (3 * (size_t)K + 1 + KL) + 64;
+        // host mirror: [nnz (8 B) | obj K | cost K | val KL] doubles, then [status K | colptr K+1 | ind KL] ints
+        e->pack_bytes = sizeof(double) * (1 + 2 * (size_t)K + KL) + sizeof(int) * (2 * (size_t)K + 1 + KL) + 64;
         CUE(cudaHostAlloc((void **)&e->h_pack, e->pack_bytes, cudaHostAllocMapped));
         CUE(cudaHostGetDevicePointer((void **)&e->d_pack, e->h_pack, 0));
         std::memset(e->h_pack, 0, e->pack_bytes);
+        auto carve_pack = [&](char *base, dwk::PackDst &d) {
+            d.nnz = (long long *)base;
+            double *dd = (double *)(base + sizeof(double));
+            d.obj = dd; d.cost = dd + K; d.val = dd + 2 * (size_t)K;
+            int *ii = (int *)(dd + 2 * (size_t)K + KL);
+            d.status = ii; d.colptr = ii + K; d.ind = ii + 2 * (size_t)K + 1;
+        };
+        carve_pack(e->d_pack, e->pk_dev);
+        carve_pack(e->h_pack, e->pk_host);
+        CUE(e->r_dev.alloc(K));
+        CUE(cudaMallocHost((void **)&e->h_r, sizeof(double) * (size_t)K));
     }
     CUE(e->counters.alloc((size_t)K * 8)); CUE(e->last_iters.alloc(K));
     CUE(cudaMemset(e->counters.p, 0, sizeof(unsigned long long) * (size_t)K * 8));
@@ -327,6 +370,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(e->d_list_a.upload(e->list_a));
     CUE(e->d_list_g.upload(e->list_g));
     CUE(e->d_list_b.upload(e->list_b));
+    CUE(e->d_list_c.upload(e->list_c));
 
     if (!e->list_smem.empty())
         CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -334,7 +378,29 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     if (!e->list_a.empty())
         CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 64, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)dwk::smem2_bytes(64, 128)));
-    if (const char *tg = std::getenv("DWGPU_TG_THREADS")) e->tg_threads = std::atoi(tg) == 256 ? 256 : 128;
+    if (!e->list_c.empty()) {
+        CUE(cudaFuncSetAttribute(dwk::solve_cluster_kernel<dwk::NT_CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)e->smem_dyn_c));
+        if (e->cluster_size > 8)
+            CUE(cudaFuncSetAttribute(dwk::solve_cluster_kernel<dwk::NT_CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        // the hardware may not be able to co-schedule a cluster this large with this much shared memory
+        // (GPC size): halve until at least one fits
+        while (e->cluster_size > 1) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)(e->list_c.size() * e->cluster_size)); cfg.blockDim = dim3(dwk::NT_CL);
+            cfg.dynamicSmemBytes = e->smem_dyn_c;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)e->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int ncl = 0;
+            cudaError_t oe = cudaOccupancyMaxActiveClusters(&ncl, dwk::solve_cluster_kernel<dwk::NT_CL>, &cfg);
+            if (oe == cudaSuccess && ncl >= 1) break;
+            cudaGetLastError();
+            e->cluster_size /= 2;
+        }
+    }
+    if (const char *tg = std::getenv("DWGPU_TG_THREADS")) e->tg_threads = std::atoi(tg) == 256 ? 256 : NT_TG;
     if (!e->list_g.empty()) {
         CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)e->smem_dyn_g));
@@ -374,6 +440,22 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         dwk::solve_kernel<false, NT_GMEM><<<(unsigned)e->list_gmem.size(), NT_GMEM, 0, st>>>(
             e->blocks.p, e->d_list_gmem.p, (int)e->list_gmem.size(), P);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(e->ev[1], st));
+        e->ev_used[1] = true;
+        e->last_launches++;
+    }
+    if (!e->list_c.empty()) {
+        const bool own_events = !e->ev_used[1];
+        if (own_events) CU(cudaEventRecord(e->ev[0], st));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(e->list_c.size() * e->cluster_size)); cfg.blockDim = dim3(dwk::NT_CL);
+        cfg.dynamicSmemBytes = e->smem_dyn_c; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)e->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, dwk::solve_cluster_kernel<dwk::NT_CL>, (const dwk::BlockDev *)e->blocks.p,
+                              (const int *)e->d_list_c.p, (int)e->list_c.size(), P, e->cluster_size));
         CU(cudaEventRecord(e->ev[1], st));
         e->ev_used[1] = true;
         e->last_launches++;
@@ -442,6 +524,55 @@ int dwgpu_fetch_results(dwgpu_engine *e, dwgpu_proposals *o)
     }
     CU(cudaStreamSynchronize(st));
     return 0;
+}
+
+// scan + copy of the last round's proposals into the mapped pinned mirror, then one synchronisation
+static int pack_round(dwgpu_engine *e, const double *r, dwgpu_packed *out)
+{
+    if (!out) return fail(DWGPU_E_ARGS, "out is NULL");
+    cudaStream_t st = e->stream;
+    dwk::PackSrc s;
+    s.obj = e->obj.p; s.cost = e->cost.p; s.val = e->val.p;
+    s.status = e->status.p; s.len = e->len.p; s.ind = e->ind.p;
+    s.r = nullptr; s.K = e->K; s.L = e->L; s.accept_tol = 1e-6;   // TOLERANCE, src/dw.h:71
+    if (r) {
+        std::memcpy(e->h_r, r, sizeof(double) * (size_t)e->K);
+        CU(cudaMemcpyAsync(e->r_dev.p, e->h_r, sizeof(double) * (size_t)e->K, cudaMemcpyHostToDevice, st));
+        s.r = e->r_dev.p;
+    }
+    dwk::pack_scan_kernel<1024><<<1, 1024, 0, st>>>(s, e->colptr.p, e->pk_dev);
+    CU(cudaGetLastError());
+    dwk::pack_copy_kernel<256><<<(unsigned)((e->K + 7) / 8), 256, 0, st>>>(s, e->colptr.p, e->pk_dev);
+    CU(cudaGetLastError());
+    e->last_launches += 2;
+    CU(cudaStreamSynchronize(st));
+    out->obj = e->pk_host.obj; out->cost = e->pk_host.cost; out->status = e->pk_host.status;
+    out->colptr = e->pk_host.colptr; out->ind = e->pk_host.ind; out->val = e->pk_host.val;
+    out->nnz = e->pk_host.nnz[0];
+    return 0;
+}
+
+int dwgpu_initial_solve_packed(dwgpu_engine *e, dwgpu_packed *out)
+{
+    if (!e || !e->initialised) return fail(DWGPU_E_STATE, "engine not initialised");
+    CU(cudaSetDevice(e->device));
+    int rc = launch_round(e, nullptr, 0, 1, e->stream);
+    if (rc) return rc;
+    return pack_round(e, nullptr, out);
+}
+
+int dwgpu_iterate_packed(dwgpu_engine *e, const double *pi, int phase_one, const double *r, dwgpu_packed *out)
+{
+    if (!e || !e->initialised) return fail(DWGPU_E_STATE, "engine not initialised");
+    if (!pi && e->L > 0) return fail(DWGPU_E_ARGS, "pi is NULL");
+    CU(cudaSetDevice(e->device));
+    if (e->L > 0) {
+        std::memcpy(e->h_pi, pi, sizeof(double) * e->L);
+        CU(cudaMemcpyAsync(e->pi.p, e->h_pi, sizeof(double) * e->L, cudaMemcpyHostToDevice, e->stream));
+    }
+    int rc = launch_round(e, e->pi.p, phase_one ? 1 : 0, 0, e->stream);
+    if (rc) return rc;
+    return pack_round(e, r, out);
 }
 
 int dwgpu_reset(dwgpu_engine *e, void *stream)
@@ -523,6 +654,7 @@ int dwgpu_get_counters(dwgpu_engine *e, dwgpu_counters *t)
         t->pivots += (long long)h[8 * (size_t)k]; t->flips += (long long)h[8 * (size_t)k + 1];
         t->rebuilds += (long long)h[8 * (size_t)k + 2]; t->phase1_iter += (long long)h[8 * (size_t)k + 3];
         t->rows_swept += (long long)h[8 * (size_t)k + 4];
+        t->cells_swept += (long long)h[8 * (size_t)k + 5];
     }
     t->solves = e->solves;
     return 0;

@@ -1,0 +1,99 @@
+// pack.cuh — one round's proposals compacted into ONE contiguous host-visible record.
+//
+// The reference's up-link is K mailboxes {obj, unbounded, new_obj_coeff, len, ind[1..len],
+// val[1..len]} (/root/reference/src/dw_subprob.h:44-94) that the master walks one by one
+// (src/dw_phases.c:338-437).  The dense device arrays of the engine (stride-L ind/val) would cost
+// 12*K*L bytes of D2H per round (25 MB at config B); the master only needs the len[k] real entries,
+// and — when it passes the convexity duals r_k down — only the columns it is going to accept
+// (r_k - obj_k > 1e-6, src/dw_phases.c:108,358 with TOLERANCE from src/dw.h:71).
+//
+// Two tiny kernels after the solve kernels of a round:
+//   pack_scan_kernel   one CTA: exclusive scan of the shipped lengths -> colptr[K+1]
+//   pack_copy_kernel   one warp per block: scalars + its column into the mapped pinned mirror
+// The mirror is written by the GPU directly (zero-copy stores), so a round ends with ONE stream
+// synchronisation and no cudaMemcpy whose size would have to be known on the host first.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace dwk {
+
+struct PackDst {          // device-visible aliases of the mapped pinned host mirror
+    double *obj, *cost, *val;
+    int *status, *colptr, *ind;
+    long long *nnz;
+};
+
+struct PackSrc {
+    const double *obj, *cost, *val;   // K, K, K*L
+    const int *status, *len, *ind;    // K, K, K*L
+    const double *r;                  // K convexity duals (nullptr: ship every column)
+    int K, L;
+    double accept_tol;
+};
+
+__device__ __forceinline__ int shipped_len(const PackSrc &s, int k)
+{
+    int ln = s.len[k];
+    if (s.r != nullptr && !(s.r[k] - s.obj[k] > s.accept_tol)) ln = 0;
+    return ln;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) pack_scan_kernel(PackSrc s, int *colptr_dev, PackDst d)
+{
+    __shared__ int warp_tot[NT / 32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < s.K; base += NT) {
+        const int k = base + tid;
+        const int v = k < s.K ? shipped_len(s, k) : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+        const int c0 = carry;
+        if (k < s.K) {
+            const int ex = c0 + woff + incl - v;
+            colptr_dev[k] = ex;
+            d.colptr[k] = ex;
+        }
+        __syncthreads();
+        if (tid == NT - 1) carry = c0 + woff + incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        colptr_dev[s.K] = carry;
+        d.colptr[s.K] = carry;
+        d.nnz[0] = carry;
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) pack_copy_kernel(PackSrc s, const int *colptr_dev, PackDst d)
+{
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    if (k >= s.K) return;
+    if (lane == 0) {
+        d.obj[k] = s.obj[k];
+        d.cost[k] = s.cost[k];
+        d.status[k] = s.status[k];
+    }
+    const int b = colptr_dev[k], e = colptr_dev[k + 1];
+    const int *si = s.ind + (size_t)k * s.L;
+    const double *sv = s.val + (size_t)k * s.L;
+    for (int t = lane; t < e - b; t += 32) {
+        d.ind[b + t] = si[t];
+        d.val[b + t] = sv[t];
+    }
+}
+
+}  // namespace dwk

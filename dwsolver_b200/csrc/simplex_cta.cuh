@@ -533,6 +533,7 @@ __device__ void solve_block(const BlockDev &B, const SolveParams &P, int k, Ctx 
             P.counters[8 * (size_t)k + 2] += n_reb;
             P.counters[8 * (size_t)k + 3] += n_p1;
             P.counters[8 * (size_t)k + 4] += n_piv * (unsigned long long)(m + 1);   // dense sweep bound
+            P.counters[8 * (size_t)k + 5] += n_piv * (unsigned long long)(m + 1) * (unsigned long long)n;
             P.last_iters[k] = (long long)(n_piv + n_flip);
         }
     }

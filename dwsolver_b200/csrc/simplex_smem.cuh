@@ -83,21 +83,37 @@ __host__ __device__ inline size_t smem2_bytes(int m, int n, bool tg = false)
     const size_t ld = tab_ld(n, tg);
     return align16(sizeof(double) * (size_t)(tg ? 1 : m + 1) * ld)     // (T and) the d row
          + pst_bytes(m, n)
-         + align16(sizeof(double) * 2 * (size_t)(m + n))      // rlo rup clo cup
+         // rlo rup (clo cup): column bounds and the priced costs cs are only touched a few times per
+         // pivot / solve; the global-tableau kernel reads them from HBM/L2 instead (12 KB less per CTA
+         // at 256 x 512: 9 CTAs per SM instead of 6)
+         + align16(sizeof(double) * 2 * (size_t)(tg ? m : m + n))
          + align16(sizeof(double) * ld)                       // rowp (also phase-1 prices, x staging)
-         + align16(sizeof(double) * (size_t)n)                // cs
+         + (tg ? 0 : align16(sizeof(double) * (size_t)n))     // cs
          + align16(sizeof(double) * (size_t)(m + 1))          // colq
          + align16(sizeof(double) * (size_t)m)                // w (phase-1 weights / cached ratios)
          + align16((size_t)n)                                 // cstat
-         + align16(sizeof(unsigned short) * (size_t)(m + 1)); // active rows
+         + align16(sizeof(unsigned short) * (size_t)(m + 1))  // active rows
+         + align16(sizeof(unsigned short) * (ld / 2 + 1));    // active column items of the pivot row
 }
 
 enum { K_NONE = 0, K_PIVOT = 1, K_FAIL = 2, K_REDO = 3 };
 
+// tableau accessors: global-memory tableaux (TG) bypass L1 (.cg) — rows are streamed once per basis
+// change and the strided column read touches one sector per row, so L1 only adds thrash
+template <bool TG> __device__ __forceinline__ double ld_t(const double *p) { return TG ? __ldcg(p) : *p; }
+template <bool TG> __device__ __forceinline__ double2 ld_t2(const double2 *p) { return TG ? __ldcg(p) : *p; }
+template <bool TG> __device__ __forceinline__ void st_t2(double2 *p, double2 v) { if (TG) __stcg(p, v); else *p = v; }
+
+
 struct Decision {
     int p, q, na, fail_status;
+    int nc;          // active column items of the pivot row; -1: the row is dense, sweep whole rows
     double inv;
 };
+
+// A column ITEM is the unit the sparse sweep moves: one 32-byte sector (4 doubles) of a global-memory
+// tableau row, one double2 of a shared-memory one.
+template <bool TG> struct ItemW { static constexpr int D2 = TG ? 2 : 1; };
 
 struct Sm3 {
     int m, n, ld;
@@ -105,10 +121,12 @@ struct Sm3 {
     double *beta;
     int *head, *nbv;
     signed char *vstat;
-    double *rlo, *rup, *clo, *cup;
+    double *rlo, *rup, *clo, *cup;       // per row / per column bounds (clo/cup: shared-memory tableau only)
+    const double *glo, *gup;             // bounds by variable id in HBM (column bounds when TG)
     double *rowp, *cs, *colq, *w;
     signed char *cstat;
     unsigned short *arow;
+    unsigned short *acol;
 };
 
 // lane holding the maximum of non-negative keys (ties: lowest lane); -1 if no lane is valid
@@ -140,7 +158,7 @@ template <bool INF, int MC, int NC, bool TG>
 __device__ __forceinline__ int decide_warp0(Sm3 &c, const double *dd, bool d_live, bool &bland, int &degen, int degen_limit,
                             double tol_dj, double tol_bnd, double tol_piv,
                             unsigned long long &n_piv, unsigned long long &n_flip, unsigned long long &n_rows,
-                            Decision *dec)
+                            unsigned long long &n_cells, Decision *dec)
 {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -165,16 +183,30 @@ __device__ __forceinline__ int decide_warp0(Sm3 &c, const double *dd, bool d_liv
         const double dq = dd[q];
         const double s = dq < 0.0 ? 1.0 : -1.0;
         const signed char stq = c.cstat[q];
-        const double loq = c.clo[q], upq = c.cup[q];
+        const double loq = TG ? __ldg(c.glo + c.nbv[q]) : c.clo[q];
+        const double upq = TG ? __ldg(c.gup + c.nbv[q]) : c.cup[q];
         // ---- ratio test, pass 1: Harris bound; caches exact ratios in w, builds the active-row list
         double tmax = CUDART_INF;
         int na = 0;
-        for (int i0 = 0; i0 < m; i0 += 32) {
+        // the column is fetched in batches of 8 rows per lane: all loads of a batch are in flight
+        // together (one memory round trip per 256 rows instead of one per 32)
+        constexpr int CB = MC ? 8 : 2;
+        for (int i00 = 0; i00 < m; i00 += 32 * CB) {
+          double tcol[CB];
+#pragma unroll
+          for (int r = 0; r < CB; ++r) {
+              const int i = i00 + r * 32 + lane;
+              tcol[r] = i < m ? ld_t<TG>(c.T + (size_t)i * ld + q) : 0.0;
+          }
+#pragma unroll
+          for (int r = 0; r < CB; ++r) {
+            const int i0 = i00 + r * 32;
+            if (i0 >= m) break;
             const int i = i0 + lane;
             const bool in = i < m;
             double tiq = 0.0, tex = CUDART_INF;
             if (in) {
-                tiq = c.T[(size_t)i * ld + q];
+                tiq = tcol[r];
                 c.colq[i] = tiq;
                 const double a = s * tiq;
                 double lo = c.rlo[i], up = c.rup[i];
@@ -197,6 +229,7 @@ __device__ __forceinline__ int decide_warp0(Sm3 &c, const double *dd, bool d_liv
             const unsigned bal = __ballot_sync(0xffffffffu, in && tiq != 0.0);
             if (in && tiq != 0.0) c.arow[na + __popc(bal & lt_mask)] = (unsigned short)i;
             na += __popc(bal);
+          }
         }
         tmax = warp_min_nonneg(tmax);
         // ---- pass 2: largest |pivot| among rows whose exact ratio is within the bound
@@ -253,25 +286,58 @@ __device__ __forceinline__ int decide_warp0(Sm3 &c, const double *dd, bool d_liv
         {
             const double2 *prow = reinterpret_cast<const double2 *>(c.T + (size_t)p * ld);
             double2 *rp2 = reinterpret_cast<double2 *>(c.rowp);
-            for (int j2 = lane; j2 < (ld >> 1); j2 += 32) {
-                double2 v = prow[j2];
-                v.x *= inv; v.y *= inv;
-                rp2[j2] = v;
+            constexpr int RB = NC ? 8 : 2;        // 8 x 16 B per lane in flight (a 512-column row in one trip)
+            for (int j0 = 0; j0 < (ld >> 1); j0 += 32 * RB) {
+                double2 v[RB];
+#pragma unroll
+                for (int t = 0; t < RB; ++t) {
+                    const int j2 = j0 + t * 32 + lane;
+                    if (j2 < (ld >> 1)) v[t] = ld_t2<TG>(prow + j2);
+                }
+#pragma unroll
+                for (int t = 0; t < RB; ++t) {
+                    const int j2 = j0 + t * 32 + lane;
+                    if (j2 < (ld >> 1)) { v[t].x *= inv; v[t].y *= inv; rp2[j2] = v[t]; }
+                }
             }
+        }
+        // non-zero items of the scaled pivot row: T'[i][j] = T[i][j] - colq[i] * rowp[j] leaves every
+        // column with rowp[j] == 0 untouched, so only (active row) x (active item) cells are rewritten
+        int nc = 0;
+        {
+            constexpr int IW = ItemW<TG>::D2;
+            const int nitems = (ld >> 1) / IW;
+            const double2 *rp2 = reinterpret_cast<const double2 *>(c.rowp);
+            __syncwarp();
+            for (int t0 = 0; t0 < nitems; t0 += 32) {
+                const int t = t0 + lane;
+                bool nz = false;
+                if (t < nitems) {
+#pragma unroll
+                    for (int u = 0; u < IW; ++u) { const double2 v = rp2[t * IW + u]; nz |= (v.x != 0.0) | (v.y != 0.0); }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                if (nz) c.acol[nc + __popc(bal & lt_mask)] = (unsigned short)t;
+                nc += __popc(bal);
+            }
+            if (2 * nc > nitems) nc = -1;       // dense pivot row: whole-row sweeps are cheaper
         }
         if (lane == 0) {
             const signed char ns = (lov == upv) ? ST_FIX : (target == lov ? ST_LO : ST_UP);
             const int vleave = c.head[p], vq = c.nbv[q];
-            c.rlo[p] = loq; c.rup[p] = upq; c.clo[q] = lov; c.cup[q] = upv;
+            c.rlo[p] = loq; c.rup[p] = upq;
+            if (!TG) { c.clo[q] = lov; c.cup[q] = upv; }
             c.cstat[q] = ns; c.vstat[vleave] = ns; c.vstat[vq] = ST_BASIC;
             c.head[p] = vq; c.nbv[q] = vleave;
             const bool with_d = d_live && dq != 0.0;
             c.colq[m] = with_d ? dq : 0.0;
             if (with_d) c.arow[na] = (unsigned short)m;      // the reduced-cost row rides along
-            dec->p = p; dec->q = q; dec->inv = inv; dec->na = na + (with_d ? 1 : 0);
+            dec->p = p; dec->q = q; dec->inv = inv; dec->na = na + (with_d ? 1 : 0); dec->nc = nc;
         }
         ++n_piv;
         n_rows += (unsigned long long)na;
+        n_cells += nc < 0 ? (unsigned long long)(na + (d_live && dq != 0.0 ? 1 : 0)) * (unsigned long long)ld
+                          : (unsigned long long)(na + (d_live && dq != 0.0 ? 1 : 0)) * (unsigned long long)nc * (2 * ItemW<TG>::D2);
         if (theta <= 1e-11) { if (++degen > degen_limit) bland = true; }
         else { degen = 0; bland = false; }
         return K_PIVOT;
@@ -286,6 +352,59 @@ __device__ __forceinline__ double cost_delta(double cs_new, double cs_saved)
 {
     const double d = cs_new - cs_saved;
     return fabs(d) > 1e-11 * (1.0 + fabs(cs_new)) ? d : 0.0;
+}
+
+// rank-1 sweep over (active rows) x (active column items): every load of a batch is issued before the
+// first dependent instruction, so a typical network pivot (13 rows x 30 items) is ONE memory round trip
+template <int NT, int NC, bool TG>
+__device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, int na, int nc)
+{
+    constexpr int IW = ItemW<TG>::D2;
+    constexpr int SB = TG ? 4 : 2;                         // items per thread in flight
+    const int nc2 = (NC ? tab_ld(NC, TG) : c.ld) >> 1;    // row pitch in double2
+    double2 *T2 = reinterpret_cast<double2 *>(c.T);
+    double2 *d2 = reinterpret_cast<double2 *>(c.drow);
+    const double2 *rowp2 = reinterpret_cast<const double2 *>(c.rowp);
+    const int total = na * nc;
+    for (int e0 = 0; e0 < total; e0 += NT * SB) {
+        double2 v[SB][IW];
+        int ri[SB], jj[SB];
+#pragma unroll
+        for (int t = 0; t < SB; ++t) {
+            const int e = e0 + t * NT + threadIdx.x;
+            ri[t] = -1;
+            if (e < total) {
+                const int a = e / nc;
+                const int i = c.arow[a];
+                const int j = (int)c.acol[e - a * nc] * IW;
+                ri[t] = i; jj[t] = j;
+                const double2 *src = (i == c.m ? d2 : T2 + (size_t)i * nc2) + j;
+#pragma unroll
+                for (int u = 0; u < IW; ++u) v[t][u] = (TG && i != c.m) ? __ldcg(src + u) : src[u];
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < SB; ++t) {
+            const int i = ri[t];
+            if (i >= 0) {
+                const double ci = c.colq[i];
+                const double cq = ci * inv;
+                const bool is_p = i == p;
+                double2 *dst = (i == c.m ? d2 : T2 + (size_t)i * nc2) + jj[t];
+#pragma unroll
+                for (int u = 0; u < IW; ++u) {
+                    const double2 ra = rowp2[jj[t] + u];
+                    const int jq = q - 2 * (jj[t] + u);
+                    double2 r;
+                    r.x = is_p ? -ra.x : fma(-ci, ra.x, v[t][u].x);
+                    r.y = is_p ? -ra.y : fma(-ci, ra.y, v[t][u].y);
+                    if (jq == 0) r.x = is_p ? inv : cq;
+                    if (jq == 1) r.y = is_p ? inv : cq;
+                    if (TG && i != c.m) __stcg(dst + u, r); else dst[u] = r;
+                }
+            }
+        }
+    }
 }
 
 // rank-1 sweep over the active rows only (row m = reduced costs when it is in the list)
@@ -305,6 +424,34 @@ __device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, i
         const double cq = ci * inv;
         double2 *row = (i == c.m) ? d2 : T2 + (size_t)i * nc2;
         const bool is_p = i == p;
+        if (TG) {
+            // global-memory tableau: issue every load of (up to) 256 double2 of the row before the
+            // first dependent instruction — the sweep is a chain of DRAM round trips otherwise
+            constexpr int SB = NC ? 8 : 2;
+            const bool glob = i != c.m;
+            for (int j0 = 0; j0 < nc2a; j0 += 32 * SB) {
+                double2 v[SB];
+#pragma unroll
+                for (int t = 0; t < SB; ++t) {
+                    const int j = j0 + t * 32 + lane;
+                    if (j < nc2a) v[t] = glob ? __ldcg(row + j) : row[j];
+                }
+#pragma unroll
+                for (int t = 0; t < SB; ++t) {
+                    const int j = j0 + t * 32 + lane;
+                    if (j < nc2a) {
+                        const double2 ra = rowp2[j];
+                        const int jq = q - 2 * j;
+                        double2 r;
+                        r.x = is_p ? -ra.x : fma(-ci, ra.x, v[t].x);
+                        r.y = is_p ? -ra.y : fma(-ci, ra.y, v[t].y);
+                        if (jq == 0) r.x = is_p ? inv : cq;
+                        if (jq == 1) r.y = is_p ? inv : cq;
+                        if (glob) __stcg(row + j, r); else row[j] = r;
+                    }
+                }
+            }
+        } else
         for (int j0 = 0; j0 < nc2a; j0 += 64) {
             const int ja = j0 + lane, jb = j0 + 32 + lane;
             const bool oa = ja < nc2a, ob = jb < nc2a;
@@ -334,7 +481,7 @@ __device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, i
 }
 
 // per-row / per-column bounds and column status from the by-variable arrays in HBM
-template <int NT>
+template <int NT, bool TG>
 __device__ __forceinline__ void gather_bounds(const BlockDev &B, Sm3 &c)
 {
     for (int i = threadIdx.x; i < c.m; i += NT) {
@@ -343,9 +490,57 @@ __device__ __forceinline__ void gather_bounds(const BlockDev &B, Sm3 &c)
     }
     for (int j = threadIdx.x; j < c.n; j += NT) {
         const int v = c.nbv[j];
-        c.clo[j] = __ldg(B.lo + v); c.cup[j] = __ldg(B.up + v);
+        if (!TG) { c.clo[j] = __ldg(B.lo + v); c.cup[j] = __ldg(B.up + v); }
         c.cstat[j] = c.vstat[v];
     }
+}
+
+// value of the nonbasic variable in column j
+template <bool TG>
+__device__ __forceinline__ double nb_col_value(const Sm3 &c, int j)
+{
+    const signed char st = c.cstat[j];
+    if (st == ST_FREE) return 0.0;
+    if (TG) { const int v = c.nbv[j]; return st == ST_UP ? __ldg(c.gup + v) : __ldg(c.glo + v); }
+    return st == ST_UP ? c.cup[j] : c.clo[j];
+}
+
+// rows with a non-zero weight, ascending, into arow (warp 0); returns the count to warp 0's lanes
+__device__ __forceinline__ int list_weighted_rows(Sm3 &c, const double *wt, int m)
+{
+    const int lane = threadIdx.x & 31;
+    int nl = 0;
+    for (int i0 = 0; i0 < m; i0 += 32) {
+        const int i = i0 + lane;
+        const bool nz = i < m && wt[i] != 0.0;
+        const unsigned bal = __ballot_sync(0xffffffffu, nz);
+        if (nz) c.arow[nl + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)i;
+        nl += __popc(bal);
+    }
+    return nl;
+}
+
+// s + sum over the listed rows (ascending) of wt[i] * T[i][j]; 8 loads in flight per thread
+template <bool TG>
+__device__ __forceinline__ double weighted_colsum(const Sm3 &c, const double *wt, int nl, int ld, int j, double s)
+{
+    int a = 0;
+    for (; a + 8 <= nl; a += 8) {
+        double v[8], wv[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int i = c.arow[a + t];
+            wv[t] = wt[i];
+            v[t] = ld_t<TG>(c.T + (size_t)i * ld + j);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) s = fma(wv[t], v[t], s);
+    }
+    for (; a < nl; ++a) {
+        const int i = c.arow[a];
+        s = fma(wt[i], ld_t<TG>(c.T + (size_t)i * ld + j), s);
+    }
+    return s;
 }
 
 // MC/NC != 0: block shape known at compile time (all shared-memory offsets and trip counts are
@@ -353,7 +548,7 @@ __device__ __forceinline__ void gather_bounds(const BlockDev &B, Sm3 &c)
 // TG = true: the tableau stays in global memory (L2/HBM) and only the vectors live in shared memory
 // (blocks too large for one CTA's shared memory, config B class); the decision/sweep code is shared.
 template <int NT, int MC, int NC, bool TG>
-__global__ void __launch_bounds__(NT, TG ? (NT <= 128 ? 6 : 4) : 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
+__global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? 8 : (NT <= 128 ? 6 : 4)) : 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
                                                           SolveParams P)
 {
     extern __shared__ __align__(16) char smem_raw[];
@@ -363,7 +558,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 128 ? 6 : 4) : 3) solve_smem_k
     __shared__ int s_kind, s_changed;
     if ((int)blockIdx.x >= count) return;
     const int k = list[blockIdx.x];
-    const BlockDev B = blocks[k];
+    const BlockDev &B = blocks[k];      // fields are fetched where they are used (read-only, cached)
     const int m = MC ? MC : B.m, n = NC ? NC : B.n, L = B.L, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double tol_dj = P.tol_dj, tol_bnd = P.tol_bnd, tol_piv = P.tol_piv;
 
@@ -384,13 +579,16 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 128 ? 6 : 4) : 3) solve_smem_k
     c.nbv = c.head + m;
     c.vstat = (signed char *)(c.nbv + n);
     c.rlo = (double *)sp; c.rup = c.rlo + m; c.clo = c.rup + m; c.cup = c.clo + n;
-    sp += align16(sizeof(double) * 2 * (size_t)(m + n));
+    sp += align16(sizeof(double) * 2 * (size_t)(TG ? m : m + n));
+    c.glo = B.lo; c.gup = B.up;
     c.rowp = (double *)sp;         sp += align16(sizeof(double) * ld);
-    c.cs = (double *)sp;           sp += align16(sizeof(double) * (size_t)n);
+    if (TG) c.cs = B.ws;           // priced costs in HBM (written and read by this CTA only)
+    else { c.cs = (double *)sp;    sp += align16(sizeof(double) * (size_t)n); }
     c.colq = (double *)sp;         sp += align16(sizeof(double) * (size_t)(m + 1));
     c.w = (double *)sp;            sp += align16(sizeof(double) * (size_t)m);
     c.cstat = (signed char *)sp;   sp += align16((size_t)n);
-    c.arow = (unsigned short *)sp;
+    c.arow = (unsigned short *)sp; sp += align16(sizeof(unsigned short) * (size_t)(m + 1));
+    c.acol = (unsigned short *)sp;
 
     // ---- state in: two bulk copies, one mbarrier
     const uint32_t t_bytes = TG ? 0u : (uint32_t)(sizeof(double) * (size_t)m * ld);
@@ -417,13 +615,13 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 128 ? 6 : 4) : 3) solve_smem_k
     }
     __syncthreads();            // mbarrier init + cs visible
     mbar_wait(&bar, 0);
-    gather_bounds<NT>(B, c);
+    gather_bounds<NT, TG>(B, c);
     __syncthreads();
 
     int status = 0;
     long long iter = 0;
     const long long max_iter = (long long)P.max_iter_mult * (m + n) + 1000;
-    unsigned long long n_piv = 0, n_flip = 0, n_reb = 0, n_p1 = 0, n_rows = 0;   // n_piv/n_flip/n_rows live in warp 0
+    unsigned long long n_piv = 0, n_flip = 0, n_reb = 0, n_p1 = 0, n_rows = 0, n_cells = 0;   // n_piv/n_flip/n_rows/n_cells live in warp 0
     bool need_check = true, infeasible = false, d_valid = false, bland = false, d_full = false;
     int degen = 0;
     const int degen_limit = 100 + (m + n) / 2;
@@ -449,13 +647,11 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 128 ? 6 : 4) : 3) solve_smem_k
         }
         if (infeasible) {
             // phase-1 prices T'w into rowp (consumed by the pricing loop before rowp is restaged)
-            for (int j = tid; j < n; j += NT) {
-                double s = 0.0;
-                for (int i = 0; i < m; ++i) {
-                    const double wi = c.w[i];
-                    if (wi != 0.0) s = fma(wi, c.T[(size_t)i * ld + j], s);      // block-uniform branch
-                }
-                c.rowp[j] = s;
+            if (warp == 0) { const int nl = list_weighted_rows(c, c.w, m); if (lane == 0) dec.na = nl; }
+            __syncthreads();
+            {
+                const int nl = dec.na;
+                for (int j = tid; j < n; j += NT) c.rowp[j] = weighted_colsum<TG>(c, c.w, nl, ld, j, 0.0);
             }
             ++n_p1;
             __syncthreads();
@@ -472,16 +668,16 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 128 ? 6 : 4) : 3) solve_smem_k
                 c.colq[i] = cb;
             }
             __syncthreads();
+            if (warp == 0) { const int nl = list_weighted_rows(c, c.colq, m); if (lane == 0) dec.na = nl; }
+            __syncthreads();
+            const int nl = dec.na;
             for (int j = tid; j < ld; j += NT) {
                 double s = 0.0;
                 if (j < n) {
                     const int v = c.nbv[j];
                     if (v >= m) s = inc ? cost_delta(c.cs[v - m], B.cssave[v - m]) : c.cs[v - m];
                     if (inc) s += B.dsave[j];
-                    for (int i = 0; i < m; ++i) {
-                        const double cb = c.colq[i];
-                        if (cb != 0.0) s = fma(cb, c.T[(size_t)i * ld + j], s);  // block-uniform branch
-                    }
+                    s = weighted_colsum<TG>(c, c.colq, nl, ld, j, s);
                 }
                 c.drow[j] = s;
             }
@@ -494,16 +690,17 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 128 ? 6 : 4) : 3) solve_smem_k
             int kind;
             if (infeasible)
                 kind = decide_warp0<true, MC, NC, TG>(c, c.rowp, false, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
-                                          n_piv, n_flip, n_rows, &dec);
+                                          n_piv, n_flip, n_rows, n_cells, &dec);
             else
                 kind = decide_warp0<false, MC, NC, TG>(c, c.drow, true, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
-                                           n_piv, n_flip, n_rows, &dec);
+                                           n_piv, n_flip, n_rows, n_cells, &dec);
             if (lane == 0) { s_kind = kind; if (n_piv + n_flip) s_changed = 1; }
         }
         __syncthreads();
         const int kind = s_kind;
         if (kind == K_PIVOT) {
-            sweep_active<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na);
+            if (dec.nc >= 0) sweep_sparse<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na, dec.nc);
+            else sweep_active<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na);
             __syncthreads();
             continue;
         }
@@ -514,7 +711,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 128 ? 6 : 4) : 3) solve_smem_k
         // claimed optimal: x into rowp, auxiliary values into colq
         for (int j = tid; j < n; j += NT) {
             const int v = c.nbv[j];
-            const double xv = nb_value(c.cstat[j], c.clo[j], c.cup[j]);
+            const double xv = nb_col_value<TG>(c, j);
             if (v >= m) c.rowp[v - m] = xv; else c.colq[v] = xv;
         }
         for (int i = tid; i < m; i += NT) {
@@ -548,7 +745,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 128 ? 6 : 4) : 3) solve_smem_k
                 double pk = -1.0; int pr = INT_MAX;
                 for (int i = tid; i < m; i += NT) {
                     const int h = c.head[i];
-                    const double tq = c.T[(size_t)i * ld + j];
+                    const double tq = ld_t<TG>(c.T + (size_t)i * ld + j);
                     c.colq[i] = tq;
                     if (h < m && c.vstat[h] != ST_BASIC) {
                         const double a = fabs(tq);
@@ -558,7 +755,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 128 ? 6 : 4) : 3) solve_smem_k
                 block_argmax<NT>(pk, pr, scr);
                 if (pr == INT_MAX || pk < 1e-11) { singular = true; break; }
                 const double inv = 1.0 / c.colq[pr];
-                for (int jj = tid; jj < ld; jj += NT) c.rowp[jj] = c.T[(size_t)pr * ld + jj] * inv;
+                for (int jj = tid; jj < ld; jj += NT) c.rowp[jj] = ld_t<TG>(c.T + (size_t)pr * ld + jj) * inv;
                 for (int i = tid; i < m; i += NT) c.arow[i] = (unsigned short)i;
                 __syncthreads();
                 sweep_active<NT, NC, TG>(c, pr, j, inv, m);
@@ -566,14 +763,14 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 128 ? 6 : 4) : 3) solve_smem_k
                 __syncthreads();
             }
             if (singular) { status = 1; break; }
-            gather_bounds<NT>(B, c);
+            gather_bounds<NT, TG>(B, c);
             __syncthreads();
             {   // beta = T x_N, one warp per row
                 constexpr int NW = NT / 32;
                 for (int i = warp; i < m; i += NW) {
                     double s = 0.0;
                     for (int j = lane; j < n; j += 32)
-                        s += c.T[(size_t)i * ld + j] * nb_value(c.cstat[j], c.clo[j], c.cup[j]);
+                        s += ld_t<TG>(c.T + (size_t)i * ld + j) * nb_col_value<TG>(c, j);
 #pragma unroll
                     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                     if (lane == 0) c.beta[i] = s;
@@ -593,7 +790,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 128 ? 6 : 4) : 3) solve_smem_k
     if (status != 5) {
         for (int j = tid; j < n; j += NT) {
             const int v = c.nbv[j];
-            if (v >= m) c.rowp[v - m] = nb_value(c.cstat[j], c.clo[j], c.cup[j]);
+            if (v >= m) c.rowp[v - m] = nb_col_value<TG>(c, j);
         }
         for (int i = tid; i < m; i += NT) {
             const int v = c.head[i];
@@ -676,6 +873,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 128 ? 6 : 4) : 3) solve_smem_k
             P.counters[8 * (size_t)k + 2] += n_reb;
             P.counters[8 * (size_t)k + 3] += n_p1;
             P.counters[8 * (size_t)k + 4] += n_rows;
+            P.counters[8 * (size_t)k + 5] += n_cells;
             P.last_iters[k] = (long long)(n_piv + n_flip);
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }

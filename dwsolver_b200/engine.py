@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "dwgpu_iterate_device", "dwgpu_device_results", "dwgpu_fetch_results", "dwgpu_fetch_x",
     "dwgpu_get_counters", "dwgpu_get_block_iterations", "dwgpu_last_launch_count", "dwgpu_get_block_paths",
     "dwgpu_sync", "dwgpu_last_error", "dwgpu_version", "dwgpu_last_kernel_ms", "dwgpu_measure_smem_bandwidth",
-    "dwgpu_reset", "dwgpu_initial_solve_device",
+    "dwgpu_reset", "dwgpu_initial_solve_device", "dwgpu_initial_solve_packed", "dwgpu_iterate_packed",
 ]
 
 
@@ -41,7 +41,7 @@ class BlockDesc(C.Structure):
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("clamp_lo_cols", C.c_int), ("force_path", C.c_int),
                 ("max_iter_mult", C.c_int), ("tol_dj", C.c_double), ("tol_bnd", C.c_double),
-                ("tol_piv", C.c_double), ("reserved", C.c_int * 8)]
+                ("tol_piv", C.c_double), ("cluster_size", C.c_int), ("reserved", C.c_int * 7)]
 
 
 class Proposals(C.Structure):
@@ -49,9 +49,15 @@ class Proposals(C.Structure):
                 ("val", c_dp), ("x", c_dp)]
 
 
+class Packed(C.Structure):
+    _fields_ = [("obj", c_dp), ("cost", c_dp), ("status", c_ip), ("colptr", c_ip), ("ind", c_ip), ("val", c_dp),
+                ("nnz", C.c_longlong)]
+
+
 class Counters(C.Structure):
     _fields_ = [("pivots", C.c_longlong), ("flips", C.c_longlong), ("rebuilds", C.c_longlong),
-                ("phase1_iter", C.c_longlong), ("solves", C.c_longlong), ("rows_swept", C.c_longlong)]
+                ("phase1_iter", C.c_longlong), ("solves", C.c_longlong), ("rows_swept", C.c_longlong),
+                ("cells_swept", C.c_longlong)]
 
 
 _LIB = None
@@ -83,6 +89,8 @@ def load_library():
         L.dwgpu_sync.argtypes = [C.c_void_p]
         L.dwgpu_reset.argtypes = [C.c_void_p, C.c_void_p]
         L.dwgpu_initial_solve_device.argtypes = [C.c_void_p, C.c_void_p]
+        L.dwgpu_initial_solve_packed.argtypes = [C.c_void_p, C.POINTER(Packed)]
+        L.dwgpu_iterate_packed.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, C.POINTER(Packed)]
         L.dwgpu_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.dwgpu_measure_smem_bandwidth.argtypes = [C.c_int, c_dp]
         L.dwgpu_last_error.restype = C.c_char_p
@@ -181,6 +189,29 @@ class Engine:
         _check(self._lib.dwgpu_iterate(self._h, pi.ctypes.data_as(c_dp), int(bool(phase_one)), C.byref(self._out)),
                "dwgpu_iterate")
 
+    # ---- rounds, packed record (engine-owned pinned memory; views valid until the next call) ----
+    def _packed_views(self, pk: "Packed") -> dict:
+        K, nnz = self.K, int(pk.nnz)
+        as_np = np.ctypeslib.as_array
+        return dict(obj=as_np(pk.obj, (K,)), cost=as_np(pk.cost, (K,)), status=as_np(pk.status, (K,)),
+                    colptr=as_np(pk.colptr, (K + 1,)),
+                    ind=as_np(pk.ind, (nnz,)) if nnz else np.zeros(0, np.int32),
+                    val=as_np(pk.val, (nnz,)) if nnz else np.zeros(0), nnz=nnz)
+
+    def initial_solve_packed(self) -> dict:
+        pk = Packed()
+        _check(self._lib.dwgpu_initial_solve_packed(self._h, C.byref(pk)), "dwgpu_initial_solve_packed")
+        return self._packed_views(pk)
+
+    def iterate_packed(self, pi, phase_one: bool, r=None) -> dict:
+        pi = _f64(pi)
+        rr = _f64(r) if r is not None else None
+        pk = Packed()
+        _check(self._lib.dwgpu_iterate_packed(self._h, pi.ctypes.data_as(c_dp), int(bool(phase_one)),
+                                              rr.ctypes.data_as(c_dp) if rr is not None else None, C.byref(pk)),
+               "dwgpu_iterate_packed")
+        return self._packed_views(pk)
+
     def iterate_device(self, d_pi_ptr: int, phase_one: bool, stream: int = 0):
         _check(self._lib.dwgpu_iterate_device(self._h, C.c_void_p(d_pi_ptr), int(bool(phase_one)),
                                               C.c_void_p(stream) if stream else None), "dwgpu_iterate_device")
@@ -227,7 +258,7 @@ class Engine:
         c = Counters()
         _check(self._lib.dwgpu_get_counters(self._h, C.byref(c)), "dwgpu_get_counters")
         return dict(pivots=c.pivots, flips=c.flips, rebuilds=c.rebuilds, phase1_iter=c.phase1_iter, solves=c.solves,
-                    rows_swept=c.rows_swept)
+                    rows_swept=c.rows_swept, cells_swept=c.cells_swept)
 
     def block_iterations(self) -> np.ndarray:
         it = np.zeros(self.K, np.int64)

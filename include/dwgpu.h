@@ -68,12 +68,15 @@ typedef struct dwgpu_options {
     int    device;        /* CUDA device ordinal (default 0) */
     int    clamp_lo_cols; /* 1: finite-lb/no-ub columns get ub = 3000 (dw_subprob.c:116-120) */
     int    force_path;    /* 0 auto; 1 shared-memory tableau; 2 legacy all-global kernel;
-                             3 global-memory tableau + shared-memory vectors */
+                             3 global-memory tableau + shared-memory vectors (one CTA per block);
+                             4 thread-block cluster per block, tableau striped over the CTAs in HBM */
     int    max_iter_mult; /* iteration limit = max_iter_mult*(m+n) + 1000 (default 50) */
     double tol_dj;        /* dual feasibility   (default 1e-9) */
     double tol_bnd;       /* primal feasibility, scaled by 1+|bound| (default 1e-9) */
     double tol_piv;       /* minimum |pivot|    (default 1e-9) */
-    int    reserved[8];
+    int    cluster_size;  /* path 4: CTAs per block (power of two <= 16); 0 = as many as keep every
+                             block of the shard co-resident (148 SMs / blocks) */
+    int    reserved[7];
 } dwgpu_options;
 
 /* Host-side result buffers for one round; any pointer may be NULL (that field is skipped).
@@ -89,13 +92,28 @@ typedef struct dwgpu_proposals {
     double *x;      /* sum n_k                                         (current_solution) */
 } dwgpu_proposals;
 
+/* One round's results in compact form, in engine-owned PINNED host memory that the GPU writes
+ * directly (valid until the next call on this engine).  Block k's compacted column is
+ * ind/val[colptr[k] .. colptr[k+1]) — the K mailboxes of src/dw_subprob.h:44-94 laid end to end. */
+typedef struct dwgpu_packed {
+    const double *obj;    /* K */
+    const double *cost;   /* K */
+    const int    *status; /* K */
+    const int    *colptr; /* K+1 */
+    const int    *ind;    /* nnz: 1-based master rows */
+    const double *val;    /* nnz */
+    long long     nnz;
+} dwgpu_packed;
+
 typedef struct dwgpu_counters {
     long long pivots;      /* basis changes (a rank-1 tableau update happened) */
     long long flips;       /* bound flips (no update) */
     long long rebuilds;    /* tableau rebuilt from A_k after a residual check */
     long long phase1_iter; /* iterations spent restoring primal feasibility */
     long long solves;      /* block solves */
-    long long rows_swept;  /* tableau rows (incl. the reduced-cost row) rewritten by basis changes */
+    long long rows_swept;  /* tableau rows (incl. the reduced-cost row) touched by basis changes */
+    long long cells_swept; /* tableau doubles rewritten by basis changes: only (active row) x (non-zero
+                              item of the pivot row) cells move, so this is the algorithmic traffic / 16 B */
 } dwgpu_counters;
 
 typedef struct dwgpu_engine dwgpu_engine;
@@ -119,6 +137,16 @@ int  dwgpu_initial_solve(dwgpu_engine *e, dwgpu_proposals *out);
  * and re-solved from its stored basis, and the proposals are copied back into *out. */
 int  dwgpu_iterate(dwgpu_engine *e, const double *pi, int phase_one, dwgpu_proposals *out);
 
+/* The same two calls with the proposals returned as ONE packed record (a single device-written
+ * pinned buffer, one synchronisation, no stride-L arrays over PCIe).  r (K doubles, may be NULL)
+ * are the convexity-row duals the master publishes next to pi (sub_data[k].r,
+ * src/dw_phases.c:276-279, 531-534): when given, only the columns the master would accept,
+ * r_k - obj_k > 1e-6 (src/dw_phases.c:108, 358; TOLERANCE src/dw.h:71), are shipped; the others
+ * come back with an empty column.  obj/cost/status are always filled for every block. */
+int  dwgpu_initial_solve_packed(dwgpu_engine *e, dwgpu_packed *out);
+int  dwgpu_iterate_packed(dwgpu_engine *e, const double *pi, int phase_one, const double *r,
+                          dwgpu_packed *out);
+
 /* Cold solve on the caller's stream, results left on the device (see dwgpu_iterate_device). */
 int  dwgpu_initial_solve_device(dwgpu_engine *e, void *stream);
 
@@ -140,7 +168,8 @@ int  dwgpu_get_block_iterations(dwgpu_engine *e, long long *iters);
 /* kernels launched by the last iterate / initial_solve call */
 int  dwgpu_last_launch_count(dwgpu_engine *e);
 /* per block: 1 = shared-memory tableau, 3 = global-memory tableau with shared-memory vectors,
- * 2 = legacy kernel with everything in global memory */
+ * 4 = cluster per block (HBM tableau striped over the CTAs), 2 = legacy kernel with everything in
+ * global memory */
 int  dwgpu_get_block_paths(dwgpu_engine *e, int *paths);
 /* device time (CUDA events on the launching stream) of the last round's solve kernels:
  * ms[0] = shared-memory path launch, ms[1] = global-memory path launch (0 when not launched).

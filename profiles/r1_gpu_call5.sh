@@ -1,0 +1,5 @@
+set -x
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r5_bench_B.json 2> gpurun_out/r5_bench_B.err; echo rc=$?
+timeout 300 python bench.py --config A --no-cpu-baseline > gpurun_out/r5_bench_A.json 2> gpurun_out/r5_bench_A.err; echo rc=$?
+tail -n 3 gpurun_out/r5_bench_B.err gpurun_out/r5_bench_A.err

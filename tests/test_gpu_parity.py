@@ -64,7 +64,7 @@ def compare_round(prob, gp, op, pi, phase_one, initial=False):
         assert abs(g["cost"] - b.c_master @ x) <= 1e-12 * (1 + abs(g["cost"]))
 
 
-@pytest.mark.parametrize("force_path", [0, 2, 3])
+@pytest.mark.parametrize("force_path", [0, 2, 3, 4])
 @pytest.mark.parametrize("name", EXAMPLES)
 def test_examples_fixed_pi_parity(name, force_path):
     from oracle import oracle as O
@@ -184,4 +184,80 @@ def test_edge_cases():
     eng = engine(prob, clamp_lo_cols=0)
     props = eng.initial()
     assert props[2]["status"] == 6                                             # truly unbounded
+    eng.close()
+
+
+def test_packed_record_matches_dense_results():
+    """dwgpu_iterate_packed ships the same proposals as dwgpu_iterate, laid end to end; with the
+    convexity duals r given, only the columns the master would accept (r_k - obj_k > 1e-6)."""
+    prob = P.gen_mcf(200, 16, 40, 8, seed=5)
+    e1, e2 = engine(prob, fetch_x=False), engine(prob, fetch_x=False)
+    e1.initial_solve()
+    pk = e2.initial_solve_packed()
+    rng = np.random.default_rng(1)
+    for trial in range(4):
+        if trial:
+            pi = -rng.random(prob.L) * 4.0 * trial
+            r = rng.standard_normal(prob.K) * 50.0 if trial >= 2 else None
+            e1.iterate_arrays(pi, trial == 1)
+            pk = e2.iterate_packed(pi, trial == 1, r)
+        else:
+            r = None
+        assert np.array_equal(pk["obj"], e1.obj) and np.array_equal(pk["cost"], e1.cost)
+        assert np.array_equal(pk["status"], e1.status)
+        ship = np.ones(prob.K, bool) if r is None else (r - e1.obj > 1e-6)
+        want_len = np.where(ship, e1.len, 0)
+        assert np.array_equal(np.diff(pk["colptr"]), want_len) and pk["colptr"][0] == 0
+        assert pk["nnz"] == want_len.sum()
+        if r is not None:
+            assert 0 < ship.sum() < prob.K
+        for k in range(prob.K):
+            a, b = pk["colptr"][k], pk["colptr"][k + 1]
+            s = k * prob.L
+            assert np.array_equal(pk["ind"][a:b], e1.ind[s:s + (b - a)])
+            assert np.array_equal(pk["val"][a:b], e1.val[s:s + (b - a)])
+    e1.close(); e2.close()
+
+
+@pytest.mark.parametrize("cluster_size", [1, 2, 4, 8, 16])
+def test_cluster_path_dense_blocks(cluster_size):
+    """Config C class blocks (dense-ish random LPs, phase 1 needed) on the cluster-per-block kernel:
+    the tableau is striped over `cluster_size` CTAs, results must not depend on the stripe count."""
+    from oracle import oracle as O
+    prob = P.gen_dense(4, 150, 300, 12, 64001, dens_a=0.05)
+    eng = engine(prob, force_path=4, cluster_size=cluster_size)
+    assert set(eng.block_paths()) == {4}
+    orc = O.OracleBlocks(prob)
+    compare_round(prob, eng.initial(), orc.initial(4), None, False, initial=True)
+    assert eng.counters()["phase1_iter"] > 0
+    rng = np.random.default_rng(5)
+    for trial in range(3):
+        pi = -rng.random(prob.L) * (1 + trial)
+        compare_round(prob, eng.iterate(pi, trial == 0), orc.iterate(pi, trial == 0, 4), pi, trial == 0)
+    before = eng.counters()
+    eng.iterate(pi, False)                      # same prices again: nothing moves
+    after = eng.counters()
+    assert after["pivots"] == before["pivots"] and after["flips"] == before["flips"]
+    eng.close()
+
+
+def test_cluster_path_mcf_and_dw():
+    """network blocks (equality rows, degenerate) through the cluster kernel, then a full DW run"""
+    from oracle import oracle as O
+    prob = P.gen_mcf(24, 64, 128, 32, 1024001)
+    eng = engine(prob, force_path=4, cluster_size=4)
+    assert set(eng.block_paths()) == {4}
+    orc = O.OracleBlocks(prob)
+    compare_round(prob, eng.initial(), orc.initial(8), None, False, initial=True)
+    rng = np.random.default_rng(11)
+    for trial in range(3):
+        pi = -rng.random(prob.L) * 10.0 * (trial + 1)
+        compare_round(prob, eng.iterate(pi, trial == 0), orc.iterate(pi, trial == 0, 8), pi, trial == 0)
+    eng.close()
+    eng = engine(prob, force_path=4, cluster_size=2)
+    res = run_dw(prob, eng)
+    from highs_util import solve_monolithic
+    ref = solve_monolithic(prob)["objective"]
+    assert res["status"] == "optimal"
+    assert abs(res["objective"] - ref) <= 1e-7 * (1 + abs(ref))
     eng.close()
