@@ -40,7 +40,7 @@ int fail(int code, const std::string &msg)
 
 constexpr int NT_SMEM = 256;
 constexpr int NT_GMEM = 1024;
-constexpr int NT_TG = 64;      // global-tableau kernel: 64-thread CTAs, 9 per SM (DWGPU_TG_THREADS=256: 4 per SM)
+constexpr int NT_TG = 64;      // global-tableau kernel: 64-thread CTAs, 6 per SM (DWGPU_TG_THREADS=256: 4 per SM)
 
 template <typename T>
 struct DevBuf {
@@ -88,6 +88,7 @@ struct dwgpu_engine {
     size_t smem_dyn_c = 0;
     size_t smem_dyn_g = 0;
     int tg_threads = NT_TG;
+    bool reorder = true;
     size_t smem_dyn = 0;
     int max_smem_optin = 0;
     // device arenas
@@ -400,6 +401,9 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
             e->cluster_size /= 2;
         }
     }
+    CUE(cudaFuncSetAttribute(dwk::order_by_last_iterations_kernel<1024, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(8192 * sizeof(unsigned long long))));
+    if (const char *nr = std::getenv("DWGPU_NO_REORDER")) e->reorder = std::atoi(nr) == 0;
     if (const char *tg = std::getenv("DWGPU_TG_THREADS")) e->tg_threads = std::atoi(tg) == 256 ? 256 : NT_TG;
     if (!e->list_g.empty()) {
         CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -433,6 +437,17 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
     P.obj = e->obj.p; P.cost = e->cost.p; P.status = e->status.p; P.len = e->len.p;
     P.ind = e->ind.p; P.val = e->val.p; P.counters = e->counters.p; P.last_iters = e->last_iters.p;
     e->last_launches = 0;
+    // longest-processing-time-first inside each list (DWGPU_NO_REORDER=1 keeps the natural order)
+    if (!initial && e->reorder) {
+        auto order = [&](DevBuf<int> &d, size_t n) -> cudaError_t {
+            if (n < 512 || n > 8192) return cudaSuccess;
+            dwk::order_by_last_iterations_kernel<1024, 8192><<<1, 1024, 8192 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p);
+            e->last_launches++;
+            return cudaGetLastError();
+        };
+        CU(order(e->d_list_b, e->list_b.size())); CU(order(e->d_list_g, e->list_g.size()));
+        CU(order(e->d_list_a, e->list_a.size())); CU(order(e->d_list_smem, e->list_smem.size()));
+    }
     // large blocks first: they are the long poles
     e->ev_used[0] = e->ev_used[1] = false;
     if (!e->list_gmem.empty()) {

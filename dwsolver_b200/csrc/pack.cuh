@@ -96,4 +96,38 @@ __global__ void __launch_bounds__(NT) pack_copy_kernel(PackSrc s, const int *col
     }
 }
 
+// ---- longest-processing-time-first launch order -----------------------------------------------------
+// A round's kernel time is max(total work / resident CTAs, longest block).  Blocks differ by 100x in
+// pivots (most need none), and the blocks that pivoted a lot in the previous round tend to do so
+// again; dispatching them first keeps the long poles off the tail of the launch.  One CTA sorts the
+// (<= 8192-entry) block list by last round's iteration count, descending (bitonic, shared memory).
+template <int NT, int CAP>
+__global__ void __launch_bounds__(NT) order_by_last_iterations_kernel(int *list, int count, const long long *last_iters)
+{
+    extern __shared__ unsigned long long key[];          // CAP entries (64 KB at 8192: dynamic, opt-in)
+    for (int e = threadIdx.x; e < CAP; e += NT) {
+        unsigned long long kv = 0ull;                       // padding sorts last
+        if (e < count) {
+            const int k = list[e];
+            unsigned long long it = (unsigned long long)last_iters[k];
+            if (it > 0xfffffffeull) it = 0xfffffffeull;
+            kv = ((it + 1ull) << 32) | (unsigned long long)(0xffffffffu - (unsigned)k);   // ties: lower id first
+        }
+        key[e] = kv;
+    }
+    __syncthreads();
+    for (int size = 2; size <= CAP; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int e = threadIdx.x; e < CAP / 2; e += NT) {
+                const int lo = 2 * e - (e & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;           // overall descending order
+                const unsigned long long a = key[lo], b = key[hi];
+                if ((a < b) == desc) { key[lo] = b; key[hi] = a; }
+            }
+            __syncthreads();
+        }
+    for (int e = threadIdx.x; e < count; e += NT) list[e] = (int)(0xffffffffu - (unsigned)(key[e] & 0xffffffffull));
+}
+
 }  // namespace dwk

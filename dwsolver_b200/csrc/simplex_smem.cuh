@@ -25,6 +25,19 @@
 
 #include "simplex_cta.cuh"
 
+#ifndef DWK_TG_BLOCK_DECIDE
+#define DWK_TG_BLOCK_DECIDE 1   // 1: the whole CTA takes the pivot decision (list-based); 0: warp 0 alone
+#endif
+#ifndef DWK_TG_SB
+#define DWK_TG_SB 4         // 32-byte items per thread in flight in the sparse sweep (TG)
+#endif
+#ifndef DWK_TG_RB
+#define DWK_TG_RB 4         // double2 per thread in flight while staging the pivot row (TG)
+#endif
+#ifndef DWK_TG_OCC
+#define DWK_TG_OCC 6        // CTAs per SM the 64-thread global-tableau kernel is compiled for (measured best of 3..8: no spills at 167 registers)
+#endif
+
 namespace dwk {
 
 // ---- TMA bulk copy / mbarrier helpers (sm_90+ PTX, emitted as UBLKCP / SYNCS on sm_100a) -------
@@ -93,7 +106,8 @@ __host__ __device__ inline size_t smem2_bytes(int m, int n, bool tg = false)
          + align16(sizeof(double) * (size_t)m)                // w (phase-1 weights / cached ratios)
          + align16((size_t)n)                                 // cstat
          + align16(sizeof(unsigned short) * (size_t)(m + 1))  // active rows
-         + align16(sizeof(unsigned short) * (ld / 2 + 1));    // active column items of the pivot row
+         + align16(sizeof(unsigned short) * (ld / 2 + 1))     // active column items of the pivot row
+         + (tg ? align16(sizeof(unsigned short) * (size_t)(m + 32 * 8)) : 0);   // per-warp column segments
 }
 
 enum { K_NONE = 0, K_PIVOT = 1, K_FAIL = 2, K_REDO = 3 };
@@ -127,6 +141,7 @@ struct Sm3 {
     signed char *cstat;
     unsigned short *arow;
     unsigned short *acol;
+    unsigned short *arow2;               // per-warp column segments before compaction (TG)
 };
 
 // lane holding the maximum of non-negative keys (ties: lowest lane); -1 if no lane is valid
@@ -344,6 +359,261 @@ __device__ __forceinline__ int decide_warp0(Sm3 &c, const double *dd, bool d_liv
     }
 }
 
+// ---- block-cooperative decision for the global-memory tableau (TG) kernel ----------------------------
+// With the tableau in HBM a basis change is a chain of dependent memory round trips (column, pivot
+// row, sweep); what sits between them must be as short as possible.  Here every thread of the CTA
+// takes part: pricing is split over all threads, each warp fetches a contiguous quarter/half of the
+// pivot column in ONE batch of loads and compacts its non-zero rows, and the ratio test, the beta
+// update and the bookkeeping then run over that short list only (network blocks: ~13 of 256 rows)
+// instead of all m rows.  Same pivoting rules as decide_warp0.
+struct DecShared {
+    double key[8];
+    int q[8];
+    int cnt[8];
+    int kind, bland;
+};
+enum { K_FLIPPED = 4 };
+
+template <bool INF, int NT, int MC, int NC>
+__device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_live, bool &bland, int &degen, int degen_limit,
+                            double tol_dj, double tol_bnd, double tol_piv,
+                            unsigned long long &n_piv, unsigned long long &n_flip, unsigned long long &n_rows,
+                            unsigned long long &n_cells, Decision *dec, DecShared *ds)
+{
+    constexpr int NW = NT / 32;
+    static_assert(NW <= 8, "DecShared holds 8 warp slots");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int m = MC ? MC : c.m, n = NC ? NC : c.n, ld = NC ? tab_ld(NC, true) : c.ld;
+    const double harris = 0.5 * tol_bnd;
+    const int RW = ((m + NW - 1) / NW + 31) & ~31;          // rows of the column each warp fetches
+    for (;;) {
+        // ---- pricing, all threads
+        double key = 0.0; int q = -1;
+#pragma unroll 8
+        for (int j = tid; j < n; j += NT) {
+            const double dj = dd[j];
+            const signed char st = c.cstat[j];
+            const bool ok = (st == ST_LO && dj < -tol_dj) || (st == ST_UP && dj > tol_dj) ||
+                            (st == ST_FREE && fabs(dj) > tol_dj);
+            const double kj = bland ? 2147483648.0 - (double)c.nbv[j] : fabs(dj);
+            if (ok && kj > key) { key = kj; q = j; }
+        }
+        {
+            const int src = warp_argmax_nonneg(key, q >= 0);
+            const int sl = src < 0 ? 0 : src;
+            const double kw = __shfl_sync(0xffffffffu, key, sl);
+            const int qw = __shfl_sync(0xffffffffu, q, sl);
+            if (lane == 0) { ds->key[warp] = kw; ds->q[warp] = src < 0 ? -1 : qw; }
+        }
+        __syncthreads();
+        q = -1; key = -1.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const double kw = ds->key[w];
+            const int qw = ds->q[w];
+            if (qw >= 0 && kw > key) { key = kw; q = qw; }
+        }
+        if (q < 0) return K_NONE;                                // block-uniform
+        const double dq = dd[q];
+        const double s = dq < 0.0 ? 1.0 : -1.0;
+        const signed char stq = c.cstat[q];
+        const int vq = c.nbv[q];
+        const double loq = __ldg(c.glo + vq), upq = __ldg(c.gup + vq);
+        // ---- pivot column: warp w fetches rows [w RW, (w+1) RW) in one batch and lists its non-zeros
+        int cnt = 0;
+        {
+            const int rbeg = warp * RW, rend = min(m, rbeg + RW);
+            constexpr int CB = MC ? (MC / NW + 31) / 32 : 4;
+            for (int i00 = rbeg; i00 < rend; i00 += 32 * CB) {
+                double tcol[CB];
+#pragma unroll
+                for (int r = 0; r < CB; ++r) {
+                    const int i = i00 + r * 32 + lane;
+                    tcol[r] = i < rend ? __ldcg(c.T + (size_t)i * ld + q) : 0.0;
+                }
+#pragma unroll
+                for (int r = 0; r < CB; ++r) {
+                    const int i = i00 + r * 32 + lane;
+                    const bool nz = i < rend && tcol[r] != 0.0;
+                    const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                    if (nz) {
+                        c.colq[i] = tcol[r];
+                        c.arow2[rbeg + cnt + __popc(bal & lt_mask)] = (unsigned short)i;
+                    }
+                    cnt += __popc(bal);
+                }
+            }
+            if (lane == 0) ds->cnt[warp] = cnt;
+        }
+        __syncthreads();
+        int na = 0;
+        {
+            int my_off = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { if (w == warp) my_off = na; na += ds->cnt[w]; }
+            for (int e = lane; e < cnt; e += 32) c.arow[my_off + e] = c.arow2[warp * RW + e];
+        }
+        __syncthreads();
+        // ---- ratio test, flips and the staging of a basis change over the list: warp 0
+        if (warp == 0) {
+            int kind = K_PIVOT;
+            double tmax = CUDART_INF;
+            for (int e = lane; e < na; e += 32) {
+                const int i = c.arow[e];
+                const double tiq = c.colq[i];
+                const double a = s * tiq;
+                double lo = c.rlo[i], up = c.rup[i];
+                const double b = c.beta[i];
+                if (INF) {
+                    if (b < lo - tol_bnd * (1.0 + fabs(lo))) { up = lo; lo = -CUDART_INF; }
+                    else if (b > up + tol_bnd * (1.0 + fabs(up))) { lo = up; up = CUDART_INF; }
+                }
+                bool blocks = false; double slack = 0.0, target = 0.0, tex = CUDART_INF;
+                if (a > tol_piv) { if (up < BIG) { blocks = true; slack = up - b; target = up; } }
+                else if (a < -tol_piv) { if (lo > -BIG) { blocks = true; slack = b - lo; target = lo; } }
+                if (blocks) {
+                    const double r = __drcp_rn(fabs(a));
+                    tex = slack * r;
+                    const double delta = bland ? 0.0 : harris * (1.0 + fabs(target));
+                    tmax = fmin(tmax, fmax((slack + delta) * r, 0.0));
+                }
+                c.w[e] = tex;                                    // cached by list position
+            }
+            tmax = warp_min_nonneg(tmax);
+            int p = -1, pe = -1;
+            if (tmax < CUDART_INF) {
+                const double lim = bland ? tmax + 1e-12 * (1.0 + tmax) : tmax;
+                double pk = 0.0;
+                __syncwarp();
+                for (int e = lane; e < na; e += 32) {
+                    if (c.w[e] <= lim) {
+                        const int i = c.arow[e];
+                        const double kk = bland ? 2147483648.0 - (double)c.head[i] : fabs(c.colq[i]);
+                        if (kk > pk) { pk = kk; p = i; pe = e; }
+                    }
+                }
+                const int src = warp_argmax_nonneg(pk, p >= 0);
+                const int sl = src < 0 ? 0 : src;
+                p = __shfl_sync(0xffffffffu, p, sl);
+                pe = __shfl_sync(0xffffffffu, pe, sl);
+                if (src < 0) { p = -1; pe = -1; }
+            }
+            __syncwarp();
+            const double theta = p >= 0 ? fmax(0.0, c.w[pe]) : CUDART_INF;
+            const double range = (stq == ST_FREE) ? CUDART_INF : upq - loq;
+            if (range <= theta) {
+                if (!(range < BIG)) { if (lane == 0) dec->fail_status = INF ? 1 : 6; kind = K_FAIL; }
+                else {
+                    for (int e = lane; e < na; e += 32) {
+                        const int i = c.arow[e];
+                        c.beta[i] = fma(s * range, c.colq[i], c.beta[i]);
+                    }
+                    if (lane == 0) {
+                        const signed char ns = (stq == ST_LO) ? ST_UP : ST_LO;
+                        c.cstat[q] = ns;
+                        c.vstat[vq] = ns;
+                    }
+                    ++n_flip;
+                    degen = 0; bland = false;
+                    kind = INF ? K_REDO : K_FLIPPED;             // phase-1 prices depend on beta
+                }
+            } else if (p < 0) {
+                if (lane == 0) dec->fail_status = INF ? 1 : 6;
+                kind = K_FAIL;
+            } else {
+                const double piv = c.colq[p];
+                const double inv = __drcp_rn(piv);
+                const double xq_new = nb_value(stq, loq, upq) + s * theta;
+                const double lov = c.rlo[p], upv = c.rup[p];
+                double target;
+                {
+                    double lo = lov, up = upv;
+                    if (INF) {
+                        const double bp = c.beta[p];
+                        if (bp < lo - tol_bnd * (1.0 + fabs(lo))) up = lo;
+                        else if (bp > up + tol_bnd * (1.0 + fabs(up))) lo = up;
+                    }
+                    target = (s * piv > 0.0) ? up : lo;
+                }
+                __syncwarp();
+                for (int e = lane; e < na; e += 32) {
+                    const int i = c.arow[e];
+                    c.beta[i] = (i == p) ? xq_new : fma(s * theta, c.colq[i], c.beta[i]);
+                }
+                if (lane == 0) {
+                    const signed char ns = (lov == upv) ? ST_FIX : (target == lov ? ST_LO : ST_UP);
+                    const int vleave = c.head[p];
+                    c.rlo[p] = loq; c.rup[p] = upq;
+                    c.cstat[q] = ns; c.vstat[vleave] = ns; c.vstat[vq] = ST_BASIC;
+                    c.head[p] = vq; c.nbv[q] = vleave;
+                    const bool with_d = d_live && dq != 0.0;
+                    c.colq[m] = with_d ? dq : 0.0;
+                    if (with_d) c.arow[na] = (unsigned short)m;      // the reduced-cost row rides along
+                    dec->p = p; dec->q = q; dec->inv = inv; dec->na = na + (with_d ? 1 : 0);
+                }
+                ++n_piv;
+                n_rows += (unsigned long long)na;
+                if (theta <= 1e-11) { if (++degen > degen_limit) bland = true; }
+                else { degen = 0; bland = false; }
+            }
+            if (lane == 0) { ds->kind = kind; ds->bland = bland ? 1 : 0; }
+        }
+        __syncthreads();
+        const int kind = ds->kind;
+        bland = ds->bland != 0;
+        if (kind == K_FLIPPED) continue;
+        if (kind != K_PIVOT) return kind;
+        // ---- pivot row -> rowp (scaled), every thread, one batch of loads
+        {
+            const int p = dec->p;
+            const double inv = dec->inv;
+            const double2 *prow = reinterpret_cast<const double2 *>(c.T + (size_t)p * ld);
+            double2 *rp2 = reinterpret_cast<double2 *>(c.rowp);
+            constexpr int RB = NC ? ((NC / 2 + NT - 1) / NT < DWK_TG_RB ? (NC / 2 + NT - 1) / NT : DWK_TG_RB) : 2;
+            for (int j0 = 0; j0 < (ld >> 1); j0 += NT * RB) {
+                double2 v[RB];
+#pragma unroll
+                for (int t = 0; t < RB; ++t) {
+                    const int j2 = j0 + t * NT + tid;
+                    if (j2 < (ld >> 1)) v[t] = __ldcg(prow + j2);
+                }
+#pragma unroll
+                for (int t = 0; t < RB; ++t) {
+                    const int j2 = j0 + t * NT + tid;
+                    if (j2 < (ld >> 1)) { v[t].x *= inv; v[t].y *= inv; rp2[j2] = v[t]; }
+                }
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // non-zero 32-byte items of the scaled pivot row (see sweep_sparse)
+            constexpr int IW = ItemW<true>::D2;
+            const int nitems = (ld >> 1) / IW;
+            const double2 *rp2 = reinterpret_cast<const double2 *>(c.rowp);
+            int nc = 0;
+            for (int t0 = 0; t0 < nitems; t0 += 32) {
+                const int t = t0 + lane;
+                bool nz = false;
+                if (t < nitems) {
+#pragma unroll
+                    for (int u = 0; u < IW; ++u) { const double2 v = rp2[t * IW + u]; nz |= (v.x != 0.0) | (v.y != 0.0); }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                if (nz) c.acol[nc + __popc(bal & lt_mask)] = (unsigned short)t;
+                nc += __popc(bal);
+            }
+            if (2 * nc > nitems) nc = -1;
+            const int na_all = dec->na;
+            n_cells += nc < 0 ? (unsigned long long)na_all * (unsigned long long)ld
+                              : (unsigned long long)na_all * (unsigned long long)nc * (2 * IW);
+            if (lane == 0) dec->nc = nc;
+        }
+        __syncthreads();
+        return K_PIVOT;
+    }
+}
+
 // Change of a priced cost that the saved reduced costs still have to absorb.  Differences at the
 // noise level of the master's duals (<= 1e-11 relative) are NOT applied and the saved cost is left
 // as it is, so they keep accumulating until they matter; the reduced costs used for pricing are
@@ -355,53 +625,72 @@ __device__ __forceinline__ double cost_delta(double cs_new, double cs_saved)
 }
 
 // rank-1 sweep over (active rows) x (active column items): every load of a batch is issued before the
-// first dependent instruction, so a typical network pivot (13 rows x 30 items) is ONE memory round trip
+// first dependent instruction, so a typical network pivot (13 rows x 30 items) is ONE memory round trip.
+// The reduced-cost row (last list entry when it rides along) lives in shared memory and is done apart,
+// so the tableau loop is pure global (TG) or pure shared traffic with 32-bit cell offsets.
 template <int NT, int NC, bool TG>
 __device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, int na, int nc)
 {
     constexpr int IW = ItemW<TG>::D2;
-    constexpr int SB = TG ? 4 : 2;                         // items per thread in flight
+    constexpr int SB = TG ? DWK_TG_SB : 2;                 // items per thread in flight
     const int nc2 = (NC ? tab_ld(NC, TG) : c.ld) >> 1;    // row pitch in double2
     double2 *T2 = reinterpret_cast<double2 *>(c.T);
-    double2 *d2 = reinterpret_cast<double2 *>(c.drow);
     const double2 *rowp2 = reinterpret_cast<const double2 *>(c.rowp);
-    const int total = na * nc;
+    const bool with_d = na > 0 && c.arow[na - 1] == c.m;
+    const int nat = with_d ? na - 1 : na;
+    const int total = nat * nc;
     for (int e0 = 0; e0 < total; e0 += NT * SB) {
         double2 v[SB][IW];
-        int ri[SB], jj[SB];
+        int off[SB];                                       // double2 offset of the item; -1: none
 #pragma unroll
         for (int t = 0; t < SB; ++t) {
             const int e = e0 + t * NT + threadIdx.x;
-            ri[t] = -1;
+            off[t] = -1;
             if (e < total) {
                 const int a = e / nc;
-                const int i = c.arow[a];
-                const int j = (int)c.acol[e - a * nc] * IW;
-                ri[t] = i; jj[t] = j;
-                const double2 *src = (i == c.m ? d2 : T2 + (size_t)i * nc2) + j;
+                off[t] = (int)c.arow[a] * nc2 + (int)c.acol[e - a * nc] * IW;
 #pragma unroll
-                for (int u = 0; u < IW; ++u) v[t][u] = (TG && i != c.m) ? __ldcg(src + u) : src[u];
+                for (int u = 0; u < IW; ++u) v[t][u] = ld_t2<TG>(T2 + off[t] + u);
             }
         }
 #pragma unroll
         for (int t = 0; t < SB; ++t) {
-            const int i = ri[t];
-            if (i >= 0) {
+            if (off[t] >= 0) {
+                const int i = off[t] / nc2;
+                const int j = off[t] - i * nc2;
                 const double ci = c.colq[i];
                 const double cq = ci * inv;
                 const bool is_p = i == p;
-                double2 *dst = (i == c.m ? d2 : T2 + (size_t)i * nc2) + jj[t];
 #pragma unroll
                 for (int u = 0; u < IW; ++u) {
-                    const double2 ra = rowp2[jj[t] + u];
-                    const int jq = q - 2 * (jj[t] + u);
+                    const double2 ra = rowp2[j + u];
+                    const int jq = q - 2 * (j + u);
                     double2 r;
                     r.x = is_p ? -ra.x : fma(-ci, ra.x, v[t][u].x);
                     r.y = is_p ? -ra.y : fma(-ci, ra.y, v[t][u].y);
                     if (jq == 0) r.x = is_p ? inv : cq;
                     if (jq == 1) r.y = is_p ? inv : cq;
-                    if (TG && i != c.m) __stcg(dst + u, r); else dst[u] = r;
+                    st_t2<TG>(T2 + off[t] + u, r);
                 }
+            }
+        }
+    }
+    if (with_d) {
+        double2 *d2 = reinterpret_cast<double2 *>(c.drow);
+        const double dq = c.colq[c.m];
+        const double cq = dq * inv;
+        for (int t = threadIdx.x; t < nc; t += NT) {
+            const int j = (int)c.acol[t] * IW;
+#pragma unroll
+            for (int u = 0; u < IW; ++u) {
+                const double2 ra = rowp2[j + u];
+                const int jq = q - 2 * (j + u);
+                double2 r = d2[j + u];
+                r.x = fma(-dq, ra.x, r.x);
+                r.y = fma(-dq, ra.y, r.y);
+                if (jq == 0) r.x = cq;
+                if (jq == 1) r.y = cq;
+                d2[j + u] = r;
             }
         }
     }
@@ -548,12 +837,13 @@ __device__ __forceinline__ double weighted_colsum(const Sm3 &c, const double *wt
 // TG = true: the tableau stays in global memory (L2/HBM) and only the vectors live in shared memory
 // (blocks too large for one CTA's shared memory, config B class); the decision/sweep code is shared.
 template <int NT, int MC, int NC, bool TG>
-__global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? 8 : (NT <= 128 ? 6 : 4)) : 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
+__global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : (NT <= 128 ? 6 : 4)) : 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
                                                           SolveParams P)
 {
     extern __shared__ __align__(16) char smem_raw[];
     __shared__ Scratch<NT> scr;
     __shared__ Decision dec;
+    __shared__ DecShared dsh;
     __shared__ __align__(8) uint64_t bar;
     __shared__ int s_kind, s_changed;
     if ((int)blockIdx.x >= count) return;
@@ -588,7 +878,8 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? 8 : (NT <= 128 ? 6 : 4)) 
     c.w = (double *)sp;            sp += align16(sizeof(double) * (size_t)m);
     c.cstat = (signed char *)sp;   sp += align16((size_t)n);
     c.arow = (unsigned short *)sp; sp += align16(sizeof(unsigned short) * (size_t)(m + 1));
-    c.acol = (unsigned short *)sp;
+    c.acol = (unsigned short *)sp; sp += align16(sizeof(unsigned short) * (size_t)(ld / 2 + 1));
+    c.arow2 = (unsigned short *)sp;
 
     // ---- state in: two bulk copies, one mbarrier
     const uint32_t t_bytes = TG ? 0u : (uint32_t)(sizeof(double) * (size_t)m * ld);
@@ -685,8 +976,17 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? 8 : (NT <= 128 ? 6 : 4)) 
             d_full = !inc;
             __syncthreads();
         }
-        // ---- B. decision (warp 0)
-        if (warp == 0) {
+        // ---- B. decision (TG: the whole CTA; shared-memory tableau: warp 0)
+        if (TG && DWK_TG_BLOCK_DECIDE) {
+            int kind;
+            if (infeasible)
+                kind = decide_block_tg<true, NT, MC, NC>(c, c.rowp, false, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
+                                                         n_piv, n_flip, n_rows, n_cells, &dec, &dsh);
+            else
+                kind = decide_block_tg<false, NT, MC, NC>(c, c.drow, true, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
+                                                          n_piv, n_flip, n_rows, n_cells, &dec, &dsh);
+            if (tid == 0) { s_kind = kind; if (n_piv + n_flip) s_changed = 1; }
+        } else if (warp == 0) {
             int kind;
             if (infeasible)
                 kind = decide_warp0<true, MC, NC, TG>(c, c.rowp, false, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,

@@ -13,7 +13,8 @@ from typing import List, Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdwgpu.so")
+# DWGPU_LIB: another build of the same library (tuning experiments, e.g. a different -DDWK_TG_OCC)
+LIB_PATH = os.environ.get("DWGPU_LIB") or os.path.join(_HERE, "lib", "libdwgpu.so")
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)
