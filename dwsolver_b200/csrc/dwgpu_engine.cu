@@ -111,6 +111,7 @@ struct dwgpu_engine {
     dwk::PackDst pk_dev{}, pk_host{};  // the same mirror through its device alias / its host address
     DevBuf<double> r_dev;              // K convexity duals of the packed call
     double *h_r = nullptr;
+    long long *h_dbg = nullptr, *d_dbg = nullptr;   // DWGPU_DEBUG=1: progress markers the kernels leave behind
     DevBuf<unsigned long long> counters;
     DevBuf<long long> last_iters;
     // pinned staging
@@ -153,6 +154,7 @@ void dwgpu_destroy(dwgpu_engine *e)
     e->d_list_gmem.release(); e->d_list_a.release(); e->d_list_g.release(); e->d_list_b.release(); e->d_list_c.release(); e->pi.release(); e->rec.release(); e->colptr.release();
     if (e->h_pack) cudaFreeHost(e->h_pack);
     if (e->h_r) cudaFreeHost(e->h_r);
+    if (e->h_dbg) cudaFreeHost(e->h_dbg);
     e->r_dev.release();
     e->counters.release(); e->last_iters.release();
     if (e->h_pi) cudaFreeHost(e->h_pi);
@@ -339,6 +341,11 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         };
         carve_pack(e->d_pack, e->pk_dev);
         carve_pack(e->h_pack, e->pk_host);
+        if (std::getenv("DWGPU_DEBUG")) {
+            CUE(cudaHostAlloc((void **)&e->h_dbg, sizeof(long long) * 32 * (size_t)K, cudaHostAllocMapped));
+            CUE(cudaHostGetDevicePointer((void **)&e->d_dbg, e->h_dbg, 0));
+            std::memset(e->h_dbg, 0, sizeof(long long) * 32 * (size_t)K);
+        }
         CUE(e->r_dev.alloc(K));
         CUE(cudaMallocHost((void **)&e->h_r, sizeof(double) * (size_t)K));
     }
@@ -433,6 +440,8 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
     dwk::SolveParams P;
     P.pi = d_pi; P.phase_one = phase_one; P.initial = initial;
     P.max_iter_mult = e->opt.max_iter_mult;
+    P.no_dual_start = e->opt.no_dual_start;
+    P.dbg = e->d_dbg;
     P.tol_dj = e->opt.tol_dj; P.tol_bnd = e->opt.tol_bnd; P.tol_piv = e->opt.tol_piv;
     P.obj = e->obj.p; P.cost = e->cost.p; P.status = e->status.p; P.len = e->len.p;
     P.ind = e->ind.p; P.val = e->val.p; P.counters = e->counters.p; P.last_iters = e->last_iters.p;
@@ -527,6 +536,17 @@ int dwgpu_fetch_results(dwgpu_engine *e, dwgpu_proposals *o)
     if (!e) return fail(DWGPU_E_ARGS, "engine is NULL");
     CU(cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
+    if (e->h_dbg) {
+        cudaError_t se = cudaStreamSynchronize(st);
+        if (se != cudaSuccess) {
+            for (int k = 0; k < e->K && k < 16; ++k) {
+                std::fprintf(stderr, "dwgpu debug block %d:", k);
+                for (int t = 0; t < 32; ++t) std::fprintf(stderr, " %lld", e->h_dbg[32 * (size_t)k + t]);
+                std::fprintf(stderr, "\n");
+            }
+        }
+        CU(se);
+    }
     if (o) {
         const size_t K = e->K, KL = (size_t)e->K * e->L;
         if (o->obj) CU(cudaMemcpyAsync(o->obj, e->obj.p, sizeof(double) * K, cudaMemcpyDeviceToHost, st));

@@ -50,6 +50,9 @@ __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arri
 __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cl_sync() { cl_arrive(); cl_wait(); }
 
+// progress markers (DWGPU_DEBUG): slot 8*rank + t of the block's 32-entry record, written by thread 0
+#define CL_MARK(t, v) do { if (P.dbg && tid == 0) { volatile long long *d_ = P.dbg + 32 * (size_t)k + 8 * (rank & 3) + (t); *d_ = (long long)(v); } } while (0)
+
 struct Cl {
     int m, n, ld, G, rank, r0, r1;
     double *T;
@@ -215,6 +218,41 @@ __device__ __forceinline__ void cl_colsum(Cl &c, ClShared &sh, const double *wt,
     cl_sync();                                   // nobody still reads a peer's rowp
 }
 
+// ---- beta = T x_N: every CTA does its own rows (one warp per row) and stores the result into every
+// peer's beta through DSMEM.  rowp is used as scratch for x_N.  Ends with a cluster barrier.
+__device__ __forceinline__ void cl_recompute_beta(Cl &c, const BlockDev &B)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j = tid; j < c.n; j += NT_CL) {
+        const int v = c.nbv[j];
+        c.rowp[j] = nb_value(c.cstat[j], __ldg(B.lo + v), __ldg(B.up + v));
+    }
+    __syncthreads();
+    const double2 *x2 = reinterpret_cast<const double2 *>(c.rowp);
+    const int n2a = c.n >> 1;
+    for (int i = c.r0 + warp; i < c.r1; i += NT_CL / 32) {
+        const double2 *row = reinterpret_cast<const double2 *>(c.T + (size_t)i * c.ld);
+        double s = 0.0;
+        for (int j0 = 0; j0 < n2a; j0 += 32 * 8) {
+            double2 v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { const int j = j0 + t * 32 + lane; if (j < n2a) v[t] = __ldcg(row + j); }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int j = j0 + t * 32 + lane;
+                if (j < n2a) { const double2 x = x2[j]; s = fma(v[t].x, x.x, s); s = fma(v[t].y, x.y, s); }
+            }
+        }
+        if ((c.n & 1) && lane == 0) s = fma(__ldcg(c.T + (size_t)i * c.ld + c.n - 1), c.rowp[c.n - 1], s);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0)
+            for (int r = 0; r < c.G; ++r) cluster.map_shared_rank(c.beta, r)[i] = s;
+    }
+    cl_sync();
+}
+
 // exact ratio of row i for a step of the entering variable in direction s; +inf when it does not block
 template <bool INF>
 __device__ __forceinline__ void cl_row_ratio(const Cl &c, int i, double s, double tiq, double tol_bnd, double tol_piv,
@@ -308,6 +346,7 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
         cs[j] = cj;
     }
     cl_sync();          // all CTAs of the cluster are resident and initialised before any DSMEM traffic
+    CL_MARK(0, 1);
 
     int status = 0;
     long long iter = 0;
@@ -319,8 +358,172 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
     const int degen_limit = 100 + (m + n) / 2;
     int p1_leave_col = -1; double p1_leave_w = 0.0;      // column / frozen weight of the variable that just left
 
+    // ---- dual simplex start ----------------------------------------------------------------------------
+    // A primal-infeasible start (the cold solve: all-logical basis) is repaired by the DUAL simplex when
+    // every nonbasic column can be put on the bound that makes its reduced cost sign-correct (boxed
+    // columns, e.g. 0 <= x <= u): leaving row by dual devex (infeasibility^2 / reference weight), entering
+    // column by a two-pass Harris dual ratio test on the pivot row, then the same rank-1 update as a
+    // primal step.  On config C class blocks this needs an order of magnitude fewer basis changes than
+    // primal phase 1 + phase 2 with Dantzig pricing.  Anything it cannot handle (free / one-sided
+    // columns with the wrong sign, dual unboundedness, too many iterations) falls through to the primal
+    // loop below, which also certifies the final basis (pricing, residual check, rebuild).
+    if (m > 0 && !P.no_dual_start) {
+        int viol0 = 0;
+        for (int i = tid; i < m; i += NT)
+            viol0 |= (cl_phase1_weight(c.beta[i], c.rlo[i], c.rup[i], tol_bnd) != 0.0);
+        if (__syncthreads_or(viol0)) {
+            // reduced costs of the current basis
+            for (int i = tid; i < m; i += NT) {
+                const int v = c.head[i];
+                c.w[i] = v >= m ? cs[v - m] : 0.0;
+            }
+            __syncthreads();
+            cl_colsum(c, sh, c.w, [&](int j) { const int v = c.nbv[j]; return v >= m ? cs[v - m] : 0.0; });
+            // sign-correct bounds; count flips and impossible columns
+            int bad = 0, nfl = 0;
+            for (int j = tid; j < n; j += NT) {
+                const double dj = c.drow[j];
+                const signed char st = c.cstat[j];
+                const int v = c.nbv[j];
+                if (st == ST_LO && dj < -tol_dj) {
+                    if (__ldg(B.up + v) < BIG) { c.cstat[j] = ST_UP; ++nfl; } else bad = 1;
+                } else if (st == ST_UP && dj > tol_dj) {
+                    if (__ldg(B.lo + v) > -BIG) { c.cstat[j] = ST_LO; ++nfl; } else bad = 1;
+                } else if (st == ST_FREE && fabs(dj) > tol_dj) bad = 1;
+            }
+            const int any_bad = __syncthreads_or(bad);
+            const int any_flip = __syncthreads_or(nfl);
+            if (any_flip) {
+                n_flip += (unsigned long long)block_sum<NT>((double)nfl, sh.scr);
+                changed = true;
+                cl_recompute_beta(c, B);
+            }
+            for (int i = tid; i < m; i += NT) c.w[i] = 1.0;       // dual devex reference weights
+            __syncthreads();
+            d_valid = true;
+            const long long dual_limit = 20LL * (m + n) + 1000;
+            long long dit = 0;
+            CL_MARK(0, 2);
+            while (!any_bad) {
+                if (++dit > dual_limit) break;
+                CL_MARK(1, dit);
+                // ---- leaving row: largest infeasibility^2 / weight (replicated)
+                double key = 0.0; int p = INT_MAX;
+                for (int i = tid; i < m; i += NT) {
+                    const double b = c.beta[i], lo = c.rlo[i], up = c.rup[i];
+                    double v = 0.0;
+                    if (b < lo - tol_bnd * (1.0 + fabs(lo))) v = lo - b;
+                    else if (b > up + tol_bnd * (1.0 + fabs(up))) v = b - up;
+                    if (v > 0.0) {
+                        const double kk = v * v / c.w[i];
+                        if (kk > key) { key = kk; p = i; }
+                    }
+                }
+                if (key <= 0.0) p = INT_MAX;
+                block_argmax<NT>(key, p, sh.scr);
+                CL_MARK(2, p);
+                if (p == INT_MAX) break;                          // primal feasible: done
+                // everything read here is rewritten further down: read it before the barriers below
+                const double bp = c.beta[p], lop = c.rlo[p], upp = c.rup[p], wp = c.w[p];
+                const bool below = bp < lop;
+                const double target = below ? lop : upp;
+                const double sg = below ? 1.0 : -1.0;
+                cl_sync();                                        // every sweep of the previous step has landed
+                cl_stage_row(c, p, 1.0);                          // alpha = T[p][:], unscaled
+                __syncthreads();
+                // ---- entering column: dual ratio test, two passes (Harris)
+                double rmin = CUDART_INF;
+                for (int j = tid; j < n; j += NT) {
+                    const double a = sg * c.rowp[j];
+                    const signed char st = c.cstat[j];
+                    const bool cand = (st == ST_LO && a > tol_piv) || (st == ST_UP && a < -tol_piv) ||
+                                      (st == ST_FREE && fabs(a) > tol_piv);
+                    if (cand) rmin = fmin(rmin, (fabs(c.drow[j]) + tol_dj) / fabs(a));
+                }
+                rmin = block_min<NT>(rmin, sh.scr);
+                if (!(rmin < CUDART_INF)) break;                  // dual unbounded: let the primal loop decide
+                double pk = -1.0; int q = INT_MAX;
+                for (int j = tid; j < n; j += NT) {
+                    const double a = sg * c.rowp[j];
+                    const signed char st = c.cstat[j];
+                    const bool cand = (st == ST_LO && a > tol_piv) || (st == ST_UP && a < -tol_piv) ||
+                                      (st == ST_FREE && fabs(a) > tol_piv);
+                    if (cand && fabs(c.drow[j]) / fabs(a) <= rmin && fabs(a) > pk) { pk = fabs(a); q = j; }
+                }
+                block_argmax<NT>(pk, q, sh.scr);
+                CL_MARK(3, q);
+                if (q == INT_MAX) break;
+                // ---- the step: same update as a primal basis change on (p, q)
+                const signed char stq = c.cstat[q];
+                const int vq = c.nbv[q];
+                const double loq = __ldg(B.lo + vq), upq = __ldg(B.up + vq);
+                const double piv = c.rowp[q];
+                const double inv = __drcp_rn(piv);
+                const double dq = c.drow[q];
+                const int vleave = c.head[p];
+                cl_exchange_column(c, sh, q, buf);                // barrier: everybody has read row p as well
+                const double *colq = c.colq[buf];
+                const int na_own = sh.na;
+                buf ^= 1;
+                const double dxq = (target - bp) * inv;
+                const double xq_new = nb_value(stq, loq, upq) + dxq;
+                unsigned nz_local = 0;
+                int wbig = 0;
+                for (int i = tid; i < m; i += NT) {
+                    const double ci = colq[i];
+                    nz_local += (ci != 0.0);
+                    if (i == p) { const double wn = fmax(wp * inv * inv, 1.0); c.beta[i] = xq_new; c.w[i] = wn; wbig |= wn > 1e12; }
+                    else if (ci != 0.0) {
+                        c.beta[i] = fma(dxq, ci, c.beta[i]);
+                        const double g = ci * inv;
+                        const double wn = fmax(c.w[i], g * g * wp);
+                        c.w[i] = wn; wbig |= wn > 1e12;
+                    }
+                }
+                if (__syncthreads_or(wbig))                       // devex: new reference framework
+                    for (int i = tid; i < m; i += NT) c.w[i] = 1.0;
+                {
+                    double2 *rp2 = reinterpret_cast<double2 *>(c.rowp);
+                    double2 *d2 = reinterpret_cast<double2 *>(c.drow);
+                    const double cqd = dq * inv;
+                    for (int j = tid; j < (ld >> 1); j += NT) {
+                        double2 ra = rp2[j];
+                        ra.x *= inv; ra.y *= inv;
+                        rp2[j] = ra;
+                        if (dq != 0.0 && j < ((n + 1) >> 1)) {
+                            double2 r = d2[j];
+                            const int jq = q - 2 * j;
+                            r.x = fma(-dq, ra.x, r.x);
+                            r.y = fma(-dq, ra.y, r.y);
+                            if (jq == 0) r.x = cqd;
+                            if (jq == 1) r.y = cqd;
+                            d2[j] = r;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    c.rlo[p] = loq; c.rup[p] = upq;
+                    c.cstat[q] = (lop == upp) ? ST_FIX : (below ? ST_LO : ST_UP);
+                    c.head[p] = vq; c.nbv[q] = vleave;
+                }
+                cl_sweep(c, colq, na_own, p, q, inv);
+                cl_write_pivot_row(c, p, q, inv);
+                ++n_piv;
+                n_rows += nz_local;
+                changed = true;
+                __syncthreads();
+            }
+            CL_MARK(0, 4);
+            cl_sync();                                            // sweeps complete before the primal loop reads T
+            for (int i = tid; i < m; i += NT) c.w[i] = 0.0;       // w is the phase-1 weight array again
+            __syncthreads();
+        }
+    }
+
     for (;;) {
         if (++iter > max_iter) { status = 1; break; }
+        CL_MARK(0, 5); CL_MARK(4, iter);
         // ---- A. feasibility scan (replicated); in phase 1 also the list of rows whose weight changed
         if (need_check || infeasible) {
             if (tid == 0) sh.nchg = 0;
@@ -439,6 +642,7 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
             if (worst > 0.1 * tol_bnd && n_reb < 3) {
                 // ---- rebuild T from A_k for the current basis (Gauss-Jordan with the cluster sweeps)
                 ++n_reb;
+                CL_MARK(0, 6); CL_MARK(5, n_reb);
                 // target basis by variable id -> global vstat (rank 0), visible to all after the barrier
                 if (rank == 0) {
                     for (int i = tid; i < m; i += NT) B.vstat[c.head[i]] = ST_BASIC;
@@ -494,20 +698,8 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
                     const int v = c.head[i];
                     c.rlo[i] = __ldg(B.lo + v); c.rup[i] = __ldg(B.up + v);
                 }
-                for (int j = tid; j < n; j += NT) {
-                    const int v = c.nbv[j];
-                    c.rowp[j] = nb_value(c.cstat[j], __ldg(B.lo + v), __ldg(B.up + v));
-                }
                 __syncthreads();
-                for (int i = c.r0 + warp; i < c.r1; i += NT / 32) {
-                    double s = 0.0;
-                    for (int j = lane; j < n; j += 32) s += __ldcg(c.T + (size_t)i * ld + j) * c.rowp[j];
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (lane == 0)
-                        for (int r = 0; r < G; ++r) cluster.map_shared_rank(c.beta, r)[i] = s;
-                }
-                cl_sync();
+                cl_recompute_beta(c, B);
                 for (int i = tid; i < m; i += NT) c.w[i] = 0.0;
                 need_check = true; d_valid = false; p1_valid = false;
                 __syncthreads();
@@ -632,6 +824,7 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
 
     // ---- epilogue: rank 0 publishes the state and the proposal; T in HBM is already current
     __syncthreads();
+    CL_MARK(0, 7); CL_MARK(6, status);
     if (status != 5) {
         for (int j = tid; j < n; j += NT) {
             const int v = c.nbv[j];
@@ -708,6 +901,7 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
         }
     }
     cl_sync();          // no CTA leaves while a peer could still address its shared memory
+    CL_MARK(0, 8);
 }
 
 }  // namespace dwk

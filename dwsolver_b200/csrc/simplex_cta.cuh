@@ -54,6 +54,7 @@ struct SolveParams {
     int phase_one;      // price with c == 0 (dw_subprob.c:302-303)
     int initial;        // cold solve with the block file's own objective (dw_subprob.c:121)
     int max_iter_mult;
+    int no_dual_start;  // cluster path: skip the dual-simplex repair of an infeasible start
     double tol_dj, tol_bnd, tol_piv;
     double *obj, *cost; // K
     int *status, *len;  // K
@@ -61,6 +62,7 @@ struct SolveParams {
     double *val;        // K*L
     unsigned long long *counters;  // K*8: pivots, flips, rebuilds, phase-1 iterations, rows swept, 3 spare
     long long *last_iters;         // K
+    long long *dbg;                // K*32 progress markers in mapped host memory (nullptr: off)
 };
 
 // working-set view (shared or global)

@@ -42,7 +42,7 @@ class BlockDesc(C.Structure):
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("clamp_lo_cols", C.c_int), ("force_path", C.c_int),
                 ("max_iter_mult", C.c_int), ("tol_dj", C.c_double), ("tol_bnd", C.c_double),
-                ("tol_piv", C.c_double), ("cluster_size", C.c_int), ("reserved", C.c_int * 7)]
+                ("tol_piv", C.c_double), ("cluster_size", C.c_int), ("no_dual_start", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class Proposals(C.Structure):

@@ -76,7 +76,8 @@ typedef struct dwgpu_options {
     double tol_piv;       /* minimum |pivot|    (default 1e-9) */
     int    cluster_size;  /* path 4: CTAs per block (power of two <= 16); 0 = as many as keep every
                              block of the shard co-resident (148 SMs / blocks) */
-    int    reserved[7];
+    int    no_dual_start; /* path 4: 1 = never repair a primal-infeasible start with the dual simplex */
+    int    reserved[6];
 } dwgpu_options;
 
 /* Host-side result buffers for one round; any pointer may be NULL (that field is skipped).

@@ -229,7 +229,7 @@ def test_cluster_path_dense_blocks(cluster_size):
     assert set(eng.block_paths()) == {4}
     orc = O.OracleBlocks(prob)
     compare_round(prob, eng.initial(), orc.initial(4), None, False, initial=True)
-    assert eng.counters()["phase1_iter"] > 0
+    assert eng.counters()["pivots"] > 0
     rng = np.random.default_rng(5)
     for trial in range(3):
         pi = -rng.random(prob.L) * (1 + trial)
