@@ -41,7 +41,8 @@ __host__ __device__ inline size_t cl_smem_bytes(int m, int n)
          + 4 * align16(sizeof(double) * (size_t)m)           // beta, w, rlo, rup
          + align16(sizeof(int) * (size_t)m) + align16(sizeof(int) * (size_t)n)   // head, nbv
          + align16((size_t)n)                                // cstat
-         + align16(sizeof(unsigned short) * (size_t)(m + 1));   // arow
+         + align16(sizeof(unsigned short) * (size_t)(m + 1)) // arow
+         + align16(sizeof(float) * (size_t)n);               // devex reference weights of the columns
 }
 // per block and rank: priced costs cs[n]
 __host__ __device__ inline size_t cl_ws_doubles(int n, int G) { return (size_t)G * (size_t)((n + 1) & ~1); }
@@ -60,6 +61,7 @@ struct Cl {
     int *head, *nbv;
     signed char *cstat;
     unsigned short *arow;
+    float *dvx;
 };
 
 struct ClShared {
@@ -321,7 +323,8 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
     c.head = (int *)sp;           sp += align16(sizeof(int) * (size_t)m);
     c.nbv = (int *)sp;            sp += align16(sizeof(int) * (size_t)n);
     c.cstat = (signed char *)sp;  sp += align16((size_t)n);
-    c.arow = (unsigned short *)sp;
+    c.arow = (unsigned short *)sp; sp += align16(sizeof(unsigned short) * (size_t)(m + 1));
+    c.dvx = (float *)sp;
     double *cs = B.ws + (size_t)rank * (size_t)((n + 1) & ~1);     // this CTA's copy of the priced costs
 
     // ---- state in (replicated) + priced objective (same arithmetic as the reference, dw_subprob.c:291-321)
@@ -334,6 +337,7 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
         const int v = B.nbv[j];
         c.nbv[j] = v;
         c.cstat[j] = B.vstat[v];
+        c.dvx[j] = 1.0f;
         double cj;
         if (P.initial) cj = B.c_file[j];
         else {
@@ -609,7 +613,8 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
             const bool ok = (st == ST_LO && dj < -tol_dj) || (st == ST_UP && dj > tol_dj) ||
                             (st == ST_FREE && fabs(dj) > tol_dj);
             if (ok) {
-                const double kj = bland ? -(double)c.nbv[j] : fabs(dj);
+                // devex pricing: d_j^2 over the reference weight (Bland: lowest variable id)
+                const double kj = bland ? -(double)c.nbv[j] : dj * dj / (double)c.dvx[j];
                 if (kj > key) { key = kj; q = j; }
             }
         }
@@ -788,20 +793,38 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
         __syncthreads();                      // rowp complete
         cl_arrive();                          // barrier #2, first half: this CTA has read row p
         // the price row rides along (phase 2: reduced costs; phase 1: frozen-weight prices)
-        if (dq != 0.0) {
+        {
             double2 *d2 = reinterpret_cast<double2 *>(c.drow);
             const double2 *rowp2 = reinterpret_cast<const double2 *>(c.rowp);
+            float2 *w2 = reinterpret_cast<float2 *>(c.dvx);
             const double cqd = dq * inv;
+            const double wq = (double)c.dvx[q];
+            const float wq_new = (float)fmax(wq * inv * inv, 1.0);
+            int wbig = 0;
+            __syncthreads();                  // every thread holds wq before dvx[q] is rewritten
             for (int j = tid; j < ((n + 1) >> 1); j += NT) {
                 const double2 ra = rowp2[j];
-                double2 r = d2[j];
                 const int jq = q - 2 * j;
-                r.x = fma(-dq, ra.x, r.x);
-                r.y = fma(-dq, ra.y, r.y);
-                if (jq == 0) r.x = cqd;
-                if (jq == 1) r.y = cqd;
-                d2[j] = r;
+                if (dq != 0.0) {
+                    double2 r = d2[j];
+                    r.x = fma(-dq, ra.x, r.x);
+                    r.y = fma(-dq, ra.y, r.y);
+                    if (jq == 0) r.x = cqd;
+                    if (jq == 1) r.y = cqd;
+                    d2[j] = r;
+                }
+                // devex: w_j = max(w_j, (alpha_pj / alpha_pq)^2 w_q); the leaving variable gets max(w_q / alpha_pq^2, 1)
+                float2 w = w2[j];
+                w.x = fmaxf(w.x, (float)(ra.x * ra.x * wq));
+                w.y = fmaxf(w.y, (float)(ra.y * ra.y * wq));
+                if (jq == 0) w.x = wq_new;
+                if (jq == 1) w.y = wq_new;
+                if (2 * j + 1 >= n) w.y = 1.0f;
+                wbig |= (w.x > 1e12f) | (w.y > 1e12f);
+                w2[j] = w;
             }
+            if (__syncthreads_or(wbig))       // new reference framework
+                for (int j = tid; j < n; j += NT) c.dvx[j] = 1.0f;
         }
         if (tid == 0) {
             const signed char ns = (lov == upv) ? ST_FIX : (target == lov ? ST_LO : ST_UP);
