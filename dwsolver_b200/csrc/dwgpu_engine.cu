@@ -449,8 +449,11 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
     // longest-processing-time-first inside each list (DWGPU_NO_REORDER=1 keeps the natural order)
     if (!initial && e->reorder) {
         auto order = [&](DevBuf<int> &d, size_t n) -> cudaError_t {
-            if (n < 512 || n > 8192) return cudaSuccess;
-            dwk::order_by_last_iterations_kernel<1024, 8192><<<1, 1024, 8192 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p);
+            if (n < 2048 || n > 8192) return cudaSuccess;          // pays off from ~3 waves of CTAs on
+            if (n <= 4096)
+                dwk::order_by_last_iterations_kernel<1024, 4096><<<1, 1024, 4096 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p);
+            else
+                dwk::order_by_last_iterations_kernel<1024, 8192><<<1, 1024, 8192 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p);
             e->last_launches++;
             return cudaGetLastError();
         };

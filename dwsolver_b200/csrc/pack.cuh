@@ -105,6 +105,12 @@ template <int NT, int CAP>
 __global__ void __launch_bounds__(NT) order_by_last_iterations_kernel(int *list, int count, const long long *last_iters)
 {
     extern __shared__ unsigned long long key[];          // CAP entries (64 KB at 8192: dynamic, opt-in)
+    // nothing to gain when the previous round was light everywhere (late DW rounds): keep the order
+    {
+        int heavy = 0;
+        for (int e = threadIdx.x; e < count; e += NT) heavy |= last_iters[list[e]] >= 16;
+        if (!__syncthreads_or(heavy)) return;
+    }
     for (int e = threadIdx.x; e < CAP; e += NT) {
         unsigned long long kv = 0ull;                       // padding sorts last
         if (e < count) {
