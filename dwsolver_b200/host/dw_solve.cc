@@ -1,0 +1,430 @@
+// dw_solve.cc — the Dantzig-Wolfe driver behind the reference's public API (include/dwsolver.h).
+//
+// Follows the reference's control flow (all paths relative to /root/reference):
+//   set-up            src/dw_solver.c:918-1016 (argument checks, option defaults), :154-184 (workers),
+//                     src/dw_subprob.c:100-269 (block set-up: 3000 clamp, c_k, COO D_k by column name)
+//   restricted master src/dw_solver.c:247-440 (rows made FX, su_/sl_/y_ columns, convexity rows = 1)
+//   Phase I           src/dw_solver.c:461-628 + src/dw_phases.c:54-304 (prices with c = 0, first-round
+//                     artificial sign fix :165-171, 201-217, stop on |obj| < 1e-6 or no column)
+//   Phase II          src/dw_solver.c:649-694 + src/dw_phases.c:321-554 (accept r_k - obj_k > 1e-6,
+//                     stop rule on master simplex progress :462-484)
+//   reconstruction    src/dw_rounding.c:115-168, 561-597 (x_k = sum lambda_{k,t} x_k^t, relaxed_solution)
+// What differs by design: the K subproblem threads, their mailboxes and the semaphore/cond-var round
+// (src/dw_subprob.c:415-448, src/dw_phases.c:338-350, 526-548) are ONE synchronous call into the GPU
+// engine per round (include/dwgpu.h); blocks are visited in index order, so runs are deterministic.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/dwgpu.h"
+#include "../../include/dwsolver.h"
+#include "lp_model.h"
+#include "master_lp.h"
+
+namespace {
+
+using namespace dwh;
+
+constexpr double kTolerance = 1e-6;     // TOLERANCE, src/dw.h:71
+constexpr double kDwInfinity = 1e6;     // DW_INFINITY, src/dw.h:72 (initial r_k)
+
+dw_stats_t g_stats;
+
+double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct BlockHost {
+    int m = 0, n = 0;
+    std::vector<int> a_rowptr, a_col;
+    std::vector<double> a_val, row_lb, row_ub, col_lb, col_ub, c_file, c_master;
+    std::vector<int> d_row, d_col;
+    std::vector<double> d_val;
+    std::vector<std::string> col_names;
+};
+
+double to_engine_bound(double v) { return v >= 1e300 ? DWGPU_INF : (v <= -1e300 ? -DWGPU_INF : v); }
+
+// CSR of the block's rows (duplicate entries of a row are summed, like glp_read_lp's coefficient merge)
+void build_block(const LpModel &sub, const LpModel &master, const std::vector<std::vector<std::pair<int, double>>> &mcols,
+                 BlockHost &b)
+{
+    b.m = sub.m(); b.n = sub.n();
+    std::vector<std::map<int, double>> rows(b.m);
+    for (size_t t = 0; t < sub.a_val.size(); ++t) rows[sub.a_row[t]][sub.a_col[t]] += sub.a_val[t];
+    b.a_rowptr.assign(b.m + 1, 0);
+    for (int i = 0; i < b.m; ++i) {
+        for (auto &e : rows[i]) { b.a_col.push_back(e.first); b.a_val.push_back(e.second); }
+        b.a_rowptr[i + 1] = (int)b.a_col.size();
+    }
+    b.row_lb.resize(b.m); b.row_ub.resize(b.m);
+    for (int i = 0; i < b.m; ++i) { b.row_lb[i] = to_engine_bound(sub.row_lb[i]); b.row_ub[i] = to_engine_bound(sub.row_ub[i]); }
+    b.col_lb.resize(b.n); b.col_ub.resize(b.n); b.c_file = sub.obj; b.c_master.assign(b.n, 0.0);
+    b.col_names = sub.col_names;
+    for (int j = 0; j < b.n; ++j) {
+        b.col_lb[j] = to_engine_bound(sub.col_lb[j]); b.col_ub[j] = to_engine_bound(sub.col_ub[j]);
+        auto it = master.col_index.find(sub.col_names[j]);
+        if (it == master.col_index.end())
+            throw std::runtime_error("block column '" + sub.col_names[j] + "' not found in the master problem");
+        const int mj = it->second;
+        b.c_master[j] = master.obj[mj];                              // src/dw_subprob.c:228
+        for (auto &e : mcols[mj]) {                                  // :230-253, raw coefficients
+            b.d_row.push_back(e.first); b.d_col.push_back(j); b.d_val.push_back(e.second);
+        }
+    }
+}
+
+struct Proposal {            // X[k][iter] of the reference (src/dw_phases.c:173-179, 427-433)
+    int k, iter;
+    std::vector<double> x;
+};
+
+}  // namespace
+
+extern "C" {
+
+void dw_options_init(dw_options_t *o)
+{
+    if (!o) return;
+    o->verbosity = DW_OUTPUT_NORMAL;       // src/dw_solver.c:60-75
+    o->mip_gap = 0.01;
+    o->max_phase1_iterations = 100;
+    o->max_phase2_iterations = 3000;
+    o->rounding_flag = 0;
+    o->integerize_flag = 0;
+    o->enforce_sub_integrality = 0;
+    o->print_timing_data = 0;
+    o->print_final_master = 0;
+    o->print_relaxed_sol = 1;
+    o->perturb = 0;
+    o->shift = 0.0;
+}
+
+const char *dw_version(void) { return "dwsolver-b200 0.1 (API of dwsolver 1.2.1; subproblems on sm_100a)"; }
+
+void dw_result_free(dw_result_t *r)
+{
+    if (!r) return;
+    std::free(r->x);
+    std::memset(r, 0, sizeof(*r));
+}
+
+void dw_last_stats(dw_stats_t *out) { if (out) *out = g_stats; }
+
+int dw_solve(const char *master_file, const char *const *subproblem_files, int num_subproblems, const dw_options_t *opts_in,
+             dw_result_t *result)
+{
+    if (!result) return DW_STATUS_ERR_BAD_ARGS;
+    std::memset(result, 0, sizeof(*result));
+    auto fail = [&](int code) { result->status = code; return code; };
+    if (!master_file || !subproblem_files || num_subproblems < 1) return fail(DW_STATUS_ERR_BAD_ARGS);
+    for (int k = 0; k < num_subproblems; ++k) if (!subproblem_files[k]) return fail(DW_STATUS_ERR_BAD_ARGS);
+    dw_options_t opt;
+    if (opts_in) opt = *opts_in; else dw_options_init(&opt);
+    const int verb = opt.verbosity;
+    std::memset(&g_stats, 0, sizeof(g_stats));
+    const double t_begin = now_s();
+    if (opt.enforce_sub_integrality || opt.integerize_flag || opt.rounding_flag) {
+        if (verb >= DW_OUTPUT_QUIET)
+            std::fprintf(stderr, "dwsolver-b200: integer options (-e, -i, -r) are not supported by the GPU path; solving the LP relaxation.\n");
+    }
+
+    // ---- read the problem -------------------------------------------------------------------------
+    const int K = num_subproblems;
+    LpModel master;
+    std::vector<BlockHost> blocks(K);
+    try {
+        master = read_lp_file(master_file);
+        std::vector<std::vector<std::pair<int, double>>> mcols(master.n());
+        for (size_t t = 0; t < master.a_val.size(); ++t) mcols[master.a_col[t]].emplace_back(master.a_row[t], master.a_val[t]);
+        for (int k = 0; k < K; ++k) {
+            LpModel sub = read_lp_file(subproblem_files[k]);
+            build_block(sub, master, mcols, blocks[k]);
+        }
+    } catch (const std::exception &e) {
+        if (verb >= DW_OUTPUT_QUIET) std::fprintf(stderr, "dwsolver-b200: %s\n", e.what());
+        return fail(DW_STATUS_ERR_FILE);
+    }
+    const int L = master.m();
+    g_stats.seconds_read = now_s() - t_begin;
+
+    // ---- GPU engine: replaces pthread_create(subproblem_thread) x K (src/dw_solver.c:154-184) --------
+    std::vector<dwgpu_block_desc> desc(K);
+    for (int k = 0; k < K; ++k) {
+        BlockHost &b = blocks[k];
+        dwgpu_block_desc &d = desc[k];
+        d.m = b.m; d.n = b.n;
+        d.a_rowptr = b.a_rowptr.data(); d.a_col = b.a_col.data(); d.a_val = b.a_val.data();
+        d.row_lb = b.row_lb.data(); d.row_ub = b.row_ub.data(); d.col_lb = b.col_lb.data(); d.col_ub = b.col_ub.data();
+        d.c_file = b.c_file.data(); d.c_master = b.c_master.data();
+        d.d_nnz = (int)b.d_val.size(); d.d_row = b.d_row.data(); d.d_col = b.d_col.data(); d.d_val = b.d_val.data();
+    }
+    dwgpu_options gopt;
+    dwgpu_options_init(&gopt);
+    if (const char *dev = std::getenv("DWSOLVER_DEVICE")) gopt.device = std::atoi(dev);
+    dwgpu_engine *eng = nullptr;
+    if (dwgpu_create(K, L, desc.data(), &gopt, &eng) != 0) {
+        std::fprintf(stderr, "dwsolver-b200: cannot create the GPU engine: %s\n", dwgpu_last_error());
+        return fail(DW_STATUS_ERR_INTERNAL);
+    }
+    struct EngineGuard { dwgpu_engine *e; ~EngineGuard() { dwgpu_destroy(e); } } guard{eng};
+
+    // ---- restricted master (src/dw_solver.c:247-440) ---------------------------------------------------
+    MasterLP M(L + K);
+    std::vector<int> art_col(L, -1);
+    std::vector<char> is_art;
+    auto add = [&](const std::string &name, double cost, double ub, std::vector<int> idx, std::vector<double> val, bool art) {
+        const int j = M.add_col(name, cost, ub, idx, val);
+        if ((int)is_art.size() <= j) is_art.resize(j + 1, 0);
+        is_art[j] = art;
+        return j;
+    };
+    for (int i = 0; i < L; ++i) {
+        const double lb = master.row_lb[i], ub = master.row_ub[i];
+        const std::string id = std::to_string(i + 1);
+        if (lb == ub) {                                          // FX: artificial only (:321-336)
+            M.set_rhs(i, ub);
+            art_col[i] = add("y_" + id, 1.0, kInf, {i}, {ub < 0.0 ? -1.0 : 1.0}, true);
+        } else if (lb <= -1e300 && ub < 1e300) {                 // UP: su_ (+1) and y_ (-1) (:338-375)
+            M.set_rhs(i, ub);
+            add("su_" + id, 0.0, kInf, {i}, {1.0}, false);
+            art_col[i] = add("y_" + id, 1.0, kInf, {i}, {-1.0}, true);
+        } else if (ub >= 1e300 && lb > -1e300) {                 // LO: sl_ (-1) and y_ (+1) (:381-419)
+            M.set_rhs(i, lb);
+            add("sl_" + id, 0.0, kInf, {i}, {-1.0}, false);
+            art_col[i] = add("y_" + id, 1.0, kInf, {i}, {1.0}, true);
+        } else {
+            std::fprintf(stderr, "dwsolver-b200: linking row %d is free or ranged, which the reference does not support (src/dw_solver.c:420-425)\n", i + 1);
+            return fail(DW_STATUS_ERR_INTERNAL);
+        }
+    }
+    for (int k = 0; k < K; ++k) M.set_rhs(L + k, 1.0);
+    const bool need_phase1 = L > 0;
+
+    // ---- per-round plumbing ---------------------------------------------------------------------------
+    std::vector<double> r(K, kDwInfinity), pi(std::max(L, 1), 0.0);
+    std::vector<Proposal> X;
+    std::vector<std::pair<int, double>> remembered;              // Phase I: (column, true cost) (:143-144, 163)
+    std::vector<double> xbuf;
+    int iter = 0;
+    dwgpu_packed pk;
+    auto consume = [&](bool phase_one, int *n_added) -> int {
+        int added = 0;
+        for (int k = 0; k < K; ++k) {
+            if (pk.status[k] == DWGPU_UNBND) {
+                std::fprintf(stderr, "dwsolver-b200: subproblem %d is unbounded; unbounded subproblems are not supported (src/dw_phases.c:111-115)\n", k);
+                return DW_STATUS_ERR_UNBOUNDED;
+            }
+            if (!(r[k] - pk.obj[k] > kTolerance)) continue;      // src/dw_phases.c:108, 358
+            std::vector<int> idx;
+            std::vector<double> val;
+            for (int t = pk.colptr[k]; t < pk.colptr[k + 1]; ++t) { idx.push_back(pk.ind[t] - 1); val.push_back(pk.val[t]); }
+            idx.push_back(L + k); val.push_back(1.0);
+            const std::string name = "lambda_" + std::to_string(k) + "_" + std::to_string(iter);
+            const int j = add(name, phase_one ? 0.0 : pk.cost[k], 1.0, idx, val, false);
+            if (phase_one) remembered.emplace_back(j, pk.cost[k]);
+            Proposal p; p.k = k; p.iter = iter; p.x.resize(blocks[k].n);
+            if (dwgpu_fetch_x(eng, k, p.x.data()) != 0) return DW_STATUS_ERR_INTERNAL;
+            X.push_back(std::move(p));
+            ++added;
+        }
+        *n_added = added;
+        return 0;
+    };
+    auto solve_master = [&]() {
+        const double t0 = now_s();
+        const int rc = M.solve();
+        g_stats.seconds_master += now_s() - t0;
+        for (int i = 0; i < L; ++i) pi[i] = M.row_dual(i);
+        for (int k = 0; k < K; ++k) r[k] = M.row_dual(L + k);
+        return rc;
+    };
+    auto banner = [&]() {
+        if (verb >= DW_OUTPUT_NORMAL) {
+            std::printf("################################################\n");
+            std::printf("####  Master objective value = %e \n", M.obj_val());
+            std::printf("################################################\n");
+        }
+    };
+    auto round = [&](bool phase_one) -> int {
+        const double t0 = now_s();
+        // with r given the engine ships only the columns the acceptance test below will take
+        const int rc = dwgpu_iterate_packed(eng, pi.data(), phase_one ? 1 : 0, r.data(), &pk);
+        g_stats.seconds_subproblems += now_s() - t0;
+        return rc;
+    };
+
+    // first proposals: cold solve with the file objective, always accepted (r = 1e6) (src/dw_subprob.c:121-122, 184)
+    {
+        const double t0 = now_s();
+        if (dwgpu_initial_solve_packed(eng, &pk) != 0) {
+            std::fprintf(stderr, "dwsolver-b200: %s\n", dwgpu_last_error());
+            return fail(DW_STATUS_ERR_INTERNAL);
+        }
+        g_stats.seconds_subproblems += now_s() - t0;
+    }
+    for (int k = 0; k < K; ++k)
+        if (pk.status[k] == DWGPU_NOFEAS) {
+            if (verb >= DW_OUTPUT_QUIET) std::printf("Subproblem %d is infeasible.\n", k);
+        }
+
+    int status = DW_STATUS_OK;
+    int added = 0;
+    // ---- Phase I (src/dw_solver.c:461-628) ---------------------------------------------------------------
+    if (need_phase1) {
+        M.set_obj_const(0.0);                                    // shift zeroed during Phase I (:463)
+        bool first = true, feasible = false;
+        int p1 = 0;
+        for (; p1 < opt.max_phase1_iterations; ++p1) {
+            const int n_before = M.cols();
+            int rc = consume(true, &added);
+            if (rc) return fail(rc);
+            if (first) {                                         // src/dw_phases.c:165-171, 201-217
+                std::vector<double> acc(L, 0.0);
+                for (int j = n_before; j < M.cols(); ++j) {
+                    const auto &ix = M.col_idx(j);
+                    const auto &vv = M.col_val(j);
+                    for (size_t t = 0; t + 1 < ix.size(); ++t) acc[ix[t]] += vv[t];
+                }
+                for (int i = 0; i < L; ++i)
+                    if (M.rhs(i) - acc[i] < 0.0 && art_col[i] >= 0) M.set_coef(art_col[i], 0, -1.0);
+                first = false;
+            }
+            const int mrc = solve_master();
+            ++iter;
+            ++g_stats.phase1_iterations;
+            if (verb >= DW_OUTPUT_NORMAL) {
+                std::printf("################################################\n");
+                std::printf("####  Master objective value = %.8e \n", M.obj_val());      // src/dw_phases.c:250
+                std::printf("################################################\n");
+            }
+            if (mrc != 0) { std::fprintf(stderr, "dwsolver-b200: Phase I master LP failed (code %d)\n", mrc); return fail(DW_STATUS_ERR_INTERNAL); }
+            if (std::fabs(M.obj_val()) < kTolerance) { feasible = true; break; }     // :509-514
+            if (added == 0) break;                                                   // :516-521
+            if (round(true) != 0) { std::fprintf(stderr, "dwsolver-b200: %s\n", dwgpu_last_error()); return fail(DW_STATUS_ERR_INTERNAL); }
+        }
+        if (!feasible) {
+            if (p1 >= opt.max_phase1_iterations) {
+                if (verb >= DW_OUTPUT_QUIET) std::printf("Phase I iteration limit reached.\n");
+                status = DW_STATUS_ERR_PHASE1_LIMIT;
+            } else {
+                if (verb >= DW_OUTPUT_QUIET) std::printf("Problem is infeasible.\n");
+                status = DW_STATUS_ERR_INFEASIBLE;
+            }
+        }
+        // leave Phase I: drop the artificials, install the remembered costs, re-solve (:535-562)
+        {
+            std::vector<char> flag(M.cols(), 0);
+            std::vector<int> remap(M.cols(), -1);
+            int w = 0;
+            for (int j = 0; j < M.cols(); ++j) { flag[j] = is_art[j]; if (!flag[j]) remap[j] = w++; }
+            M.del_cols(flag);
+            std::vector<char> na(w, 0);
+            is_art.swap(na);
+            for (auto &e : remembered) if (remap[e.first] >= 0) M.set_cost(remap[e.first], e.second);
+            remembered.clear();
+        }
+        M.set_obj_const(opt.shift);                              // :568
+        const int mrc = solve_master();
+        ++iter;                                                  // :618 (the drained round is simply not launched)
+        if (mrc == 1 && status == DW_STATUS_OK) status = DW_STATUS_ERR_INFEASIBLE;
+    } else {
+        M.set_obj_const(opt.shift);
+        int rc = consume(false, &added);
+        if (rc) return fail(rc);
+        solve_master();
+        ++iter;
+    }
+
+    // ---- Phase II (src/dw_solver.c:649-694, stop rule src/dw_phases.c:462-484) --------------------------------
+    if (status == DW_STATUS_OK) {
+        long long simplex_iterations = 0;                        // per solve (the reference's is function-static)
+        int p2 = 0;
+        bool done = false;
+        for (; p2 < opt.max_phase2_iterations && !done; ++p2) {
+            if (round(false) != 0) { std::fprintf(stderr, "dwsolver-b200: %s\n", dwgpu_last_error()); return fail(DW_STATUS_ERR_INTERNAL); }
+            int rc = consume(false, &added);
+            if (rc) return fail(rc);
+            const int mrc = solve_master();
+            ++iter;
+            if (mrc == 2) { status = DW_STATUS_ERR_UNBOUNDED; break; }
+            if (mrc != 0) { std::fprintf(stderr, "dwsolver-b200: master LP failed (code %d)\n", mrc); return fail(DW_STATUS_ERR_INTERNAL); }
+            const bool prog = simplex_iterations < M.it_cnt();
+            if (prog) {
+                simplex_iterations = M.it_cnt();
+                if (added == 0 && verb >= DW_OUTPUT_NORMAL) std::printf("No columns added, but simplex made progress.\n");
+            } else if (added > 0) {
+                if (p2 != 0) {
+                    if (verb >= DW_OUTPUT_NORMAL)
+                        std::printf("There was no simplex progress made despite columns being added. Finishing now.\n");
+                    done = true;
+                }
+            } else {
+                if (verb >= DW_OUTPUT_NORMAL) std::printf("I think we've converged on an optimum.\n");
+                done = true;
+            }
+            banner();
+        }
+        if (!done && status == DW_STATUS_OK && p2 >= opt.max_phase2_iterations) status = DW_STATUS_ERR_PHASE2_LIMIT;
+    }
+    if (verb >= DW_OUTPUT_NORMAL) {                              // src/dw_solver.c:721
+        std::printf("################################################\n");
+        std::printf("####  Master objective value = %e \n", M.obj_val());
+        std::printf("################################################\n");
+    }
+
+    // ---- results (src/dw_solver.c:877-889) ---------------------------------------------------------------------
+    result->objective_value = M.obj_val();
+    result->num_vars = M.cols();
+    result->x = (double *)std::malloc(sizeof(double) * (size_t)std::max(M.cols(), 1));
+    if (!result->x) return fail(DW_STATUS_ERR_INTERNAL);
+    for (int j = 0; j < M.cols(); ++j) result->x[j] = M.col_prim(j);
+
+    // ---- relaxed_solution: x_k = sum_t lambda_{k,t} x_k^t (src/dw_rounding.c:115-168, 561-597) -------------------
+    if (opt.print_relaxed_sol) {
+        std::vector<std::vector<double>> xs(K);
+        for (int k = 0; k < K; ++k) xs[k].assign(blocks[k].n, 0.0);
+        std::map<std::pair<int, int>, const Proposal *> by_id;
+        for (auto &p : X) by_id[{p.k, p.iter}] = &p;
+        for (int j = 0; j < M.cols(); ++j) {                     // every column is scanned (the reference skips the first L)
+            const double v = M.col_prim(j);
+            if (v == 0.0) continue;
+            int k = -1, t = -1;
+            if (std::sscanf(M.name(j).c_str(), "lambda_%d_%d", &k, &t) != 2) continue;
+            auto it = by_id.find({k, t});
+            if (it == by_id.end()) continue;
+            const std::vector<double> &x = it->second->x;
+            for (size_t c = 0; c < x.size(); ++c) xs[k][c] += v * x[c];
+        }
+        FILE *f = std::fopen("relaxed_solution", "w");
+        if (f) {
+            for (int k = 0; k < K; ++k)
+                for (int c = 0; c < blocks[k].n; ++c) std::fprintf(f, "%s\t%f\n", blocks[k].col_names[c].c_str(), xs[k][c]);
+            std::fclose(f);
+        } else if (verb >= DW_OUTPUT_QUIET) {
+            std::fprintf(stderr, "dwsolver-b200: cannot write relaxed_solution\n");
+        }
+    }
+
+    dwgpu_counters cnt;
+    if (dwgpu_get_counters(eng, &cnt) == 0) g_stats.sub_pivots = cnt.pivots + cnt.flips;
+    g_stats.dw_iterations = iter;
+    g_stats.master_columns = M.cols();
+    g_stats.seconds_total = now_s() - t_begin;
+    if (opt.print_timing_data && verb >= DW_OUTPUT_SILENT) {
+        std::printf("Total wall time: %.6f s (read %.6f, subproblems on the GPU %.6f, master %.6f); %d DW iterations, %lld subproblem pivots\n",
+                    g_stats.seconds_total, g_stats.seconds_read, g_stats.seconds_subproblems, g_stats.seconds_master,
+                    g_stats.dw_iterations, g_stats.sub_pivots);
+    }
+    return fail(status);
+}
+
+}  // extern "C"

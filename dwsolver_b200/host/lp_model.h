@@ -1,12 +1,13 @@
 // lp_model.h — in-memory LP as read from a CPLEX-LP text file, and the block-angular assembly.
 #pragma once
+#include <limits>
 #include <string>
 #include <unordered_map>
 #include <vector>
 
 namespace dwh {
 
-constexpr double kInf = 1e300 * 1e300;   // IEEE +inf
+constexpr double kInf = std::numeric_limits<double>::infinity();
 
 struct LpModel {
     std::vector<std::string> col_names, row_names;

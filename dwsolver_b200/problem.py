@@ -370,13 +370,15 @@ def _fmt(v: float) -> str:
     return repr(float(v))
 
 
-def write_lp(model: LPModel, path: str, name: str = "obj") -> None:
-    """Emit an LP file in the subset above (our own layout: one term per line chunk)."""
+def write_lp(model: LPModel, path: str, name: str = "obj", obj_all: bool = False) -> None:
+    """Emit an LP file in the subset above (our own layout: one term per line chunk).
+    ``obj_all`` lists every column in the objective (zero coefficients included) so that a column
+    without any other occurrence still exists for a reader."""
     rowptr, colidx, vals = model.csr()
     with open(path, "w") as fh:
         fh.write("Maximize\n" if model.maximize else "Minimize\n")
         terms = [f"{'+' if model.obj[j] >= 0 else '-'} {_fmt(abs(model.obj[j]))} {model.col_names[j]}"
-                 for j in range(model.n) if model.obj[j] != 0.0]
+                 for j in range(model.n) if obj_all or model.obj[j] != 0.0]
         if not terms and model.n:
             terms = [f"+ 0 {model.col_names[0]}"]
         fh.write(f" {name}:")
@@ -561,6 +563,45 @@ def load_guidefile(path: str) -> BlockAngularLP:
     master, subs, shift = read_guidefile(path)
     return assemble(read_lp(master), [read_lp(s) for s in subs], shift=shift,
                     name=os.path.basename(os.path.dirname(os.path.abspath(path))))
+
+
+def write_block_angular(p: BlockAngularLP, directory: str) -> dict:
+    """The instance in the reference's input format (dw_main.c:213-259): one CPLEX-LP file per block
+    (its own rows, bounds and file objective), the master LP file (linking rows over all block columns,
+    costs c_k) and the guidefile listing them.  Returns the paths.  Column names are the blocks'
+    ``col_names`` or ``x_<k>_<j>``."""
+    os.makedirs(directory, exist_ok=True)
+    names = [list(b.col_names) if b.col_names is not None else [f"x_{k}_{j}" for j in range(b.n)]
+             for k, b in enumerate(p.blocks)]
+    subs = []
+    for k, b in enumerate(p.blocks):
+        rows = np.repeat(np.arange(b.m, dtype=np.int32), np.diff(b.a_rowptr))
+        sub = LPModel(col_names=names[k], row_names=[f"n_{k}_{i}" for i in range(b.m)], obj=np.asarray(b.c_file, float),
+                      obj_const=0.0, a_rows=rows, a_cols=np.asarray(b.a_col, np.int32), a_vals=np.asarray(b.a_val, float),
+                      row_lb=np.asarray(b.row_lb, float), row_ub=np.asarray(b.row_ub, float),
+                      col_lb=np.asarray(b.col_lb, float), col_ub=np.asarray(b.col_ub, float), maximize=False)
+        path = os.path.join(directory, f"sub{k + 1}.lp")
+        write_lp(sub, path, obj_all=True)
+        subs.append(path)
+    off = np.concatenate([[0], np.cumsum([b.n for b in p.blocks])])
+    m_rows = np.concatenate([np.asarray(b.d_row, np.int32) for b in p.blocks]) if p.blocks else np.zeros(0, np.int32)
+    m_cols = np.concatenate([np.asarray(b.d_col, np.int32) + off[k] for k, b in enumerate(p.blocks)]).astype(np.int32)
+    m_vals = np.concatenate([np.asarray(b.d_val, float) for b in p.blocks])
+    link_names = list(p.link_names) if getattr(p, "link_names", None) else [f"cap_{i}" for i in range(p.L)]
+    master = LPModel(col_names=[nm for ns in names for nm in ns], row_names=link_names,
+                     obj=np.concatenate([np.asarray(b.c_master, float) for b in p.blocks]), obj_const=0.0,
+                     a_rows=m_rows, a_cols=m_cols, a_vals=m_vals, row_lb=np.asarray(p.link_lb, float),
+                     row_ub=np.asarray(p.link_ub, float), col_lb=np.zeros(int(off[-1])), col_ub=np.full(int(off[-1]), INF),
+                     maximize=False)
+    mpath = os.path.join(directory, "master.lp")
+    write_lp(master, mpath, obj_all=True)
+    gpath = os.path.join(directory, "guidefile")
+    with open(gpath, "w") as fh:
+        fh.write(f"{p.K}\n")
+        for s_ in subs:
+            fh.write(os.path.basename(s_) + "\n")
+        fh.write("master.lp\nmonolithic.lp\n" + repr(float(p.shift)) + "\n")
+    return {"master": mpath, "subs": subs, "guidefile": gpath}
 
 
 # --------------------------------------------------------------------------------------

@@ -1,0 +1,184 @@
+"""Host side of the drop-in (dwsolver_b200/host -> libdwsolver_b200.so, bin/dwsolver).
+
+CPU part: the C++ CPLEX-LP reader against the package's reader on LP text written from every golden
+example, the master LP solver against HiGHS, the public symbols and struct layouts of
+include/dwsolver.h (the reference's src/dw_solver.h:88-183).
+GPU part (-m gpu): the reference's own test strategy (tests/dw-tests.sh) — run the CLI on a guidefile
+and compare the `Master objective value` banner / the sorted relaxed_solution with the goldens; and
+tests/test_lib_api.c — dw_solve() through the C API, bad-argument and missing-file status codes.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from scipy.optimize import linprog
+
+from conftest import EXAMPLES, ROOT, load_example
+from dwsolver_b200 import problem as P
+
+LIB = os.path.join(ROOT, "dwsolver_b200", "lib", "libdwsolver_b200.so")
+CLI = os.path.join(ROOT, "dwsolver_b200", "bin", "dwsolver")
+c_dp, c_ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+
+
+class DwOptions(C.Structure):          # include/dwsolver.h, same order as src/dw_solver.h:105-118
+    _fields_ = [("verbosity", C.c_int), ("mip_gap", C.c_double), ("max_phase1_iterations", C.c_int),
+                ("max_phase2_iterations", C.c_int), ("rounding_flag", C.c_int), ("integerize_flag", C.c_int),
+                ("enforce_sub_integrality", C.c_int), ("print_timing_data", C.c_int), ("print_final_master", C.c_int),
+                ("print_relaxed_sol", C.c_int), ("perturb", C.c_int), ("shift", C.c_double)]
+
+
+class DwResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("objective_value", C.c_double), ("num_vars", C.c_int), ("x", c_dp)]
+
+
+def lib():
+    if not os.path.exists(LIB):
+        pytest.fail(f"{LIB} is missing: run __graft_entry__.build()")
+    L = C.CDLL(LIB)
+    L.dw_version.restype = C.c_char_p
+    L.dw_solve.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(DwOptions), C.POINTER(DwResult)]
+    return L
+
+
+def write_example(prob, d):
+    """LP text + guidefile of a BlockAngularLP (the reference's input format) into directory d."""
+    paths = P.write_block_angular(prob, str(d))
+    return paths
+
+
+def test_public_api_symbols_and_defaults():
+    L = lib()
+    for name in ("dw_options_init", "dw_solve", "dw_result_free", "dw_version", "dw_last_stats"):
+        assert hasattr(L, name)
+    o = DwOptions()
+    L.dw_options_init(C.byref(o))
+    assert (o.verbosity, o.max_phase1_iterations, o.max_phase2_iterations, o.print_relaxed_sol) == (5, 100, 3000, 1)
+    assert (o.mip_gap, o.shift, o.print_final_master, o.perturb) == (0.01, 0.0, 0, 0)
+    assert C.sizeof(DwResult) == 32 and C.sizeof(DwOptions) == 64
+    assert b"dwsolver" in L.dw_version()
+
+
+def test_bad_arguments_and_missing_files():
+    L = lib()
+    res = DwResult()
+    assert L.dw_solve(None, None, 0, None, C.byref(res)) == 1          # DW_STATUS_ERR_BAD_ARGS
+    arr = (C.c_char_p * 1)(b"/nonexistent/sub.lp")
+    o = DwOptions()
+    L.dw_options_init(C.byref(o))
+    o.verbosity = -1
+    assert L.dw_solve(b"/nonexistent/master.lp", arr, 1, C.byref(o), C.byref(res)) == 2   # DW_STATUS_ERR_FILE
+    assert res.status == 2
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_cpp_lp_reader_matches_package_reader(name, tmp_path):
+    L = lib()
+    prob = load_example(name)
+    paths = write_example(prob, tmp_path)
+    for path in [paths["master"]] + paths["subs"]:
+        ref = P.read_lp(path)
+        dims = (C.c_int * 3)()
+        assert L.dwhost_lp_dims(path.encode(), dims) == 0
+        m, n, nnz = dims[0], dims[1], dims[2]
+        assert (m, n, nnz) == (ref.m, ref.n, len(ref.a_vals))
+        obj, lb, ub = np.zeros(n), np.zeros(n), np.zeros(n)
+        rlb, rub = np.zeros(m), np.zeros(m)
+        ar, ac, av = np.zeros(nnz, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
+        names = C.create_string_buffer(64 * (n + 1))
+        mx = C.c_int(0)
+        d = lambda a: a.ctypes.data_as(c_dp)
+        i = lambda a: a.ctypes.data_as(c_ip)
+        assert L.dwhost_lp_read(path.encode(), d(obj), d(lb), d(ub), d(rlb), d(rub), i(ar), i(ac), d(av), names,
+                                len(names), C.byref(mx)) == 0
+        assert names.value.decode().split("\n")[:-1] == list(ref.col_names)
+        assert np.array_equal(obj, ref.obj) and np.array_equal(lb, ref.col_lb) and np.array_equal(ub, ref.col_ub)
+        assert np.array_equal(rlb, ref.row_lb) and np.array_equal(rub, ref.row_ub)
+        assert np.array_equal(ar, ref.a_rows) and np.array_equal(ac, ref.a_cols) and np.array_equal(av, ref.a_vals)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_master_lp_matches_highs(seed):
+    """random equality-form LPs with boxed and unboxed columns, solved cold and with a warm second stage"""
+    L = lib()
+    rng = np.random.default_rng(seed)
+    m, n = 12 + 3 * seed, 40 + 10 * seed
+    A = sp.random(m, n, density=0.3, random_state=seed, data_rvs=lambda k: rng.integers(-4, 5, k).astype(float)).tocsc()
+    A.eliminate_zeros()
+    x0 = rng.random(n)
+    ub = np.where(rng.random(n) < 0.5, 1.0, 1e300)
+    rhs = A @ x0
+    cost = rng.integers(-5, 6, n).astype(float)
+    cost[ub >= 1e300] = np.abs(cost[ub >= 1e300]) + 1.0          # keep it bounded
+    ref = linprog(cost, A_eq=A, b_eq=rhs, bounds=[(0, None if u >= 1e300 else u) for u in ub], method="highs")
+    assert ref.status == 0
+    for n_first in (0, n // 2):
+        x, y = np.zeros(n), np.zeros(m)
+        obj, its = C.c_double(0), C.c_longlong(0)
+        cp = A.indptr.astype(np.int32)
+        ix = A.indices.astype(np.int32)
+        rc = L.dwhost_master_solve(m, n, cp.ctypes.data_as(c_ip), ix.ctypes.data_as(c_ip), A.data.ctypes.data_as(c_dp),
+                                   cost.ctypes.data_as(c_dp), ub.ctypes.data_as(c_dp), rhs.ctypes.data_as(c_dp), n_first,
+                                   x.ctypes.data_as(c_dp), y.ctypes.data_as(c_dp), C.byref(obj), C.byref(its))
+        assert rc == 0
+        assert abs(obj.value - ref.fun) <= 1e-8 * (1 + abs(ref.fun))
+        assert np.abs(A @ x - rhs).max() <= 1e-8 and x.min() >= -1e-9 and (x - np.minimum(ub, 1e300)).max() <= 1e-9
+        d = cost - A.T @ y                                        # dual feasibility of the returned duals
+        at_lb, at_ub = x <= 1e-9, (ub < 1e300) & (x >= ub - 1e-9)
+        assert d[at_lb & ~at_ub].min(initial=0.0) >= -1e-7 and d[at_ub & ~at_lb].max(initial=0.0) <= 1e-7
+
+
+def run_cli(tmp_path, prob, *flags):
+    write_example(prob, tmp_path)
+    return subprocess.run([CLI, "-g", "guidefile", *flags], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_cli_reaches_reference_objective(name, golden, tmp_path):
+    """tests/dw-tests.sh: `dwsolver -g guidefile`, last `Master objective value` banner (7 significant digits)"""
+    prob = load_example(name)
+    out = run_cli(tmp_path, prob)
+    assert out.returncode == 0, out.stderr
+    lines = [ln for ln in out.stdout.splitlines() if "Master objective value" in ln]
+    assert lines
+    want = golden["objective"][name]
+    got = float(lines[-1].split("=")[1])
+    assert abs(got - want) <= 1e-6 * (1 + abs(want))
+    if name in golden["objective_literal"]:
+        assert lines[-1].split("=")[1].strip() == golden["objective_literal"][name]
+    sol = golden["relaxed_solution"].get(name)
+    if sol:                                                       # the five deterministic fixtures
+        rs = dict(ln.split("\t") for ln in open(tmp_path / "relaxed_solution").read().splitlines())
+        for nm, v in sol.items():
+            assert "%f" % (float(rs[nm]) + 0.0) == "%f" % v, (nm, rs[nm], v)
+
+
+@pytest.mark.gpu
+def test_dw_solve_api_on_synthetic_mcf(tmp_path):
+    """tests/test_lib_api.c: dw_solve through the C API (twice in one process), objective vs the monolithic LP"""
+    from highs_util import solve_monolithic
+    L = lib()
+    prob = P.gen_mcf(40, 16, 40, 8, seed=3)
+    paths = write_example(prob, tmp_path)
+    ref = solve_monolithic(prob)["objective"]
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        for _ in range(2):
+            o = DwOptions()
+            L.dw_options_init(C.byref(o))
+            o.verbosity = -1
+            subs = (C.c_char_p * prob.K)(*[s.encode() for s in paths["subs"]])
+            res = DwResult()
+            rc = L.dw_solve(paths["master"].encode(), subs, prob.K, C.byref(o), C.byref(res))
+            assert rc == 0 and res.status == 0
+            assert abs(res.objective_value - ref) <= 1e-7 * (1 + abs(ref))
+            assert res.num_vars > 0 and np.isfinite(res.x[0])
+            L.dw_result_free(C.byref(res))
+            assert not res.x
+    finally:
+        os.chdir(cwd)
