@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--cpu-blocks", type=int, default=0, help="blocks in the CPU arm's sample (0 = auto)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--single-pass", action="store_true",
+                    help="time e2e only and take the kernel times from that pass (config C: a step takes minutes)")
     return ap.parse_args()
 
 
@@ -160,7 +162,11 @@ def main():
     R = len(phases)
     workload = (f"synthetic {'multicommodity flow' if cfg['kind'] == 'mcf' else 'dense'} config {args.config}: "
                 f"{K_total} blocks x {m} rows x {n} cols, {L} linking rows (seed {cfg['seed']}); "
-                f"step = cold solve + {R} priced rounds of a recorded DW run")
+                f"step = cold solve + {R} priced rounds of " +
+                ("a recorded DW run" if np.isfinite(dw_objective) else "a synthetic, shrinking dual sequence (tests/golden/traj_C.npz)"))
+    if args.config == "C":
+        args.single_pass = True
+        args.no_cpu_baseline = True
     W, S = args.warmup, args.steps
     cores = os.cpu_count() or 1
     cpu_note = ("pthreads + this repo's CPU restatement (oracle/), NOT GLPK: GLPK is absent from the reference "
@@ -268,7 +274,7 @@ def main():
         return 8 + K_loc * (8 + 8 + 4) + (K_loc + 1) * 4 + pk["nnz"] * 12
 
     # ---- one step, end to end: host buffers in, host buffers out, every round
-    def step_e2e():
+    def step_e2e(kern_acc=None):
         eng.reset(sptr if dist is not None else 0)    # single GPU: the engine's own stream end to end
         launches[0] = 1
         d2h[0] = 0
@@ -276,10 +282,14 @@ def main():
             pk = eng.initial_solve_packed()                        # kernels + packed proposals to pinned host
             launches[0] += eng.last_launch_count()
             d2h[0] += packed_bytes(pk)
+            if kern_acc is not None:
+                kern_acc.append(eng.last_kernel_ms())
             for r in range(R):
                 pk = eng.iterate_packed(pis[r], phases[r])         # H2D pi_r, kernels, packed proposals back
                 launches[0] += eng.last_launch_count()
                 d2h[0] += packed_bytes(pk)
+                if kern_acc is not None:
+                    kern_acc.append(eng.last_kernel_ms())
             last_status[0] = np.array(pk["status"])
         else:
             eng.initial_solve_device(sptr)
@@ -318,27 +328,42 @@ def main():
         return np.array([c["pivots"], c["flips"], c["rebuilds"], c["rows_swept"], c["cells_swept"]], dtype=np.float64)
 
     # =========================== e2e ===========================
+    single = args.single_pass and dist is None
     e2e_time, e2e_cnt = 0.0, np.zeros(5)
+    sp_kern, sp_kcnt, sp_ksum = [], np.zeros(5), 0.0
+    sp_clocks = ClockSampler(local_rank) if single else None
     for step in range(W + S):
         flush_buf.fill_(1)
         barrier()
+        if single and step == W:
+            sp_clocks.start()
         c0 = count()
         t0 = time.perf_counter()
-        step_e2e()
+        kacc = [] if single else None
+        step_e2e(kacc)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if step >= W:
             e2e_time += dt
             e2e_cnt += count() - c0
+            if single:
+                sp_kern, sp_kcnt = kacc, count() - c0
+                sp_ksum += float(np.sum(kacc)) * 1e-3
     status_ok = bool((last_status[0] == 5).all()) if dist is None else bool((h_pin["status"].numpy() == 5).all()) if rank == 0 else True
 
     # =========================== device only ===========================
+    if single:
+        # one pass only: `value` is pivots over the summed CUDA-event time of the solve kernels of that pass
+        clk = sp_clocks.stop()
+        dev_cnt, t_dev = e2e_cnt.copy(), sp_ksum
+        kern, kcnt = np.array(sp_kern), sp_kcnt
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + S)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + S)]
-    dev_cnt = np.zeros(5)
-    kern = []
+    if not single:
+        dev_cnt = np.zeros(5)
+        kern = []
     clocks = ClockSampler(local_rank)
-    for step in range(W + S):
+    for step in range(0 if single else W + S):
         flush_buf.fill_(1)
         barrier()
         if step == W:
@@ -350,11 +375,12 @@ def main():
         torch.cuda.synchronize()
         if step >= W:
             dev_cnt += count() - c0
-    clk = clocks.stop()
-    t_dev = sum(ev0[i].elapsed_time(ev1[i]) for i in range(W, W + S)) * 1e-3
+    if not single:
+        clk = clocks.stop()
+        t_dev = sum(ev0[i].elapsed_time(ev1[i]) for i in range(W, W + S)) * 1e-3
     # kernel-only time of the dominant kernel: separate pass with a sync after every launch (the
     # per-launch events live inside the engine), same work, not part of `value`
-    for step in range(2):
+    for step in range(0 if single else 2):
         kern = []
         flush_buf.fill_(1)
         barrier()
@@ -412,8 +438,18 @@ def main():
     achieved = alg_bytes / k_time / 1e9 if k_time > 0 else 0.0
     kname = {("A", True): "dwk::solve_smem_kernel<256,64,128,false>", ("B", False): "dwk::solve_smem_kernel<128,256,512,true>",
              ("C", False): "dwk::solve_cluster_kernel<512>"}
+    traffic, traffic_note = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tr = json.load(fh).get(args.config)
+        if tr:
+            traffic = tr["dram_bytes_per_launch"]
+            traffic_note = f"{tr['which_launch']}; {tr['source']}"
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": None,
+                "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_note": traffic_note,
+                "algorithmic_bytes_per_launch": alg_bytes / n_launch,
                 "kernel": kname.get((args.config, on_smem), "dwk::solve_kernel<false,1024>"),
                 "bytes_definition": "touched: 16 B per rewritten tableau double + 8(m+n) per basis change"
                                     + (" + 16mn state image per block-launch" if on_smem else ""),
@@ -447,6 +483,8 @@ def main():
         "n_gpus": world, "steps": S, "warmup": W, "ms_per_step": 1e3 * t_dev / S, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "l2": "flushed between steps (256 MiB write)",
+                   "passes": "single pass: value = pivots / summed CUDA-event time of the solve kernels of the e2e pass" if single
+                   else "separate e2e and device-resident passes",
                    "parallelism": f"blocks sharded over {world} GPU(s)" +
                    ("; pi broadcast + proposal all-gather over NCCL every round" if world > 1 else ""),
                    "dw_objective_of_trajectory": dw_objective},

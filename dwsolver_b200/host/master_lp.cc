@@ -126,7 +126,8 @@ int MasterLP::solve()
     const int m = m_;
     if (!factor_valid_) refactor();
     if (!xb_valid_) compute_xb();
-    std::vector<double> y(m), alpha(m), w(m);
+    std::vector<double> y(m), alpha(m), w(m), cb(m), cb_used(m, 0.0);
+    bool y_valid = false, y_fresh = false;
     int degen_run = 0, refactors = 0;
     bool bland = false;
     const long long it_limit = iters_ + 200LL * (m + cols()) + 20000LL;
@@ -144,13 +145,25 @@ int MasterLP::solve()
             w[i] = wi;
             phase1 |= wi != 0.0;
         }
-        // ---- duals y = c_B' B^-1  (phase 1: c_B = w)
-        std::fill(y.begin(), y.end(), 0.0);
+        // ---- duals y = c_B' B^-1  (phase 1: c_B = w).  A basis change updates y in O(m) (below); the
+        // O(m^2) product is only redone when some other basic cost changed (phase switch, a phase-1
+        // weight flipping) or after a refactorisation.
+        bool same = y_valid;
         for (int i = 0; i < m; ++i) {
-            const double cb = phase1 ? w[i] : var_cost(head_[i]);
-            if (cb == 0.0) continue;
-            const double *ri = &binv_[(size_t)i * m];
-            for (int k = 0; k < m; ++k) y[k] += cb * ri[k];
+            cb[i] = phase1 ? w[i] : var_cost(head_[i]);
+            same = same && cb[i] == cb_used[i];
+        }
+        if (!same) {
+            std::fill(y.begin(), y.end(), 0.0);
+            for (int i = 0; i < m; ++i) {
+                if (cb[i] == 0.0) continue;
+                const double *ri = &binv_[(size_t)i * m];
+                const double c = cb[i];
+                for (int k = 0; k < m; ++k) y[k] += c * ri[k];
+            }
+            cb_used = cb;
+            y_valid = true;
+            y_fresh = true;
         }
         // ---- pricing
         int q = -1;
@@ -168,6 +181,7 @@ int MasterLP::solve()
             if (std::fabs(d) > best) { best = std::fabs(d); q = j; dq = d; }
         }
         if (q < 0) {
+            if (!y_fresh) { y_valid = false; continue; }      // confirm with duals computed from scratch
             if (phase1) { status = 1; break; }
             // optimal: verify A x = b, refactor once or twice if the inverse has drifted
             std::vector<double> act(m, 0.0);
@@ -176,19 +190,13 @@ int MasterLP::solve()
             for (int j = 0; j < n; ++j)
                 if (x_[j] != 0.0) for (size_t t = 0; t < idx_[j].size(); ++t) act[idx_[j][t]] += val_[j][t] * x_[j];
             double worst = 0.0;
-            for (int i = 0; i < m; ++i) {
-                const double slack = logical_basic_[i] ? 0.0 : 0.0;
-                (void)slack;
-                double s = act[i];
-                for (int r = 0; r < m; ++r) if (head_[r] == -(i + 1)) s += xb_[r];
-                worst = std::max(worst, std::fabs(s - b_[i]) / (1.0 + std::fabs(b_[i])));
-            }
-            if (worst > 1e-9 && refactors < 3) { ++refactors; refactor(); compute_xb(); continue; }
+            for (int r = 0; r < m; ++r) if (head_[r] < 0) act[-head_[r] - 1] += xb_[r];       // basic logicals
+            for (int i = 0; i < m; ++i) worst = std::max(worst, std::fabs(act[i] - b_[i]) / (1.0 + std::fabs(b_[i])));
+            if (worst > 1e-9 && refactors < 3) { ++refactors; refactor(); compute_xb(); y_valid = false; continue; }
             status = 0;
             break;
         }
         const double s = stat_[q] == AT_LB ? 1.0 : -1.0;          // entering variable increases / decreases
-        (void)dq;
         // ---- FTRAN
         std::fill(alpha.begin(), alpha.end(), 0.0);
         for (size_t t = 0; t < idx_[q].size(); ++t) {
@@ -252,6 +260,10 @@ int MasterLP::solve()
                 double *ri = &binv_[(size_t)i * m];
                 for (int k = 0; k < m; ++k) ri[k] -= a * rp[k];
             }
+            // y' = y + d_q * (new row p of B^-1); the entering variable's basic cost is what it was priced with
+            for (int k = 0; k < m; ++k) y[k] += dq * rp[k];
+            y_fresh = false;
+            cb_used[p] = phase1 ? 0.0 : cost_[q];
         }
         ++iters_;
         if (tmin <= 1e-11) { if (++degen_run > 200) bland = true; }
