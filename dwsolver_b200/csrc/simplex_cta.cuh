@@ -641,6 +641,11 @@ __global__ void __launch_bounds__(NT) init_kernel(const BlockDev *blocks, int K)
         }
         B.beta[i] = s;
     }
+    // x_k of the initial state (the no-pivot fast path of a later round reads it back)
+    for (int j = threadIdx.x; j < B.n; j += NT) {
+        const int v = B.m + j;
+        B.x[j] = nb_value(B.vstat[v], B.lo[v], B.up[v]);
+    }
 }
 
 }  // namespace dwk

@@ -773,13 +773,24 @@ __device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, i
 template <int NT, bool TG>
 __device__ __forceinline__ void gather_bounds(const BlockDev &B, Sm3 &c)
 {
-    for (int i = threadIdx.x; i < c.m; i += NT) {
-        const int v = c.head[i];
-        c.rlo[i] = __ldg(B.lo + v); c.rup[i] = __ldg(B.up + v);
+    const double *glo = B.lo, *gup = B.up;
+    constexpr int U = 4;
+    for (int i0 = threadIdx.x; i0 < c.m; i0 += NT * U) {
+        double lo[U], up[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * NT;
+            if (i < c.m) { const int v = c.head[i]; lo[u] = __ldg(glo + v); up[u] = __ldg(gup + v); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * NT;
+            if (i < c.m) { c.rlo[i] = lo[u]; c.rup[i] = up[u]; }
+        }
     }
     for (int j = threadIdx.x; j < c.n; j += NT) {
         const int v = c.nbv[j];
-        if (!TG) { c.clo[j] = __ldg(B.lo + v); c.cup[j] = __ldg(B.up + v); }
+        if (!TG) { c.clo[j] = __ldg(glo + v); c.cup[j] = __ldg(gup + v); }
         c.cstat[j] = c.vstat[v];
     }
 }
@@ -892,17 +903,46 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : (NT <= 128 ?
         s_changed = 0;
     }
     // priced objective while the copies fly (same arithmetic as the generic kernel / reference)
-    for (int j = tid; j < n; j += NT) {
-        double cj;
-        if (P.initial) cj = B.c_file[j];
-        else {
-            double y = 0.0;
-            for (int e = B.dc_ptr[j]; e < B.dc_ptr[j + 1]; ++e)
-                y = __dadd_rn(y, __dmul_rn(__ldg(P.pi + B.dc_row[e]), B.dc_val[e]));
-            const double base = P.phase_one ? 0.0 : B.c_master[j];
-            cj = __dadd_rn(__dmul_rn(-1.0, y), base);
+    // (four columns per thread at a time, every level of the CSC walk issued as one batch of read-only
+    //  loads: a chain of 3 dependent loads per column otherwise, which dominated the no-pivot rounds)
+    if (P.initial) {
+        const double *cf = B.c_file;
+        for (int j = tid; j < n; j += NT) c.cs[j] = __ldg(cf + j);
+    } else {
+        const int *dcp = B.dc_ptr, *dcr = B.dc_row;
+        const double *dcv = B.dc_val, *cm = B.c_master;
+        constexpr int U = 4;
+        for (int j0 = tid; j0 < n; j0 += NT * U) {
+            int pb[U], pe[U], r0[U];
+            double v0[U], p0[U], base[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = j0 + u * NT;
+                pb[u] = pe[u] = 0;
+                if (j < n) { pb[u] = __ldg(dcp + j); pe[u] = __ldg(dcp + j + 1); }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = j0 + u * NT;
+                base[u] = (j < n && !P.phase_one) ? __ldg(cm + j) : 0.0;
+                r0[u] = 0; v0[u] = 0.0;
+                if (pb[u] < pe[u]) { r0[u] = __ldg(dcr + pb[u]); v0[u] = __ldg(dcv + pb[u]); }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) p0[u] = pb[u] < pe[u] ? __ldg(P.pi + r0[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = j0 + u * NT;
+                if (j >= n) continue;
+                double y = 0.0;
+                if (pb[u] < pe[u]) {
+                    y = __dadd_rn(y, __dmul_rn(p0[u], v0[u]));
+                    for (int e = pb[u] + 1; e < pe[u]; ++e)
+                        y = __dadd_rn(y, __dmul_rn(__ldg(P.pi + __ldg(dcr + e)), __ldg(dcv + e)));
+                }
+                c.cs[j] = __dadd_rn(__dmul_rn(-1.0, y), base[u]);
+            }
         }
-        c.cs[j] = cj;
     }
     __syncthreads();            // mbarrier init + cs visible
     mbar_wait(&bar, 0);
@@ -913,7 +953,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : (NT <= 128 ?
     long long iter = 0;
     const long long max_iter = (long long)P.max_iter_mult * (m + n) + 1000;
     unsigned long long n_piv = 0, n_flip = 0, n_reb = 0, n_p1 = 0, n_rows = 0, n_cells = 0;   // n_piv/n_flip/n_rows/n_cells live in warp 0
-    bool need_check = true, infeasible = false, d_valid = false, bland = false, d_full = false;
+    bool need_check = true, infeasible = false, d_valid = false, bland = false, d_full = false, x_in_rowp = true;
     int degen = 0;
     const int degen_limit = 100 + (m + n) / 2;
     const int dflag_in = B.dflag[0];
@@ -952,25 +992,55 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : (NT <= 128 ?
             // which only touches the rows of T whose basic cost changed (late rounds: a handful);
             // otherwise (and every 32nd solve, to stop drift) recompute d = c_N + T' c_B in full.
             const bool inc = use_saved && !s_changed && n_reb == 0;
-            for (int i = tid; i < m; i += NT) {
-                const int v = c.head[i];
-                double cb = 0.0;
-                if (v >= m) cb = inc ? cost_delta(c.cs[v - m], B.cssave[v - m]) : c.cs[v - m];
-                c.colq[i] = cb;
+            const double *cssave = B.cssave, *dsave = B.dsave;     // only written in the epilogue: read-only here
+            constexpr int U = 4;
+            for (int i0 = tid; i0 < m; i0 += NT * U) {
+                double a[U], b[U];
+                bool st[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u * NT;
+                    st[u] = false; a[u] = 0.0; b[u] = 0.0;
+                    if (i < m) {
+                        const int v = c.head[i];
+                        if (v >= m) { st[u] = true; a[u] = c.cs[v - m]; if (inc) b[u] = __ldg(cssave + v - m); }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u * NT;
+                    if (i < m) c.colq[i] = st[u] ? (inc ? cost_delta(a[u], b[u]) : a[u]) : 0.0;
+                }
             }
             __syncthreads();
             if (warp == 0) { const int nl = list_weighted_rows(c, c.colq, m); if (lane == 0) dec.na = nl; }
             __syncthreads();
             const int nl = dec.na;
-            for (int j = tid; j < ld; j += NT) {
-                double s = 0.0;
-                if (j < n) {
-                    const int v = c.nbv[j];
-                    if (v >= m) s = inc ? cost_delta(c.cs[v - m], B.cssave[v - m]) : c.cs[v - m];
-                    if (inc) s += B.dsave[j];
-                    s = weighted_colsum<TG>(c, c.colq, nl, ld, j, s);
+            for (int j0 = tid; j0 < ld; j0 += NT * U) {
+                double a[U], b[U], dsv[U];
+                bool st[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = j0 + u * NT;
+                    st[u] = false; a[u] = 0.0; b[u] = 0.0; dsv[u] = 0.0;
+                    if (j < n) {
+                        const int v = c.nbv[j];
+                        if (v >= m) { st[u] = true; a[u] = c.cs[v - m]; if (inc) b[u] = __ldg(cssave + v - m); }
+                        if (inc) dsv[u] = __ldg(dsave + j);
+                    }
                 }
-                c.drow[j] = s;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = j0 + u * NT;
+                    if (j >= ld) continue;
+                    double s = 0.0;
+                    if (j < n) {
+                        if (st[u]) s = inc ? cost_delta(a[u], b[u]) : a[u];
+                        if (inc) s += dsv[u];
+                        s = weighted_colsum<TG>(c, c.colq, nl, ld, j, s);
+                    }
+                    c.drow[j] = s;
+                }
             }
             d_valid = true;
             d_full = !inc;
@@ -1008,6 +1078,8 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : (NT <= 128 ?
         if (kind == K_FAIL) { status = dec.fail_status; break; }
         // ---- K_NONE
         if (infeasible) { status = 4; break; }
+        // nothing moved since the last optimal solve of this block: x_k is still what B.x holds
+        if (!s_changed && n_reb == 0 && !P.initial) { status = 5; x_in_rowp = false; break; }
         // claimed optimal: x into rowp, auxiliary values into colq
         for (int j = tid; j < n; j += NT) {
             const int v = c.nbv[j];
@@ -1019,7 +1091,6 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : (NT <= 128 ?
             if (v >= m) c.rowp[v - m] = c.beta[i]; else c.colq[v] = c.beta[i];
         }
         __syncthreads();
-        if (!s_changed && n_reb == 0 && !P.initial) { status = 5; break; }   // nothing moved: already verified
         // residual of the state against the original rows
         double worst = 0.0;
         for (int i = tid; i < m; i += NT) {
@@ -1102,10 +1173,27 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : (NT <= 128 ?
         // the block was already optimal under the new prices: x_k, D_k x_k, c_k.x_k and the whole
         // state in HBM are still those of the previous round; only the priced optimum moves
         double zo = 0.0;
-        for (int j = tid; j < n; j += NT) {
-            zo = fma(c.cs[j], c.rowp[j], zo);
-            B.dsave[j] = c.drow[j];
-            if (d_full || cost_delta(c.cs[j], B.cssave[j]) != 0.0) B.cssave[j] = c.cs[j];
+        {
+            const double *xk = B.x;
+            double *dsave = B.dsave, *cssave = B.cssave;
+            constexpr int U = 4;
+            for (int j0 = tid; j0 < n; j0 += NT * U) {
+                double cv[U], xv[U], sv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = j0 + u * NT;
+                    if (j < n) { cv[u] = c.cs[j]; xv[u] = x_in_rowp ? c.rowp[j] : __ldcg(xk + j); sv[u] = __ldcg(cssave + j); }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = j0 + u * NT;
+                    if (j < n) {
+                        zo = fma(cv[u], xv[u], zo);
+                        dsave[j] = c.drow[j];
+                        if (d_full || cost_delta(cv[u], sv[u]) != 0.0) cssave[j] = cv[u];
+                    }
+                }
+            }
         }
         zo = block_sum<NT>(zo, scr);
         if (tid == 0) {

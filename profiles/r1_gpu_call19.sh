@@ -1,0 +1,4 @@
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/r1d_bench_B.json 2> gpurun_out/r1d_bench_B.err; echo rc=$?
+timeout 300 python bench.py --config A --no-cpu-baseline > gpurun_out/r1d_bench_A.json 2> gpurun_out/r1d_bench_A.err; echo rc=$?
+tail -n 3 gpurun_out/r1d_bench_B.err
