@@ -40,7 +40,10 @@ int fail(int code, const std::string &msg)
 
 constexpr int NT_SMEM = 256;
 constexpr int NT_GMEM = 1024;
-constexpr int NT_TG = 64;      // global-tableau kernel: 64-thread CTAs, 6 per SM (DWGPU_TG_THREADS=256: 4 per SM)
+// global-tableau kernel: 64-thread CTAs at 6 per SM give the best throughput when a shard has many
+// waves of blocks; 128-thread CTAs at 4 per SM finish a single block ~25 % sooner, which is what bounds a
+// launch when the shard is only a wave or two deep (multi-GPU shards of config B: 1024 blocks at N = 8)
+constexpr int NT_TG = 64, NT_TG_WIDE = 128;
 
 template <typename T>
 struct DevBuf {
@@ -87,7 +90,7 @@ struct dwgpu_engine {
     int cluster_size = 1;              // CTAs per block on the cluster path (list_c)
     size_t smem_dyn_c = 0;
     size_t smem_dyn_g = 0;
-    int tg_threads = NT_TG;
+    int tg_threads = 0;                // 0: by shard size; DWGPU_TG_THREADS=64|128|256 forces one
     bool reorder = true;
     size_t smem_dyn = 0;
     int max_smem_optin = 0;
@@ -411,17 +414,24 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(cudaFuncSetAttribute(dwk::order_by_last_iterations_kernel<1024, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(8192 * sizeof(unsigned long long))));
     if (const char *nr = std::getenv("DWGPU_NO_REORDER")) e->reorder = std::atoi(nr) == 0;
-    if (const char *tg = std::getenv("DWGPU_TG_THREADS")) e->tg_threads = std::atoi(tg) == 256 ? 256 : NT_TG;
+    if (const char *tg = std::getenv("DWGPU_TG_THREADS")) {
+        const int v = std::atoi(tg);
+        e->tg_threads = (v == 256 || v == NT_TG_WIDE || v == NT_TG) ? v : 0;
+    }
     if (!e->list_g.empty()) {
         CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)e->smem_dyn_g));
         CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_TG, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)e->smem_dyn_g));
+        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_TG_WIDE, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)e->smem_dyn_g));
     }
     if (!e->list_b.empty()) {
         CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 256, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)dwk::smem2_bytes(256, 512, true)));
         CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_TG, 256, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)dwk::smem2_bytes(256, 512, true)));
+        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)dwk::smem2_bytes(256, 512, true)));
     }
 
@@ -490,23 +500,32 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
     if (!e->list_g.empty() || !e->list_b.empty()) {
         const bool own_events = !e->ev_used[1];
         if (own_events) CU(cudaEventRecord(e->ev[0], st));
+        auto threads_for = [&](size_t nblocks) {
+            if (e->tg_threads) return e->tg_threads;
+            return nblocks < 3000 ? NT_TG_WIDE : NT_TG;         // < ~3.4 waves of 64-thread CTAs
+        };
         if (!e->list_b.empty()) {
-            if (e->tg_threads == 256)
-                dwk::solve_smem_kernel<NT_SMEM, 256, 512, true><<<(unsigned)e->list_b.size(), NT_SMEM, dwk::smem2_bytes(256, 512, true), st>>>(
-                    e->blocks.p, e->d_list_b.p, (int)e->list_b.size(), P);
+            const unsigned nb = (unsigned)e->list_b.size();
+            const size_t sm = dwk::smem2_bytes(256, 512, true);
+            const int nt = threads_for(nb);
+            if (nt == 256)
+                dwk::solve_smem_kernel<NT_SMEM, 256, 512, true><<<nb, NT_SMEM, sm, st>>>(e->blocks.p, e->d_list_b.p, (int)nb, P);
+            else if (nt == NT_TG_WIDE)
+                dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true><<<nb, NT_TG_WIDE, sm, st>>>(e->blocks.p, e->d_list_b.p, (int)nb, P);
             else
-                dwk::solve_smem_kernel<NT_TG, 256, 512, true><<<(unsigned)e->list_b.size(), NT_TG, dwk::smem2_bytes(256, 512, true), st>>>(
-                    e->blocks.p, e->d_list_b.p, (int)e->list_b.size(), P);
+                dwk::solve_smem_kernel<NT_TG, 256, 512, true><<<nb, NT_TG, sm, st>>>(e->blocks.p, e->d_list_b.p, (int)nb, P);
             CU(cudaGetLastError());
             e->last_launches++;
         }
         if (!e->list_g.empty()) {
-            if (e->tg_threads == 256)
-                dwk::solve_smem_kernel<NT_SMEM, 0, 0, true><<<(unsigned)e->list_g.size(), NT_SMEM, e->smem_dyn_g, st>>>(
-                    e->blocks.p, e->d_list_g.p, (int)e->list_g.size(), P);
+            const unsigned nb = (unsigned)e->list_g.size();
+            const int nt = threads_for(nb);
+            if (nt == 256)
+                dwk::solve_smem_kernel<NT_SMEM, 0, 0, true><<<nb, NT_SMEM, e->smem_dyn_g, st>>>(e->blocks.p, e->d_list_g.p, (int)nb, P);
+            else if (nt == NT_TG_WIDE)
+                dwk::solve_smem_kernel<NT_TG_WIDE, 0, 0, true><<<nb, NT_TG_WIDE, e->smem_dyn_g, st>>>(e->blocks.p, e->d_list_g.p, (int)nb, P);
             else
-                dwk::solve_smem_kernel<NT_TG, 0, 0, true><<<(unsigned)e->list_g.size(), NT_TG, e->smem_dyn_g, st>>>(
-                    e->blocks.p, e->d_list_g.p, (int)e->list_g.size(), P);
+                dwk::solve_smem_kernel<NT_TG, 0, 0, true><<<nb, NT_TG, e->smem_dyn_g, st>>>(e->blocks.p, e->d_list_g.p, (int)nb, P);
             CU(cudaGetLastError());
             e->last_launches++;
         }

@@ -848,7 +848,7 @@ __device__ __forceinline__ double weighted_colsum(const Sm3 &c, const double *wt
 // TG = true: the tableau stays in global memory (L2/HBM) and only the vectors live in shared memory
 // (blocks too large for one CTA's shared memory, config B class); the decision/sweep code is shared.
 template <int NT, int MC, int NC, bool TG>
-__global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : (NT <= 128 ? 6 : 4)) : 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
+__global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
                                                           SolveParams P)
 {
     extern __shared__ __align__(16) char smem_raw[];

@@ -140,9 +140,12 @@ def test_dense_blocks_global_path(force_path):
     eng.close()
 
 
-def test_mcf_config_b_shape_global_tableau_kernel():
-    """256 x 512 blocks take the specialised global-tableau kernel (path 3)."""
+@pytest.mark.parametrize("threads", [64, 128, 256])
+def test_mcf_config_b_shape_global_tableau_kernel(threads, monkeypatch):
+    """256 x 512 blocks take the specialised global-tableau kernel (path 3); the engine picks 64- or
+    128-thread CTAs by shard size, DWGPU_TG_THREADS forces each instantiation here."""
     from oracle import oracle as O
+    monkeypatch.setenv("DWGPU_TG_THREADS", str(threads))
     prob = P.gen_mcf(48, 256, 512, 256, 8192001)
     eng = engine(prob)
     assert set(eng.block_paths()) == {3}
