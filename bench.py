@@ -252,7 +252,6 @@ def main():
     gat = None
     if dist is not None:   # every rank receives every shard's proposals; rank 0 is the consumer
         gat = SH.alloc_gathered(torch, K_total, L, dev)
-        h_pin = {k_: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k_, v in gat.items()}
     pi_pin = torch.zeros(L, dtype=torch.float64).pin_memory()
     pi_dev = torch.zeros(L, dtype=torch.float64, device=dev)
     pis_dev = torch.from_numpy(pis).to(dev)
@@ -261,9 +260,12 @@ def main():
         SH.proposals_up(dist, views, gat)
 
     def up_to_host():
+        # rank 0: the gathered proposals of all ranks, packed by the engine into its pinned record
         if rank == 0:
-            for key in h_pin:
-                h_pin[key].copy_(gat[key], non_blocking=True)
+            pk = eng.pack_gathered(K_total, {k_: v.data_ptr() for k_, v in gat.items()}, sptr)
+            d2h[0] += 8 + K_total * (8 + 8 + 4) + (K_total + 1) * 4 + pk["nnz"] * 12
+            launches[0] += 2
+            last_status[0] = np.array(pk["status"])
         torch.cuda.synchronize()
 
     launches = [0]
@@ -325,12 +327,13 @@ def main():
 
     def count():
         c = eng.counters()
-        return np.array([c["pivots"], c["flips"], c["rebuilds"], c["rows_swept"], c["cells_swept"]], dtype=np.float64)
+        return np.array([c["pivots"], c["flips"], c["rebuilds"], c["rows_swept"], c["cells_swept"], c["price_cells"]],
+                        dtype=np.float64)
 
     # =========================== e2e ===========================
     single = args.single_pass and dist is None
-    e2e_time, e2e_cnt = 0.0, np.zeros(5)
-    sp_kern, sp_kcnt, sp_ksum = [], np.zeros(5), 0.0
+    e2e_time, e2e_cnt = 0.0, np.zeros(6)
+    sp_kern, sp_kcnt, sp_ksum = [], np.zeros(6), 0.0
     sp_clocks = ClockSampler(local_rank) if single else None
     for step in range(W + S):
         flush_buf.fill_(1)
@@ -349,7 +352,7 @@ def main():
             if single:
                 sp_kern, sp_kcnt = kacc, count() - c0
                 sp_ksum += float(np.sum(kacc)) * 1e-3
-    status_ok = bool((last_status[0] == 5).all()) if dist is None else bool((h_pin["status"].numpy() == 5).all()) if rank == 0 else True
+    status_ok = bool((last_status[0] == 5).all()) if rank == 0 else True
 
     # =========================== device only ===========================
     if single:
@@ -360,7 +363,7 @@ def main():
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + S)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + S)]
     if not single:
-        dev_cnt = np.zeros(5)
+        dev_cnt = np.zeros(6)
         kern = []
     clocks = ClockSampler(local_rank)
     for step in range(0 if single else W + S):
@@ -400,7 +403,7 @@ def main():
         dist.all_reduce(pv, op=dist.ReduceOp.SUM)
         t_dev, e2e_time, k_time = (float(v) for v in tt.tolist())
         pv = pv.cpu().numpy()
-        dev_cnt, e2e_cnt, kcnt = pv[0:5], pv[5:10], pv[10:15]
+        dev_cnt, e2e_cnt, kcnt = pv[0:6], pv[6:12], pv[12:18]
     eng.close()
     if rank != 0:
         if dist is not None:
@@ -414,12 +417,14 @@ def main():
     #   per rewritten cell 16       read + write of every tableau double that changes: only
     #                               (rows with a non-zero pivot-column entry) x (non-zero items of the
     #                               pivot row) move; the device counts them (dwgpu_counters.cells_swept)
+    #   per price-row cell 8        tableau doubles read to recompute reduced costs / phase-1 prices at the
+    #                               start of a solve (only rows whose basic cost changed; device-counted)
     #   per launch & block 16 m n   (shared-memory path only): tableau image loaded + stored
     # The survey's dense figure 16(m+1)(n+1) per basis change is reported next to it.
     on_smem = dom == 0
     n_launch = R + 1
     state_bytes = n_launch * K_total * 2.0 * 8.0 * m * n if on_smem else 0.0
-    touched = kcnt[4] * 16.0 + kcnt[0] * 8.0 * (m + n)
+    touched = kcnt[4] * 16.0 + kcnt[0] * 8.0 * (m + n) + kcnt[5] * 8.0
     alg_bytes = touched + state_bytes
     dense_bytes = kcnt[0] * bpp + state_bytes
     if on_smem:
@@ -451,7 +456,7 @@ def main():
                 "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_note": traffic_note,
                 "algorithmic_bytes_per_launch": alg_bytes / n_launch,
                 "kernel": kname.get((args.config, on_smem), "dwk::solve_kernel<false,1024>"),
-                "bytes_definition": "touched: 16 B per rewritten tableau double + 8(m+n) per basis change"
+                "bytes_definition": "touched: 16 B per rewritten tableau double + 8(m+n) per basis change + 8 B per tableau double read for price rows"
                                     + (" + 16mn state image per block-launch" if on_smem else ""),
                 "dense_equivalent_GBps": dense_bytes / k_time / 1e9 if k_time > 0 else None,
                 "dense_equivalent_frac": dense_bytes / k_time / 1e9 / peak if k_time > 0 and peak else None,
@@ -490,9 +495,10 @@ def main():
                    "dw_objective_of_trajectory": dw_objective},
         "e2e": {"value": (e2e_cnt[0] + e2e_cnt[1]) / e2e_time if e2e_time > 0 else 0.0, "unit": UNIT,
                 "h2d_bytes_per_step": 8 * L * R,
-                "d2h_bytes_per_step": d2h[0] if world == 1 else (R + 1) * (K_total * (8 + 8 + 4 + 4) + K_total * L * 12),
+                "d2h_bytes_per_step": d2h[0],
                 "api": "dwgpu_initial_solve_packed + dwgpu_iterate_packed (host pi in, pinned packed record out)"
-                       if world == 1 else "dwgpu_iterate_device + NCCL broadcast/all-gather + D2H on rank 0",
+                       if world == 1 else "per rank dwgpu_iterate_device; NCCL broadcast of pi, all-gather of the proposals, "
+                                          "dwgpu_pack_gathered into rank 0's pinned record",
                 "ms_per_step": 1e3 * e2e_time / S},
         "gpu_launches": launches[0] * S,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,

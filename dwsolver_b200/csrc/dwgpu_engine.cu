@@ -114,6 +114,11 @@ struct dwgpu_engine {
     dwk::PackDst pk_dev{}, pk_host{};  // the same mirror through its device alias / its host address
     DevBuf<double> r_dev;              // K convexity duals of the packed call
     double *h_r = nullptr;
+    // second mirror for dwgpu_pack_gathered (K_total blocks of all ranks), allocated on first use
+    char *h_gpack = nullptr, *d_gpack = nullptr;
+    int gpack_K = 0;
+    dwk::PackDst gpk_dev{}, gpk_host{};
+    DevBuf<int> gcolptr;
     long long *h_dbg = nullptr, *d_dbg = nullptr;   // DWGPU_DEBUG=1: progress markers the kernels leave behind
     DevBuf<unsigned long long> counters;
     DevBuf<long long> last_iters;
@@ -158,6 +163,8 @@ void dwgpu_destroy(dwgpu_engine *e)
     if (e->h_pack) cudaFreeHost(e->h_pack);
     if (e->h_r) cudaFreeHost(e->h_r);
     if (e->h_dbg) cudaFreeHost(e->h_dbg);
+    if (e->h_gpack) cudaFreeHost(e->h_gpack);
+    e->gcolptr.release();
     e->r_dev.release();
     e->counters.release(); e->last_iters.release();
     if (e->h_pi) cudaFreeHost(e->h_pi);
@@ -609,6 +616,49 @@ static int pack_round(dwgpu_engine *e, const double *r, dwgpu_packed *out)
     return 0;
 }
 
+int dwgpu_pack_gathered(dwgpu_engine *e, int K_total, const dwgpu_proposals *dev, const double *r_dev, void *stream,
+                        dwgpu_packed *out)
+{
+    if (!e || !dev || !out || K_total < 1) return fail(DWGPU_E_ARGS, "bad arguments");
+    if (!dev->obj || !dev->cost || !dev->status || !dev->len || (e->L > 0 && (!dev->ind || !dev->val)))
+        return fail(DWGPU_E_ARGS, "dev_arrays must hold obj, cost, status, len, ind, val");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    const size_t K = (size_t)K_total, KL = K * (size_t)e->L;
+    if (e->gpack_K < K_total) {
+        if (e->h_gpack) { CU(cudaStreamSynchronize(st)); cudaFreeHost(e->h_gpack); e->h_gpack = nullptr; }
+        e->gcolptr.release();
+        const size_t bytes = sizeof(double) * (1 + 2 * K + KL) + sizeof(int) * (2 * K + 1 + KL) + 64;
+        CU(cudaHostAlloc((void **)&e->h_gpack, bytes, cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer((void **)&e->d_gpack, e->h_gpack, 0));
+        std::memset(e->h_gpack, 0, bytes);
+        auto carve = [&](char *base, dwk::PackDst &d) {
+            d.nnz = (long long *)base;
+            double *dd = (double *)(base + sizeof(double));
+            d.obj = dd; d.cost = dd + K; d.val = dd + 2 * K;
+            int *ii = (int *)(dd + 2 * K + KL);
+            d.status = ii; d.colptr = ii + K; d.ind = ii + 2 * K + 1;
+        };
+        carve(e->d_gpack, e->gpk_dev);
+        carve(e->h_gpack, e->gpk_host);
+        CU(e->gcolptr.alloc(K + 1));
+        e->gpack_K = K_total;
+    }
+    dwk::PackSrc s;
+    s.obj = dev->obj; s.cost = dev->cost; s.val = dev->val; s.status = dev->status; s.len = dev->len; s.ind = dev->ind;
+    s.r = r_dev; s.K = K_total; s.L = e->L; s.accept_tol = 1e-6;
+    dwk::pack_scan_kernel<1024><<<1, 1024, 0, st>>>(s, e->gcolptr.p, e->gpk_dev);
+    CU(cudaGetLastError());
+    dwk::pack_copy_kernel<256><<<(unsigned)((K_total + 7) / 8), 256, 0, st>>>(s, e->gcolptr.p, e->gpk_dev);
+    CU(cudaGetLastError());
+    e->last_launches += 2;
+    CU(cudaStreamSynchronize(st));
+    out->obj = e->gpk_host.obj; out->cost = e->gpk_host.cost; out->status = e->gpk_host.status;
+    out->colptr = e->gpk_host.colptr; out->ind = e->gpk_host.ind; out->val = e->gpk_host.val;
+    out->nnz = e->gpk_host.nnz[0];
+    return 0;
+}
+
 int dwgpu_initial_solve_packed(dwgpu_engine *e, dwgpu_packed *out)
 {
     if (!e || !e->initialised) return fail(DWGPU_E_STATE, "engine not initialised");
@@ -712,6 +762,7 @@ int dwgpu_get_counters(dwgpu_engine *e, dwgpu_counters *t)
         t->rebuilds += (long long)h[8 * (size_t)k + 2]; t->phase1_iter += (long long)h[8 * (size_t)k + 3];
         t->rows_swept += (long long)h[8 * (size_t)k + 4];
         t->cells_swept += (long long)h[8 * (size_t)k + 5];
+        t->price_cells += (long long)h[8 * (size_t)k + 6];
     }
     t->solves = e->solves;
     return 0;

@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
     long long iter = 0;
     const long long max_iter = (long long)P.max_iter_mult * (m + n) + 1000;
     unsigned long long n_piv = 0, n_flip = 0, n_reb = 0, n_p1 = 0, n_rows = 0;
+    unsigned long long n_price = 0;     // tableau doubles read for price rows / beta (replicated count)
     bool need_check = true, infeasible = false, d_valid = false, p1_valid = false, p1_fresh = false, bland = false;
     bool changed = false;
     int degen = 0, buf = 0;
@@ -401,6 +402,7 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
                 n_flip += (unsigned long long)block_sum<NT>((double)nfl, sh.scr);
                 changed = true;
                 cl_recompute_beta(c, B);
+                n_price += (unsigned long long)m * (unsigned long long)n;
             }
             for (int i = tid; i < m; i += NT) c.w[i] = 1.0;       // dual devex reference weights
             __syncthreads();
@@ -556,6 +558,11 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
             if (!p1_valid) {
                 // phase-1 prices from scratch: d1 = T' w
                 cl_colsum(c, sh, c.w, [](int) { return 0.0; });
+                {
+                    unsigned cnt = 0;
+                    for (int i = 0; i < m; ++i) cnt += c.w[i] != 0.0;
+                    n_price += (unsigned long long)cnt * (unsigned long long)n;
+                }
                 p1_valid = true; p1_fresh = true;
             } else {
                 // incremental: the rank-1 update already ran with frozen weights; take out the cost the
@@ -918,6 +925,7 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
                     P.counters[8 * (size_t)k + 3] += n_p1;
                     P.counters[8 * (size_t)k + 4] += (unsigned long long)rows_total;
                     P.counters[8 * (size_t)k + 5] += (unsigned long long)rows_total * (unsigned long long)ld;
+                    P.counters[8 * (size_t)k + 6] += n_price;
                     P.last_iters[k] = (long long)(n_piv + n_flip);
                 }
             }

@@ -953,6 +953,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
     long long iter = 0;
     const long long max_iter = (long long)P.max_iter_mult * (m + n) + 1000;
     unsigned long long n_piv = 0, n_flip = 0, n_reb = 0, n_p1 = 0, n_rows = 0, n_cells = 0;   // n_piv/n_flip/n_rows/n_cells live in warp 0
+    unsigned long long n_price = 0;     // tableau doubles read to (re)compute price rows (block-uniform)
     bool need_check = true, infeasible = false, d_valid = false, bland = false, d_full = false, x_in_rowp = true;
     int degen = 0;
     const int degen_limit = 100 + (m + n) / 2;
@@ -983,6 +984,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
             {
                 const int nl = dec.na;
                 for (int j = tid; j < n; j += NT) c.rowp[j] = weighted_colsum<TG>(c, c.w, nl, ld, j, 0.0);
+                n_price += (unsigned long long)nl * (unsigned long long)n;
             }
             ++n_p1;
             __syncthreads();
@@ -1016,6 +1018,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
             if (warp == 0) { const int nl = list_weighted_rows(c, c.colq, m); if (lane == 0) dec.na = nl; }
             __syncthreads();
             const int nl = dec.na;
+            n_price += (unsigned long long)nl * (unsigned long long)n;
             for (int j0 = tid; j0 < ld; j0 += NT * U) {
                 double a[U], b[U], dsv[U];
                 bool st[U];
@@ -1198,6 +1201,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
         zo = block_sum<NT>(zo, scr);
         if (tid == 0) {
             P.obj[k] = zo; P.status[k] = 5; P.last_iters[k] = 0;
+            P.counters[8 * (size_t)k + 6] += n_price;
             B.dflag[0] = d_full ? 1 : dflag_in + 1;
         }
         return;
@@ -1262,6 +1266,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
             P.counters[8 * (size_t)k + 3] += n_p1;
             P.counters[8 * (size_t)k + 4] += n_rows;
             P.counters[8 * (size_t)k + 5] += n_cells;
+            P.counters[8 * (size_t)k + 6] += n_price;
             P.last_iters[k] = (long long)(n_piv + n_flip);
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }

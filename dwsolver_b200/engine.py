@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "dwgpu_iterate_device", "dwgpu_device_results", "dwgpu_fetch_results", "dwgpu_fetch_x",
     "dwgpu_get_counters", "dwgpu_get_block_iterations", "dwgpu_last_launch_count", "dwgpu_get_block_paths",
     "dwgpu_sync", "dwgpu_last_error", "dwgpu_version", "dwgpu_last_kernel_ms", "dwgpu_measure_smem_bandwidth",
-    "dwgpu_reset", "dwgpu_initial_solve_device", "dwgpu_initial_solve_packed", "dwgpu_iterate_packed",
+    "dwgpu_reset", "dwgpu_initial_solve_device", "dwgpu_initial_solve_packed", "dwgpu_iterate_packed", "dwgpu_pack_gathered",
 ]
 
 
@@ -58,7 +58,7 @@ class Packed(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("pivots", C.c_longlong), ("flips", C.c_longlong), ("rebuilds", C.c_longlong),
                 ("phase1_iter", C.c_longlong), ("solves", C.c_longlong), ("rows_swept", C.c_longlong),
-                ("cells_swept", C.c_longlong)]
+                ("cells_swept", C.c_longlong), ("price_cells", C.c_longlong)]
 
 
 _LIB = None
@@ -92,6 +92,8 @@ def load_library():
         L.dwgpu_initial_solve_device.argtypes = [C.c_void_p, C.c_void_p]
         L.dwgpu_initial_solve_packed.argtypes = [C.c_void_p, C.POINTER(Packed)]
         L.dwgpu_iterate_packed.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, C.POINTER(Packed)]
+        L.dwgpu_pack_gathered.argtypes = [C.c_void_p, C.c_int, C.POINTER(Proposals), C.c_void_p, C.c_void_p,
+                                          C.POINTER(Packed)]
         L.dwgpu_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.dwgpu_measure_smem_bandwidth.argtypes = [C.c_int, c_dp]
         L.dwgpu_last_error.restype = C.c_char_p
@@ -213,6 +215,23 @@ class Engine:
                "dwgpu_iterate_packed")
         return self._packed_views(pk)
 
+    def pack_gathered(self, K_total: int, ptrs: dict, stream: int = 0, r_dev_ptr: int = 0) -> dict:
+        """dwgpu_pack_gathered: ``ptrs`` maps obj/cost/status/len/ind/val to device addresses of arrays
+        holding K_total gathered proposals; returns the same views as iterate_packed()."""
+        p = Proposals()
+        for name in ("obj", "cost", "val"):
+            setattr(p, name, C.cast(C.c_void_p(ptrs[name]), c_dp))
+        for name in ("status", "len", "ind"):
+            setattr(p, name, C.cast(C.c_void_p(ptrs[name]), c_ip))
+        pk = Packed()
+        _check(self._lib.dwgpu_pack_gathered(self._h, K_total, C.byref(p), C.c_void_p(r_dev_ptr) if r_dev_ptr else None,
+                                             C.c_void_p(stream) if stream else None, C.byref(pk)), "dwgpu_pack_gathered")
+        K, nnz = K_total, int(pk.nnz)
+        as_np = np.ctypeslib.as_array
+        return dict(obj=as_np(pk.obj, (K,)), cost=as_np(pk.cost, (K,)), status=as_np(pk.status, (K,)),
+                    colptr=as_np(pk.colptr, (K + 1,)), ind=as_np(pk.ind, (nnz,)) if nnz else np.zeros(0, np.int32),
+                    val=as_np(pk.val, (nnz,)) if nnz else np.zeros(0), nnz=nnz)
+
     def iterate_device(self, d_pi_ptr: int, phase_one: bool, stream: int = 0):
         _check(self._lib.dwgpu_iterate_device(self._h, C.c_void_p(d_pi_ptr), int(bool(phase_one)),
                                               C.c_void_p(stream) if stream else None), "dwgpu_iterate_device")
@@ -259,7 +278,7 @@ class Engine:
         c = Counters()
         _check(self._lib.dwgpu_get_counters(self._h, C.byref(c)), "dwgpu_get_counters")
         return dict(pivots=c.pivots, flips=c.flips, rebuilds=c.rebuilds, phase1_iter=c.phase1_iter, solves=c.solves,
-                    rows_swept=c.rows_swept, cells_swept=c.cells_swept)
+                    rows_swept=c.rows_swept, cells_swept=c.cells_swept, price_cells=c.price_cells)
 
     def block_iterations(self) -> np.ndarray:
         it = np.zeros(self.K, np.int64)

@@ -115,6 +115,8 @@ typedef struct dwgpu_counters {
     long long rows_swept;  /* tableau rows (incl. the reduced-cost row) touched by basis changes */
     long long cells_swept; /* tableau doubles rewritten by basis changes: only (active row) x (non-zero
                               item of the pivot row) cells move, so this is the algorithmic traffic / 16 B */
+    long long price_cells; /* tableau doubles READ to (re)compute price rows: reduced costs at the start of a
+                              solve (only the rows whose basic cost changed), phase-1 prices, beta rebuilds */
 } dwgpu_counters;
 
 typedef struct dwgpu_engine dwgpu_engine;
@@ -147,6 +149,12 @@ int  dwgpu_iterate(dwgpu_engine *e, const double *pi, int phase_one, dwgpu_propo
 int  dwgpu_initial_solve_packed(dwgpu_engine *e, dwgpu_packed *out);
 int  dwgpu_iterate_packed(dwgpu_engine *e, const double *pi, int phase_one, const double *r,
                           dwgpu_packed *out);
+
+/* Multi-GPU up-link: pack K_total proposals that an all-gather left in DEVICE arrays (same layout as
+ * dwgpu_device_results(), ind/val with stride L) into one pinned record on the calling rank, on the
+ * caller's stream; synchronises that stream.  r_dev: K_total convexity duals on the device, or NULL. */
+int  dwgpu_pack_gathered(dwgpu_engine *e, int K_total, const dwgpu_proposals *dev_arrays, const double *r_dev,
+                         void *stream, dwgpu_packed *out);
 
 /* Cold solve on the caller's stream, results left on the device (see dwgpu_iterate_device). */
 int  dwgpu_initial_solve_device(dwgpu_engine *e, void *stream);

@@ -219,6 +219,17 @@ def test_packed_record_matches_dense_results():
             s = k * prob.L
             assert np.array_equal(pk["ind"][a:b], e1.ind[s:s + (b - a)])
             assert np.array_equal(pk["val"][a:b], e1.val[s:s + (b - a)])
+    # the multi-GPU up-link packs arrays an all-gather left on the device: same record
+    import ctypes as C
+    d = e1.device_results()
+    addr = lambda q: C.cast(q, C.c_void_p).value
+    pg = e1.pack_gathered(prob.K, dict(obj=addr(d.obj), cost=addr(d.cost), status=addr(d.status), len=addr(d.len),
+                                       ind=addr(d.ind), val=addr(d.val)))
+    assert np.array_equal(pg["obj"], e1.obj) and np.array_equal(np.diff(pg["colptr"]), e1.len)
+    assert pg["nnz"] == e1.len.sum()
+    for k in (0, prob.K // 2, prob.K - 1):
+        a, b = pg["colptr"][k], pg["colptr"][k + 1]
+        assert np.array_equal(pg["val"][a:b], e1.val[k * prob.L:k * prob.L + (b - a)])
     e1.close(); e2.close()
 
 
