@@ -249,20 +249,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    gat = None
-    if dist is not None:   # every rank receives every shard's proposals; rank 0 is the consumer
-        gat = SH.alloc_gathered(torch, K_total, L, dev)
+    rec_t = gath = None
+    if dist is not None:   # every rank receives every shard's result record; rank 0 is the consumer
+        rec_ptr, rec_bytes = eng.device_record()
+        rec_t = torch.as_tensor(Cai(rec_ptr, (rec_bytes,), "|u1"), device=dev)
+        gath = torch.empty(world * rec_bytes, dtype=torch.uint8, device=dev)
     pi_pin = torch.zeros(L, dtype=torch.float64).pin_memory()
     pi_dev = torch.zeros(L, dtype=torch.float64, device=dev)
     pis_dev = torch.from_numpy(pis).to(dev)
 
     def exchange_up():
-        SH.proposals_up(dist, views, gat)
+        SH.proposals_up_record(dist, rec_t, gath)            # one NCCL all-gather per round
 
     def up_to_host():
         # rank 0: the gathered proposals of all ranks, packed by the engine into its pinned record
         if rank == 0:
-            pk = eng.pack_gathered(K_total, {k_: v.data_ptr() for k_, v in gat.items()}, sptr)
+            pk = eng.pack_gathered_records(world, gath.data_ptr(), sptr)
             d2h[0] += 8 + K_total * (8 + 8 + 4) + (K_total + 1) * 4 + pk["nnz"] * 12
             launches[0] += 2
             last_status[0] = np.array(pk["status"])
@@ -491,14 +493,14 @@ def main():
                    "passes": "single pass: value = pivots / summed CUDA-event time of the solve kernels of the e2e pass" if single
                    else "separate e2e and device-resident passes",
                    "parallelism": f"blocks sharded over {world} GPU(s)" +
-                   ("; pi broadcast + proposal all-gather over NCCL every round" if world > 1 else ""),
+                   ("; pi broadcast + one all-gather of the result records over NCCL every round" if world > 1 else ""),
                    "dw_objective_of_trajectory": dw_objective},
         "e2e": {"value": (e2e_cnt[0] + e2e_cnt[1]) / e2e_time if e2e_time > 0 else 0.0, "unit": UNIT,
                 "h2d_bytes_per_step": 8 * L * R,
                 "d2h_bytes_per_step": d2h[0],
                 "api": "dwgpu_initial_solve_packed + dwgpu_iterate_packed (host pi in, pinned packed record out)"
-                       if world == 1 else "per rank dwgpu_iterate_device; NCCL broadcast of pi, all-gather of the proposals, "
-                                          "dwgpu_pack_gathered into rank 0's pinned record",
+                       if world == 1 else "per rank dwgpu_iterate_device; NCCL broadcast of pi, ONE all-gather of the result records, "
+                                          "dwgpu_pack_gathered_records into rank 0's pinned record",
                 "ms_per_step": 1e3 * e2e_time / S},
         "gpu_launches": launches[0] * S,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,

@@ -328,7 +328,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     {
         const size_t KL = (size_t)K * L;
         const size_t nd = 2 * (size_t)K + KL, ni = 2 * (size_t)K + KL;
-        e->rec_bytes = sizeof(double) * nd + sizeof(int) * ni;
+        e->rec_bytes = (sizeof(double) * nd + sizeof(int) * ni + 15) & ~(size_t)15;   // records concatenate 16-byte aligned
         CUE(e->rec.alloc(e->rec_bytes));
         CUE(cudaMemset(e->rec.p, 0, e->rec_bytes));
         double *dp = (double *)e->rec.p;
@@ -599,6 +599,7 @@ static int pack_round(dwgpu_engine *e, const double *r, dwgpu_packed *out)
     s.obj = e->obj.p; s.cost = e->cost.p; s.val = e->val.p;
     s.status = e->status.p; s.len = e->len.p; s.ind = e->ind.p;
     s.r = nullptr; s.K = e->K; s.L = e->L; s.accept_tol = 1e-6;   // TOLERANCE, src/dw.h:71
+    s.recs = nullptr; s.rec_bytes = 0; s.seg_K = 0;
     if (r) {
         std::memcpy(e->h_r, r, sizeof(double) * (size_t)e->K);
         CU(cudaMemcpyAsync(e->r_dev.p, e->h_r, sizeof(double) * (size_t)e->K, cudaMemcpyHostToDevice, st));
@@ -616,12 +617,35 @@ static int pack_round(dwgpu_engine *e, const double *r, dwgpu_packed *out)
     return 0;
 }
 
+static int pack_gathered_impl(dwgpu_engine *e, int K_total, const dwgpu_proposals *dev, const void *recs, int world,
+                              const double *r_dev, void *stream, dwgpu_packed *out);
+
 int dwgpu_pack_gathered(dwgpu_engine *e, int K_total, const dwgpu_proposals *dev, const double *r_dev, void *stream,
                         dwgpu_packed *out)
 {
     if (!e || !dev || !out || K_total < 1) return fail(DWGPU_E_ARGS, "bad arguments");
     if (!dev->obj || !dev->cost || !dev->status || !dev->len || (e->L > 0 && (!dev->ind || !dev->val)))
         return fail(DWGPU_E_ARGS, "dev_arrays must hold obj, cost, status, len, ind, val");
+    return pack_gathered_impl(e, K_total, dev, nullptr, 0, r_dev, stream, out);
+}
+
+int dwgpu_device_record(dwgpu_engine *e, void **dev_ptr, size_t *bytes)
+{
+    if (!e || !dev_ptr || !bytes) return fail(DWGPU_E_ARGS, "NULL argument");
+    *dev_ptr = e->rec.p; *bytes = e->rec_bytes;
+    return 0;
+}
+
+int dwgpu_pack_gathered_records(dwgpu_engine *e, int world, const void *records, const double *r_dev, void *stream,
+                                dwgpu_packed *out)
+{
+    if (!e || !records || !out || world < 1) return fail(DWGPU_E_ARGS, "bad arguments");
+    return pack_gathered_impl(e, world * e->K, nullptr, records, world, r_dev, stream, out);
+}
+
+static int pack_gathered_impl(dwgpu_engine *e, int K_total, const dwgpu_proposals *dev, const void *recs, int world,
+                              const double *r_dev, void *stream, dwgpu_packed *out)
+{
     CU(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     const size_t K = (size_t)K_total, KL = K * (size_t)e->L;
@@ -645,7 +669,9 @@ int dwgpu_pack_gathered(dwgpu_engine *e, int K_total, const dwgpu_proposals *dev
         e->gpack_K = K_total;
     }
     dwk::PackSrc s;
-    s.obj = dev->obj; s.cost = dev->cost; s.val = dev->val; s.status = dev->status; s.len = dev->len; s.ind = dev->ind;
+    std::memset(&s, 0, sizeof(s));
+    if (dev) { s.obj = dev->obj; s.cost = dev->cost; s.val = dev->val; s.status = dev->status; s.len = dev->len; s.ind = dev->ind; }
+    else { s.recs = (const char *)recs; s.rec_bytes = e->rec_bytes; s.seg_K = e->K; (void)world; }
     s.r = r_dev; s.K = K_total; s.L = e->L; s.accept_tol = 1e-6;
     dwk::pack_scan_kernel<1024><<<1, 1024, 0, st>>>(s, e->gcolptr.p, e->gpk_dev);
     CU(cudaGetLastError());

@@ -29,12 +29,39 @@ struct PackSrc {
     const double *r;                  // K convexity duals (nullptr: ship every column)
     int K, L;
     double accept_tol;
+    // segmented source (multi-GPU up-link): `recs` holds one engine record per rank, back to back, each
+    // [obj seg_K | cost seg_K | val seg_K*L] doubles then [status seg_K | len seg_K | ind seg_K*L] ints
+    const char *recs;
+    size_t rec_bytes;
+    int seg_K;
 };
+
+struct PackBlk {                      // where block k's fields live
+    const double *obj, *cost, *val;
+    const int *status, *len, *ind;
+};
+
+__device__ __forceinline__ PackBlk pack_block(const PackSrc &s, int k)
+{
+    PackBlk b;
+    if (s.recs == nullptr) {
+        b.obj = s.obj + k; b.cost = s.cost + k; b.val = s.val + (size_t)k * s.L;
+        b.status = s.status + k; b.len = s.len + k; b.ind = s.ind + (size_t)k * s.L;
+    } else {
+        const int rk = k / s.seg_K, kk = k - rk * s.seg_K;
+        const double *dp = reinterpret_cast<const double *>(s.recs + (size_t)rk * s.rec_bytes);
+        const int *ip = reinterpret_cast<const int *>(dp + 2 * (size_t)s.seg_K + (size_t)s.seg_K * s.L);
+        b.obj = dp + kk; b.cost = dp + s.seg_K + kk; b.val = dp + 2 * (size_t)s.seg_K + (size_t)kk * s.L;
+        b.status = ip + kk; b.len = ip + s.seg_K + kk; b.ind = ip + 2 * (size_t)s.seg_K + (size_t)kk * s.L;
+    }
+    return b;
+}
 
 __device__ __forceinline__ int shipped_len(const PackSrc &s, int k)
 {
-    int ln = s.len[k];
-    if (s.r != nullptr && !(s.r[k] - s.obj[k] > s.accept_tol)) ln = 0;
+    const PackBlk b = pack_block(s, k);
+    int ln = b.len[0];
+    if (s.r != nullptr && !(s.r[k] - b.obj[0] > s.accept_tol)) ln = 0;
     return ln;
 }
 
@@ -82,14 +109,15 @@ __global__ void __launch_bounds__(NT) pack_copy_kernel(PackSrc s, const int *col
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
     if (k >= s.K) return;
+    const PackBlk blk = pack_block(s, k);
     if (lane == 0) {
-        d.obj[k] = s.obj[k];
-        d.cost[k] = s.cost[k];
-        d.status[k] = s.status[k];
+        d.obj[k] = blk.obj[0];
+        d.cost[k] = blk.cost[0];
+        d.status[k] = blk.status[0];
     }
     const int b = colptr_dev[k], e = colptr_dev[k + 1];
-    const int *si = s.ind + (size_t)k * s.L;
-    const double *sv = s.val + (size_t)k * s.L;
+    const int *si = blk.ind;
+    const double *sv = blk.val;
     for (int t = lane; t < e - b; t += 32) {
         d.ind[b + t] = si[t];
         d.val[b + t] = sv[t];

@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "dwgpu_get_counters", "dwgpu_get_block_iterations", "dwgpu_last_launch_count", "dwgpu_get_block_paths",
     "dwgpu_sync", "dwgpu_last_error", "dwgpu_version", "dwgpu_last_kernel_ms", "dwgpu_measure_smem_bandwidth",
     "dwgpu_reset", "dwgpu_initial_solve_device", "dwgpu_initial_solve_packed", "dwgpu_iterate_packed", "dwgpu_pack_gathered",
+    "dwgpu_device_record", "dwgpu_pack_gathered_records",
 ]
 
 
@@ -94,6 +95,8 @@ def load_library():
         L.dwgpu_iterate_packed.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, C.POINTER(Packed)]
         L.dwgpu_pack_gathered.argtypes = [C.c_void_p, C.c_int, C.POINTER(Proposals), C.c_void_p, C.c_void_p,
                                           C.POINTER(Packed)]
+        L.dwgpu_device_record.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.dwgpu_pack_gathered_records.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Packed)]
         L.dwgpu_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.dwgpu_measure_smem_bandwidth.argtypes = [C.c_int, c_dp]
         L.dwgpu_last_error.restype = C.c_char_p
@@ -227,6 +230,24 @@ class Engine:
         _check(self._lib.dwgpu_pack_gathered(self._h, K_total, C.byref(p), C.c_void_p(r_dev_ptr) if r_dev_ptr else None,
                                              C.c_void_p(stream) if stream else None, C.byref(pk)), "dwgpu_pack_gathered")
         K, nnz = K_total, int(pk.nnz)
+        as_np = np.ctypeslib.as_array
+        return dict(obj=as_np(pk.obj, (K,)), cost=as_np(pk.cost, (K,)), status=as_np(pk.status, (K,)),
+                    colptr=as_np(pk.colptr, (K + 1,)), ind=as_np(pk.ind, (nnz,)) if nnz else np.zeros(0, np.int32),
+                    val=as_np(pk.val, (nnz,)) if nnz else np.zeros(0), nnz=nnz)
+
+    def device_record(self):
+        """(device address, bytes) of the contiguous result record of this engine (one all-gather per round)."""
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(self._lib.dwgpu_device_record(self._h, C.byref(p), C.byref(n)), "dwgpu_device_record")
+        return p.value, n.value
+
+    def pack_gathered_records(self, world: int, records_ptr: int, stream: int = 0, r_dev_ptr: int = 0) -> dict:
+        pk = Packed()
+        _check(self._lib.dwgpu_pack_gathered_records(self._h, world, C.c_void_p(records_ptr),
+                                                     C.c_void_p(r_dev_ptr) if r_dev_ptr else None,
+                                                     C.c_void_p(stream) if stream else None, C.byref(pk)),
+               "dwgpu_pack_gathered_records")
+        K, nnz = world * self.K, int(pk.nnz)
         as_np = np.ctypeslib.as_array
         return dict(obj=as_np(pk.obj, (K,)), cost=as_np(pk.cost, (K,)), status=as_np(pk.status, (K,)),
                     colptr=as_np(pk.colptr, (K + 1,)), ind=as_np(pk.ind, (nnz,)) if nnz else np.zeros(0, np.int32),

@@ -32,6 +32,13 @@ def proposals_up(dist, local: dict, gathered: dict):
     return gathered
 
 
+def proposals_up_record(dist, local_record, gathered_records):
+    """ONE all-gather per round: every rank's whole result record (dwgpu_device_record, a uint8 view) into
+    the rank-major concatenation that dwgpu_pack_gathered_records() reads."""
+    dist.all_gather_into_tensor(gathered_records, local_record)
+    return gathered_records
+
+
 def alloc_gathered(torch, K_total: int, L: int, device):
     return {"obj": torch.empty(K_total, dtype=torch.float64, device=device),
             "cost": torch.empty(K_total, dtype=torch.float64, device=device),

@@ -156,6 +156,14 @@ int  dwgpu_iterate_packed(dwgpu_engine *e, const double *pi, int phase_one, cons
 int  dwgpu_pack_gathered(dwgpu_engine *e, int K_total, const dwgpu_proposals *dev_arrays, const double *r_dev,
                          void *stream, dwgpu_packed *out);
 
+/* The same for ONE all-gather per round: every rank's results live in one contiguous device record
+ * (dwgpu_device_record: [obj K | cost K | val K*L] doubles, then [status K | len K | ind K*L] ints; all
+ * ranks must hold the same K); `records` is the rank-major concatenation an all-gather of those
+ * buffers produces. */
+int  dwgpu_device_record(dwgpu_engine *e, void **dev_ptr, size_t *bytes);
+int  dwgpu_pack_gathered_records(dwgpu_engine *e, int world, const void *records, const double *r_dev,
+                                 void *stream, dwgpu_packed *out);
+
 /* Cold solve on the caller's stream, results left on the device (see dwgpu_iterate_device). */
 int  dwgpu_initial_solve_device(dwgpu_engine *e, void *stream);
 

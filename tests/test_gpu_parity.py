@@ -230,6 +230,20 @@ def test_packed_record_matches_dense_results():
     for k in (0, prob.K // 2, prob.K - 1):
         a, b = pg["colptr"][k], pg["colptr"][k + 1]
         assert np.array_equal(pg["val"][a:b], e1.val[k * prob.L:k * prob.L + (b - a)])
+    # and the one-all-gather form: two "ranks" with the same record layout, concatenated on the device
+    import torch
+    ptr, nbytes = e1.device_record()
+    class Cai:
+        def __init__(self, p, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (p, False), "version": 2}
+    rec = torch.as_tensor(Cai(ptr, nbytes), device="cuda")
+    both = torch.cat([rec, rec]).contiguous()
+    pr = e1.pack_gathered_records(2, both.data_ptr())
+    K = prob.K
+    assert np.array_equal(pr["obj"][:K], e1.obj) and np.array_equal(pr["obj"][K:], e1.obj)
+    assert np.array_equal(np.diff(pr["colptr"]), np.concatenate([e1.len, e1.len])) and pr["nnz"] == 2 * e1.len.sum()
+    a, b = pr["colptr"][K + 3], pr["colptr"][K + 4]
+    assert np.array_equal(pr["ind"][a:b], e1.ind[3 * prob.L:3 * prob.L + (b - a)])
     e1.close(); e2.close()
 
 
