@@ -134,7 +134,7 @@ struct dwgpu_engine {
 extern "C" {
 
 const char *dwgpu_last_error(void) { return g_err.c_str(); }
-const char *dwgpu_version(void) { return "dwgpu 0.1 (sm_100a)"; }
+const char *dwgpu_version(void) { return "dwgpu 0.2 (sm_100a)"; }
 
 void dwgpu_options_init(dwgpu_options *o)
 {
@@ -189,7 +189,6 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
 
     dwgpu_engine *e = new dwgpu_engine();
     e->K = K; e->L = L; e->device = opt.device; e->opt = opt;
-    int rc = 0;
     auto bail = [&](int code) { dwgpu_destroy(e); return code; };
 #define CUE(call)                                                                             \
     do {                                                                                      \
@@ -446,7 +445,6 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(cudaGetLastError());
     CUE(cudaStreamSynchronize(e->stream));
     e->initialised = true;
-    (void)rc;
     *out = e;
     return 0;
 #undef CUE

@@ -289,3 +289,71 @@ def test_cluster_path_mcf_and_dw():
     assert res["status"] == "optimal"
     assert abs(res["objective"] - ref) <= 1e-7 * (1 + abs(ref))
     eng.close()
+
+
+def _full_size_properties(prob, eng, pis, phases):
+    """Size-independent checks at BASELINE.json's full sizes: every block optimal, the reported optimum equals
+    d.x for the reference's pricing formula, rows/bounds hold to 1e-9 (vectorised over all blocks), the proposal
+    column equals D_k x_k bit for bit on a sample, and re-pricing with the same duals is idempotent."""
+    K, L = prob.K, prob.L
+
+    def check(props, pi, phase_one, initial=False):
+        assert all(p["status"] == OPT for p in props)
+        for k in range(0, K, max(1, K // 64)):                       # 64 blocks in full detail
+            b, g = prob.blocks[k], props[k]
+            assert residual(b, g["x"]) <= 1e-9
+            if initial:
+                d = b.c_file
+            else:
+                y = np.zeros(b.n)
+                np.add.at(y, b.d_col, pi[b.d_row] * b.d_val)
+                d = (0.0 if phase_one else b.c_master) + (-1.0 * y)
+            assert abs(d @ g["x"] - g["obj"]) <= 1e-9 * (1 + abs(g["obj"]))
+            yc = np.zeros(L)
+            for r_, c_, v_ in zip(b.d_row, b.d_col, b.d_val):
+                yc[r_] += g["x"][c_] * v_
+            nz = np.nonzero(yc != 0.0)[0]
+            assert np.array_equal(g["ind"], nz + 1) and np.array_equal(g["val"], yc[nz])
+    check(eng.initial(), None, False, initial=True)
+    for pi, ph in zip(pis, phases):
+        props = eng.iterate(pi, ph)
+        check(props, pi, ph)
+    before = eng.counters()
+    again = eng.iterate(pis[-1], phases[-1])
+    after = eng.counters()
+    assert after["pivots"] == before["pivots"] and after["flips"] == before["flips"]
+    assert all(abs(a["obj"] - b_["obj"]) <= 1e-12 * (1 + abs(a["obj"])) for a, b_ in zip(again, props))
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_full_size_configs_properties(tag):
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"traj_{tag}.npz"))
+    prob = P.make_config(tag)
+    eng = engine(prob)
+    rounds = [0, 1, len(z["pis"]) // 2, len(z["pis"]) - 1]
+    _full_size_properties(prob, eng, [z["pis"][r] for r in rounds], [bool(z["phase_one"][r]) for r in rounds])
+    eng.close()
+
+
+def test_config_c_block_size_against_highs():
+    """two blocks of config C's full shape (2048 x 4096) on 16-CTA clusters: dual-simplex start, devex warm
+    round; optimum against HiGHS (its tolerances are 1e-7, so 1e-7 relative here), residuals to 1e-9"""
+    from highs_util import solve_block
+    prob = P.make_config("C", block_range=range(2))
+    eng = engine(prob)
+    assert set(eng.block_paths()) == {4}
+    props = eng.initial()
+    for k, b in enumerate(prob.blocks):
+        assert props[k]["status"] == OPT and residual(b, props[k]["x"]) <= 1e-9
+        ref = solve_block(b, b.c_file)
+        assert abs(props[k]["obj"] - ref.fun) <= 1e-7 * (1 + abs(ref.fun))
+    pi = -np.random.default_rng(2).random(prob.L) * 0.005
+    props = eng.iterate(pi, False)
+    for k, b in enumerate(prob.blocks):
+        assert props[k]["status"] == OPT and residual(b, props[k]["x"]) <= 1e-9
+        y = np.zeros(b.n)
+        np.add.at(y, b.d_col, pi[b.d_row] * b.d_val)
+        ref = solve_block(b, b.c_master - y)
+        assert abs(props[k]["obj"] - ref.fun) <= 1e-7 * (1 + abs(ref.fun))
+    eng.close()
