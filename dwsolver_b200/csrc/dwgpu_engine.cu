@@ -99,6 +99,7 @@ struct dwgpu_engine {
     DevBuf<int> a_rp, a_ci, dc_ptr, dc_row, dr_ptr, dr_col;
     DevBuf<char> pst;
     DevBuf<int> dflag;
+    DevBuf<unsigned> rmask;            // path 3: row-item masks
     DevBuf<dwk::BlockDev> blocks;
     DevBuf<int> d_list_smem, d_list_gmem, d_list_a, d_list_g, d_list_b, d_list_c;
     // round inputs / outputs
@@ -154,7 +155,7 @@ void dwgpu_destroy(dwgpu_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    e->T.release(); e->bnd.release(); e->pst.release(); e->a_v.release(); e->dsave.release(); e->cssave.release(); e->dflag.release();
+    e->T.release(); e->bnd.release(); e->pst.release(); e->a_v.release(); e->dsave.release(); e->cssave.release(); e->dflag.release(); e->rmask.release();
     e->dc_val.release(); e->dr_val.release(); e->c_file.release(); e->c_master.release();
     e->x.release(); e->ws.release(); e->a_rp.release();
     e->a_ci.release(); e->dc_ptr.release(); e->dc_row.release(); e->dr_ptr.release();
@@ -208,6 +209,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     std::vector<long long> t_off(K + 1, 0), r_off(K + 1, 0), v_off(K + 1, 0), a_off(K + 1, 0),
         arp_off(K + 1, 0), d_off(K + 1, 0), dcp_off(K + 1, 0), drp_off(K + 1, 0), ws_off(K + 1, 0), pst_off(K + 1, 0);
     std::vector<int> ldg(K);
+    std::vector<long long> rm_off(K + 1, 0);
     e->xoff[0] = 0;
     int n_cluster_blocks = 0;
     const size_t smem_cap = (size_t)e->max_smem_optin - 2048;   // static scratch + reserve
@@ -232,6 +234,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         const int nnz = b.m > 0 ? b.a_rowptr[b.m] : 0;
         t_off[k + 1] = t_off[k] + (long long)b.m * ldg[k];
         pst_off[k + 1] = pst_off[k] + (long long)dwk::pst_bytes(b.m, b.n);
+        rm_off[k + 1] = rm_off[k] + (path == 3 ? (long long)(dwk::rmask_bytes(b.m, b.n) / sizeof(unsigned)) : 0);
         r_off[k + 1] = r_off[k] + b.m;
         e->xoff[k + 1] = e->xoff[k] + b.n;
         v_off[k + 1] = v_off[k] + b.m + b.n;
@@ -323,6 +326,8 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(e->dsave.alloc(e->ntot)); CUE(e->cssave.alloc(e->ntot)); CUE(e->dflag.alloc(K));
     CUE(cudaMemset(e->dflag.p, 0, sizeof(int) * (size_t)K));
     CUE(e->ws.alloc(ws_off[K]));
+    CUE(e->rmask.alloc((size_t)rm_off[K]));
+    CUE(cudaMemset(e->rmask.p, 0, sizeof(unsigned) * std::max<size_t>((size_t)rm_off[K], 1)));
     CUE(e->pi.alloc(L));
     {
         const size_t KL = (size_t)K * L;
@@ -380,6 +385,8 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         B.x = e->x.p + e->xoff[k];
         B.dsave = e->dsave.p + e->xoff[k]; B.cssave = e->cssave.p + e->xoff[k]; B.dflag = e->dflag.p + k;
         B.ws = e->ws.p + ws_off[k];
+        B.rmask = e->path[k] == 3 ? e->rmask.p + rm_off[k] : nullptr;
+        B.rwd = dwk::rmask_words(B.n);
     }
     CUE(e->blocks.upload(hb));
     CUE(e->d_list_smem.upload(e->list_smem));

@@ -47,6 +47,9 @@ struct BlockDev {
     double *dsave;          // n: reduced costs by column position at the end of the last optimal solve
     double *cssave;         // n: priced structural costs they were computed with
     int *dflag;             // solves since dsave was last recomputed in full (0 = dsave invalid)
+    unsigned *rmask;        // path 3: per row, one bit per 32-byte item of T that may be non-zero (nullptr: none)
+    int rwd;                // 32-bit words per row of rmask
+    int pad2;
 };
 
 struct SolveParams {
@@ -640,6 +643,16 @@ __global__ void __launch_bounds__(NT) init_kernel(const BlockDev *blocks, int K)
             s = fma(B.a_v[p], nb_value(B.vstat[v], B.lo[v], B.up[v]), s);
         }
         B.beta[i] = s;
+    }
+    // row-item masks of T = A_k (path 3)
+    if (B.rmask != nullptr) {
+        for (int e = threadIdx.x; e < B.m * B.rwd; e += NT) B.rmask[e] = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < B.m; i += NT)
+            for (int p = B.a_rp[i]; p < B.a_rp[i + 1]; ++p) {
+                const int t = B.a_ci[p] >> 2;
+                B.rmask[(size_t)i * B.rwd + (t >> 5)] |= 1u << (t & 31);      // one thread per row: no race
+            }
     }
     // x_k of the initial state (the no-pivot fast path of a later round reads it back)
     for (int j = threadIdx.x; j < B.n; j += NT) {

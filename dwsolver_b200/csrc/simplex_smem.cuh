@@ -91,6 +91,10 @@ __host__ __device__ inline size_t pst_bytes(int m, int n)
 }
 // leading dimension of the tableau: shared (TG = false) or global-memory resident (TG = true)
 __host__ __device__ inline int tab_ld(int n, bool tg) { return tg ? ((n + 3) & ~3) : smem2_ld(n); }
+// row-item mask: one bit per 32-byte item (4 doubles) of a global-memory tableau row
+__host__ __device__ inline int rmask_words(int n) { return (((n + 3) & ~3) / 4 + 31) / 32; }
+__host__ __device__ inline size_t rmask_bytes(int m, int n) { return align16(sizeof(unsigned) * (size_t)m * rmask_words(n)); }
+
 __host__ __device__ inline size_t smem2_bytes(int m, int n, bool tg = false)
 {
     const size_t ld = tab_ld(n, tg);
@@ -107,7 +111,8 @@ __host__ __device__ inline size_t smem2_bytes(int m, int n, bool tg = false)
          + align16((size_t)n)                                 // cstat
          + align16(sizeof(unsigned short) * (size_t)(m + 1))  // active rows
          + align16(sizeof(unsigned short) * (ld / 2 + 1))     // active column items of the pivot row
-         + (tg ? align16(sizeof(unsigned short) * (size_t)(m + 32 * 8)) : 0);   // per-warp column segments
+         + (tg ? align16(sizeof(unsigned short) * (size_t)(m + 32 * 8)) : 0)    // per-warp column segments
+         + (tg ? rmask_bytes(m, n) : 0);                                        // row-item masks
 }
 
 enum { K_NONE = 0, K_PIVOT = 1, K_FAIL = 2, K_REDO = 3 };
@@ -142,6 +147,8 @@ struct Sm3 {
     unsigned short *arow;
     unsigned short *acol;
     unsigned short *arow2;               // per-warp column segments before compaction (TG)
+    unsigned *rmask;                     // row-item masks (TG), rwd words per row
+    int rwd;
 };
 
 // lane holding the maximum of non-negative keys (ties: lowest lane); -1 if no lane is valid
@@ -564,33 +571,53 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
         bland = ds->bland != 0;
         if (kind == K_FLIPPED) continue;
         if (kind != K_PIVOT) return kind;
-        // ---- pivot row -> rowp (scaled), every thread, one batch of loads
+        // ---- pivot row -> rowp (scaled): only the 32-byte items whose mask bit is set are fetched (a network
+        // row has ~25 of 128), everything else is written as zero; warp 0 turns the mask into the item list
         {
+            constexpr int IW = ItemW<true>::D2;
             const int p = dec->p;
             const double inv = dec->inv;
+            const int nitems = (ld >> 1) / IW;
+            const unsigned *mp = c.rmask + (size_t)p * c.rwd;
             const double2 *prow = reinterpret_cast<const double2 *>(c.T + (size_t)p * ld);
             double2 *rp2 = reinterpret_cast<double2 *>(c.rowp);
-            constexpr int RB = NC ? ((NC / 2 + NT - 1) / NT < DWK_TG_RB ? (NC / 2 + NT - 1) / NT : DWK_TG_RB) : 2;
-            for (int j0 = 0; j0 < (ld >> 1); j0 += NT * RB) {
-                double2 v[RB];
+            constexpr int RB = NC ? ((NC / 4 + NT - 1) / NT < DWK_TG_RB ? (NC / 4 + NT - 1) / NT : DWK_TG_RB) : 2;
+            for (int t0 = 0; t0 < nitems; t0 += NT * RB) {
+                double2 v[RB][IW];
+                bool on[RB];
 #pragma unroll
-                for (int t = 0; t < RB; ++t) {
-                    const int j2 = j0 + t * NT + tid;
-                    if (j2 < (ld >> 1)) v[t] = __ldcg(prow + j2);
+                for (int u = 0; u < RB; ++u) {
+                    const int t = t0 + u * NT + tid;
+                    on[u] = t < nitems && ((mp[t >> 5] >> (t & 31)) & 1u);
+                    if (on[u]) {
+#pragma unroll
+                        for (int x = 0; x < IW; ++x) v[u][x] = __ldcg(prow + t * IW + x);
+                    }
                 }
 #pragma unroll
-                for (int t = 0; t < RB; ++t) {
-                    const int j2 = j0 + t * NT + tid;
-                    if (j2 < (ld >> 1)) { v[t].x *= inv; v[t].y *= inv; rp2[j2] = v[t]; }
+                for (int u = 0; u < RB; ++u) {
+                    const int t = t0 + u * NT + tid;
+                    if (t < nitems) {
+#pragma unroll
+                        for (int x = 0; x < IW; ++x) {
+                            double2 r = make_double2(0.0, 0.0);
+                            if (on[u]) { r.x = v[u][x].x * inv; r.y = v[u][x].y * inv; }
+                            rp2[t * IW + x] = r;
+                        }
+                    }
                 }
             }
         }
         __syncthreads();
         if (warp == 0) {
-            // non-zero 32-byte items of the scaled pivot row (see sweep_sparse)
+            // exact non-zero items of the scaled pivot row -> acol; the row's mask is refreshed to exactly
+            // that pattern, and every swept row may fill in there (its mask takes the union; the sweep
+            // clears the bit again when an item comes out all zero)
             constexpr int IW = ItemW<true>::D2;
-            const int nitems = (ld >> 1) / IW;
+            const int p = dec->p;
+            const int nitems = (ld >> 1) / IW, rwd = c.rwd;
             const double2 *rp2 = reinterpret_cast<const double2 *>(c.rowp);
+            unsigned *mp = c.rmask + (size_t)p * rwd;
             int nc = 0;
             for (int t0 = 0; t0 < nitems; t0 += 32) {
                 const int t = t0 + lane;
@@ -602,8 +629,17 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
                 const unsigned bal = __ballot_sync(0xffffffffu, nz);
                 if (nz) c.acol[nc + __popc(bal & lt_mask)] = (unsigned short)t;
                 nc += __popc(bal);
+                if (lane == 0) mp[t0 >> 5] = bal;
             }
-            if (2 * nc > nitems) nc = -1;
+            __syncwarp();
+            const int na_rows = dec->na - ((dec->na > 0 && c.arow[dec->na - 1] == m) ? 1 : 0);
+            for (int e = lane; e < na_rows; e += 32) {
+                const int i = c.arow[e];
+                if (i == p) continue;
+                unsigned *mi = c.rmask + (size_t)i * rwd;
+                for (int w_ = 0; w_ < rwd; ++w_) mi[w_] |= mp[w_];
+            }
+            if (2 * nc > nitems) nc = -1;       // dense pivot row: whole-row sweeps are cheaper
             const int na_all = dec->na;
             n_cells += nc < 0 ? (unsigned long long)na_all * (unsigned long long)ld
                               : (unsigned long long)na_all * (unsigned long long)nc * (2 * IW);
@@ -661,6 +697,7 @@ __device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, i
                 const double ci = c.colq[i];
                 const double cq = ci * inv;
                 const bool is_p = i == p;
+                bool all_zero = true;
 #pragma unroll
                 for (int u = 0; u < IW; ++u) {
                     const double2 ra = rowp2[j + u];
@@ -670,7 +707,12 @@ __device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, i
                     r.y = is_p ? -ra.y : fma(-ci, ra.y, v[t][u].y);
                     if (jq == 0) r.x = is_p ? inv : cq;
                     if (jq == 1) r.y = is_p ? inv : cq;
+                    all_zero = all_zero && r.x == 0.0 && r.y == 0.0;
                     st_t2<TG>(T2 + off[t] + u, r);
+                }
+                if (TG && all_zero) {        // the item cancelled exactly (network tableaux do that a lot): keep the mask tight
+                    const int item = j / IW;
+                    atomicAnd(c.rmask + (size_t)i * c.rwd + (item >> 5), ~(1u << (item & 31)));
                 }
             }
         }
@@ -843,6 +885,57 @@ __device__ __forceinline__ double weighted_colsum(const Sm3 &c, const double *wt
     return s;
 }
 
+// out[4t .. 4t+3] += sum over the listed rows (ascending) of wt[i] * T[i][4t .. 4t+3], visiting only the rows whose
+// mask says item t may be non-zero (global-memory tableau).  Deterministic order; 4 predicated item loads in flight.
+template <int NT>
+__device__ __forceinline__ void weighted_itemsum_tg(const Sm3 &c, const double *wt, int nl, int ld, double *out)
+{
+    const int nitems = ld >> 2, rwd = c.rwd, n2 = ld >> 1;
+    const double2 *T2 = reinterpret_cast<const double2 *>(c.T);
+    double2 *o2 = reinterpret_cast<double2 *>(out);
+    for (int t = threadIdx.x; t < nitems; t += NT) {
+        double2 a0 = o2[2 * t], a1 = o2[2 * t + 1];
+        const int wsel = t >> 5;
+        const unsigned bit = 1u << (t & 31);
+        for (int a = 0; a < nl; a += 4) {
+            double2 v0[4], v1[4];
+            double wv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                wv[u] = 0.0; v0[u] = make_double2(0.0, 0.0); v1[u] = v0[u];      // w = 0 contributes exactly nothing
+                if (a + u < nl) {
+                    const int i = c.arow[a + u];
+                    if (c.rmask[(size_t)i * rwd + wsel] & bit) {
+                        wv[u] = wt[i];
+                        v0[u] = __ldcg(T2 + (size_t)i * n2 + 2 * t);
+                        v1[u] = __ldcg(T2 + (size_t)i * n2 + 2 * t + 1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a0.x = fma(wv[u], v0[u].x, a0.x); a0.y = fma(wv[u], v0[u].y, a0.y);
+                a1.x = fma(wv[u], v1[u].x, a1.x); a1.y = fma(wv[u], v1[u].y, a1.y);
+            }
+        }
+        o2[2 * t] = a0; o2[2 * t + 1] = a1;
+    }
+}
+
+// tableau doubles the masked price pass reads for the listed rows (warp 0; result in every lane)
+__device__ __forceinline__ unsigned masked_cells(const Sm3 &c, int nl)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned cnt = 0;
+    for (int a = lane; a < nl; a += 32) {
+        const unsigned *mi = c.rmask + (size_t)c.arow[a] * c.rwd;
+        for (int w_ = 0; w_ < c.rwd; ++w_) cnt += __popc(mi[w_]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    return cnt * 4u;
+}
+
 // MC/NC != 0: block shape known at compile time (all shared-memory offsets and trip counts are
 // constants); MC = NC = 0: any shape that fits.
 // TG = true: the tableau stays in global memory (L2/HBM) and only the vectors live in shared memory
@@ -890,15 +983,19 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
     c.cstat = (signed char *)sp;   sp += align16((size_t)n);
     c.arow = (unsigned short *)sp; sp += align16(sizeof(unsigned short) * (size_t)(m + 1));
     c.acol = (unsigned short *)sp; sp += align16(sizeof(unsigned short) * (size_t)(ld / 2 + 1));
-    c.arow2 = (unsigned short *)sp;
+    c.arow2 = (unsigned short *)sp; sp += TG ? align16(sizeof(unsigned short) * (size_t)(m + 32 * 8)) : 0;
+    c.rmask = TG ? (unsigned *)sp : nullptr;
+    c.rwd = rmask_words(n);
 
-    // ---- state in: two bulk copies, one mbarrier
+    // ---- state in: bulk copies (tableau or row masks, state image), one mbarrier
     const uint32_t t_bytes = TG ? 0u : (uint32_t)(sizeof(double) * (size_t)m * ld);
     const uint32_t p_bytes = (uint32_t)pst_bytes(m, n);
+    const uint32_t k_bytes = TG ? (uint32_t)rmask_bytes(m, n) : 0u;
     if (tid == 0) {
         mbar_init(&bar, 1);
-        mbar_expect_tx(&bar, t_bytes + p_bytes);
+        mbar_expect_tx(&bar, t_bytes + p_bytes + k_bytes);
         if (t_bytes) bulk_g2s(c.T, B.T, t_bytes, &bar);
+        if (k_bytes) bulk_g2s(c.rmask, B.rmask, k_bytes, &bar);
         bulk_g2s(pst, B.beta, p_bytes, &bar);
         s_changed = 0;
     }
@@ -979,12 +1076,17 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
         }
         if (infeasible) {
             // phase-1 prices T'w into rowp (consumed by the pricing loop before rowp is restaged)
-            if (warp == 0) { const int nl = list_weighted_rows(c, c.w, m); if (lane == 0) dec.na = nl; }
+            if (warp == 0) {
+                const int nl = list_weighted_rows(c, c.w, m);
+                if (lane == 0) dec.na = nl;
+                if (TG) { __syncwarp(); n_price += masked_cells(c, nl); } else n_price += (unsigned long long)nl * (unsigned long long)n;
+            }
+            if (TG) for (int j = tid; j < ld; j += NT) c.rowp[j] = 0.0;
             __syncthreads();
             {
                 const int nl = dec.na;
-                for (int j = tid; j < n; j += NT) c.rowp[j] = weighted_colsum<TG>(c, c.w, nl, ld, j, 0.0);
-                n_price += (unsigned long long)nl * (unsigned long long)n;
+                if (TG) weighted_itemsum_tg<NT>(c, c.w, nl, ld, c.rowp);
+                else for (int j = tid; j < n; j += NT) c.rowp[j] = weighted_colsum<TG>(c, c.w, nl, ld, j, 0.0);
             }
             ++n_p1;
             __syncthreads();
@@ -1015,10 +1117,13 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
                 }
             }
             __syncthreads();
-            if (warp == 0) { const int nl = list_weighted_rows(c, c.colq, m); if (lane == 0) dec.na = nl; }
+            if (warp == 0) {
+                const int nl = list_weighted_rows(c, c.colq, m);
+                if (lane == 0) dec.na = nl;
+                if (TG) { __syncwarp(); n_price += masked_cells(c, nl); } else n_price += (unsigned long long)nl * (unsigned long long)n;
+            }
             __syncthreads();
             const int nl = dec.na;
-            n_price += (unsigned long long)nl * (unsigned long long)n;
             for (int j0 = tid; j0 < ld; j0 += NT * U) {
                 double a[U], b[U], dsv[U];
                 bool st[U];
@@ -1040,10 +1145,14 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
                     if (j < n) {
                         if (st[u]) s = inc ? cost_delta(a[u], b[u]) : a[u];
                         if (inc) s += dsv[u];
-                        s = weighted_colsum<TG>(c, c.colq, nl, ld, j, s);
+                        if (!TG) s = weighted_colsum<TG>(c, c.colq, nl, ld, j, s);
                     }
                     c.drow[j] = s;
                 }
+            }
+            if (TG) {           // base row written above; now the masked row contributions, item by item
+                __syncthreads();
+                weighted_itemsum_tg<NT>(c, c.colq, nl, ld, c.drow);
             }
             d_valid = true;
             d_full = !inc;
@@ -1151,6 +1260,10 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
                 }
                 __syncthreads();
             }
+            if (TG) {       // the rebuilt tableau's pattern is unknown: every item may be non-zero
+                for (int e = tid; e < m * c.rwd; e += NT) c.rmask[e] = 0xffffffffu;
+                __syncthreads();
+            }
             need_check = true; d_valid = false;
             continue;
         }
@@ -1218,6 +1331,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
         const bool t_dirty = (n_piv + n_reb) != 0;        // thread 0 sits in warp 0, which owns n_piv
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (t_dirty && t_bytes) bulk_s2g(B.T, c.T, t_bytes);
+        if (t_dirty && k_bytes) bulk_s2g(B.rmask, c.rmask, k_bytes);
         bulk_s2g(B.beta, pst, p_bytes);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
