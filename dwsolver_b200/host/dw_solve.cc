@@ -26,6 +26,7 @@
 #include "../../include/dwgpu.h"
 #include "../../include/dwsolver.h"
 #include "lp_model.h"
+#include "gub_master.h"
 #include "master_lp.h"
 
 namespace {
@@ -89,84 +90,15 @@ struct Proposal {            // X[k][iter] of the reference (src/dw_phases.c:173
 
 }  // namespace
 
-extern "C" {
-
-void dw_options_init(dw_options_t *o)
+// The solve proper, on in-memory blocks (what both dw_solve and dw_solve_blocks end up calling).
+static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *link_lb, const double *link_ub,
+                   const std::vector<std::vector<std::string>> *names, const dw_options_t &opt, double t_begin,
+                   dw_result_t *result)
 {
-    if (!o) return;
-    o->verbosity = DW_OUTPUT_NORMAL;       // src/dw_solver.c:60-75
-    o->mip_gap = 0.01;
-    o->max_phase1_iterations = 100;
-    o->max_phase2_iterations = 3000;
-    o->rounding_flag = 0;
-    o->integerize_flag = 0;
-    o->enforce_sub_integrality = 0;
-    o->print_timing_data = 0;
-    o->print_final_master = 0;
-    o->print_relaxed_sol = 1;
-    o->perturb = 0;
-    o->shift = 0.0;
-}
-
-const char *dw_version(void) { return "dwsolver-b200 0.1 (API of dwsolver 1.2.1; subproblems on sm_100a)"; }
-
-void dw_result_free(dw_result_t *r)
-{
-    if (!r) return;
-    std::free(r->x);
-    std::memset(r, 0, sizeof(*r));
-}
-
-void dw_last_stats(dw_stats_t *out) { if (out) *out = g_stats; }
-
-int dw_solve(const char *master_file, const char *const *subproblem_files, int num_subproblems, const dw_options_t *opts_in,
-             dw_result_t *result)
-{
-    if (!result) return DW_STATUS_ERR_BAD_ARGS;
-    std::memset(result, 0, sizeof(*result));
     auto fail = [&](int code) { result->status = code; return code; };
-    if (!master_file || !subproblem_files || num_subproblems < 1) return fail(DW_STATUS_ERR_BAD_ARGS);
-    for (int k = 0; k < num_subproblems; ++k) if (!subproblem_files[k]) return fail(DW_STATUS_ERR_BAD_ARGS);
-    dw_options_t opt;
-    if (opts_in) opt = *opts_in; else dw_options_init(&opt);
     const int verb = opt.verbosity;
-    std::memset(&g_stats, 0, sizeof(g_stats));
-    const double t_begin = now_s();
-    if (opt.enforce_sub_integrality || opt.integerize_flag || opt.rounding_flag) {
-        if (verb >= DW_OUTPUT_QUIET)
-            std::fprintf(stderr, "dwsolver-b200: integer options (-e, -i, -r) are not supported by the GPU path; solving the LP relaxation.\n");
-    }
-
-    // ---- read the problem -------------------------------------------------------------------------
-    const int K = num_subproblems;
-    LpModel master;
-    std::vector<BlockHost> blocks(K);
-    try {
-        master = read_lp_file(master_file);
-        std::vector<std::vector<std::pair<int, double>>> mcols(master.n());
-        for (size_t t = 0; t < master.a_val.size(); ++t) mcols[master.a_col[t]].emplace_back(master.a_row[t], master.a_val[t]);
-        for (int k = 0; k < K; ++k) {
-            LpModel sub = read_lp_file(subproblem_files[k]);
-            build_block(sub, master, mcols, blocks[k]);
-        }
-    } catch (const std::exception &e) {
-        if (verb >= DW_OUTPUT_QUIET) std::fprintf(stderr, "dwsolver-b200: %s\n", e.what());
-        return fail(DW_STATUS_ERR_FILE);
-    }
-    const int L = master.m();
-    g_stats.seconds_read = now_s() - t_begin;
-
+    std::vector<dwgpu_block_desc> desc(desc_in, desc_in + K);
     // ---- GPU engine: replaces pthread_create(subproblem_thread) x K (src/dw_solver.c:154-184) --------
-    std::vector<dwgpu_block_desc> desc(K);
-    for (int k = 0; k < K; ++k) {
-        BlockHost &b = blocks[k];
-        dwgpu_block_desc &d = desc[k];
-        d.m = b.m; d.n = b.n;
-        d.a_rowptr = b.a_rowptr.data(); d.a_col = b.a_col.data(); d.a_val = b.a_val.data();
-        d.row_lb = b.row_lb.data(); d.row_ub = b.row_ub.data(); d.col_lb = b.col_lb.data(); d.col_ub = b.col_ub.data();
-        d.c_file = b.c_file.data(); d.c_master = b.c_master.data();
-        d.d_nnz = (int)b.d_val.size(); d.d_row = b.d_row.data(); d.d_col = b.d_col.data(); d.d_val = b.d_val.data();
-    }
     dwgpu_options gopt;
     dwgpu_options_init(&gopt);
     if (const char *dev = std::getenv("DWSOLVER_DEVICE")) gopt.device = std::atoi(dev);
@@ -178,7 +110,12 @@ int dw_solve(const char *master_file, const char *const *subproblem_files, int n
     struct EngineGuard { dwgpu_engine *e; ~EngineGuard() { dwgpu_destroy(e); } } guard{eng};
 
     // ---- restricted master (src/dw_solver.c:247-440) ---------------------------------------------------
-    MasterLP M(L + K);
+    // master LP: GUB working basis (L x L) by default; DWSOLVER_MASTER=dense selects the (L+K)^2 dense inverse
+    const char *mk = std::getenv("DWSOLVER_MASTER");
+    std::unique_ptr<IMaster> master_lp;
+    if (mk && std::strcmp(mk, "dense") == 0) master_lp.reset(new MasterLP(L + K));
+    else master_lp.reset(new GubMaster(L, K));
+    IMaster &M = *master_lp;
     std::vector<int> art_col(L, -1);
     std::vector<char> is_art;
     auto add = [&](const std::string &name, double cost, double ub, std::vector<int> idx, std::vector<double> val, bool art) {
@@ -188,16 +125,16 @@ int dw_solve(const char *master_file, const char *const *subproblem_files, int n
         return j;
     };
     for (int i = 0; i < L; ++i) {
-        const double lb = master.row_lb[i], ub = master.row_ub[i];
+        const double lb = link_lb[i], ub = link_ub[i];
         const std::string id = std::to_string(i + 1);
         if (lb == ub) {                                          // FX: artificial only (:321-336)
             M.set_rhs(i, ub);
             art_col[i] = add("y_" + id, 1.0, kInf, {i}, {ub < 0.0 ? -1.0 : 1.0}, true);
-        } else if (lb <= -1e300 && ub < 1e300) {                 // UP: su_ (+1) and y_ (-1) (:338-375)
+        } else if (lb <= -DWGPU_INF && ub < DWGPU_INF) {                 // UP: su_ (+1) and y_ (-1) (:338-375)
             M.set_rhs(i, ub);
             add("su_" + id, 0.0, kInf, {i}, {1.0}, false);
             art_col[i] = add("y_" + id, 1.0, kInf, {i}, {-1.0}, true);
-        } else if (ub >= 1e300 && lb > -1e300) {                 // LO: sl_ (-1) and y_ (+1) (:381-419)
+        } else if (ub >= DWGPU_INF && lb > -DWGPU_INF) {                 // LO: sl_ (-1) and y_ (+1) (:381-419)
             M.set_rhs(i, lb);
             add("sl_" + id, 0.0, kInf, {i}, {-1.0}, false);
             art_col[i] = add("y_" + id, 1.0, kInf, {i}, {1.0}, true);
@@ -231,7 +168,7 @@ int dw_solve(const char *master_file, const char *const *subproblem_files, int n
             const std::string name = "lambda_" + std::to_string(k) + "_" + std::to_string(iter);
             const int j = add(name, phase_one ? 0.0 : pk.cost[k], 1.0, idx, val, false);
             if (phase_one) remembered.emplace_back(j, pk.cost[k]);
-            Proposal p; p.k = k; p.iter = iter; p.x.resize(blocks[k].n);
+            Proposal p; p.k = k; p.iter = iter; p.x.resize(desc[k].n);
             if (dwgpu_fetch_x(eng, k, p.x.data()) != 0) return DW_STATUS_ERR_INTERNAL;
             X.push_back(std::move(p));
             ++added;
@@ -391,7 +328,7 @@ int dw_solve(const char *master_file, const char *const *subproblem_files, int n
     // ---- relaxed_solution: x_k = sum_t lambda_{k,t} x_k^t (src/dw_rounding.c:115-168, 561-597) -------------------
     if (opt.print_relaxed_sol) {
         std::vector<std::vector<double>> xs(K);
-        for (int k = 0; k < K; ++k) xs[k].assign(blocks[k].n, 0.0);
+        for (int k = 0; k < K; ++k) xs[k].assign(desc[k].n, 0.0);
         std::map<std::pair<int, int>, const Proposal *> by_id;
         for (auto &p : X) by_id[{p.k, p.iter}] = &p;
         for (int j = 0; j < M.cols(); ++j) {                     // every column is scanned (the reference skips the first L)
@@ -407,7 +344,10 @@ int dw_solve(const char *master_file, const char *const *subproblem_files, int n
         FILE *f = std::fopen("relaxed_solution", "w");
         if (f) {
             for (int k = 0; k < K; ++k)
-                for (int c = 0; c < blocks[k].n; ++c) std::fprintf(f, "%s\t%f\n", blocks[k].col_names[c].c_str(), xs[k][c]);
+                for (int c = 0; c < desc[k].n; ++c) {
+                    if (names) std::fprintf(f, "%s\t%f\n", (*names)[k][c].c_str(), xs[k][c]);
+                    else std::fprintf(f, "x_%d_%d\t%f\n", k, c, xs[k][c]);
+                }
             std::fclose(f);
         } else if (verb >= DW_OUTPUT_QUIET) {
             std::fprintf(stderr, "dwsolver-b200: cannot write relaxed_solution\n");
@@ -427,4 +367,100 @@ int dw_solve(const char *master_file, const char *const *subproblem_files, int n
     return fail(status);
 }
 
+extern "C" {
+
+void dw_options_init(dw_options_t *o)
+{
+    if (!o) return;
+    o->verbosity = DW_OUTPUT_NORMAL;       // src/dw_solver.c:60-75
+    o->mip_gap = 0.01;
+    o->max_phase1_iterations = 100;
+    o->max_phase2_iterations = 3000;
+    o->rounding_flag = 0;
+    o->integerize_flag = 0;
+    o->enforce_sub_integrality = 0;
+    o->print_timing_data = 0;
+    o->print_final_master = 0;
+    o->print_relaxed_sol = 1;
+    o->perturb = 0;
+    o->shift = 0.0;
+}
+
+const char *dw_version(void) { return "dwsolver-b200 0.1 (API of dwsolver 1.2.1; subproblems on sm_100a)"; }
+
+void dw_result_free(dw_result_t *r)
+{
+    if (!r) return;
+    std::free(r->x);
+    std::memset(r, 0, sizeof(*r));
+}
+
+void dw_last_stats(dw_stats_t *out) { if (out) *out = g_stats; }
+
+int dw_solve(const char *master_file, const char *const *subproblem_files, int num_subproblems, const dw_options_t *opts_in,
+             dw_result_t *result)
+{
+    if (!result) return DW_STATUS_ERR_BAD_ARGS;
+    std::memset(result, 0, sizeof(*result));
+    auto fail = [&](int code) { result->status = code; return code; };
+    if (!master_file || !subproblem_files || num_subproblems < 1) return fail(DW_STATUS_ERR_BAD_ARGS);
+    for (int k = 0; k < num_subproblems; ++k) if (!subproblem_files[k]) return fail(DW_STATUS_ERR_BAD_ARGS);
+    dw_options_t opt;
+    if (opts_in) opt = *opts_in; else dw_options_init(&opt);
+    const int verb = opt.verbosity;
+    std::memset(&g_stats, 0, sizeof(g_stats));
+    const double t_begin = now_s();
+    if (opt.enforce_sub_integrality || opt.integerize_flag || opt.rounding_flag) {
+        if (verb >= DW_OUTPUT_QUIET)
+            std::fprintf(stderr, "dwsolver-b200: integer options (-e, -i, -r) are not supported by the GPU path; solving the LP relaxation.\n");
+    }
+
+    // ---- read the problem -------------------------------------------------------------------------
+    const int K = num_subproblems;
+    LpModel master;
+    std::vector<BlockHost> blocks(K);
+    try {
+        master = read_lp_file(master_file);
+        std::vector<std::vector<std::pair<int, double>>> mcols(master.n());
+        for (size_t t = 0; t < master.a_val.size(); ++t) mcols[master.a_col[t]].emplace_back(master.a_row[t], master.a_val[t]);
+        for (int k = 0; k < K; ++k) {
+            LpModel sub = read_lp_file(subproblem_files[k]);
+            build_block(sub, master, mcols, blocks[k]);
+        }
+    } catch (const std::exception &e) {
+        if (verb >= DW_OUTPUT_QUIET) std::fprintf(stderr, "dwsolver-b200: %s\n", e.what());
+        return fail(DW_STATUS_ERR_FILE);
+    }
+    const int L = master.m();
+    g_stats.seconds_read = now_s() - t_begin;
+    std::vector<dwgpu_block_desc> desc(K);
+    std::vector<std::vector<std::string>> names(K);
+    for (int k = 0; k < K; ++k) {
+        BlockHost &b = blocks[k];
+        dwgpu_block_desc &d = desc[k];
+        d.m = b.m; d.n = b.n;
+        d.a_rowptr = b.a_rowptr.data(); d.a_col = b.a_col.data(); d.a_val = b.a_val.data();
+        d.row_lb = b.row_lb.data(); d.row_ub = b.row_ub.data(); d.col_lb = b.col_lb.data(); d.col_ub = b.col_ub.data();
+        d.c_file = b.c_file.data(); d.c_master = b.c_master.data();
+        d.d_nnz = (int)b.d_val.size(); d.d_row = b.d_row.data(); d.d_col = b.d_col.data(); d.d_val = b.d_val.data();
+        names[k] = b.col_names;
+    }
+    std::vector<double> llb(L), lub(L);
+    for (int i = 0; i < L; ++i) { llb[i] = to_engine_bound(master.row_lb[i]); lub[i] = to_engine_bound(master.row_ub[i]); }
+    return dw_core(K, L, desc.data(), llb.data(), lub.data(), &names, opt, t_begin, result);
+}
+
+int dw_solve_blocks(int K, int L, const dwgpu_block_desc *blocks, const double *link_lb, const double *link_ub,
+                    const dw_options_t *opts_in, dw_result_t *result)
+{
+    if (!result) return DW_STATUS_ERR_BAD_ARGS;
+    std::memset(result, 0, sizeof(*result));
+    if (K < 1 || L < 0 || !blocks || (L > 0 && (!link_lb || !link_ub))) { result->status = DW_STATUS_ERR_BAD_ARGS; return DW_STATUS_ERR_BAD_ARGS; }
+    dw_options_t opt;
+    if (opts_in) opt = *opts_in; else dw_options_init(&opt);
+    std::memset(&g_stats, 0, sizeof(g_stats));
+    return dw_core(K, L, blocks, link_lb, link_ub, nullptr, opt, now_s(), result);
+}
+
 }  // extern "C"
+

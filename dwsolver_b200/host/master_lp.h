@@ -16,31 +16,57 @@
 
 namespace dwh {
 
-class MasterLP {
+// what the master loop needs from an LP object (the glp_* calls of the reference)
+class IMaster {
+public:
+    virtual ~IMaster() {}
+    virtual int rows() const = 0;
+    virtual int cols() const = 0;
+    virtual void set_rhs(int i, double b) = 0;
+    virtual double rhs(int i) const = 0;
+    // returns the column index; the new column is nonbasic at 0
+    virtual int add_col(const std::string &name, double cost, double ub, const std::vector<int> &idx,
+                        const std::vector<double> &val) = 0;
+    virtual void set_cost(int j, double c) = 0;
+    virtual double cost(int j) const = 0;
+    virtual void set_coef(int j, int pos, double v) = 0;
+    virtual const std::string &name(int j) const = 0;
+    virtual const std::vector<int> &col_idx(int j) const = 0;
+    virtual const std::vector<double> &col_val(int j) const = 0;
+    // delete the columns whose flag is set; the basis is repaired with logicals (glp_del_cols + glp_adv_basis)
+    virtual void del_cols(const std::vector<char> &flag) = 0;
+    virtual void set_obj_const(double c0) = 0;
+    // 0 = optimal, 1 = infeasible, 2 = unbounded, 3 = iteration limit / numerical failure
+    virtual int solve() = 0;
+    virtual double obj_val() const = 0;
+    virtual double row_dual(int i) const = 0;
+    virtual double col_prim(int j) const = 0;
+    virtual long long it_cnt() const = 0;              // cumulative, like glp_get_it_cnt
+};
+
+class MasterLP : public IMaster {
 public:
     explicit MasterLP(int rows);
-    int rows() const { return m_; }
-    int cols() const { return (int)cost_.size(); }
-    void set_rhs(int i, double b) { b_[i] = b; xb_valid_ = false; }
-    double rhs(int i) const { return b_[i]; }
-    // returns the column index; the new column is nonbasic at 0
-    int add_col(const std::string &name, double cost, double ub, const std::vector<int> &idx, const std::vector<double> &val);
-    void set_cost(int j, double c) { cost_[j] = c; }
-    double cost(int j) const { return cost_[j]; }
-    void set_coef(int j, int pos, double v) { val_[j][pos] = v; factor_valid_ = false; }
-    const std::string &name(int j) const { return name_[j]; }
-    const std::vector<int> &col_idx(int j) const { return idx_[j]; }
-    const std::vector<double> &col_val(int j) const { return val_[j]; }
+    int rows() const override { return m_; }
+    int cols() const override { return (int)cost_.size(); }
+    void set_rhs(int i, double b) override { b_[i] = b; xb_valid_ = false; }
+    double rhs(int i) const override { return b_[i]; }
+    int add_col(const std::string &name, double cost, double ub, const std::vector<int> &idx,
+                const std::vector<double> &val) override;
+    void set_cost(int j, double c) override { cost_[j] = c; }
+    double cost(int j) const override { return cost_[j]; }
+    void set_coef(int j, int pos, double v) override { val_[j][pos] = v; factor_valid_ = false; }
+    const std::string &name(int j) const override { return name_[j]; }
+    const std::vector<int> &col_idx(int j) const override { return idx_[j]; }
+    const std::vector<double> &col_val(int j) const override { return val_[j]; }
     double col_ub(int j) const { return ub_[j]; }
-    // delete the columns whose flag is set; the basis is repaired with logicals (glp_del_cols + glp_adv_basis)
-    void del_cols(const std::vector<char> &flag);
-    void set_obj_const(double c0) { c0_ = c0; }
-    // 0 = optimal, 1 = infeasible, 2 = unbounded, 3 = iteration limit / numerical failure
-    int solve();
-    double obj_val() const { return obj_; }
-    double row_dual(int i) const { return y_[i]; }
-    double col_prim(int j) const { return x_[j]; }
-    long long it_cnt() const { return iters_; }        // cumulative, like glp_get_it_cnt
+    void del_cols(const std::vector<char> &flag) override;
+    void set_obj_const(double c0) override { c0_ = c0; }
+    int solve() override;
+    double obj_val() const override { return obj_; }
+    double row_dual(int i) const override { return y_[i]; }
+    double col_prim(int j) const override { return x_[j]; }
+    long long it_cnt() const override { return iters_; }
 
 private:
     enum { AT_LB = 0, AT_UB = 1, BASIC = 2 };

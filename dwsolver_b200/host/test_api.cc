@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "lp_model.h"
+#include "gub_master.h"
 #include "master_lp.h"
 
 extern "C" {
@@ -59,6 +60,69 @@ int dwhost_master_solve(int m, int n, const int *colptr, const int *idx, const d
     *obj = M.obj_val();
     *iters = M.it_cnt();
     return rc;
+}
+
+// The same through the GUB master: rows 0..L-1 are linking rows, rows L..L+K-1 convexity rows (every column has at
+// most one entry there, coefficient 1).  A is given by columns over all L+K rows.
+int dwhost_gub_solve(int L, int K, int n, const int *colptr, const int *idx, const double *val, const double *cost,
+                     const double *rhs, int n_first, double *x, double *y, double *obj, long long *iters)
+{
+    dwh::GubMaster M(L, K);
+    for (int i = 0; i < L + K; ++i) M.set_rhs(i, rhs[i]);
+    auto add = [&](int j) {
+        std::vector<int> ix(idx + colptr[j], idx + colptr[j + 1]);
+        std::vector<double> vv(val + colptr[j], val + colptr[j + 1]);
+        M.add_col("c" + std::to_string(j), cost[j], dwh::kInf, ix, vv);
+    };
+    int rc = 0;
+    for (int j = 0; j < n_first && j < n; ++j) add(j);
+    if (n_first > 0 && n_first < n) rc = M.solve();
+    for (int j = (n_first > 0 ? n_first : 0); j < n; ++j) add(j);
+    rc = M.solve();
+    for (int j = 0; j < n; ++j) x[j] = M.col_prim(j);
+    for (int i = 0; i < L + K; ++i) y[i] = M.row_dual(i);
+    *obj = M.obj_val();
+    *iters = M.it_cnt();
+    return rc;
+}
+
+}  // extern "C"
+
+// ---- incremental handle API over IMaster: lets the Python DW harness (tests/dw_loop.py) drive the product's master
+// LP with the CPU oracle as the subproblem engine (no GPU needed), e.g. to profile the master at config B scale
+extern "C" {
+
+void *dwhost_im_new(int L, int K, int gub)
+{
+    if (gub) return new dwh::GubMaster(L, K);
+    return new dwh::MasterLP(L + K);
+}
+void dwhost_im_free(void *h) { delete static_cast<dwh::IMaster *>(h); }
+void dwhost_im_set_rhs(void *h, int i, double b) { static_cast<dwh::IMaster *>(h)->set_rhs(i, b); }
+int dwhost_im_add_col(void *h, double cost, double ub, int nnz, const int *idx, const double *val)
+{
+    return static_cast<dwh::IMaster *>(h)->add_col("c", cost, ub >= 1e300 ? dwh::kInf : ub, std::vector<int>(idx, idx + nnz),
+                                                   std::vector<double>(val, val + nnz));
+}
+void dwhost_im_set_cost(void *h, int j, double c) { static_cast<dwh::IMaster *>(h)->set_cost(j, c); }
+void dwhost_im_set_coef(void *h, int j, int pos, double v) { static_cast<dwh::IMaster *>(h)->set_coef(j, pos, v); }
+void dwhost_im_del_cols(void *h, int n, const char *flag)
+{
+    static_cast<dwh::IMaster *>(h)->del_cols(std::vector<char>(flag, flag + n));
+}
+int dwhost_im_solve(void *h, double *obj, double *duals, long long *iters)
+{
+    dwh::IMaster *M = static_cast<dwh::IMaster *>(h);
+    const int rc = M->solve();
+    *obj = M->obj_val();
+    for (int i = 0; i < M->rows(); ++i) duals[i] = M->row_dual(i);
+    *iters = M->it_cnt();
+    return rc;
+}
+void dwhost_im_primal(void *h, double *x)
+{
+    dwh::IMaster *M = static_cast<dwh::IMaster *>(h);
+    for (int j = 0; j < M->cols(); ++j) x[j] = M->col_prim(j);
 }
 
 }  // extern "C"

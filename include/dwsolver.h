@@ -72,8 +72,17 @@ typedef struct {
     double seconds_subproblems;  /* dwgpu_* calls (device time + transfers) */
     double seconds_master;       /* restricted master solves */
 } dw_stats_t;
-/* statistics of the last dw_solve() of this process */
+/* statistics of the last dw_solve() / dw_solve_blocks() of this process */
 void dw_last_stats(dw_stats_t *out);
+
+/* dw_solve() on an in-memory instance: K blocks in the engine's descriptor format (include/dwgpu.h: CSR rows,
+ * bounds, file and master costs, COO of D_k) and the L linking rows' bounds (+-DWGPU_INF = none; each row must be
+ * <=, >= or =, like the reference's master, src/dw_solver.c:321-425).  Skips the LP text files — the reference
+ * parses them under a global mutex (src/dw_subprob.c:105-111), which dominates at thousands of blocks
+ * (SURVEY.md §8f-2).  relaxed_solution names the variables x_<k>_<j>. */
+struct dwgpu_block_desc;
+int dw_solve_blocks(int K, int L, const struct dwgpu_block_desc *blocks, const double *link_lb, const double *link_ub,
+                    const dw_options_t *opts, dw_result_t *result);
 
 #ifdef __cplusplus
 }

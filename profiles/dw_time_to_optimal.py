@@ -41,34 +41,45 @@ def main():
     K = int(os.environ.get("DW_K", "0")) or None
     prob = P.make_config(tag, K=K)
     out = {"config": tag, "K": prob.K, "L": prob.L}
-    with tempfile.TemporaryDirectory() as d:
-        t0 = time.time()
-        paths = P.write_block_angular(prob, d)
-        out["write_lp_files_s"] = round(time.time() - t0, 2)
-        L = C.CDLL(os.path.join(ROOT, "dwsolver_b200", "lib", "libdwsolver_b200.so"))
-        L.dw_solve.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(DwOptions), C.POINTER(DwResult)]
-        cwd = os.getcwd()
-        os.chdir(d)
-        try:
-            for rep in range(2):                       # the second solve has a warm CUDA context
-                o = DwOptions()
-                L.dw_options_init(C.byref(o))
-                o.verbosity = -1
-                o.print_relaxed_sol = 0
-                subs = (C.c_char_p * prob.K)(*[s.encode() for s in paths["subs"]])
-                res = DwResult()
-                t0 = time.time()
-                rc = L.dw_solve(paths["master"].encode(), subs, prob.K, C.byref(o), C.byref(res))
-                wall = time.time() - t0
-                st = DwStats()
-                L.dw_last_stats(C.byref(st))
-                out[f"gpu_solve_{rep}"] = dict(status=rc, objective=res.objective_value, wall_s=round(wall, 4),
-                                               read_s=round(st.seconds_read, 4), subproblems_s=round(st.seconds_subproblems, 4),
-                                               master_s=round(st.seconds_master, 4), dw_iterations=st.dw_iterations,
-                                               master_columns=st.master_columns, sub_pivots=st.sub_pivots)
-                L.dw_result_free(C.byref(res))
-        finally:
-            os.chdir(cwd)
+    if "--no-files" not in sys.argv:        # the reference's input path: guidefile + CPLEX-LP text
+        with tempfile.TemporaryDirectory() as d:
+            t0 = time.time()
+            paths = P.write_block_angular(prob, d)
+            out["write_lp_files_s"] = round(time.time() - t0, 2)
+            L = C.CDLL(os.path.join(ROOT, "dwsolver_b200", "lib", "libdwsolver_b200.so"))
+            L.dw_solve.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(DwOptions), C.POINTER(DwResult)]
+            cwd = os.getcwd()
+            os.chdir(d)
+            try:
+                for rep in range(2):                       # the second solve has a warm CUDA context
+                    o = DwOptions()
+                    L.dw_options_init(C.byref(o))
+                    o.verbosity = -1
+                    o.print_relaxed_sol = 0
+                    subs = (C.c_char_p * prob.K)(*[s.encode() for s in paths["subs"]])
+                    res = DwResult()
+                    t0 = time.time()
+                    rc = L.dw_solve(paths["master"].encode(), subs, prob.K, C.byref(o), C.byref(res))
+                    wall = time.time() - t0
+                    st = DwStats()
+                    L.dw_last_stats(C.byref(st))
+                    out[f"gpu_solve_{rep}"] = dict(status=rc, objective=res.objective_value, wall_s=round(wall, 4),
+                                                   read_s=round(st.seconds_read, 4), subproblems_s=round(st.seconds_subproblems, 4),
+                                                   master_s=round(st.seconds_master, 4), dw_iterations=st.dw_iterations,
+                                                   master_columns=st.master_columns, sub_pivots=st.sub_pivots)
+                    L.dw_result_free(C.byref(res))
+            finally:
+                os.chdir(cwd)
+    if "--arrays" in sys.argv:                  # in-memory entry point: no LP text at all
+        from dwsolver_b200.solver import dw_solve_blocks
+        for rep in range(2):
+            t0 = time.time()
+            r = dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=0)
+            st = r["stats"]
+            out[f"gpu_blocks_{rep}"] = dict(status=r["status"], objective=r["objective"], wall_s=round(time.time() - t0, 4),
+                                            solve_s=round(st["seconds_total"], 4), subproblems_s=round(st["seconds_subproblems"], 4),
+                                            master_s=round(st["seconds_master"], 4), dw_iterations=st["dw_iterations"],
+                                            master_columns=st["master_columns"], sub_pivots=st["sub_pivots"])
     if "--cpu" in sys.argv:
         from dw_loop import run_dw
         from oracle import oracle as O

@@ -69,10 +69,76 @@ class HighsMaster:
         return dict(obj=res.fun, x=res.x, pi=duals[:self.L].copy(), r=duals[self.L:].copy())
 
 
-def run_dw(prob, engine, max_p1=100, max_p2=3000, record=None, verbose=False):
+class ProductMaster(HighsMaster):
+    """Same bookkeeping as HighsMaster, but the LP is solved by the PRODUCT's master solver (dwsolver_b200/host:
+    GubMaster or the dense-inverse MasterLP) through its incremental test API, warm-started across rounds.
+    Lets the whole DW loop run on the CPU (oracle subproblems) with the product's master."""
+
+    def __init__(self, prob, gub=True):
+        super().__init__(prob)
+        import ctypes as C
+        import os
+        here = os.path.dirname(os.path.abspath(__file__))
+        self.C = C
+        self.lib = C.CDLL(os.path.join(here, "..", "dwsolver_b200", "lib", "libdwsolver_b200.so"))
+        self.lib.dwhost_im_new.restype = C.c_void_p
+        self.lib.dwhost_im_new.argtypes = [C.c_int, C.c_int, C.c_int]
+        self.lib.dwhost_im_free.argtypes = [C.c_void_p]
+        self.lib.dwhost_im_set_rhs.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        self.lib.dwhost_im_add_col.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        self.lib.dwhost_im_set_cost.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        self.lib.dwhost_im_del_cols.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+        self.lib.dwhost_im_solve.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+        self.lib.dwhost_im_primal.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self.h = None
+        self.gub = gub
+        self.synced = []          # (dict object, cost sent)
+        self.seconds = 0.0
+        self.iterations = 0
+
+    def _push(self, c):
+        C = self.C
+        idx = np.ascontiguousarray(c["rows"], np.int32)
+        val = np.ascontiguousarray(c["vals"], np.float64)
+        self.lib.dwhost_im_add_col(self.h, float(c["cost"]), 1e300 if np.isinf(c["ub"]) else float(c["ub"]), len(idx),
+                                   idx.ctypes.data_as(C.POINTER(C.c_int)), val.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def solve(self):
+        import time
+        C = self.C
+        if self.h is None:
+            self.h = self.lib.dwhost_im_new(self.L, self.K, 1 if self.gub else 0)
+            for i, b in enumerate(self.rhs):
+                self.lib.dwhost_im_set_rhs(self.h, i, float(b))
+        present = {id(c) for c in self.cols}
+        if any(id(c) not in present for c, _ in self.synced):
+            flags = bytes(0 if id(c) in present else 1 for c, _ in self.synced)
+            self.lib.dwhost_im_del_cols(self.h, len(flags), flags)
+            self.synced = [(c, cs) for c, cs in self.synced if id(c) in present]
+        for j, (c, cs) in enumerate(self.synced):
+            if c["cost"] != cs:
+                self.lib.dwhost_im_set_cost(self.h, j, float(c["cost"]))
+                self.synced[j] = (c, c["cost"])
+        for c in self.cols[len(self.synced):]:
+            self._push(c)
+            self.synced.append((c, c["cost"]))
+        obj, its = C.c_double(0), C.c_longlong(0)
+        duals = np.zeros(self.L + self.K)
+        t0 = time.perf_counter()
+        rc = self.lib.dwhost_im_solve(self.h, C.byref(obj), duals.ctypes.data_as(C.POINTER(C.c_double)), C.byref(its))
+        self.seconds += time.perf_counter() - t0
+        self.iterations = its.value
+        if rc != 0:
+            return None
+        x = np.zeros(len(self.cols))
+        self.lib.dwhost_im_primal(self.h, x.ctypes.data_as(C.POINTER(C.c_double)))
+        return dict(obj=obj.value, x=x, pi=duals[:self.L].copy(), r=duals[self.L:].copy())
+
+
+def run_dw(prob, engine, max_p1=100, max_p2=3000, record=None, verbose=False, master=None):
     """Returns dict(objective, iterations, x (per-block reconstructed), trajectory)."""
     K, L = prob.K, prob.L
-    master = HighsMaster(prob)
+    master = master if master is not None else HighsMaster(prob)
     need_phase_one = any(c["art"] for c in master.cols)
     r = np.full(K, DW_INFINITY)
     X = {}                    # (k, iter) -> x

@@ -182,3 +182,92 @@ def test_dw_solve_api_on_synthetic_mcf(tmp_path):
             assert not res.x
     finally:
         os.chdir(cwd)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_gub_master_matches_highs(seed):
+    """random DW-shaped masters: L linking equalities with slack/surplus columns, K convexity rows, several columns
+    per block; solved cold and with a warm second stage (columns added to an optimal basis)"""
+    L_ = lib()
+    rng = np.random.default_rng(100 + seed)
+    L, K = 4 + seed, 3 + 2 * seed
+    cols, cost = [], []
+    x0 = []
+    for k in range(K):                                  # 3-6 columns per block; the first carries weight in x0
+        nk = int(rng.integers(3, 7))
+        wts = rng.dirichlet(np.ones(nk))
+        for t in range(nk):
+            a = np.where(rng.random(L) < 0.5, rng.integers(-3, 4, L), 0).astype(float)
+            cols.append((list(np.nonzero(a)[0]) + [L + k], list(a[np.nonzero(a)[0]]) + [1.0]))
+            cost.append(float(rng.integers(-5, 6)))
+            x0.append(wts[t])
+    lam = len(cols)
+    A_link = np.zeros((L, lam))
+    for j, (ix, vv) in enumerate(cols):
+        for i, v in zip(ix, vv):
+            if i < L:
+                A_link[i, j] = v
+    act = A_link @ np.array(x0)
+    rhs = np.concatenate([act + rng.integers(0, 3, L), np.ones(K)])      # slack needed on some rows
+    for i in range(L):                                   # one +1 slack and one -1 artificial-like column per row
+        cols.append(([i], [1.0])); cost.append(0.0)
+        cols.append(([i], [-1.0])); cost.append(7.0)
+    n = len(cols)
+    m = L + K
+    A = sp.lil_matrix((m, n))
+    for j, (ix, vv) in enumerate(cols):
+        for i, v in zip(ix, vv):
+            A[i, j] = v
+    A = A.tocsc()
+    cost = np.array(cost)
+    ref = linprog(cost, A_eq=A, b_eq=rhs, bounds=[(0, None)] * n, method="highs")
+    assert ref.status == 0
+    colptr = np.zeros(n + 1, np.int32)
+    idx, val = [], []
+    for j, (ix, vv) in enumerate(cols):
+        idx += [int(i) for i in ix]; val += [float(v) for v in vv]
+        colptr[j + 1] = len(idx)
+    idx = np.array(idx, np.int32); val = np.array(val)
+    for n_first in (0, lam // 2 + 2 * L):                # (second variant: not all blocks have a column at first -> skipped)
+        if n_first:
+            have = {ix[-1] - L for (ix, vv) in cols[:n_first] if ix[-1] >= L}
+            if len(have) < K:
+                continue
+        x, y = np.zeros(n), np.zeros(m)
+        obj, its = C.c_double(0), C.c_longlong(0)
+        rc = L_.dwhost_gub_solve(L, K, n, colptr.ctypes.data_as(c_ip), idx.ctypes.data_as(c_ip), val.ctypes.data_as(c_dp),
+                                 cost.ctypes.data_as(c_dp), rhs.ctypes.data_as(c_dp), n_first, x.ctypes.data_as(c_dp),
+                                 y.ctypes.data_as(c_dp), C.byref(obj), C.byref(its))
+        assert rc == 0
+        assert abs(obj.value - ref.fun) <= 1e-8 * (1 + abs(ref.fun)), (obj.value, ref.fun)
+        assert np.abs(A @ x - rhs).max() <= 1e-8 and x.min() >= -1e-9
+        d = cost - A.T @ y
+        assert d.min() >= -1e-7                            # dual feasibility of (pi, mu)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["book_dantzig", "four_sea", "web_trick", "book_lasdon"])
+def test_dw_solve_blocks_matches_goldens(name, golden, tmp_path, monkeypatch):
+    """the in-memory entry point (no LP text) reaches the same optimum as the reference's test-suite pins"""
+    from dwsolver_b200.solver import dw_solve_blocks
+    monkeypatch.chdir(tmp_path)
+    prob = load_example(name)
+    out = dw_solve_blocks(prob, verbosity=-1)
+    want = golden["objective"][name]
+    assert out["status"] == 0 and abs(out["objective"] - want) <= 1e-7 * (1 + abs(want))
+    assert out["stats"]["dw_iterations"] > 0 and os.path.exists(tmp_path / "relaxed_solution")
+
+
+@pytest.mark.gpu
+def test_dw_solve_blocks_config_a_both_masters(monkeypatch, tmp_path):
+    """config A (1024 blocks) through dw_solve_blocks with the GUB master and with the dense-inverse master"""
+    from dwsolver_b200.solver import dw_solve_blocks
+    monkeypatch.chdir(tmp_path)
+    prob = P.make_config("A")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "traj_A.npz"))
+    want = float(z["objective"])
+    a = dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=0)
+    assert a["status"] == 0 and abs(a["objective"] - want) <= 1e-7 * (1 + abs(want))
+    monkeypatch.setenv("DWSOLVER_MASTER", "dense")
+    b = dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=0)
+    assert b["status"] == 0 and abs(b["objective"] - want) <= 1e-7 * (1 + abs(want))

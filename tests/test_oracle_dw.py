@@ -37,3 +37,15 @@ def test_examples_reach_reference_objective(name, golden):
         for k, b in enumerate(prob.blocks):
             for j, nm in enumerate(b.col_names):
                 assert "%f" % res["x"][k][j] == "%f" % sol[nm], (nm, res["x"][k][j], sol[nm])
+
+
+@pytest.mark.parametrize("gub", [True, False])
+@pytest.mark.parametrize("name", ["book_dantzig", "four_sea", "web_trick", "book_lasdon", "single_sub"])
+def test_product_master_reaches_reference_objective(name, gub, golden):
+    """the whole DW loop on the CPU: oracle subproblems + the PRODUCT's master LP (GUB working basis / dense inverse)"""
+    from dw_loop import ProductMaster, run_dw
+    prob = load_example(name)
+    res = run_dw(prob, OracleEngine(prob), master=ProductMaster(prob, gub=gub))
+    exp = golden["objective"][name]
+    assert res["status"] == "optimal"
+    assert abs(res["objective"] - exp) <= 1e-7 * (1 + abs(exp))
