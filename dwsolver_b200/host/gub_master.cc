@@ -223,7 +223,8 @@ int GubMaster::solve()
     long long stamp = 0;
     int degen_run = 0, since_refactor = 0, verify_rounds = 0;
     long long n_degen = 0, n_trivial = 0, n_full = 0, n_keyswap = 0, it_begin = iters_;
-    bool bland = false, pi_valid = false, last_phase1 = false;
+    bool bland = false, pi_valid = false, last_phase1 = false, scan_keys = true;
+    int n_key_infeasible = 0;
     std::vector<int> wq_nz;
     const long long it_limit = iters_ + 200LL * (L + K + cols()) + 20000LL;
     int status = 3;
@@ -231,7 +232,7 @@ int GubMaster::solve()
     auto is_logical = [&](int r) { return pos_var_[r] < 0; };
     for (;;) {
         if (iters_ > it_limit) { status = 3; break; }
-        if (since_refactor >= kRefactorEvery) { refactor(); compute_values(); since_refactor = 0; pi_valid = false; }
+        if (since_refactor >= kRefactorEvery) { refactor(); compute_values(); since_refactor = 0; pi_valid = false; scan_keys = true; }
         const int n = cols();
         ++stamp;
         // ---- phase: infeasibility weights (all variables >= 0; logicals are fixed at 0)
@@ -243,9 +244,14 @@ int GubMaster::solve()
             wn[r] = w;
             phase1 |= w != 0.0;
         }
-        bool key_infeasible = false;
-        for (int k = 0; k < K; ++k) { wk[k] = xkey_[k] < -kTolBnd ? -1.0 : 0.0; key_infeasible |= wk[k] != 0.0; }
-        phase1 |= key_infeasible;
+        // key variables: a full scan only after the values were recomputed; otherwise only the blocks the last
+        // step touched can have changed sign (K = 8192 at config B: this loop would cost more than the pivot)
+        if (scan_keys) {
+            n_key_infeasible = 0;
+            for (int k = 0; k < K; ++k) { wk[k] = xkey_[k] < -kTolBnd ? -1.0 : 0.0; n_key_infeasible += wk[k] != 0.0; }
+            scan_keys = false;
+        }
+        phase1 |= n_key_infeasible > 0;
         auto cost_of_key = [&](int k) { return phase1 ? wk[k] : cost_[key_[k]]; };
         // ---- duals of the working basis.  pi only depends on the working basis and on the costs of the blocks that
         // have non-key basic columns; the most common iteration of a DW master — a block's only basic column (its key)
@@ -328,7 +334,7 @@ int GubMaster::solve()
             // optimal for the current inverse: verify with a fresh factorisation once
             if (verify_rounds < 3 && since_refactor > 0) {
                 ++verify_rounds;
-                refactor(); compute_values(); since_refactor = 0; pi_valid = false;
+                refactor(); compute_values(); since_refactor = 0; pi_valid = false; scan_keys = true;
                 continue;
             }
             status = 0;
@@ -390,7 +396,13 @@ int GubMaster::solve()
         const double theta = tmin;
         // ---- values
         for (int r = 0; r < L; ++r) if (y[r] != 0.0) xn_[r] -= theta * y[r];
-        for (size_t t = 0; t < touched.size(); ++t) xkey_[touched[t]] += theta * rate[touched[t]];
+        for (size_t t = 0; t < touched.size(); ++t) {
+            const int k = touched[t];
+            xkey_[k] += theta * rate[k];
+            const double w = xkey_[k] < -kTolBnd ? -1.0 : 0.0;
+            n_key_infeasible += (w != 0.0) - (wk[k] != 0.0);
+            wk[k] = w;
+        }
         // ---- basis change
         if (leave_key >= 0 && leave_key == sq) {
             // the key of the entering column's own block leaves: the entering column becomes the key.  The block's
@@ -420,6 +432,7 @@ int GubMaster::solve()
             key_[s] = q;
             stat_[q] = KEY;
             xkey_[s] = theta;
+            n_key_infeasible -= wk[s] != 0.0; wk[s] = 0.0;
         } else {
             int r = leave_pos;
             if (leave_key >= 0) {
@@ -448,13 +461,18 @@ int GubMaster::solve()
                 pos_var_[t] = oldkey; stat_[oldkey] = NONKEY;
                 key_[s] = newkey; stat_[newkey] = KEY;
                 std::swap(xn_[t], xkey_[s]);
+                {
+                    const double w = xkey_[s] < -kTolBnd ? -1.0 : 0.0;
+                    n_key_infeasible += (w != 0.0) - (wk[s] != 0.0);
+                    wk[s] = w;
+                }
                 y[t] = -ysum;                                    // y' = M y
                 r = t;
             }
             // column replacement at position r
             const int vleave = pos_var_[r];
             const double piv = y[r];
-            if (std::fabs(piv) < 1e-12) { refactor(); compute_values(); since_refactor = 0; pi_valid = false; ++iters_; continue; }
+            if (std::fabs(piv) < 1e-12) { refactor(); compute_values(); since_refactor = 0; pi_valid = false; scan_keys = true; ++iters_; continue; }
             const double inv = 1.0 / piv;
             double *rp = &winv_[(size_t)r * L];
             scale(L, inv, rp);
