@@ -27,7 +27,7 @@ constexpr double kTolDj = 1e-9, kTolBnd = 1e-9, kTolPiv = 1e-9, kTolTie = 1e-12;
 constexpr double kInfD = std::numeric_limits<double>::infinity();
 constexpr int kRefactorEvery = 2000;     // counted in iterations that changed the working inverse (a refactorisation
                                           // costs ~2 L^3 flops: ~150 ordinary updates at L = 256)
-constexpr size_t kMaxCandidates = 512, kCandidateChunk = 32;
+constexpr size_t kMaxCandidates = 512, kCandidateChunk = 128;
 }  // namespace
 
 GubMaster::GubMaster(int linking_rows, int blocks)
