@@ -357,3 +357,39 @@ def test_config_c_block_size_against_highs():
         ref = solve_block(b, b.c_master - y)
         assert abs(props[k]["obj"] - ref.fun) <= 1e-7 * (1 + abs(ref.fun))
     eng.close()
+
+
+def test_mixed_shapes_take_three_kernel_paths_in_one_round():
+    """one instance whose blocks land on the shared-memory kernel, the global-tableau kernel and the cluster kernel:
+    a round is three launches, every block still matches an independent optimum (HiGHS) and its own pricing formula"""
+    from highs_util import solve_block
+    L = 8
+    small = P.gen_mcf(6, 16, 40, L, seed=21).blocks
+    mid = P.gen_mcf(5, 256, 512, L, seed=22).blocks
+    big = P.gen_dense(2, 600, 3000, L, seed=23, dens_a=0.01).blocks
+    blocks = small[:3] + mid[:2] + big + small[3:] + mid[2:]
+    prob = P.BlockAngularLP(K=len(blocks), L=L, blocks=blocks, link_lb=np.full(L, -np.inf), link_ub=np.full(L, 50.0))
+    eng = engine(prob)
+    paths = eng.block_paths()
+    assert set(paths) == {1, 3, 4}
+    props = eng.initial()
+    assert eng.last_launch_count() == 3
+    rng = np.random.default_rng(9)
+    for trial in range(3):
+        if trial:
+            pi = -rng.random(L) * 3.0 * trial
+            props = eng.iterate(pi, False)
+        for k, b in enumerate(prob.blocks):
+            g = props[k]
+            assert g["status"] == OPT, (k, paths[k], g["status"])
+            assert residual(b, g["x"]) <= 1e-9
+            if trial:
+                y = np.zeros(b.n)
+                np.add.at(y, b.d_col, pi[b.d_row] * b.d_val)
+                d = b.c_master - y
+            else:
+                d = b.c_file
+            assert abs(d @ g["x"] - g["obj"]) <= 1e-9 * (1 + abs(g["obj"]))
+            ref = solve_block(b, d)
+            assert abs(g["obj"] - ref.fun) <= 1e-7 * (1 + abs(ref.fun)), (k, paths[k], g["obj"], ref.fun)
+    eng.close()
