@@ -120,6 +120,11 @@ struct dwgpu_engine {
     int gpack_K = 0;
     dwk::PackDst gpk_dev{}, gpk_host{};
     DevBuf<int> gcolptr;
+    // proposal history: one growing device arena; per kept copy its offset, block and length
+    DevBuf<double> hist;
+    long long hist_used = 0, hist_cap = 0;
+    std::vector<long long> hist_off;
+    std::vector<int> hist_block;
     long long *h_dbg = nullptr, *d_dbg = nullptr;   // DWGPU_DEBUG=1: progress markers the kernels leave behind
     DevBuf<unsigned long long> counters;
     DevBuf<long long> last_iters;
@@ -165,6 +170,7 @@ void dwgpu_destroy(dwgpu_engine *e)
     if (e->h_r) cudaFreeHost(e->h_r);
     if (e->h_dbg) cudaFreeHost(e->h_dbg);
     if (e->h_gpack) cudaFreeHost(e->h_gpack);
+    e->hist.release();
     e->gcolptr.release();
     e->r_dev.release();
     e->counters.release(); e->last_iters.release();
@@ -777,6 +783,86 @@ int dwgpu_fetch_x(dwgpu_engine *e, int k, double *x)
     CU(cudaStreamSynchronize(e->stream));
     if (e->n[k] > 0)
         CU(cudaMemcpy(x, e->x.p + e->xoff[k], sizeof(double) * e->n[k], cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dwgpu_history_push(dwgpu_engine *e, int count, const int *blocks, long long *ids_out)
+{
+    if (!e || count < 0 || (count > 0 && (!blocks || !ids_out))) return fail(DWGPU_E_ARGS, "bad arguments");
+    if (count == 0) return 0;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    long long need = 0;
+    for (int i = 0; i < count; ++i) {
+        if (blocks[i] < 0 || blocks[i] >= e->K) return fail(DWGPU_E_ARGS, "block index out of range");
+        need += e->n[blocks[i]];
+    }
+    if (e->hist_used + need > e->hist_cap) {                 // grow geometrically, keep what is there
+        long long cap = std::max<long long>(2 * e->hist_cap, e->hist_used + need);
+        cap = std::max<long long>(cap, 2 * e->ntot);
+        DevBuf<double> bigger;
+        CU(bigger.alloc((size_t)cap));
+        if (e->hist_used > 0)
+            CU(cudaMemcpyAsync(bigger.p, e->hist.p, sizeof(double) * (size_t)e->hist_used, cudaMemcpyDeviceToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        e->hist.release();
+        e->hist = bigger;
+        e->hist_cap = cap;
+    }
+    std::vector<long long> src(count), dst(count);
+    std::vector<int> len(count);
+    for (int i = 0; i < count; ++i) {
+        const int k = blocks[i];
+        src[i] = e->xoff[k]; dst[i] = e->hist_used; len[i] = e->n[k];
+        ids_out[i] = (long long)e->hist_off.size();
+        e->hist_off.push_back(e->hist_used);
+        e->hist_block.push_back(k);
+        e->hist_used += e->n[k];
+    }
+    DevBuf<long long> d_src, d_dst;
+    DevBuf<int> d_len;
+    CU(d_src.upload(src)); CU(d_dst.upload(dst)); CU(d_len.upload(len));
+    dwk::history_push_kernel<<<(unsigned)count, 256, 0, st>>>(e->x.p, e->hist.p, d_src.p, d_dst.p, d_len.p, count);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    d_src.release(); d_dst.release(); d_len.release();
+    return 0;
+}
+
+int dwgpu_history_combine(dwgpu_engine *e, int nterms, const long long *ids, const double *weights, double *x_out)
+{
+    if (!e || nterms < 0 || !x_out || (nterms > 0 && (!ids || !weights))) return fail(DWGPU_E_ARGS, "bad arguments");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    // group the terms by block, keeping the given order inside a block
+    std::vector<int> cnt(e->K + 1, 0);
+    for (int t = 0; t < nterms; ++t) {
+        if (ids[t] < 0 || ids[t] >= (long long)e->hist_off.size()) return fail(DWGPU_E_ARGS, "unknown history id");
+        cnt[e->hist_block[(size_t)ids[t]] + 1]++;
+    }
+    for (int k = 0; k < e->K; ++k) cnt[k + 1] += cnt[k];
+    std::vector<long long> tid((size_t)std::max(nterms, 1));
+    std::vector<double> tw((size_t)std::max(nterms, 1));
+    {
+        std::vector<int> pos(cnt.begin(), cnt.end() - 1);
+        for (int t = 0; t < nterms; ++t) {
+            const int k = e->hist_block[(size_t)ids[t]];
+            tid[(size_t)pos[k]] = e->hist_off[(size_t)ids[t]];
+            tw[(size_t)pos[k]] = weights[t];
+            pos[k]++;
+        }
+    }
+    std::vector<long long> xoff(e->xoff.begin(), e->xoff.end() - 1);
+    DevBuf<long long> d_xoff, d_tid;
+    DevBuf<int> d_len, d_ptr;
+    DevBuf<double> d_tw, d_out;
+    CU(d_xoff.upload(xoff)); CU(d_len.upload(e->n)); CU(d_ptr.upload(cnt)); CU(d_tid.upload(tid)); CU(d_tw.upload(tw));
+    CU(d_out.alloc((size_t)std::max<long long>(e->ntot, 1)));
+    dwk::history_combine_kernel<<<(unsigned)e->K, 256, 0, st>>>(e->hist.p, d_out.p, d_xoff.p, d_len.p, d_ptr.p, d_tid.p, d_tw.p, e->K);
+    CU(cudaGetLastError());
+    if (e->ntot > 0) CU(cudaMemcpyAsync(x_out, d_out.p, sizeof(double) * (size_t)e->ntot, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    d_xoff.release(); d_tid.release(); d_len.release(); d_ptr.release(); d_tw.release(); d_out.release();
     return 0;
 }
 

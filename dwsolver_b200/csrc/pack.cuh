@@ -164,4 +164,30 @@ __global__ void __launch_bounds__(NT) order_by_last_iterations_kernel(int *list,
     for (int e = threadIdx.x; e < count; e += NT) list[e] = (int)(0xffffffffu - (unsigned)(key[e] & 0xffffffffull));
 }
 
+// ---- device-resident proposal history (see dwgpu_history_push / _combine in include/dwgpu.h) -------------
+// one CTA per listed block: hist[dst[i] ..) <- x[src[i] ..)
+__global__ void __launch_bounds__(256) history_push_kernel(const double *x, double *hist, const long long *src,
+                                                           const long long *dst, const int *len, int count)
+{
+    const int i = blockIdx.x;
+    if (i >= count) return;
+    const double *s = x + src[i];
+    double *d = hist + dst[i];
+    for (int j = threadIdx.x; j < len[i]; j += 256) d[j] = s[j];
+}
+
+// one CTA per block that has terms: x_out[xoff ..) = sum_t w[t] * hist[id[t] ..), terms applied in the given order
+__global__ void __launch_bounds__(256) history_combine_kernel(const double *hist, double *x_out, const long long *xoff,
+                                                              const int *len, const int *term_ptr, const long long *term_id,
+                                                              const double *term_w, int nblocks)
+{
+    const int b = blockIdx.x;
+    if (b >= nblocks) return;
+    for (int j = threadIdx.x; j < len[b]; j += 256) {
+        double s = 0.0;
+        for (int t = term_ptr[b]; t < term_ptr[b + 1]; ++t) s = fma(term_w[t], hist[term_id[t] + j], s);
+        x_out[xoff[b] + j] = s;
+    }
+}
+
 }  // namespace dwk

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "dwgpu_get_counters", "dwgpu_get_block_iterations", "dwgpu_last_launch_count", "dwgpu_get_block_paths",
     "dwgpu_sync", "dwgpu_last_error", "dwgpu_version", "dwgpu_last_kernel_ms", "dwgpu_measure_smem_bandwidth",
     "dwgpu_reset", "dwgpu_initial_solve_device", "dwgpu_initial_solve_packed", "dwgpu_iterate_packed", "dwgpu_pack_gathered",
-    "dwgpu_device_record", "dwgpu_pack_gathered_records",
+    "dwgpu_device_record", "dwgpu_pack_gathered_records", "dwgpu_history_push", "dwgpu_history_combine",
 ]
 
 
@@ -97,6 +97,8 @@ def load_library():
                                           C.POINTER(Packed)]
         L.dwgpu_device_record.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.dwgpu_pack_gathered_records.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Packed)]
+        L.dwgpu_history_push.argtypes = [C.c_void_p, C.c_int, c_ip, C.POINTER(C.c_longlong)]
+        L.dwgpu_history_combine.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), c_dp, c_dp]
         L.dwgpu_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.dwgpu_measure_smem_bandwidth.argtypes = [C.c_int, c_dp]
         L.dwgpu_last_error.restype = C.c_char_p
@@ -252,6 +254,23 @@ class Engine:
         return dict(obj=as_np(pk.obj, (K,)), cost=as_np(pk.cost, (K,)), status=as_np(pk.status, (K,)),
                     colptr=as_np(pk.colptr, (K + 1,)), ind=as_np(pk.ind, (nnz,)) if nnz else np.zeros(0, np.int32),
                     val=as_np(pk.val, (nnz,)) if nnz else np.zeros(0), nnz=nnz)
+
+    def history_push(self, blocks) -> np.ndarray:
+        """keep the current x_k of the listed blocks on the device; returns their history ids"""
+        b = _i32(blocks)
+        ids = np.zeros(len(b), np.int64)
+        _check(self._lib.dwgpu_history_push(self._h, len(b), b.ctypes.data_as(c_ip),
+                                            ids.ctypes.data_as(C.POINTER(C.c_longlong))), "dwgpu_history_push")
+        return ids
+
+    def history_combine(self, ids, weights) -> np.ndarray:
+        """x (block-major) = sum of weights[t] * kept copy ids[t]"""
+        ids = np.ascontiguousarray(ids, np.int64)
+        w = _f64(weights)
+        x = np.zeros(max(int(self.xoff[-1]), 1))
+        _check(self._lib.dwgpu_history_combine(self._h, len(ids), ids.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                               w.ctypes.data_as(c_dp), x.ctypes.data_as(c_dp)), "dwgpu_history_combine")
+        return x
 
     def iterate_device(self, d_pi_ptr: int, phase_one: bool, stream: int = 0):
         _check(self._lib.dwgpu_iterate_device(self._h, C.c_void_p(d_pi_ptr), int(bool(phase_one)),

@@ -83,9 +83,9 @@ void build_block(const LpModel &sub, const LpModel &master, const std::vector<st
     }
 }
 
-struct Proposal {            // X[k][iter] of the reference (src/dw_phases.c:173-179, 427-433)
+struct Proposal {            // X[k][iter] of the reference (src/dw_phases.c:173-179, 427-433): kept on the device
     int k, iter;
-    std::vector<double> x;
+    long long id;            // dwgpu_history_push id of the copy of x_k
 };
 
 }  // namespace
@@ -153,8 +153,12 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
     std::vector<double> xbuf;
     int iter = 0;
     dwgpu_packed pk;
+    std::vector<int> accepted;
+    std::vector<long long> kept_ids;
     auto consume = [&](bool phase_one, int *n_added) -> int {
         int added = 0;
+        accepted.clear();
+        const size_t first_new = X.size();
         for (int k = 0; k < K; ++k) {
             if (pk.status[k] == DWGPU_UNBND) {
                 std::fprintf(stderr, "dwsolver-b200: subproblem %d is unbounded; unbounded subproblems are not supported (src/dw_phases.c:111-115)\n", k);
@@ -168,11 +172,15 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
             const std::string name = "lambda_" + std::to_string(k) + "_" + std::to_string(iter);
             const int j = add(name, phase_one ? 0.0 : pk.cost[k], 1.0, idx, val, false);
             if (phase_one) remembered.emplace_back(j, pk.cost[k]);
-            Proposal p; p.k = k; p.iter = iter; p.x.resize(desc[k].n);
-            if (dwgpu_fetch_x(eng, k, p.x.data()) != 0) return DW_STATUS_ERR_INTERNAL;
-            X.push_back(std::move(p));
+            Proposal p; p.k = k; p.iter = iter; p.id = -1;
+            X.push_back(p);
+            accepted.push_back(k);
             ++added;
         }
+        // one device-to-device launch keeps the x_k of every accepted block (no per-column host copies)
+        kept_ids.resize(accepted.size());
+        if (dwgpu_history_push(eng, (int)accepted.size(), accepted.data(), kept_ids.data()) != 0) return DW_STATUS_ERR_INTERNAL;
+        for (size_t t = 0; t < accepted.size(); ++t) X[first_new + t].id = kept_ids[t];
         *n_added = added;
         return 0;
     };
@@ -327,10 +335,10 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
 
     // ---- relaxed_solution: x_k = sum_t lambda_{k,t} x_k^t (src/dw_rounding.c:115-168, 561-597) -------------------
     if (opt.print_relaxed_sol) {
-        std::vector<std::vector<double>> xs(K);
-        for (int k = 0; k < K; ++k) xs[k].assign(desc[k].n, 0.0);
         std::map<std::pair<int, int>, const Proposal *> by_id;
         for (auto &p : X) by_id[{p.k, p.iter}] = &p;
+        std::vector<long long> term_id;
+        std::vector<double> term_w;
         for (int j = 0; j < M.cols(); ++j) {                     // every column is scanned (the reference skips the first L)
             const double v = M.col_prim(j);
             if (v == 0.0) continue;
@@ -338,8 +346,20 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
             if (std::sscanf(M.name(j).c_str(), "lambda_%d_%d", &k, &t) != 2) continue;
             auto it = by_id.find({k, t});
             if (it == by_id.end()) continue;
-            const std::vector<double> &x = it->second->x;
-            for (size_t c = 0; c < x.size(); ++c) xs[k][c] += v * x[c];
+            term_id.push_back(it->second->id);
+            term_w.push_back(v);
+        }
+        long long ntot = 0;
+        for (int k = 0; k < K; ++k) ntot += desc[k].n;
+        std::vector<double> xall((size_t)std::max<long long>(ntot, 1), 0.0);
+        if (dwgpu_history_combine(eng, (int)term_id.size(), term_id.data(), term_w.data(), xall.data()) != 0) {
+            std::fprintf(stderr, "dwsolver-b200: %s\n", dwgpu_last_error());
+            return fail(DW_STATUS_ERR_INTERNAL);
+        }
+        std::vector<std::vector<double>> xs(K);
+        {
+            long long off = 0;
+            for (int k = 0; k < K; ++k) { xs[k].assign(xall.begin() + off, xall.begin() + off + desc[k].n); off += desc[k].n; }
         }
         FILE *f = std::fopen("relaxed_solution", "w");
         if (f) {

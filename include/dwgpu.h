@@ -179,6 +179,17 @@ int  dwgpu_fetch_results(dwgpu_engine *e, dwgpu_proposals *out);
 /* x_k of the last round for one block (n_k doubles). */
 int  dwgpu_fetch_x(dwgpu_engine *e, int k, double *x);
 
+/* Device-resident proposal history — what the reference keeps on the host as fg->x[k][iter], a copy of
+ * current_solution per accepted column (src/dw_phases.c:173-179, 427-433), read back only by the final
+ * reconstruction x_k = sum_t lambda_{k,t} x_k^t (src/dw_rounding.c:120-168).
+ * dwgpu_history_push: keep the CURRENT x_k of the listed blocks (one launch, device to device); ids_out[i]
+ *   identifies the kept copy of blocks[i].
+ * dwgpu_history_combine: x_out (host, sum n_k doubles, block-major like dwgpu_proposals.x) =
+ *   sum over the terms of weight[t] * kept copy ids[t] (added into the block it was pushed from; terms of a
+ *   block are applied in the order given). */
+int  dwgpu_history_push(dwgpu_engine *e, int count, const int *blocks, long long *ids_out);
+int  dwgpu_history_combine(dwgpu_engine *e, int nterms, const long long *ids, const double *weights, double *x_out);
+
 int  dwgpu_get_counters(dwgpu_engine *e, dwgpu_counters *total);
 /* per-block pivots+flips of the LAST round (K long longs) — load-balance diagnostics */
 int  dwgpu_get_block_iterations(dwgpu_engine *e, long long *iters);

@@ -393,3 +393,26 @@ def test_mixed_shapes_take_three_kernel_paths_in_one_round():
             ref = solve_block(b, d)
             assert abs(g["obj"] - ref.fun) <= 1e-7 * (1 + abs(ref.fun)), (k, paths[k], g["obj"], ref.fun)
     eng.close()
+
+
+def test_device_history_push_and_combine():
+    """x_k copies kept on the device (fg->x[k][iter] of the reference) and their weighted sum"""
+    prob = P.gen_mcf(12, 16, 40, 8, seed=31)
+    eng = engine(prob)
+    eng.initial()
+    x0 = eng.x.copy()
+    ids0 = eng.history_push(np.arange(prob.K))
+    eng.iterate(-np.random.default_rng(4).random(prob.L) * 30.0, False)
+    x1 = eng.x.copy()
+    assert np.abs(x1 - x0).max() > 0
+    ids1 = eng.history_push([3, 5, 7])
+    terms = list(ids0) + list(ids1)
+    w = np.concatenate([np.full(prob.K, 0.25), [0.75, 0.75, 0.75]])
+    got = eng.history_combine(terms, w)[:len(x0)]
+    want = 0.25 * x0
+    for k in (3, 5, 7):
+        a, b = eng.xoff[k], eng.xoff[k + 1]
+        want[a:b] = np.array([__import__("math").fma(0.75, v1, 0.25 * v0) if hasattr(__import__("math"), "fma") else 0.25 * v0 + 0.75 * v1
+                              for v0, v1 in zip(x0[a:b], x1[a:b])])
+    assert np.allclose(got, want, rtol=0, atol=1e-12)
+    eng.close()
