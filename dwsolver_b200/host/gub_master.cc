@@ -27,7 +27,7 @@ constexpr double kTolDj = 1e-9, kTolBnd = 1e-9, kTolPiv = 1e-9, kTolTie = 1e-12;
 constexpr double kInfD = std::numeric_limits<double>::infinity();
 constexpr int kRefactorEvery = 2000;     // counted in iterations that changed the working inverse (a refactorisation
                                           // costs ~2 L^3 flops: ~150 ordinary updates at L = 256)
-constexpr size_t kMaxCandidates = 512, kCandidateChunk = 128;
+constexpr size_t kMaxCandidates = 2048, kCandidateChunk = 128, kEnoughCandidates = 192;
 }  // namespace
 
 GubMaster::GubMaster(int linking_rows, int blocks)
@@ -218,7 +218,8 @@ int GubMaster::solve()
     if (!vals_valid_) compute_values();
     std::vector<double> pi(L), ct(L), y(L), wq(L), wn(L), u(L);
     std::vector<double> wk(K, 0.0), mu(K, 0.0), rate(K, 0.0);
-    std::vector<long long> mu_stamp(K, -1), rate_stamp(K, -1);
+    std::vector<long long> mu_stamp(K, -1), rate_stamp(K, -1), best_stamp(K, -1);
+    std::vector<int> best_slot(K, 0);
     std::vector<int> touched, cand;
     long long stamp = 0;
     int degen_run = 0, since_refactor = 0, verify_rounds = 0;
@@ -313,15 +314,33 @@ int GubMaster::solve()
         if (q < 0) {
             ++n_full;
             cand.clear();
+            // full pass.  Columns of one block compete with each other (once one of them has entered, its siblings
+            // stop being attractive), so the candidate list takes only the BEST column of every block: it then lasts
+            // for hundreds of pivots instead of a handful.
             std::vector<std::pair<double, int>> neg;
-            for (int j = 0; j < n; ++j) {
+            auto offer = [&](double d, int j) {
+                const int k = set_[j];
+                if (k < 0) { neg.emplace_back(d, j); return; }
+                if (best_stamp[k] != stamp) { best_stamp[k] = stamp; best_slot[k] = (int)neg.size(); neg.emplace_back(d, j); }
+                else if (d < neg[(size_t)best_slot[k]].first) neg[(size_t)best_slot[k]] = std::make_pair(d, j);
+            };
+            // cyclic partial pass: start where the last one stopped and stop once enough blocks have offered a
+            // column (at least an eighth of the columns is always looked at); only a complete cycle without a
+            // find proves optimality.  Bland's rule needs the lowest index: always a complete pass from 0.
+            const int start = bland ? 0 : (scan_pos_ < n ? scan_pos_ : 0);
+            int scanned = 0;
+            for (; scanned < n; ++scanned) {
+                int j = start + scanned;
+                if (j >= n) j -= n;
                 if (stat_[j] != NONBASIC) continue;
                 const double d = reduced_cost(j);
                 if (d < -kTolDj) {
                     if (bland) { q = j; dq = d; break; }
-                    neg.emplace_back(d, j);
+                    offer(d, j);
+                    if (neg.size() >= kEnoughCandidates && scanned >= n / 8) { ++scanned; break; }
                 }
             }
+            if (!bland) { scan_pos_ = start + scanned; if (scan_pos_ >= n) scan_pos_ -= n; }
             if (!bland && !neg.empty()) {
                 const size_t keep = std::min(neg.size(), kMaxCandidates);
                 std::partial_sort(neg.begin(), neg.begin() + keep, neg.end());

@@ -60,6 +60,7 @@ private:
     bool factor_valid_ = false, vals_valid_ = false, crashed_ = false;
     double c0_ = 0.0, obj_ = 0.0;
     long long iters_ = 0;
+    int scan_pos_ = 0;                  // where the next (cyclic, partial) pricing pass starts
 
     void link_minus_key(int j, std::vector<double> &w) const;     // dense L-vector a_j - a_key(set(j))
     void add_link(int j, double scale, std::vector<double> &w) const;
