@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <limits>
 
 namespace dwh {
@@ -224,6 +225,9 @@ int GubMaster::solve()
     long long stamp = 0;
     int degen_run = 0, since_refactor = 0, verify_rounds = 0;
     long long n_degen = 0, n_trivial = 0, n_full = 0, n_keyswap = 0, it_begin = iters_;
+    const bool prof = std::getenv("DWSOLVER_MASTER_DEBUG") != nullptr;
+    double t_dual = 0, t_cand = 0, t_pass = 0, t_ftran = 0, t_ratio = 0, t_update = 0;
+    auto tick = [&]() { return prof ? std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0.0; };
     bool bland = false, pi_valid = false, last_phase1 = false, scan_keys = true;
     int n_key_infeasible = 0;
     std::vector<int> wq_nz;
@@ -254,6 +258,7 @@ int GubMaster::solve()
         }
         phase1 |= n_key_infeasible > 0;
         auto cost_of_key = [&](int k) { return phase1 ? wk[k] : cost_[key_[k]]; };
+        double t0 = tick();
         // ---- duals of the working basis.  pi only depends on the working basis and on the costs of the blocks that
         // have non-key basic columns; the most common iteration of a DW master — a block's only basic column (its key)
         // is replaced by a better column of the same block — changes neither, so pi is kept across it.
@@ -289,6 +294,7 @@ int GubMaster::solve()
             if (set_[j] >= 0) d -= mu_of(set_[j]);
             return d;
         };
+        t_dual += tick() - t0; t0 = tick();
         // ---- pricing: candidates of the last full pass first, a full pass when they are exhausted
         int q = -1;
         double dq = 0.0;
@@ -311,6 +317,7 @@ int GubMaster::solve()
             for (; t < cand.size(); ++t) cand[keep++] = cand[t];     // not looked at this time
             cand.resize(keep);
         }
+        t_cand += tick() - t0; t0 = tick();
         if (q < 0) {
             ++n_full;
             cand.clear();
@@ -359,6 +366,7 @@ int GubMaster::solve()
             status = 0;
             break;
         }
+        t_pass += tick() - t0; t0 = tick();
         // ---- FTRAN on the working basis
         const int sq = set_[q];
         link_minus_key(q, wq);
@@ -370,6 +378,7 @@ int GubMaster::solve()
             for (size_t t = 0; t < wq_nz.size(); ++t) s += row[wq_nz[t]] * wq[wq_nz[t]];
             y[r] = s;
         }
+        t_ftran += tick() - t0; t0 = tick();
         // d x_key(s) / d theta = sum_{r in s} y_r - [s == set(q)]
         touched.clear();
         auto touch = [&](int k) { if (rate_stamp[k] != stamp) { rate_stamp[k] = stamp; rate[k] = 0.0; touched.push_back(k); } };
@@ -422,6 +431,7 @@ int GubMaster::solve()
             n_key_infeasible += (w != 0.0) - (wk[k] != 0.0);
             wk[k] = w;
         }
+        t_ratio += tick() - t0; t0 = tick();
         // ---- basis change
         if (leave_key >= 0 && leave_key == sq) {
             // the key of the entering column's own block leaves: the entering column becomes the key.  The block's
@@ -509,6 +519,7 @@ int GubMaster::solve()
             else pi_valid = false;
             ++since_refactor;
         }
+        t_update += tick() - t0;
         ++iters_;
         verify_rounds = 0;
         if (theta <= 1e-11) ++n_degen;
@@ -518,6 +529,9 @@ int GubMaster::solve()
     if (std::getenv("DWSOLVER_MASTER_DEBUG"))
         std::fprintf(stderr, "gub master: status %d, %lld iterations (%lld degenerate, %lld trivial key swaps, %lld key hand-overs), %lld full pricing passes, %d columns\n",
                      status, iters_ - it_begin, n_degen, n_trivial, n_keyswap, n_full, cols());
+    if (prof && iters_ - it_begin > 1000)
+        std::fprintf(stderr, "  seconds: duals %.3f, candidate pricing %.3f, pricing passes %.3f, ftran %.3f, ratio+values %.3f, basis update %.3f\n",
+                     t_dual, t_cand, t_pass, t_ftran, t_ratio, t_update);
     publish(true);
     return status;
 }
