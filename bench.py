@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--cpu-blocks", type=int, default=0, help="blocks in the CPU arm's sample (0 = auto)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-time-to-optimal", action="store_true", help="skip the dw_solve_blocks() run of the instance")
     ap.add_argument("--single-pass", action="store_true",
                     help="time e2e only and take the kernel times from that pass (config C: a step takes minutes)")
     return ap.parse_args()
@@ -476,6 +477,29 @@ def main():
                 "cells_rewritten_per_basis_change": float(kcnt[4] / max(kcnt[0], 1.0)),
                 "state_bytes_per_step": state_bytes, "peak_source": peak_src}
 
+    # ---------------- DW time-to-optimal through the drop-in host library (N = 1) ----------------
+    # the other half of BASELINE.json's metric: the whole solve (Phase I + II, own GUB master, reconstruction)
+    # of the same instance through dw_solve_blocks(); not part of `value`, reported beside it
+    tto = None
+    if world == 1 and not args.no_time_to_optimal and args.config != "C":
+        try:
+            from dwsolver_b200.solver import dw_solve_blocks
+            cwd = os.getcwd()
+            import tempfile
+            with tempfile.TemporaryDirectory() as tmpd:
+                os.chdir(tmpd)
+                try:
+                    r_ = dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=0)
+                finally:
+                    os.chdir(cwd)
+            st_ = r_["stats"]
+            tto = {"seconds": st_["seconds_total"], "subproblem_seconds": st_["seconds_subproblems"],
+                   "master_seconds": st_["seconds_master"], "dw_rounds": st_["dw_iterations"], "status": r_["status"],
+                   "objective": r_["objective"], "objective_of_recorded_run": dw_objective,
+                   "api": "dw_solve_blocks (include/dwsolver.h): GPU subproblems + this build's GUB master on one host thread"}
+        except Exception as exc:                     # the bench line must not die on the optional part
+            tto = {"error": str(exc)}
+
     # ---------------- CPU baseline: same trajectory on a bounded sample of the blocks ----------------
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -509,7 +533,7 @@ def main():
                                           "dwgpu_pack_gathered_records into rank 0's pinned record",
                 "ms_per_step": 1e3 * e2e_time / S},
         "gpu_launches": launches[0] * S,
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "dw_time_to_optimal": tto,
         "pivots": {"basis_changes_per_step": dev_cnt[0] / S, "bound_flips_per_step": dev_cnt[1] / S,
                    "rebuilds_per_step": dev_cnt[2] / S, "all_optimal": status_ok},
     }
