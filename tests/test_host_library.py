@@ -271,3 +271,34 @@ def test_dw_solve_blocks_config_a_both_masters(monkeypatch, tmp_path):
     monkeypatch.setenv("DWSOLVER_MASTER", "dense")
     b = dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=0)
     assert b["status"] == 0 and abs(b["objective"] - want) <= 1e-7 * (1 + abs(want))
+
+
+def _tiny_block(lb, ub, c, d_rows=(0,), d_vals=(1.0,)):
+    z = np.zeros(0)
+    return P.Block(m=1, n=1, a_rowptr=np.array([0, 1], np.int32), a_col=np.array([0], np.int32), a_val=np.array([1.0]),
+                   row_lb=np.array([-np.inf]), row_ub=np.array([np.inf]), col_lb=np.array([lb]), col_ub=np.array([ub]),
+                   c_file=np.array([c]), c_master=np.array([c]), d_row=np.array(d_rows, np.int32),
+                   d_col=np.zeros(len(d_rows), np.int32), d_val=np.array(d_vals, float))
+
+
+@pytest.mark.gpu
+def test_dw_solve_blocks_status_codes(monkeypatch, tmp_path):
+    """infeasible linking row -> DW_STATUS_ERR_INFEASIBLE (3); a block unbounded below -> DW_STATUS_ERR_UNBOUNDED (6)
+    (src/dw_solver.h:88-97; the reference prints and carries on, this build returns the code)"""
+    from dwsolver_b200.solver import dw_solve_blocks
+    monkeypatch.chdir(tmp_path)
+    # x1 >= 1, x2 >= 1, x1 + x2 <= 1
+    inf = P.BlockAngularLP(K=2, L=1, blocks=[_tiny_block(1.0, 5.0, 1.0), _tiny_block(1.0, 5.0, 1.0)],
+                           link_lb=np.array([-np.inf]), link_ub=np.array([1.0]))
+    out = dw_solve_blocks(inf, verbosity=-1, print_relaxed_sol=0)
+    assert out["status"] == 3
+    # feasible twin: x1 + x2 <= 3 -> optimum 2 at (1, 1)
+    ok = P.BlockAngularLP(K=2, L=1, blocks=[_tiny_block(1.0, 5.0, 1.0), _tiny_block(1.0, 5.0, 1.0)],
+                          link_lb=np.array([-np.inf]), link_ub=np.array([3.0]))
+    out = dw_solve_blocks(ok, verbosity=-1, print_relaxed_sol=0)
+    assert out["status"] == 0 and abs(out["objective"] - 2.0) <= 1e-9
+    # min x with x free below: unbounded subproblem
+    unb = P.BlockAngularLP(K=1, L=1, blocks=[_tiny_block(-np.inf, 5.0, 1.0)], link_lb=np.array([-np.inf]),
+                           link_ub=np.array([3.0]))
+    out = dw_solve_blocks(unb, verbosity=-1, print_relaxed_sol=0)
+    assert out["status"] == 6
