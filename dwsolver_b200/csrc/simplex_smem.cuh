@@ -25,9 +25,6 @@
 
 #include "simplex_cta.cuh"
 
-#ifndef DWK_TG_BLOCK_DECIDE
-#define DWK_TG_BLOCK_DECIDE 1   // 1: the whole CTA takes the pivot decision (list-based); 0: warp 0 alone
-#endif
 #ifndef DWK_TG_SB
 #define DWK_TG_SB 4         // 32-byte items per thread in flight in the sparse sweep (TG)
 #endif
@@ -1159,7 +1156,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
             __syncthreads();
         }
         // ---- B. decision (TG: the whole CTA; shared-memory tableau: warp 0)
-        if (TG && DWK_TG_BLOCK_DECIDE) {
+        if (TG) {       // (the row-item masks are maintained by decide_block_tg only)
             int kind;
             if (infeasible)
                 kind = decide_block_tg<true, NT, MC, NC>(c, c.rowp, false, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
