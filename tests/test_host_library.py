@@ -302,3 +302,27 @@ def test_dw_solve_blocks_status_codes(monkeypatch, tmp_path):
                            link_ub=np.array([3.0]))
     out = dw_solve_blocks(unb, verbosity=-1, print_relaxed_sol=0)
     assert out["status"] == 6
+
+
+@pytest.mark.gpu
+def test_random_instances_match_highs(monkeypatch, tmp_path):
+    """twelve random block-angular instances (network and dense blocks, all three small-block kernel paths) through
+    dw_solve_blocks against the HiGHS optimum of the monolithic LP (profiles/stress_dw.py runs more of them)"""
+    from dwsolver_b200.solver import dw_solve_blocks
+    from highs_util import solve_monolithic
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(77)
+    for t in range(12):
+        if t % 3 == 0:
+            nodes = int(rng.choice([16, 32, 64]))
+            prob = P.gen_mcf(int(rng.integers(8, 120)), nodes, nodes * 2 + int(rng.integers(0, 20)), int(rng.integers(2, nodes // 2)),
+                             seed=int(rng.integers(1, 10**6)))
+        elif t % 3 == 1:
+            prob = P.gen_mcf(int(rng.integers(8, 40)), 256, 512, int(rng.integers(8, 64)), seed=int(rng.integers(1, 10**6)))
+        else:
+            m = int(rng.integers(20, 100))
+            prob = P.gen_dense(int(rng.integers(2, 8)), m, 2 * m + int(rng.integers(0, 40)), int(rng.integers(2, 12)),
+                               seed=int(rng.integers(1, 10**6)), dens_a=0.08)
+        out = dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=0)
+        ref = solve_monolithic(prob)["objective"]
+        assert out["status"] == 0 and abs(out["objective"] - ref) <= 1e-7 * (1 + abs(ref)), (t, out["status"], out["objective"], ref)
