@@ -142,6 +142,17 @@ extern "C" {
 const char *dwgpu_last_error(void) { return g_err.c_str(); }
 const char *dwgpu_version(void) { return "dwgpu 0.2 (sm_100a)"; }
 
+#if DWK_TIMERS
+// profiling builds only (not part of include/dwgpu.h): cycles per kernel phase summed over all CTAs since the last reset
+int dwgpu_debug_phases(unsigned long long *out16, int reset)
+{
+    cudaDeviceSynchronize();
+    if (out16 && cudaMemcpyFromSymbol(out16, dwk::g_phase, 16 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[16] = {0}; if (cudaMemcpyToSymbol(dwk::g_phase, z, sizeof z) != cudaSuccess) return 1; }
+    return 0;
+}
+#endif
+
 void dwgpu_options_init(dwgpu_options *o)
 {
     if (!o) return;

@@ -31,6 +31,12 @@
 #ifndef DWK_TG_RB
 #define DWK_TG_RB 4         // double2 per thread in flight while staging the pivot row (TG)
 #endif
+#ifndef DWK_TG_COLMASK
+#define DWK_TG_COLMASK 1    // 1: the pivot-column fetch skips rows whose item mask says "zero" (TG)
+#endif
+#ifndef DWK_TG_FUSED
+#define DWK_TG_FUSED 1      // 1: sparse pivots fetch the pivot row inside the sweep's first batch (one HBM round trip less)
+#endif
 #ifndef DWK_TG_OCC
 #define DWK_TG_OCC 6        // CTAs per SM the 64-thread global-tableau kernel is compiled for (measured best of 3..8: no spills at 167 registers)
 #endif
@@ -124,8 +130,41 @@ template <bool TG> __device__ __forceinline__ void st_t2(double2 *p, double2 v) 
 struct Decision {
     int p, q, na, fail_status;
     int nc;          // active column items of the pivot row; -1: the row is dense, sweep whole rows
+    int fused;       // 1: rowp has NOT been staged — the sparse sweep fetches row p (first in the list) with its first batch
     double inv;
 };
+
+// Phase timers (profiling builds only, -DDWK_TIMERS=1): thread 0 of every CTA charges the cycles between two
+// marks to the phase that was current; the totals are read with dwgpu_debug_phases().
+#ifndef DWK_TIMERS
+#define DWK_TIMERS 0
+#endif
+#if DWK_TIMERS
+__device__ unsigned long long g_phase[16];
+struct PhaseClock { long long acc[16]; long long last; int cur; };
+__device__ __forceinline__ PhaseClock &phase_clock() { __shared__ PhaseClock pc; return pc; }
+__device__ __forceinline__ void phase_init()
+{
+    if (threadIdx.x == 0) { PhaseClock &pc = phase_clock(); for (int i = 0; i < 16; ++i) pc.acc[i] = 0; pc.cur = 0; pc.last = clock64(); }
+}
+__device__ __forceinline__ void phase(int k)
+{
+    if (threadIdx.x == 0) { PhaseClock &pc = phase_clock(); const long long t = clock64(); pc.acc[pc.cur] += t - pc.last; pc.last = t; pc.cur = k; }
+}
+__device__ __forceinline__ void phase_flush()
+{
+    if (threadIdx.x == 0) {
+        phase(15);
+        PhaseClock &pc = phase_clock();
+        for (int i = 0; i < 15; ++i) if (pc.acc[i]) atomicAdd(&g_phase[i], (unsigned long long)pc.acc[i]);
+        atomicAdd(&g_phase[15], 1ull);
+    }
+}
+#else
+__device__ __forceinline__ void phase_init() {}
+__device__ __forceinline__ void phase(int) {}
+__device__ __forceinline__ void phase_flush() {}
+#endif
 
 // A column ITEM is the unit the sparse sweep moves: one 32-byte sector (4 doubles) of a global-memory
 // tableau row, one double2 of a shared-memory one.
@@ -351,7 +390,7 @@ __device__ __forceinline__ int decide_warp0(Sm3 &c, const double *dd, bool d_liv
             const bool with_d = d_live && dq != 0.0;
             c.colq[m] = with_d ? dq : 0.0;
             if (with_d) c.arow[na] = (unsigned short)m;      // the reduced-cost row rides along
-            dec->p = p; dec->q = q; dec->inv = inv; dec->na = na + (with_d ? 1 : 0); dec->nc = nc;
+            dec->p = p; dec->q = q; dec->inv = inv; dec->na = na + (with_d ? 1 : 0); dec->nc = nc; dec->fused = 0;
         }
         ++n_piv;
         n_rows += (unsigned long long)na;
@@ -392,6 +431,7 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
     const double harris = 0.5 * tol_bnd;
     const int RW = ((m + NW - 1) / NW + 31) & ~31;          // rows of the column each warp fetches
     for (;;) {
+        phase(3);
         // ---- pricing, all threads
         double key = 0.0; int q = -1;
 #pragma unroll 8
@@ -419,6 +459,7 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
             if (qw >= 0 && kw > key) { key = kw; q = qw; }
         }
         if (q < 0) return K_NONE;                                // block-uniform
+        phase(4);
         const double dq = dd[q];
         const double s = dq < 0.0 ? 1.0 : -1.0;
         const signed char stq = c.cstat[q];
@@ -429,12 +470,17 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
         {
             const int rbeg = warp * RW, rend = min(m, rbeg + RW);
             constexpr int CB = MC ? (MC / NW + 31) / 32 : 4;
+            // a row whose mask has no bit for q's item holds an exact zero there: its sector is not fetched
+            // (a strided column costs one 32-byte sector per row; a network column has ~5 % non-zeros)
+            const unsigned *mq = c.rmask + (q >> 7);
+            const unsigned qbit = 1u << ((q >> 2) & 31);
+            const int rwd = c.rwd;
             for (int i00 = rbeg; i00 < rend; i00 += 32 * CB) {
                 double tcol[CB];
 #pragma unroll
                 for (int r = 0; r < CB; ++r) {
                     const int i = i00 + r * 32 + lane;
-                    tcol[r] = i < rend ? __ldcg(c.T + (size_t)i * ld + q) : 0.0;
+                    tcol[r] = (i < rend && (DWK_TG_COLMASK == 0 || (mq[(size_t)i * rwd] & qbit))) ? __ldcg(c.T + (size_t)i * ld + q) : 0.0;
                 }
 #pragma unroll
                 for (int r = 0; r < CB; ++r) {
@@ -459,6 +505,7 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
             for (int e = lane; e < cnt; e += 32) c.arow[my_off + e] = c.arow2[warp * RW + e];
         }
         __syncthreads();
+        phase(5);
         // ---- ratio test, flips and the staging of a basis change over the list: warp 0
         if (warp == 0) {
             int kind = K_PIVOT;
@@ -545,7 +592,9 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
                     const int i = c.arow[e];
                     c.beta[i] = (i == p) ? xq_new : fma(s * theta, c.colq[i], c.beta[i]);
                 }
+                __syncwarp();
                 if (lane == 0) {
+                    c.arow[pe] = c.arow[0]; c.arow[0] = (unsigned short)p;      // the sweep wants the pivot row first
                     const signed char ns = (lov == upv) ? ST_FIX : (target == lov ? ST_LO : ST_UP);
                     const int vleave = c.head[p];
                     c.rlo[p] = loq; c.rup[p] = upq;
@@ -568,6 +617,39 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
         bland = ds->bland != 0;
         if (kind == K_FLIPPED) continue;
         if (kind != K_PIVOT) return kind;
+        phase(6);
+        // ---- sparse pivot row (the usual case): its item list is its mask — exact whenever the row was last
+        // written by a sparse sweep — and the row itself is fetched by the sweep's first batch together with the
+        // rows it updates, so a pivot is two dependent HBM round trips (column, sweep) instead of three
+        if (DWK_TG_FUSED) {
+            constexpr int IW = ItemW<true>::D2;
+            const int p = dec->p, rwd = c.rwd;
+            const int nitems = (ld >> 1) / IW;
+            const unsigned *mp = c.rmask + (size_t)p * rwd;
+            int ncm = 0;
+            for (int w_ = 0; w_ < rwd; ++w_) ncm += __popc(mp[w_]);
+            if (2 * ncm <= nitems && ncm <= NT * DWK_TG_SB) {        // block-uniform; the row fits the sweep's first batch
+                if (warp == 0) {
+                    int nc = 0;
+                    for (int w_ = 0; w_ < rwd; ++w_) {
+                        const unsigned bits = mp[w_];
+                        if ((bits >> lane) & 1u) c.acol[nc + __popc(bits & lt_mask)] = (unsigned short)(w_ * 32 + lane);
+                        nc += __popc(bits);
+                    }
+                    const int na_rows = dec->na - ((dec->na > 0 && c.arow[dec->na - 1] == m) ? 1 : 0);
+                    for (int e = lane; e < na_rows; e += 32) {
+                        const int i = c.arow[e];
+                        if (i == p) continue;
+                        unsigned *mi = c.rmask + (size_t)i * rwd;
+                        for (int w_ = 0; w_ < rwd; ++w_) mi[w_] |= mp[w_];
+                    }
+                    n_cells += (unsigned long long)dec->na * (unsigned long long)nc * (2 * IW);
+                    if (lane == 0) { dec->nc = nc; dec->fused = 1; }
+                }
+                __syncthreads();
+                return K_PIVOT;
+            }
+        }
         // ---- pivot row -> rowp (scaled): only the 32-byte items whose mask bit is set are fetched (a network
         // row has ~25 of 128), everything else is written as zero; warp 0 turns the mask into the item list
         {
@@ -640,7 +722,7 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
             const int na_all = dec->na;
             n_cells += nc < 0 ? (unsigned long long)na_all * (unsigned long long)ld
                               : (unsigned long long)na_all * (unsigned long long)nc * (2 * IW);
-            if (lane == 0) dec->nc = nc;
+            if (lane == 0) { dec->nc = nc; dec->fused = 0; }
         }
         __syncthreads();
         return K_PIVOT;
@@ -662,7 +744,7 @@ __device__ __forceinline__ double cost_delta(double cs_new, double cs_saved)
 // The reduced-cost row (last list entry when it rides along) lives in shared memory and is done apart,
 // so the tableau loop is pure global (TG) or pure shared traffic with 32-bit cell offsets.
 template <int NT, int NC, bool TG>
-__device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, int na, int nc)
+__device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, int na, int nc, bool fused)
 {
     constexpr int IW = ItemW<TG>::D2;
     constexpr int SB = TG ? DWK_TG_SB : 2;                 // items per thread in flight
@@ -685,6 +767,21 @@ __device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, i
 #pragma unroll
                 for (int u = 0; u < IW; ++u) v[t][u] = ld_t2<TG>(T2 + off[t] + u);
             }
+        }
+        if (TG && fused && e0 == 0) {
+            // the list starts with the pivot row: elements [0, nc) are its items, still unscaled in v — scale
+            // them into rowp for everybody (block-uniform branch)
+            double2 *rw2 = reinterpret_cast<double2 *>(c.rowp);
+#pragma unroll
+            for (int t = 0; t < SB; ++t) {
+                const int e = t * NT + threadIdx.x;
+                if (e < nc) {
+                    const int j = (int)c.acol[e] * IW;
+#pragma unroll
+                    for (int u = 0; u < IW; ++u) rw2[j + u] = make_double2(v[t][u].x * inv, v[t][u].y * inv);
+                }
+            }
+            __syncthreads();
         }
 #pragma unroll
         for (int t = 0; t < SB; ++t) {
@@ -948,6 +1045,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
     __shared__ __align__(8) uint64_t bar;
     __shared__ int s_kind, s_changed;
     if ((int)blockIdx.x >= count) return;
+    phase_init();
     const int k = list[blockIdx.x];
     const BlockDev &B = blocks[k];      // fields are fetched where they are used (read-only, cached)
     const int m = MC ? MC : B.m, n = NC ? NC : B.n, L = B.L, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1056,6 +1154,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
 
     for (;;) {
         if (++iter > max_iter) { status = 1; break; }
+        phase(1);
         // ---- A. cooperative parts: feasibility scan, phase-1 prices, fresh reduced costs
         if (need_check || infeasible) {
             int viol = 0;
@@ -1088,6 +1187,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
             ++n_p1;
             __syncthreads();
         } else if (!d_valid) {
+            phase(2);
             // reduced costs.  If the basis has not moved since the last optimal solve of this block,
             // update the saved row incrementally: d = d_saved + dc_N + T' dc_B with dc = cs - cs_saved,
             // which only touches the rows of T whose basic cost changed (late rounds: a handful);
@@ -1178,7 +1278,8 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
         __syncthreads();
         const int kind = s_kind;
         if (kind == K_PIVOT) {
-            if (dec.nc >= 0) sweep_sparse<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na, dec.nc);
+            phase(dec.nc >= 0 ? 7 : 11);
+            if (dec.nc >= 0) sweep_sparse<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na, dec.nc, TG && dec.fused != 0);
             else sweep_active<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na);
             __syncthreads();
             continue;
@@ -1189,6 +1290,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
         if (infeasible) { status = 4; break; }
         // nothing moved since the last optimal solve of this block: x_k is still what B.x holds
         if (!s_changed && n_reb == 0 && !P.initial) { status = 5; x_in_rowp = false; break; }
+        phase(8);
         // claimed optimal: x into rowp, auxiliary values into colq
         for (int j = tid; j < n; j += NT) {
             const int v = c.nbv[j];
@@ -1210,6 +1312,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
         worst = block_max<NT>(worst, scr);
         if (worst > 0.1 * tol_bnd && n_reb < 3) {          // n_reb is block-uniform
             ++n_reb;
+            phase(9);
             // rebuild T from A_k for the current basis
             for (int e = tid; e < m * ld; e += NT) c.T[e] = 0.0;
             __syncthreads();
@@ -1258,7 +1361,9 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
                 __syncthreads();
             }
             if (TG) {       // the rebuilt tableau's pattern is unknown: every item may be non-zero
-                for (int e = tid; e < m * c.rwd; e += NT) c.rmask[e] = 0xffffffffu;
+                const int nitems = ld >> 2, tail = nitems & 31;
+                for (int e = tid; e < m * c.rwd; e += NT)
+                    c.rmask[e] = (tail && (e % c.rwd) == c.rwd - 1) ? (1u << tail) - 1u : 0xffffffffu;
                 __syncthreads();
             }
             need_check = true; d_valid = false;
@@ -1270,6 +1375,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
 
     // ---- epilogue
     __syncthreads();
+    phase(10);
     const bool changed = s_changed != 0 || n_reb != 0 || P.initial != 0 || status != 5;
     if (status != 5) {
         for (int j = tid; j < n; j += NT) {
@@ -1314,6 +1420,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
             P.counters[8 * (size_t)k + 6] += n_price;
             B.dflag[0] = d_full ? 1 : dflag_in + 1;
         }
+        phase_flush();
         return;
     }
     if (status == 5 && d_valid) {
@@ -1382,6 +1489,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     }
+    phase_flush();
 }
 
 }  // namespace dwk
