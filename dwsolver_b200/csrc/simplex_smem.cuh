@@ -980,7 +980,10 @@ __device__ __forceinline__ double weighted_colsum(const Sm3 &c, const double *wt
 }
 
 // out[4t .. 4t+3] += sum over the listed rows (ascending) of wt[i] * T[i][4t .. 4t+3], visiting only the rows whose
-// mask says item t may be non-zero (global-memory tableau).  Deterministic order; 4 predicated item loads in flight.
+// mask says item t may be non-zero (global-memory tableau).  Deterministic order.  The thread that owns item t first
+// collects, 32 listed rows at a time, WHICH of them carry the item (shared-memory reads only), then fetches those —
+// four 32-byte items in flight, every one of them useful (a network row carries ~20 % of the items, so a plain
+// "4 rows at a time, predicated" loop spends most of its HBM round trips on one load or none).
 template <int NT>
 __device__ __forceinline__ void weighted_itemsum_tg(const Sm3 &c, const double *wt, int nl, int ld, double *out)
 {
@@ -989,27 +992,33 @@ __device__ __forceinline__ void weighted_itemsum_tg(const Sm3 &c, const double *
     double2 *o2 = reinterpret_cast<double2 *>(out);
     for (int t = threadIdx.x; t < nitems; t += NT) {
         double2 a0 = o2[2 * t], a1 = o2[2 * t + 1];
-        const int wsel = t >> 5;
-        const unsigned bit = 1u << (t & 31);
-        for (int a = 0; a < nl; a += 4) {
-            double2 v0[4], v1[4];
-            double wv[4];
+        const unsigned *mcol = c.rmask + (t >> 5);
+        const int sh = t & 31;
+        for (int b0 = 0; b0 < nl; b0 += 32) {
+            unsigned have = 0;
+            const int lim = min(32, nl - b0);
+#pragma unroll 8
+            for (int u = 0; u < lim; ++u) have |= ((mcol[(size_t)c.arow[b0 + u] * rwd] >> sh) & 1u) << u;
+            while (have) {
+                double2 v0[4], v1[4];
+                double wv[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                wv[u] = 0.0; v0[u] = make_double2(0.0, 0.0); v1[u] = v0[u];      // w = 0 contributes exactly nothing
-                if (a + u < nl) {
-                    const int i = c.arow[a + u];
-                    if (c.rmask[(size_t)i * rwd + wsel] & bit) {
+                for (int u = 0; u < 4; ++u) {
+                    wv[u] = 0.0; v0[u] = make_double2(0.0, 0.0); v1[u] = v0[u];      // w = 0 contributes exactly nothing
+                    if (have) {
+                        const int a = __ffs(have) - 1;
+                        have &= have - 1;
+                        const int i = c.arow[b0 + a];
                         wv[u] = wt[i];
                         v0[u] = __ldcg(T2 + (size_t)i * n2 + 2 * t);
                         v1[u] = __ldcg(T2 + (size_t)i * n2 + 2 * t + 1);
                     }
                 }
-            }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                a0.x = fma(wv[u], v0[u].x, a0.x); a0.y = fma(wv[u], v0[u].y, a0.y);
-                a1.x = fma(wv[u], v1[u].x, a1.x); a1.y = fma(wv[u], v1[u].y, a1.y);
+                for (int u = 0; u < 4; ++u) {
+                    a0.x = fma(wv[u], v0[u].x, a0.x); a0.y = fma(wv[u], v0[u].y, a0.y);
+                    a1.x = fma(wv[u], v1[u].x, a1.x); a1.y = fma(wv[u], v1[u].y, a1.y);
+                }
             }
         }
         o2[2 * t] = a0; o2[2 * t + 1] = a1;
@@ -1103,7 +1112,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
     } else {
         const int *dcp = B.dc_ptr, *dcr = B.dc_row;
         const double *dcv = B.dc_val, *cm = B.c_master;
-        constexpr int U = 4;
+        constexpr int U = (NC && NC / NT >= 8) ? 8 : 4;      // 64-thread CTAs on 512 columns: the whole walk is one batch per level
         for (int j0 = tid; j0 < n; j0 += NT * U) {
             int pb[U], pe[U], r0[U];
             double v0[U], p0[U], base[U];
@@ -1194,7 +1203,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
             // otherwise (and every 32nd solve, to stop drift) recompute d = c_N + T' c_B in full.
             const bool inc = use_saved && !s_changed && n_reb == 0;
             const double *cssave = B.cssave, *dsave = B.dsave;     // only written in the epilogue: read-only here
-            constexpr int U = 4;
+            constexpr int U = (NC && NC / NT >= 8) ? 8 : 4;
             for (int i0 = tid; i0 < m; i0 += NT * U) {
                 double a[U], b[U];
                 bool st[U];
@@ -1395,7 +1404,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
         {
             const double *xk = B.x;
             double *dsave = B.dsave, *cssave = B.cssave;
-            constexpr int U = 4;
+            constexpr int U = (NC && NC / NT >= 8) ? 8 : 4;
             for (int j0 = tid; j0 < n; j0 += NT * U) {
                 double cv[U], xv[U], sv[U];
 #pragma unroll

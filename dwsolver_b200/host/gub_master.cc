@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <chrono>
 #include <limits>
+#include <thread>
 
 namespace dwh {
 namespace {
@@ -217,9 +218,25 @@ int GubMaster::solve()
     const int L = L_, K = K_;
     if (!factor_valid_) { if (!build_basis()) return 1; }
     if (!vals_valid_) compute_values();
-    std::vector<double> pi(L), ct(L), y(L), wq(L), wn(L), u(L);
-    std::vector<double> wk(K, 0.0), mu(K, 0.0), rate(K, 0.0);
-    std::vector<long long> mu_stamp(K, -1), rate_stamp(K, -1), best_stamp(K, -1);
+    // the dense L x L work is split by rows over a persistent team (thread_team.h); small masters stay serial
+    if (!team_) {
+        // measured on the 16-core B200 host at L = 256: 4 members take the master of config B from 8.3 s to 6.3 s,
+        // 8 are no better (the serial ratio test and candidate pricing remain); on small or shared hosts the hand-offs
+        // cost more than the slices save
+        int want = 1;
+        if (L >= 128 && std::thread::hardware_concurrency() >= 12) want = 4;
+        if (const char *e = std::getenv("DWSOLVER_MASTER_THREADS")) want = std::max(1, std::min(64, std::atoi(e)));
+        team_.reset(new ThreadTeam(std::min(want, std::max(1, L / 16))));
+    }
+    ThreadTeam &team = *team_;
+    const int T = team.size();
+    std::vector<double> pi(L), ct(L), y(L), wq(L), wn(L), u(L), rpc(L);
+    std::vector<double> wk(K, 0.0), rate(K, 0.0);
+    std::vector<long long> rate_stamp(K, -1), best_stamp(K, -1);
+    // mu_k memo, one per team member (member 0 = this thread), so that a parallel pricing pass shares nothing mutable
+    std::vector<std::vector<double>> mu_m(T, std::vector<double>(K, 0.0));
+    std::vector<std::vector<long long>> mu_stamp_m(T, std::vector<long long>(K, -1));
+    std::vector<double> dbuf;
     std::vector<int> best_slot(K, 0);
     std::vector<int> touched, cand;
     long long stamp = 0;
@@ -269,15 +286,22 @@ int GubMaster::solve()
                 if (v >= 0 && set_[v] >= 0) c -= cost_of_key(set_[v]);
                 ct[r] = c;
             }
+            // pi = W^-T ct.  Every member accumulates its own slice of COLUMNS over all rows in row order — the same
+            // additions in the same order as a serial loop, so the result does not depend on the team size
             std::fill(pi.begin(), pi.end(), 0.0);
-            for (int r = 0; r < L; ++r) {
-                if (ct[r] == 0.0) continue;
-                axpy(L, ct[r], &winv_[(size_t)r * L], pi.data());
-            }
+            team.run([&](int member, int members) {
+                const int c0 = L * member / members, c1 = L * (member + 1) / members;
+                for (int r = 0; r < L; ++r) {
+                    if (ct[r] == 0.0) continue;
+                    axpy(c1 - c0, ct[r], &winv_[(size_t)r * L + c0], pi.data() + c0);
+                }
+            });
             pi_valid = true;
         }
         last_phase1 = phase1;
-        auto mu_of = [&](int k) {
+        auto mu_of = [&](int k, int member) {
+            std::vector<double> &mu = mu_m[member];
+            std::vector<long long> &mu_stamp = mu_stamp_m[member];
             if (mu_stamp[k] != stamp) {
                 const int j = key_[k];
                 double s = cost_of_key(k);
@@ -286,14 +310,15 @@ int GubMaster::solve()
             }
             return mu[k];
         };
-        auto reduced_cost = [&](int j) {
+        auto reduced_cost_m = [&](int j, int member) {
             double d = phase1 ? 0.0 : cost_[j];
             const std::vector<int> &ix = idx_[j];
             const std::vector<double> &vv = val_[j];
             for (size_t t = 0; t < ix.size(); ++t) if (ix[t] < L) d -= pi[ix[t]] * vv[t];
-            if (set_[j] >= 0) d -= mu_of(set_[j]);
+            if (set_[j] >= 0) d -= mu_of(set_[j], member);
             return d;
         };
+        auto reduced_cost = [&](int j) { return reduced_cost_m(j, 0); };
         t_dual += tick() - t0; t0 = tick();
         // ---- pricing: candidates of the last full pass first, a full pass when they are exhausted
         int q = -1;
@@ -336,6 +361,33 @@ int GubMaster::solve()
             // find proves optimality.  Bland's rule needs the lowest index: always a complete pass from 0.
             const int start = bland ? 0 : (scan_pos_ < n ? scan_pos_ : 0);
             int scanned = 0;
+            if (T > 1 && !bland) {
+                // the team prices a chunk of columns (cyclic positions [scanned, scanned + len)) into dbuf, then this
+                // thread walks the chunk exactly as the serial loop below would: same candidates, same stop
+                const int chunk = std::max(1024, (n / 8 + 1) / 2);
+                dbuf.resize((size_t)chunk);
+                bool stop_pass = false;
+                while (scanned < n && !stop_pass) {
+                    const int len = std::min(chunk, n - scanned);
+                    team.run([&](int member, int members) {
+                        const int e0 = (int)((long long)len * member / members), e1 = (int)((long long)len * (member + 1) / members);
+                        for (int e = e0; e < e1; ++e) {
+                            int j = start + scanned + e;
+                            if (j >= n) j -= n;
+                            dbuf[(size_t)e] = stat_[j] == NONBASIC ? reduced_cost_m(j, member) : 0.0;
+                        }
+                    });
+                    for (int e = 0; e < len; ++e, ++scanned) {
+                        const double d = dbuf[(size_t)e];
+                        if (d < -kTolDj) {
+                            int j = start + scanned;
+                            if (j >= n) j -= n;
+                            offer(d, j);
+                            if (neg.size() >= kEnoughCandidates && scanned >= n / 8) { ++scanned; stop_pass = true; break; }
+                        }
+                    }
+                }
+            } else
             for (; scanned < n; ++scanned) {
                 int j = start + scanned;
                 if (j >= n) j -= n;
@@ -372,12 +424,15 @@ int GubMaster::solve()
         link_minus_key(q, wq);
         wq_nz.clear();
         for (int i = 0; i < L; ++i) if (wq[i] != 0.0) wq_nz.push_back(i);
-        for (int r = 0; r < L; ++r) {
-            const double *row = &winv_[(size_t)r * L];
-            double s = 0.0;
-            for (size_t t = 0; t < wq_nz.size(); ++t) s += row[wq_nz[t]] * wq[wq_nz[t]];
-            y[r] = s;
-        }
+        team.run([&](int member, int members) {
+            const int r0 = L * member / members, r1 = L * (member + 1) / members;
+            for (int r = r0; r < r1; ++r) {
+                const double *row = &winv_[(size_t)r * L];
+                double s = 0.0;
+                for (size_t t = 0; t < wq_nz.size(); ++t) s += row[wq_nz[t]] * wq[wq_nz[t]];
+                y[r] = s;
+            }
+        });
         t_ftran += tick() - t0; t0 = tick();
         // d x_key(s) / d theta = sum_{r in s} y_r - [s == set(q)]
         touched.clear();
@@ -451,10 +506,13 @@ int GubMaster::solve()
                 pi_valid = false;
                 ++since_refactor;
                 const double f = 1.0 / (1.0 - sigma);
-                for (int r = 0; r < L; ++r) {
-                    if (y[r] == 0.0) continue;
-                    axpy(L, y[r] * f, u.data(), &winv_[(size_t)r * L]);
-                }
+                team.run([&](int member, int members) {
+                    const int r0 = L * member / members, r1 = L * (member + 1) / members;
+                    for (int r = r0; r < r1; ++r) {
+                        if (y[r] == 0.0) continue;
+                        axpy(L, y[r] * f, u.data(), &winv_[(size_t)r * L]);
+                    }
+                });
             }
             if (!any) ++n_trivial;
             stat_[key_[s]] = NONBASIC;
@@ -504,11 +562,16 @@ int GubMaster::solve()
             if (std::fabs(piv) < 1e-12) { refactor(); compute_values(); since_refactor = 0; pi_valid = false; scan_keys = true; ++iters_; continue; }
             const double inv = 1.0 / piv;
             double *rp = &winv_[(size_t)r * L];
-            scale(L, inv, rp);
-            for (int rr = 0; rr < L; ++rr) {
-                if (rr == r || y[rr] == 0.0) continue;
-                axpy(L, -y[rr], rp, &winv_[(size_t)rr * L]);
-            }
+            for (int i = 0; i < L; ++i) rpc[i] = rp[i] * inv;      // the scaled pivot row, handed to every row owner
+            team.run([&](int member, int members) {
+                const int r0 = L * member / members, r1 = L * (member + 1) / members;
+                for (int rr = r0; rr < r1; ++rr) {
+                    double *row = &winv_[(size_t)rr * L];
+                    if (rr == r) { for (int i = 0; i < L; ++i) row[i] = rpc[i]; continue; }
+                    if (y[rr] == 0.0) continue;
+                    axpy(L, -y[rr], rpc.data(), row);
+                }
+            });
             if (vleave >= 0) stat_[vleave] = NONBASIC;
             pos_var_[r] = q;
             stat_[q] = NONKEY;

@@ -13,10 +13,12 @@
 // logical per linking row as a basis placeholder.  Primal simplex with composite phase 1, multiple pricing
 // (a candidate list re-priced between full passes), periodic refactorisation of the working inverse.
 #pragma once
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "master_lp.h"
+#include "thread_team.h"
 
 namespace dwh {
 
@@ -61,6 +63,7 @@ private:
     double c0_ = 0.0, obj_ = 0.0;
     long long iters_ = 0;
     int scan_pos_ = 0;                  // where the next (cyclic, partial) pricing pass starts
+    std::unique_ptr<ThreadTeam> team_;  // row-slice owners for the dense L x L work (created by the first large solve)
 
     void link_minus_key(int j, std::vector<double> &w) const;     // dense L-vector a_j - a_key(set(j))
     void add_link(int j, double scale, std::vector<double> &w) const;
