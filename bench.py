@@ -450,7 +450,7 @@ def main():
             peak_src = "of fallback (B200_PROFILING.md)"
         bound = "hbm"
     achieved = alg_bytes / k_time / 1e9 if k_time > 0 else 0.0
-    kname = {("A", True): "dwk::solve_smem_kernel<256,64,128,false>", ("B", False): "dwk::solve_smem_kernel<128,256,512,true>",
+    kname = {("A", True): "dwk::solve_smem_kernel<256,64,128,false>", ("B", False): "dwk::solve_smem_kernel<%d,256,512,true>" % (128 if K_loc < 3000 else 64),
              ("C", False): "dwk::solve_cluster_kernel<512>"}
     traffic, traffic_note = None, None
     try:
@@ -496,7 +496,8 @@ def main():
             tto = {"seconds": st_["seconds_total"], "subproblem_seconds": st_["seconds_subproblems"],
                    "master_seconds": st_["seconds_master"], "dw_rounds": st_["dw_iterations"], "status": r_["status"],
                    "objective": r_["objective"], "objective_of_recorded_run": dw_objective,
-                   "api": "dw_solve_blocks (include/dwsolver.h): GPU subproblems + this build's GUB master on one host thread"}
+                   "api": "dw_solve_blocks (include/dwsolver.h): GPU subproblems + this build's GUB master (a team of 4 host threads "
+                          "for the dense L x L work when the host has >= 12 cores, else one)"}
         except Exception as exc:                     # the bench line must not die on the optional part
             tto = {"error": str(exc)}
 
