@@ -332,6 +332,9 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
 
     // ---- device arenas
     CUE(e->T.alloc(t_off[K]));
+    // Test hook: fill the tableau arena with NaN bit patterns before the first initialisation.  Path 3 never zeroes its
+    // tableaux (cells outside a row's item mask are never read); a kernel that did read one would now produce NaNs.
+    if (std::getenv("DWGPU_POISON_TABLEAU")) CUE(cudaMemset(e->T.p, 0xFF, sizeof(double) * (size_t)t_off[K]));
     CUE(e->pst.alloc(pst_off[K]));
     CUE(cudaMemset(e->pst.p, 0, std::max<long long>(pst_off[K], 1)));
     CUE(e->bnd.upload(h_bnd));

@@ -31,9 +31,6 @@
 #ifndef DWK_TG_RB
 #define DWK_TG_RB 4         // double2 per thread in flight while staging the pivot row (TG)
 #endif
-#ifndef DWK_TG_COLMASK
-#define DWK_TG_COLMASK 1    // 1: the pivot-column fetch skips rows whose item mask says "zero" (TG)
-#endif
 #ifndef DWK_TG_FUSED
 #define DWK_TG_FUSED 1      // 1: sparse pivots fetch the pivot row inside the sweep's first batch (one HBM round trip less)
 #endif
@@ -480,7 +477,7 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
 #pragma unroll
                 for (int r = 0; r < CB; ++r) {
                     const int i = i00 + r * 32 + lane;
-                    tcol[r] = (i < rend && (DWK_TG_COLMASK == 0 || (mq[(size_t)i * rwd] & qbit))) ? __ldcg(c.T + (size_t)i * ld + q) : 0.0;
+                    tcol[r] = (i < rend && (mq[(size_t)i * rwd] & qbit)) ? __ldcg(c.T + (size_t)i * ld + q) : 0.0;
                 }
 #pragma unroll
                 for (int r = 0; r < CB; ++r) {
@@ -636,13 +633,6 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
                         if ((bits >> lane) & 1u) c.acol[nc + __popc(bits & lt_mask)] = (unsigned short)(w_ * 32 + lane);
                         nc += __popc(bits);
                     }
-                    const int na_rows = dec->na - ((dec->na > 0 && c.arow[dec->na - 1] == m) ? 1 : 0);
-                    for (int e = lane; e < na_rows; e += 32) {
-                        const int i = c.arow[e];
-                        if (i == p) continue;
-                        unsigned *mi = c.rmask + (size_t)i * rwd;
-                        for (int w_ = 0; w_ < rwd; ++w_) mi[w_] |= mp[w_];
-                    }
                     n_cells += (unsigned long long)dec->na * (unsigned long long)nc * (2 * IW);
                     if (lane == 0) { dec->nc = nc; dec->fused = 1; }
                 }
@@ -690,8 +680,7 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
         __syncthreads();
         if (warp == 0) {
             // exact non-zero items of the scaled pivot row -> acol; the row's mask is refreshed to exactly
-            // that pattern, and every swept row may fill in there (its mask takes the union; the sweep
-            // clears the bit again when an item comes out all zero)
+            // that pattern (the sweeps keep the masks of the rows they touch exact / a superset themselves)
             constexpr int IW = ItemW<true>::D2;
             const int p = dec->p;
             const int nitems = (ld >> 1) / IW, rwd = c.rwd;
@@ -711,13 +700,6 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
                 if (lane == 0) mp[t0 >> 5] = bal;
             }
             __syncwarp();
-            const int na_rows = dec->na - ((dec->na > 0 && c.arow[dec->na - 1] == m) ? 1 : 0);
-            for (int e = lane; e < na_rows; e += 32) {
-                const int i = c.arow[e];
-                if (i == p) continue;
-                unsigned *mi = c.rmask + (size_t)i * rwd;
-                for (int w_ = 0; w_ < rwd; ++w_) mi[w_] |= mp[w_];
-            }
             if (2 * nc > nitems) nc = -1;       // dense pivot row: whole-row sweeps are cheaper
             const int na_all = dec->na;
             n_cells += nc < 0 ? (unsigned long long)na_all * (unsigned long long)ld
@@ -757,15 +739,18 @@ __device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, i
     for (int e0 = 0; e0 < total; e0 += NT * SB) {
         double2 v[SB][IW];
         int off[SB];                                       // double2 offset of the item; -1: none
+        bool had[SB];                                      // TG: the row's mask knew the item (else it is a zero that was never stored)
 #pragma unroll
         for (int t = 0; t < SB; ++t) {
             const int e = e0 + t * NT + threadIdx.x;
-            off[t] = -1;
+            off[t] = -1; had[t] = true;
             if (e < total) {
                 const int a = e / nc;
-                off[t] = (int)c.arow[a] * nc2 + (int)c.acol[e - a * nc] * IW;
+                const int i = c.arow[a], item = c.acol[e - a * nc];
+                off[t] = i * nc2 + item * IW;
+                if (TG) had[t] = (c.rmask[(size_t)i * c.rwd + (item >> 5)] >> (item & 31)) & 1u;
 #pragma unroll
-                for (int u = 0; u < IW; ++u) v[t][u] = ld_t2<TG>(T2 + off[t] + u);
+                for (int u = 0; u < IW; ++u) v[t][u] = had[t] ? ld_t2<TG>(T2 + off[t] + u) : make_double2(0.0, 0.0);
             }
         }
         if (TG && fused && e0 == 0) {
@@ -792,6 +777,7 @@ __device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, i
                 const double cq = ci * inv;
                 const bool is_p = i == p;
                 bool all_zero = true;
+                double2 res[IW];
 #pragma unroll
                 for (int u = 0; u < IW; ++u) {
                     const double2 ra = rowp2[j + u];
@@ -802,11 +788,19 @@ __device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, i
                     if (jq == 0) r.x = is_p ? inv : cq;
                     if (jq == 1) r.y = is_p ? inv : cq;
                     all_zero = all_zero && r.x == 0.0 && r.y == 0.0;
-                    st_t2<TG>(T2 + off[t] + u, r);
+                    res[u] = r;
                 }
-                if (TG && all_zero) {        // the item cancelled exactly (network tableaux do that a lot): keep the mask tight
+                if (!TG || had[t] || !all_zero) {
+#pragma unroll
+                    for (int u = 0; u < IW; ++u) st_t2<TG>(T2 + off[t] + u, res[u]);
+                }
+                if (TG) {
+                    // the row's mask stays exact for every item the sweep visits: an item that cancelled to zero
+                    // (network tableaux do that a lot) leaves it, a fill-in enters it
                     const int item = j / IW;
-                    atomicAnd(c.rmask + (size_t)i * c.rwd + (item >> 5), ~(1u << (item & 31)));
+                    unsigned *mw = c.rmask + (size_t)i * c.rwd + (item >> 5);
+                    if (all_zero) { if (had[t]) atomicAnd(mw, ~(1u << (item & 31))); }
+                    else if (!had[t]) atomicOr(mw, 1u << (item & 31));
                 }
             }
         }
@@ -839,7 +833,7 @@ __device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, i
     constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nc2 = (NC ? tab_ld(NC, TG) : c.ld) >> 1;    // row pitch in double2
-    const int nc2a = ((NC ? NC : c.n) + 1) >> 1;          // double2 columns that can be non-zero
+    const int nc2a = TG ? nc2 : ((NC ? NC : c.n) + 1) >> 1;   // double2 columns that can be non-zero (TG: whole items, padding included)
     double2 *T2 = reinterpret_cast<double2 *>(c.T);
     double2 *d2 = reinterpret_cast<double2 *>(c.drow);
     const double2 *rowp2 = reinterpret_cast<const double2 *>(c.rowp);
@@ -852,15 +846,24 @@ __device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, i
         if (TG) {
             // global-memory tableau: issue every load of (up to) 256 double2 of the row before the
             // first dependent instruction — the sweep is a chain of DRAM round trips otherwise
+            // A cell of a global row exists only if the row's mask has its item (2 double2): everything else
+            // reads as zero without a load, and a fill-in adds the item to the mask (one warp owns the row).
             constexpr int SB = NC ? 8 : 2;
             const bool glob = i != c.m;
+            unsigned *mi = glob && c.rmask != nullptr ? c.rmask + (size_t)i * c.rwd : nullptr;
             for (int j0 = 0; j0 < nc2a; j0 += 32 * SB) {
                 double2 v[SB];
+                bool had[SB], nzv[SB];
 #pragma unroll
                 for (int t = 0; t < SB; ++t) {
                     const int j = j0 + t * 32 + lane;
-                    if (j < nc2a) v[t] = glob ? __ldcg(row + j) : row[j];
+                    had[t] = true; nzv[t] = false;
+                    if (j < nc2a) {
+                        if (mi != nullptr) had[t] = (mi[j >> 6] >> ((j >> 1) & 31)) & 1u;
+                        v[t] = !had[t] ? make_double2(0.0, 0.0) : (glob ? __ldcg(row + j) : row[j]);
+                    }
                 }
+                __syncwarp();                              // all mask reads of the batch before its updates
 #pragma unroll
                 for (int t = 0; t < SB; ++t) {
                     const int j = j0 + t * 32 + lane;
@@ -872,7 +875,18 @@ __device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, i
                         r.y = is_p ? -ra.y : fma(-ci, ra.y, v[t].y);
                         if (jq == 0) r.x = is_p ? inv : cq;
                         if (jq == 1) r.y = is_p ? inv : cq;
-                        if (glob) __stcg(row + j, r); else row[j] = r;
+                        nzv[t] = r.x != 0.0 || r.y != 0.0;
+                        v[t] = r;
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < SB; ++t) {
+                    const int j = j0 + t * 32 + lane;
+                    // a new item: both halves must be written (the partner half may hold a real zero)
+                    const bool partner_nz = __shfl_xor_sync(0xffffffffu, nzv[t] ? 1 : 0, 1) != 0;
+                    if (j < nc2a) {
+                        if (glob) { if (had[t] || nzv[t] || partner_nz) __stcg(row + j, v[t]); } else row[j] = v[t];
+                        if (mi != nullptr && !had[t] && nzv[t]) atomicOr(mi + (j >> 6), 1u << ((j >> 1) & 31));
                     }
                 }
             }
@@ -1324,6 +1338,11 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
             phase(9);
             // rebuild T from A_k for the current basis
             for (int e = tid; e < m * ld; e += NT) c.T[e] = 0.0;
+            if (TG) {       // the whole image is rewritten here and the rebuilt pattern is unknown: every item exists
+                const int nitems = ld >> 2, tail = nitems & 31;
+                for (int e = tid; e < m * c.rwd; e += NT)
+                    c.rmask[e] = (tail && (e % c.rwd) == c.rwd - 1) ? (1u << tail) - 1u : 0xffffffffu;
+            }
             __syncthreads();
             for (int i = tid; i < m; i += NT) {
                 for (int e = B.a_rp[i]; e < B.a_rp[i + 1]; ++e) c.T[(size_t)i * ld + B.a_ci[e]] += B.a_v[e];
@@ -1367,12 +1386,6 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solv
                     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                     if (lane == 0) c.beta[i] = s;
                 }
-                __syncthreads();
-            }
-            if (TG) {       // the rebuilt tableau's pattern is unknown: every item may be non-zero
-                const int nitems = ld >> 2, tail = nitems & 31;
-                for (int e = tid; e < m * c.rwd; e += NT)
-                    c.rmask[e] = (tail && (e % c.rwd) == c.rwd - 1) ? (1u << tail) - 1u : 0xffffffffu;
                 __syncthreads();
             }
             need_check = true; d_valid = false;

@@ -416,3 +416,31 @@ def test_device_history_push_and_combine():
                               for v0, v1 in zip(x0[a:b], x1[a:b])])
     assert np.allclose(got, want, rtol=0, atol=1e-12)
     eng.close()
+
+
+@pytest.mark.parametrize("shape", ["B", "dense", "generic"])
+def test_path3_reads_only_masked_cells(shape, monkeypatch):
+    """Path 3 leaves its tableaux un-zeroed: a cell exists only if its row's item mask says so.  With the arena
+    poisoned with NaN patterns (DWGPU_POISON_TABLEAU) any read outside the masks would surface as a NaN or a wrong
+    optimum — across a cold solve, priced rounds, a reset and a second run over the now stale images."""
+    from oracle import oracle as O
+    monkeypatch.setenv("DWGPU_POISON_TABLEAU", "1")
+    if shape == "B":
+        prob = P.gen_mcf(40, 256, 512, 256, 8192001)
+    elif shape == "dense":
+        prob = P.gen_dense(5, 150, 300, 12, 64001, dens_a=0.05)
+    else:
+        prob = P.gen_mcf(24, 37, 91, 16, 4242)          # n not a multiple of 4: padded last item
+    eng = engine(prob, force_path=3)
+    assert set(eng.block_paths()) == {3}
+    orc = O.OracleBlocks(prob)
+    rng = np.random.default_rng(17)
+    pis = [-rng.random(prob.L) * 15.0 * (t + 1) for t in range(3)]
+    for run in range(2):
+        if run == 1:
+            eng.reset()
+            orc = O.OracleBlocks(prob)
+        compare_round(prob, eng.initial(), orc.initial(8), None, False, initial=True)
+        for t, pi in enumerate(pis):
+            compare_round(prob, eng.iterate(pi, t == 0), orc.iterate(pi, t == 0, 8), pi, t == 0)
+    eng.close()
