@@ -450,7 +450,7 @@ def main():
             peak_src = "of fallback (B200_PROFILING.md)"
         bound = "hbm"
     achieved = alg_bytes / k_time / 1e9 if k_time > 0 else 0.0
-    kname = {("A", True): "dwk::solve_smem_kernel<256,64,128,false>", ("B", False): "dwk::solve_smem_kernel<%d,256,512,true>" % (128 if K_loc < 3000 else 64),
+    kname = {("A", True): "dwk::solve_smem_kernel<256,64,128,false>", ("B", False): "dwk::solve_smem_kernel<128,256,512,true>",
              ("C", False): "dwk::solve_cluster_kernel<512>"}
     traffic, traffic_note = None, None
     try:

@@ -534,7 +534,11 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         if (own_events) CU(cudaEventRecord(e->ev[0], st));
         auto threads_for = [&](size_t nblocks) {
             if (e->tg_threads) return e->tg_threads;
-            return nblocks < 3000 ? NT_TG_WIDE : NT_TG;         // < ~3.4 waves of 64-thread CTAs
+            // 128-thread CTAs, 4 per SM: measured best at every shard size once the sweeps maintain the row masks
+            // themselves (config B, 8192 blocks: 33.1 ms per step against 34.0 ms with 64-thread CTAs at 6 per SM,
+            // 37.3 ms at 3 per SM / 168 registers, 34.7 ms at 5 per SM / 96 registers); DWGPU_TG_THREADS overrides
+            (void)nblocks;
+            return NT_TG_WIDE;
         };
         if (!e->list_b.empty()) {
             const unsigned nb = (unsigned)e->list_b.size();

@@ -34,6 +34,9 @@
 #ifndef DWK_TG_FUSED
 #define DWK_TG_FUSED 1      // 1: sparse pivots fetch the pivot row inside the sweep's first batch (one HBM round trip less)
 #endif
+#ifndef DWK_TGW_OCC
+#define DWK_TGW_OCC 4       // CTAs per SM the 128- and 256-thread global-tableau kernels are compiled for
+#endif
 #ifndef DWK_TG_OCC
 #define DWK_TG_OCC 6        // CTAs per SM the 64-thread global-tableau kernel is compiled for (measured best of 3..8: no spills at 167 registers)
 #endif
@@ -1058,7 +1061,7 @@ __device__ __forceinline__ unsigned masked_cells(const Sm3 &c, int nl)
 // TG = true: the tableau stays in global memory (L2/HBM) and only the vectors live in shared memory
 // (blocks too large for one CTA's shared memory, config B class); the decision/sweep code is shared.
 template <int NT, int MC, int NC, bool TG>
-__global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : 4) : 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
+__global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC) : 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
                                                           SolveParams P)
 {
     extern __shared__ __align__(16) char smem_raw[];

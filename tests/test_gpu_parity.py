@@ -418,13 +418,15 @@ def test_device_history_push_and_combine():
     eng.close()
 
 
+@pytest.mark.parametrize("threads", [64, 128])
 @pytest.mark.parametrize("shape", ["B", "dense", "generic"])
-def test_path3_reads_only_masked_cells(shape, monkeypatch):
+def test_path3_reads_only_masked_cells(shape, threads, monkeypatch):
     """Path 3 leaves its tableaux un-zeroed: a cell exists only if its row's item mask says so.  With the arena
     poisoned with NaN patterns (DWGPU_POISON_TABLEAU) any read outside the masks would surface as a NaN or a wrong
     optimum — across a cold solve, priced rounds, a reset and a second run over the now stale images."""
     from oracle import oracle as O
     monkeypatch.setenv("DWGPU_POISON_TABLEAU", "1")
+    monkeypatch.setenv("DWGPU_TG_THREADS", str(threads))
     if shape == "B":
         prob = P.gen_mcf(40, 256, 512, 256, 8192001)
     elif shape == "dense":
