@@ -290,18 +290,17 @@ def main():
         launches[0] = 1
         d2h[0] = 0
         if dist is None:
-            pk = eng.initial_solve_packed()                        # kernels + packed proposals to pinned host
+            mb = eng.initial_solve_mailboxes()                     # kernels store the proposals into pinned host mailboxes
             launches[0] += eng.last_launch_count()
-            d2h[0] += packed_bytes(pk)
             if kern_acc is not None:
                 kern_acc.append(eng.last_kernel_ms())
             for r in range(R):
-                pk = eng.iterate_packed(pis[r], phases[r])         # H2D pi_r, kernels, packed proposals back
+                mb = eng.iterate_mailboxes(pis[r], phases[r])      # H2D pi_r, kernels (mailboxes written from their epilogues)
                 launches[0] += eng.last_launch_count()
-                d2h[0] += packed_bytes(pk)
                 if kern_acc is not None:
                     kern_acc.append(eng.last_kernel_ms())
-            last_status[0] = np.array(pk["status"])
+            last_status[0] = np.array(mb["status"])
+            # (d2h bytes: the device counter mailbox_bytes, read outside the timed region)
         else:
             eng.initial_solve_device(sptr)
             launches[0] += eng.last_launch_count()
@@ -336,13 +335,13 @@ def main():
 
     def count():
         c = eng.counters()
-        return np.array([c["pivots"], c["flips"], c["rebuilds"], c["rows_swept"], c["cells_swept"], c["price_cells"]],
-                        dtype=np.float64)
+        return np.array([c["pivots"], c["flips"], c["rebuilds"], c["rows_swept"], c["cells_swept"], c["price_cells"],
+                         c["mailbox_bytes"]], dtype=np.float64)
 
     # =========================== e2e ===========================
     single = args.single_pass and dist is None
-    e2e_time, e2e_cnt = 0.0, np.zeros(6)
-    sp_kern, sp_kcnt, sp_ksum = [], np.zeros(6), 0.0
+    e2e_time, e2e_cnt = 0.0, np.zeros(7)
+    sp_kern, sp_kcnt, sp_ksum = [], np.zeros(7), 0.0
     sp_clocks = ClockSampler(local_rank) if single else None
     for step in range(W + S):
         flush_buf.fill_(1)
@@ -372,7 +371,7 @@ def main():
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + S)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + S)]
     if not single:
-        dev_cnt = np.zeros(6)
+        dev_cnt = np.zeros(7)
         kern = []
     clocks = ClockSampler(local_rank)
     for step in range(0 if single else W + S):
@@ -412,7 +411,7 @@ def main():
         dist.all_reduce(pv, op=dist.ReduceOp.SUM)
         t_dev, e2e_time, k_time = (float(v) for v in tt.tolist())
         pv = pv.cpu().numpy()
-        dev_cnt, e2e_cnt, kcnt = pv[0:6], pv[6:12], pv[12:18]
+        dev_cnt, e2e_cnt, kcnt = pv[0:7], pv[7:14], pv[14:21]
     eng.close()
     if rank != 0:
         if dist is not None:
@@ -528,8 +527,9 @@ def main():
                    "dw_objective_of_trajectory": dw_objective},
         "e2e": {"value": (e2e_cnt[0] + e2e_cnt[1]) / e2e_time if e2e_time > 0 else 0.0, "unit": UNIT,
                 "h2d_bytes_per_step": 8 * L * R,
-                "d2h_bytes_per_step": d2h[0],
-                "api": "dwgpu_initial_solve_packed + dwgpu_iterate_packed (host pi in, pinned packed record out)"
+                "d2h_bytes_per_step": int(e2e_cnt[6] / max(S, 1)) if world == 1 else d2h[0],
+                "api": "dwgpu_initial_solve_mailboxes + dwgpu_iterate_mailboxes (host pi in; the kernels store every block's "
+                       "proposal into pinned host mailboxes, d2h = bytes stored, device counter)"
                        if world == 1 else "per rank dwgpu_iterate_device; NCCL broadcast of pi, ONE all-gather of the result records, "
                                           "dwgpu_pack_gathered_records into rank 0's pinned record",
                 "ms_per_step": 1e3 * e2e_time / S},

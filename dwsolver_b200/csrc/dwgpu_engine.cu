@@ -119,6 +119,10 @@ struct dwgpu_engine {
     char *h_gpack = nullptr, *d_gpack = nullptr;
     int gpack_K = 0;
     dwk::PackDst gpk_dev{}, gpk_host{};
+    // host mailboxes (dwgpu_*_mailboxes): mapped pinned arrays, created by the first call
+    char *h_mail = nullptr, *d_mail = nullptr;
+    dwk::MailDst mail_dev{}, mail_host{};
+    bool mail_valid = false;           // the previous round wrote the mailboxes (unchanged blocks may keep theirs)
     DevBuf<int> gcolptr;
     // proposal history: one growing device arena; per kept copy its offset, block and length
     DevBuf<double> hist;
@@ -178,6 +182,7 @@ void dwgpu_destroy(dwgpu_engine *e)
     e->dr_col.release(); e->blocks.release(); e->d_list_smem.release();
     e->d_list_gmem.release(); e->d_list_a.release(); e->d_list_g.release(); e->d_list_b.release(); e->d_list_c.release(); e->pi.release(); e->rec.release(); e->colptr.release();
     if (e->h_pack) cudaFreeHost(e->h_pack);
+    if (e->h_mail) cudaFreeHost(e->h_mail);
     if (e->h_r) cudaFreeHost(e->h_r);
     if (e->h_dbg) cudaFreeHost(e->h_dbg);
     if (e->h_gpack) cudaFreeHost(e->h_gpack);
@@ -477,9 +482,16 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
 #undef CUE
 }
 
-static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int initial, cudaStream_t st)
+static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int initial, cudaStream_t st, bool mail = false)
 {
     dwk::SolveParams P;
+    if (mail && e->mail_valid) {
+        P.m_obj = e->mail_dev.obj; P.m_cost = e->mail_dev.cost; P.m_val = e->mail_dev.val;
+        P.m_status = e->mail_dev.status; P.m_len = e->mail_dev.len; P.m_ind = e->mail_dev.ind;
+    } else {
+        P.m_obj = P.m_cost = P.m_val = nullptr; P.m_status = P.m_len = P.m_ind = nullptr;
+        if (!mail) e->mail_valid = false;
+    }
     P.pi = d_pi; P.phase_one = phase_one; P.initial = initial;
     P.max_iter_mult = e->opt.max_iter_mult;
     P.no_dual_start = e->opt.no_dual_start;
@@ -714,6 +726,71 @@ static int pack_gathered_impl(dwgpu_engine *e, int K_total, const dwgpu_proposal
     return 0;
 }
 
+// One round whose results land in the host mailboxes.  When the previous round wrote them too, the shared-memory /
+// global-tableau kernels store into them from their epilogues and only the blocks of the legacy and cluster paths
+// are copied afterwards; otherwise (first call, or another API was used in between) every block is copied once.
+static int mailbox_round(dwgpu_engine *e, const double *d_pi, int phase_one, int initial, dwgpu_mailboxes *out)
+{
+    if (!out) return fail(DWGPU_E_ARGS, "out is NULL");
+    cudaStream_t st = e->stream;
+    const size_t K = (size_t)e->K, KL = K * (size_t)e->L;
+    if (!e->h_mail) {
+        const size_t bytes = sizeof(double) * (2 * K + KL) + sizeof(int) * (2 * K + KL) + 64;
+        CU(cudaHostAlloc((void **)&e->h_mail, bytes, cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer((void **)&e->d_mail, e->h_mail, 0));
+        std::memset(e->h_mail, 0, bytes);
+        auto carve = [&](char *base, dwk::MailDst &d) {
+            double *dd = (double *)base;
+            d.obj = dd; d.cost = dd + K; d.val = dd + 2 * K;
+            int *ii = (int *)(dd + 2 * K + KL);
+            d.status = ii; d.len = ii + K; d.ind = ii + 2 * K;
+        };
+        carve(e->d_mail, e->mail_dev);
+        carve(e->h_mail, e->mail_host);
+        e->mail_valid = false;
+    }
+    const bool direct = e->mail_valid;
+    int rc = launch_round(e, d_pi, phase_one, initial, st, true);
+    if (rc) return rc;
+    dwk::PackSrc s;
+    std::memset(&s, 0, sizeof(s));
+    s.obj = e->obj.p; s.cost = e->cost.p; s.val = e->val.p; s.status = e->status.p; s.len = e->len.p; s.ind = e->ind.p;
+    s.K = e->K; s.L = e->L;
+    auto copy = [&](const int *list, size_t count) -> cudaError_t {
+        if (!count) return cudaSuccess;
+        dwk::mailbox_copy_kernel<256><<<(unsigned)((count + 7) / 8), 256, 0, st>>>(s, list, (int)count, e->mail_dev, e->counters.p);
+        e->last_launches++;
+        return cudaGetLastError();
+    };
+    if (!direct) CU(copy(nullptr, K));
+    else { CU(copy(e->d_list_gmem.p, e->list_gmem.size())); CU(copy(e->d_list_c.p, e->list_c.size())); }
+    e->mail_valid = true;
+    CU(cudaStreamSynchronize(st));
+    out->obj = e->mail_host.obj; out->cost = e->mail_host.cost; out->val = e->mail_host.val;
+    out->status = e->mail_host.status; out->len = e->mail_host.len; out->ind = e->mail_host.ind;
+    out->K = e->K; out->L = e->L;
+    return 0;
+}
+
+int dwgpu_initial_solve_mailboxes(dwgpu_engine *e, dwgpu_mailboxes *out)
+{
+    if (!e || !e->initialised) return fail(DWGPU_E_STATE, "engine not initialised");
+    CU(cudaSetDevice(e->device));
+    return mailbox_round(e, nullptr, 0, 1, out);
+}
+
+int dwgpu_iterate_mailboxes(dwgpu_engine *e, const double *pi, int phase_one, dwgpu_mailboxes *out)
+{
+    if (!e || !e->initialised) return fail(DWGPU_E_STATE, "engine not initialised");
+    if (!pi && e->L > 0) return fail(DWGPU_E_ARGS, "pi is NULL");
+    CU(cudaSetDevice(e->device));
+    if (e->L > 0) {
+        std::memcpy(e->h_pi, pi, sizeof(double) * e->L);
+        CU(cudaMemcpyAsync(e->pi.p, e->h_pi, sizeof(double) * e->L, cudaMemcpyHostToDevice, e->stream));
+    }
+    return mailbox_round(e, e->pi.p, phase_one ? 1 : 0, 0, out);
+}
+
 int dwgpu_initial_solve_packed(dwgpu_engine *e, dwgpu_packed *out)
 {
     if (!e || !e->initialised) return fail(DWGPU_E_STATE, "engine not initialised");
@@ -898,6 +975,7 @@ int dwgpu_get_counters(dwgpu_engine *e, dwgpu_counters *t)
         t->rows_swept += (long long)h[8 * (size_t)k + 4];
         t->cells_swept += (long long)h[8 * (size_t)k + 5];
         t->price_cells += (long long)h[8 * (size_t)k + 6];
+        t->mailbox_bytes += (long long)h[8 * (size_t)k + 7];
     }
     t->solves = e->solves;
     return 0;

@@ -124,6 +124,29 @@ __global__ void __launch_bounds__(NT) pack_copy_kernel(PackSrc s, const int *col
     }
 }
 
+// ---- host mailboxes: blocks whose kernel does not write its mailbox itself (legacy and cluster paths), or every block
+// when the mailboxes were not written in the previous round: one warp per listed block (list == nullptr: blocks 0..count-1)
+struct MailDst { double *obj, *cost, *val; int *status, *len, *ind; };
+
+template <int NT>
+__global__ void __launch_bounds__(NT) mailbox_copy_kernel(PackSrc s, const int *list, int count, MailDst d, unsigned long long *counters)
+{
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    if (e >= count) return;
+    const int k = list ? list[e] : e;
+    const PackBlk blk = pack_block(s, k);
+    const int ln = blk.len[0];
+    if (lane == 0) {
+        d.obj[k] = blk.obj[0]; d.cost[k] = blk.cost[0]; d.status[k] = blk.status[0]; d.len[k] = ln;
+        if (counters) counters[8 * (size_t)k + 7] += 24ull + 12ull * (unsigned long long)ln;
+    }
+    for (int t = lane; t < ln; t += 32) {
+        d.ind[(size_t)k * s.L + t] = blk.ind[t];
+        d.val[(size_t)k * s.L + t] = blk.val[t];
+    }
+}
+
 // ---- longest-processing-time-first launch order -----------------------------------------------------
 // A round's kernel time is max(total work / resident CTAs, longest block).  Blocks differ by 100x in
 // pivots (most need none), and the blocks that pivoted a lot in the previous round tend to do so

@@ -66,6 +66,10 @@ struct SolveParams {
     unsigned long long *counters;  // K*8: pivots, flips, rebuilds, phase-1 iterations, rows swept, 3 spare
     long long *last_iters;         // K
     long long *dbg;                // K*32 progress markers in mapped host memory (nullptr: off)
+    // host mailboxes (mapped pinned memory, written by the kernels' epilogues; nullptr: off): same layout as the
+    // device arrays above.  A block whose state did not change in a round only rewrites its obj.
+    double *m_obj, *m_cost, *m_val;
+    int *m_status, *m_len, *m_ind;
 };
 
 // working-set view (shared or global)

@@ -1442,6 +1442,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
         zo = block_sum<NT>(zo, scr);
         if (tid == 0) {
             P.obj[k] = zo; P.status[k] = 5; P.last_iters[k] = 0;
+            if (P.m_obj != nullptr) { P.m_obj[k] = zo; P.m_status[k] = 5; P.counters[8 * (size_t)k + 7] += 12; }   // the rest of the mailbox still holds
             P.counters[8 * (size_t)k + 6] += n_price;
             B.dflag[0] = d_full ? 1 : dflag_in + 1;
         }
@@ -1494,6 +1495,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
                 const int pos = base + __popc(bal & ((1u << lane) - 1u));
                 yv[pos] = y;
                 yi[pos] = i + 1;
+                if (P.m_val != nullptr) { P.m_val[(size_t)k * L + pos] = y; P.m_ind[(size_t)k * L + pos] = i + 1; }
             }
             base += __popc(bal);
             __syncwarp();
@@ -1511,6 +1513,10 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
             P.counters[8 * (size_t)k + 5] += n_cells;
             P.counters[8 * (size_t)k + 6] += n_price;
             P.last_iters[k] = (long long)(n_piv + n_flip);
+            if (P.m_obj != nullptr) {
+                P.m_obj[k] = zo; P.m_cost[k] = zc; P.m_status[k] = status; P.m_len[k] = base;
+                P.counters[8 * (size_t)k + 7] += 24ull + 12ull * (unsigned long long)base;
+            }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     }

@@ -29,6 +29,7 @@ ABI_SYMBOLS = [
     "dwgpu_sync", "dwgpu_last_error", "dwgpu_version", "dwgpu_last_kernel_ms", "dwgpu_measure_smem_bandwidth",
     "dwgpu_reset", "dwgpu_initial_solve_device", "dwgpu_initial_solve_packed", "dwgpu_iterate_packed", "dwgpu_pack_gathered",
     "dwgpu_device_record", "dwgpu_pack_gathered_records", "dwgpu_history_push", "dwgpu_history_combine",
+    "dwgpu_initial_solve_mailboxes", "dwgpu_iterate_mailboxes",
 ]
 
 
@@ -59,7 +60,12 @@ class Packed(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("pivots", C.c_longlong), ("flips", C.c_longlong), ("rebuilds", C.c_longlong),
                 ("phase1_iter", C.c_longlong), ("solves", C.c_longlong), ("rows_swept", C.c_longlong),
-                ("cells_swept", C.c_longlong), ("price_cells", C.c_longlong)]
+                ("cells_swept", C.c_longlong), ("price_cells", C.c_longlong), ("mailbox_bytes", C.c_longlong)]
+
+
+class Mailboxes(C.Structure):
+    _fields_ = [("obj", c_dp), ("cost", c_dp), ("val", c_dp), ("status", c_ip), ("len", c_ip), ("ind", c_ip),
+                ("K", C.c_int), ("L", C.c_int)]
 
 
 _LIB = None
@@ -99,6 +105,8 @@ def load_library():
         L.dwgpu_pack_gathered_records.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Packed)]
         L.dwgpu_history_push.argtypes = [C.c_void_p, C.c_int, c_ip, C.POINTER(C.c_longlong)]
         L.dwgpu_history_combine.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), c_dp, c_dp]
+        L.dwgpu_initial_solve_mailboxes.argtypes = [C.c_void_p, C.POINTER(Mailboxes)]
+        L.dwgpu_iterate_mailboxes.argtypes = [C.c_void_p, c_dp, C.c_int, C.POINTER(Mailboxes)]
         L.dwgpu_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.dwgpu_measure_smem_bandwidth.argtypes = [C.c_int, c_dp]
         L.dwgpu_last_error.restype = C.c_char_p
@@ -205,6 +213,26 @@ class Engine:
                     colptr=as_np(pk.colptr, (K + 1,)),
                     ind=as_np(pk.ind, (nnz,)) if nnz else np.zeros(0, np.int32),
                     val=as_np(pk.val, (nnz,)) if nnz else np.zeros(0), nnz=nnz)
+
+    def _mailbox_views(self, mb: "Mailboxes") -> dict:
+        K, L = int(mb.K), int(mb.L)
+        as_np = np.ctypeslib.as_array
+        return dict(obj=as_np(mb.obj, (K,)), cost=as_np(mb.cost, (K,)), status=as_np(mb.status, (K,)), len=as_np(mb.len, (K,)),
+                    ind=as_np(mb.ind, (K, L)) if L else np.zeros((K, 0), np.int32),
+                    val=as_np(mb.val, (K, L)) if L else np.zeros((K, 0)))
+
+    def initial_solve_mailboxes(self) -> dict:
+        """dwgpu_initial_solve_mailboxes: views of the engine's pinned host mailboxes (the kernels store into them)."""
+        mb = Mailboxes()
+        _check(self._lib.dwgpu_initial_solve_mailboxes(self._h, C.byref(mb)), "dwgpu_initial_solve_mailboxes")
+        return self._mailbox_views(mb)
+
+    def iterate_mailboxes(self, pi, phase_one: bool) -> dict:
+        pi = _f64(pi)
+        mb = Mailboxes()
+        _check(self._lib.dwgpu_iterate_mailboxes(self._h, pi.ctypes.data_as(c_dp), int(bool(phase_one)), C.byref(mb)),
+               "dwgpu_iterate_mailboxes")
+        return self._mailbox_views(mb)
 
     def initial_solve_packed(self) -> dict:
         pk = Packed()
@@ -318,7 +346,8 @@ class Engine:
         c = Counters()
         _check(self._lib.dwgpu_get_counters(self._h, C.byref(c)), "dwgpu_get_counters")
         return dict(pivots=c.pivots, flips=c.flips, rebuilds=c.rebuilds, phase1_iter=c.phase1_iter, solves=c.solves,
-                    rows_swept=c.rows_swept, cells_swept=c.cells_swept, price_cells=c.price_cells)
+                    rows_swept=c.rows_swept, cells_swept=c.cells_swept, price_cells=c.price_cells,
+                    mailbox_bytes=c.mailbox_bytes)
 
     def block_iterations(self) -> np.ndarray:
         it = np.zeros(self.K, np.int64)

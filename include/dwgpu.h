@@ -117,6 +117,7 @@ typedef struct dwgpu_counters {
                               item of the pivot row) cells move, so this is the algorithmic traffic / 16 B */
     long long price_cells; /* tableau doubles READ to (re)compute price rows: reduced costs at the start of a
                               solve (only the rows whose basic cost changed), phase-1 prices, beta rebuilds */
+    long long mailbox_bytes; /* bytes the GPU stored into the host mailboxes (dwgpu_*_mailboxes) */
 } dwgpu_counters;
 
 typedef struct dwgpu_engine dwgpu_engine;
@@ -149,6 +150,20 @@ int  dwgpu_iterate(dwgpu_engine *e, const double *pi, int phase_one, dwgpu_propo
 int  dwgpu_initial_solve_packed(dwgpu_engine *e, dwgpu_packed *out);
 int  dwgpu_iterate_packed(dwgpu_engine *e, const double *pi, int phase_one, const double *r,
                           dwgpu_packed *out);
+
+/* The reference's up-link as it is: K per-block mailboxes {obj, new_obj_coeff, status, len, ind[1..len], val[1..len]}
+ * (/root/reference/src/dw_subprob.h:44-94), here six host arrays in pinned memory that the solve kernels' epilogues
+ * store into directly while the round runs (ind/val with stride L, row k holds len[k] entries, 1-based master rows).
+ * No pack kernels and no copy after the solve: the call returns after one stream synchronisation.  A block whose
+ * state did not change in a round only rewrites its obj — the rest of its mailbox still holds.  The arrays belong to
+ * the engine and are overwritten by the next *_mailboxes call. */
+typedef struct dwgpu_mailboxes {
+    const double *obj, *cost, *val;
+    const int *status, *len, *ind;
+    int K, L;
+} dwgpu_mailboxes;
+int  dwgpu_initial_solve_mailboxes(dwgpu_engine *e, dwgpu_mailboxes *out);
+int  dwgpu_iterate_mailboxes(dwgpu_engine *e, const double *pi, int phase_one, dwgpu_mailboxes *out);
 
 /* Multi-GPU up-link: pack K_total proposals that an all-gather left in DEVICE arrays (same layout as
  * dwgpu_device_results(), ind/val with stride L) into one pinned record on the calling rank, on the

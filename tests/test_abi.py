@@ -25,7 +25,8 @@ def test_struct_layouts_match_header():
     # sizes implied by include/dwgpu.h on LP64
     assert C.sizeof(E.BlockDesc) == 8 + 9 * 8 + 8 + 3 * 8
     assert C.sizeof(E.Proposals) == 7 * 8
-    assert C.sizeof(E.Counters) == 8 * 8
+    assert C.sizeof(E.Counters) == 9 * 8
+    assert C.sizeof(E.Mailboxes) == 6 * 8 + 2 * 4
     assert C.sizeof(E.Packed) == 7 * 8
     o = E.Options()
     E.load_library().dwgpu_options_init(C.byref(o))

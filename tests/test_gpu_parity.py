@@ -446,3 +446,36 @@ def test_path3_reads_only_masked_cells(shape, threads, monkeypatch):
         for t, pi in enumerate(pis):
             compare_round(prob, eng.iterate(pi, t == 0), orc.iterate(pi, t == 0, 8), pi, t == 0)
     eng.close()
+
+
+@pytest.mark.parametrize("force_path", [0, 2, 3, 4])
+def test_host_mailboxes_match_dense_results(force_path):
+    """dwgpu_*_mailboxes: the kernels store every block's {obj, cost, status, len, column} into pinned host arrays from
+    their epilogues (blocks of the legacy / cluster paths are copied after their kernel).  Round by round the mailboxes
+    must equal what dwgpu_iterate returns on a twin engine — including rounds in which most blocks do not move (those
+    blocks only rewrite obj), a round through another API in between (mailboxes stale: full copy), and a reset."""
+    prob = P.gen_mcf(96, 16, 40, 8, seed=5)
+    e1, e2 = engine(prob, fetch_x=False, force_path=force_path), engine(prob, fetch_x=False, force_path=force_path)
+
+    def same(mb):
+        assert np.array_equal(mb["obj"], e1.obj) and np.array_equal(mb["cost"], e1.cost)
+        assert np.array_equal(mb["status"], e1.status) and np.array_equal(mb["len"], e1.len)
+        for k in range(prob.K):
+            ln, s = int(e1.len[k]), k * prob.L
+            assert np.array_equal(mb["ind"][k, :ln], e1.ind[s:s + ln]) and np.array_equal(mb["val"][k, :ln], e1.val[s:s + ln])
+
+    rng = np.random.default_rng(2)
+    pis = [-rng.random(prob.L) * 4.0 for _ in range(3)]
+    for run in range(2):
+        if run:
+            e1.reset(); e2.reset()
+        e1.initial_solve()
+        same(e2.initial_solve_mailboxes())
+        for t, pi in enumerate(pis + [pis[-1], pis[-1] * (1 + 1e-9)]):      # the last two rounds move (almost) nothing
+            e1.iterate_arrays(pi, t == 0)
+            if t == 2:
+                e2.iterate_packed(pi, False)                                # another API in between: mailboxes go stale
+                e1.iterate_arrays(pi, False)
+            same(e2.iterate_mailboxes(pi, t == 0))
+    assert e2.counters()["mailbox_bytes"] > 0
+    e1.close(); e2.close()
