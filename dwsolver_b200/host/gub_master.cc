@@ -51,7 +51,23 @@ int GubMaster::add_col(const std::string &name, double cost, double /*ub*/, cons
     set_.push_back(k);
     stat_.push_back(NONBASIC);
     x_.push_back(0.0);
+    if (flat_valid_) {                       // keep the flat mirror in step (columns only ever arrive at the end)
+        for (size_t t = 0; t < idx.size(); ++t) if (idx[t] < L_) { lrow_.push_back(idx[t]); lval_.push_back(val[t]); }
+        lptr_.push_back((int)lrow_.size());
+    }
     return cols() - 1;
+}
+
+void GubMaster::rebuild_flat()
+{
+    const int n = cols();
+    lptr_.assign(1, 0); lrow_.clear(); lval_.clear();
+    lptr_.reserve((size_t)n + 1);
+    for (int j = 0; j < n; ++j) {
+        for (size_t t = 0; t < idx_[j].size(); ++t) if (idx_[j][t] < L_) { lrow_.push_back(idx_[j][t]); lval_.push_back(val_[j][t]); }
+        lptr_.push_back((int)lrow_.size());
+    }
+    flat_valid_ = true;
 }
 
 void GubMaster::del_cols(const std::vector<char> &flag)
@@ -72,10 +88,15 @@ void GubMaster::del_cols(const std::vector<char> &flag)
     for (int k = 0; k < K_; ++k) key_[k] = key_[k] >= 0 ? remap[key_[k]] : -1;
     factor_valid_ = false;       // build_basis() re-keys blocks whose key went away and fills holes with logicals
     vals_valid_ = false;
+    flat_valid_ = false;
 }
 
 void GubMaster::add_link(int j, double scale, std::vector<double> &w) const
 {
+    if (flat_valid_) {
+        for (int t = lptr_[j]; t < lptr_[j + 1]; ++t) w[lrow_[t]] += scale * lval_[t];
+        return;
+    }
     const std::vector<int> &ix = idx_[j];
     const std::vector<double> &vv = val_[j];
     for (size_t t = 0; t < ix.size(); ++t) if (ix[t] < L_) w[ix[t]] += scale * vv[t];
@@ -216,6 +237,7 @@ void GubMaster::publish(bool with_duals)
 int GubMaster::solve()
 {
     const int L = L_, K = K_;
+    if (!flat_valid_) rebuild_flat();
     if (!factor_valid_) { if (!build_basis()) return 1; }
     if (!vals_valid_) compute_values();
     // the dense L x L work is split by rows over a persistent team (thread_team.h); small masters stay serial
@@ -305,16 +327,14 @@ int GubMaster::solve()
             if (mu_stamp[k] != stamp) {
                 const int j = key_[k];
                 double s = cost_of_key(k);
-                for (size_t t = 0; t < idx_[j].size(); ++t) if (idx_[j][t] < L) s -= pi[idx_[j][t]] * val_[j][t];
+                for (int t = lptr_[j]; t < lptr_[j + 1]; ++t) s -= pi[lrow_[t]] * lval_[t];
                 mu[k] = s; mu_stamp[k] = stamp;
             }
             return mu[k];
         };
         auto reduced_cost_m = [&](int j, int member) {
             double d = phase1 ? 0.0 : cost_[j];
-            const std::vector<int> &ix = idx_[j];
-            const std::vector<double> &vv = val_[j];
-            for (size_t t = 0; t < ix.size(); ++t) if (ix[t] < L) d -= pi[ix[t]] * vv[t];
+            for (int t = lptr_[j]; t < lptr_[j + 1]; ++t) d -= pi[lrow_[t]] * lval_[t];
             if (set_[j] >= 0) d -= mu_of(set_[j], member);
             return d;
         };

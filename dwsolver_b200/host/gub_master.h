@@ -33,7 +33,7 @@ public:
                 const std::vector<double> &val) override;
     void set_cost(int j, double c) override { cost_[j] = c; }
     double cost(int j) const override { return cost_[j]; }
-    void set_coef(int j, int pos, double v) override { val_[j][pos] = v; factor_valid_ = false; }
+    void set_coef(int j, int pos, double v) override { val_[j][pos] = v; factor_valid_ = false; flat_valid_ = false; }
     const std::string &name(int j) const override { return name_[j]; }
     const std::vector<int> &col_idx(int j) const override { return idx_[j]; }
     const std::vector<double> &col_val(int j) const override { return val_[j]; }
@@ -53,6 +53,12 @@ private:
     std::vector<double> cost_;
     std::vector<std::vector<int>> idx_;
     std::vector<std::vector<double>> val_;
+    // the linking-row entries of all columns, end to end in column order (what pricing walks: one contiguous stream
+    // instead of two heap vectors per column); entry order inside a column = order in idx_/val_
+    std::vector<int> lptr_, lrow_;
+    std::vector<double> lval_;
+    bool flat_valid_ = false;
+    void rebuild_flat();
     std::vector<int> set_;              // block of the column, -1: none (slack / artificial)
     std::vector<char> stat_;
     std::vector<int> key_;              // per block: key column, -1: none yet
