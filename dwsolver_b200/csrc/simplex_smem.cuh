@@ -421,7 +421,7 @@ template <bool INF, int NT, int MC, int NC>
 __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_live, bool &bland, int &degen, int degen_limit,
                             double tol_dj, double tol_bnd, double tol_piv,
                             unsigned long long &n_piv, unsigned long long &n_flip, unsigned long long &n_rows,
-                            unsigned long long &n_cells, Decision *dec, DecShared *ds, int *changed)
+                            unsigned long long &n_cells, Decision *dec, DecShared *ds)
 {
     constexpr int NW = NT / 32;
     static_assert(NW <= 8, "DecShared holds 8 warp slots");
@@ -497,18 +497,17 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
             if (lane == 0) ds->cnt[warp] = cnt;
         }
         __syncthreads();
-        phase(5);
-        // ---- ratio test, flips and the staging of a basis change over the list: warp 0 (which first strings the
-        // warps' segments together; the other warps go straight to the barrier behind this section)
-        if (warp == 0) {
-            int na = 0;
+        int na = 0;
+        {
+            int my_off = 0;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                const int cw = ds->cnt[w];
-                for (int e = lane; e < cw; e += 32) c.arow[na + e] = c.arow2[w * RW + e];
-                na += cw;
-            }
-            __syncwarp();
+            for (int w = 0; w < NW; ++w) { if (w == warp) my_off = na; na += ds->cnt[w]; }
+            for (int e = lane; e < cnt; e += 32) c.arow[my_off + e] = c.arow2[warp * RW + e];
+        }
+        __syncthreads();
+        phase(5);
+        // ---- ratio test, flips and the staging of a basis change over the list: warp 0
+        if (warp == 0) {
             int kind = K_PIVOT;
             double tmax = CUDART_INF;
             for (int e = lane; e < na; e += 32) {
@@ -610,43 +609,40 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
                 n_rows += (unsigned long long)na;
                 if (theta <= 1e-11) { if (++degen > degen_limit) bland = true; }
                 else { degen = 0; bland = false; }
-                // sparse pivot row (the usual case): its item list is its mask — exact whenever the row was last
-                // written by a sparse sweep — and the row itself is fetched by the sweep's first batch together with
-                // the rows it updates, so a pivot is two dependent HBM round trips (column, sweep) instead of three.
-                // Built here, inside the serial section, so that one barrier publishes the whole decision.
-                {
-                    constexpr int IW = ItemW<true>::D2;
-                    const int rwd = c.rwd, nitems = (ld >> 1) / IW;
-                    const unsigned *mp = c.rmask + (size_t)p * rwd;
-                    int ncm = 0;
-                    for (int w_ = 0; w_ < rwd; ++w_) ncm += __popc(mp[w_]);
-                    const bool fused = DWK_TG_FUSED && 2 * ncm <= nitems && ncm <= NT * DWK_TG_SB;   // the row fits the sweep's first batch
-                    if (fused) {
-                        int nc = 0;
-                        for (int w_ = 0; w_ < rwd; ++w_) {
-                            const unsigned bits = mp[w_];
-                            if ((bits >> lane) & 1u) c.acol[nc + __popc(bits & lt_mask)] = (unsigned short)(w_ * 32 + lane);
-                            nc += __popc(bits);
-                        }
-                        const int na_all = na + ((d_live && dq != 0.0) ? 1 : 0);
-                        n_cells += (unsigned long long)na_all * (unsigned long long)nc * (2 * IW);
-                        if (lane == 0) dec->nc = nc;
-                    }
-                    if (lane == 0) dec->fused = fused ? 1 : 0;
-                }
             }
-            if (lane == 0) {
-                ds->kind = kind; ds->bland = bland ? 1 : 0;
-                if (kind == K_PIVOT || kind == K_FLIPPED || kind == K_REDO) *changed = 1;
-            }
+            if (lane == 0) { ds->kind = kind; ds->bland = bland ? 1 : 0; }
         }
         __syncthreads();
         const int kind = ds->kind;
         bland = ds->bland != 0;
         if (kind == K_FLIPPED) continue;
         if (kind != K_PIVOT) return kind;
-        if (dec->fused) return K_PIVOT;
         phase(6);
+        // ---- sparse pivot row (the usual case): its item list is its mask — exact whenever the row was last
+        // written by a sparse sweep — and the row itself is fetched by the sweep's first batch together with the
+        // rows it updates, so a pivot is two dependent HBM round trips (column, sweep) instead of three
+        if (DWK_TG_FUSED) {
+            constexpr int IW = ItemW<true>::D2;
+            const int p = dec->p, rwd = c.rwd;
+            const int nitems = (ld >> 1) / IW;
+            const unsigned *mp = c.rmask + (size_t)p * rwd;
+            int ncm = 0;
+            for (int w_ = 0; w_ < rwd; ++w_) ncm += __popc(mp[w_]);
+            if (2 * ncm <= nitems && ncm <= NT * DWK_TG_SB) {        // block-uniform; the row fits the sweep's first batch
+                if (warp == 0) {
+                    int nc = 0;
+                    for (int w_ = 0; w_ < rwd; ++w_) {
+                        const unsigned bits = mp[w_];
+                        if ((bits >> lane) & 1u) c.acol[nc + __popc(bits & lt_mask)] = (unsigned short)(w_ * 32 + lane);
+                        nc += __popc(bits);
+                    }
+                    n_cells += (unsigned long long)dec->na * (unsigned long long)nc * (2 * IW);
+                    if (lane == 0) { dec->nc = nc; dec->fused = 1; }
+                }
+                __syncthreads();
+                return K_PIVOT;
+            }
+        }
         // ---- pivot row -> rowp (scaled): only the 32-byte items whose mask bit is set are fetched (a network
         // row has ~25 of 128), everything else is written as zero; warp 0 turns the mask into the item list
         {
@@ -1286,16 +1282,15 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
             __syncthreads();
         }
         // ---- B. decision (TG: the whole CTA; shared-memory tableau: warp 0)
-        int tg_kind = K_NONE;
         if (TG) {       // (the row-item masks are maintained by decide_block_tg only)
             int kind;
             if (infeasible)
                 kind = decide_block_tg<true, NT, MC, NC>(c, c.rowp, false, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
-                                                         n_piv, n_flip, n_rows, n_cells, &dec, &dsh, &s_changed);
+                                                         n_piv, n_flip, n_rows, n_cells, &dec, &dsh);
             else
                 kind = decide_block_tg<false, NT, MC, NC>(c, c.drow, true, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
-                                                          n_piv, n_flip, n_rows, n_cells, &dec, &dsh, &s_changed);
-            tg_kind = kind;       // block-uniform, and every shared result was published by the decision's own last barrier
+                                                          n_piv, n_flip, n_rows, n_cells, &dec, &dsh);
+            if (tid == 0) { s_kind = kind; if (n_piv + n_flip) s_changed = 1; }
         } else if (warp == 0) {
             int kind;
             if (infeasible)
@@ -1306,8 +1301,8 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
                                            n_piv, n_flip, n_rows, n_cells, &dec);
             if (lane == 0) { s_kind = kind; if (n_piv + n_flip) s_changed = 1; }
         }
-        if (!TG) __syncthreads();
-        const int kind = TG ? tg_kind : s_kind;
+        __syncthreads();
+        const int kind = s_kind;
         if (kind == K_PIVOT) {
             phase(dec.nc >= 0 ? 7 : 11);
             if (dec.nc >= 0) sweep_sparse<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na, dec.nc, TG && dec.fused != 0);
