@@ -184,6 +184,70 @@ def test_dw_solve_api_on_synthetic_mcf(tmp_path):
         os.chdir(cwd)
 
 
+def _gub_case(rng, L, K):
+    """a random DW-shaped master: (cols, cost, rhs, lam) — L linking equalities, K convexity rows, 3-6 columns per
+    block, one +1 slack and one costly -1 column per linking row"""
+    cols, cost, x0 = [], [], []
+    for k in range(K):
+        nk = int(rng.integers(3, 7))
+        wts = rng.dirichlet(np.ones(nk))
+        for t in range(nk):
+            a = np.where(rng.random(L) < min(0.5, 6.0 / L), rng.integers(-3, 4, L), 0).astype(float)
+            cols.append((list(np.nonzero(a)[0]) + [L + k], list(a[np.nonzero(a)[0]]) + [1.0]))
+            cost.append(float(rng.integers(-5, 6)))
+            x0.append(wts[t])
+    lam = len(cols)
+    act = np.zeros(L)
+    for j, (ix, vv) in enumerate(cols):
+        for i, v in zip(ix, vv):
+            if i < L:
+                act[i] += v * x0[j]
+    rhs = np.concatenate([act + rng.integers(0, 3, L), np.ones(K)])
+    for i in range(L):
+        cols.append(([i], [1.0])); cost.append(0.0)
+        cols.append(([i], [-1.0])); cost.append(7.0)
+    return cols, np.array(cost), rhs, lam
+
+
+def test_gub_master_thread_team_is_deterministic(monkeypatch):
+    """L = 144 linking rows: large enough for the master's thread team (host/thread_team.h).  One, three and eight
+    members must walk the SAME simplex path — equal iteration counts and bit-equal primal and dual vectors — and
+    reach the HiGHS optimum."""
+    L_ = lib()
+    rng = np.random.default_rng(4711)
+    L, K = 144, 40
+    cols, cost, rhs, lam = _gub_case(rng, L, K)
+    n, m = len(cols), L + K
+    A = sp.lil_matrix((m, n))
+    for j, (ix, vv) in enumerate(cols):
+        for i, v in zip(ix, vv):
+            A[i, j] = v
+    A = A.tocsc()
+    ref = linprog(cost, A_eq=A, b_eq=rhs, bounds=[(0, None)] * n, method="highs")
+    assert ref.status == 0
+    colptr = np.zeros(n + 1, np.int32)
+    idx, val = [], []
+    for j, (ix, vv) in enumerate(cols):
+        idx += [int(i) for i in ix]; val += [float(v) for v in vv]
+        colptr[j + 1] = len(idx)
+    idx = np.array(idx, np.int32); val = np.array(val)
+    seen = []
+    for threads in (1, 3, 8):
+        monkeypatch.setenv("DWSOLVER_MASTER_THREADS", str(threads))
+        x, y = np.zeros(n), np.zeros(m)
+        obj, its = C.c_double(0), C.c_longlong(0)
+        rc = L_.dwhost_gub_solve(L, K, n, colptr.ctypes.data_as(c_ip), idx.ctypes.data_as(c_ip), val.ctypes.data_as(c_dp),
+                                 cost.ctypes.data_as(c_dp), rhs.ctypes.data_as(c_dp), 0, x.ctypes.data_as(c_dp),
+                                 y.ctypes.data_as(c_dp), C.byref(obj), C.byref(its))
+        assert rc == 0
+        assert abs(obj.value - ref.fun) <= 1e-8 * (1 + abs(ref.fun)), (threads, obj.value, ref.fun)
+        assert np.abs(A @ x - rhs).max() <= 1e-8 and x.min() >= -1e-9
+        seen.append((its.value, x.copy(), y.copy()))
+    assert seen[0][0] > L                                   # a real solve, not a crash basis that happened to be optimal
+    for other in seen[1:]:
+        assert other[0] == seen[0][0] and np.array_equal(other[1], seen[0][1]) and np.array_equal(other[2], seen[0][2])
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_gub_master_matches_highs(seed):
     """random DW-shaped masters: L linking equalities with slack/surplus columns, K convexity rows, several columns
