@@ -12,6 +12,7 @@
 // What differs by design: the K subproblem threads, their mailboxes and the semaphore/cond-var round
 // (src/dw_subprob.c:415-448, src/dw_phases.c:338-350, 526-548) are ONE synchronous call into the GPU
 // engine per round (include/dwgpu.h); blocks are visited in index order, so runs are deterministic.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -21,6 +22,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dwgpu.h"
@@ -81,6 +83,46 @@ void build_block(const LpModel &sub, const LpModel &master, const std::vector<st
             b.d_row.push_back(e.first); b.d_col.push_back(j); b.d_val.push_back(e.second);
         }
     }
+}
+
+// Master and block files -> in-memory blocks (src/dw_solver.c:192-198, src/dw_subprob.c:105-111, 203-258).
+// The reference reads the K block files under two process-wide mutexes (glpk_mutex, master_mutex), i.e. one after
+// the other.  Block files are independent and the master is read-only once parsed, so `readers` host threads
+// (0 = one per core, at most 16; DWSOLVER_READ_THREADS overrides) take them in an interleaved order.
+// The result does not depend on the number of readers.  Throws std::runtime_error on an unreadable file.
+void read_problem(const char *master_file, const char *const *subproblem_files, int K, int readers, LpModel &master,
+                  std::vector<BlockHost> &blocks)
+{
+    const bool dbg = std::getenv("DWSOLVER_READ_DEBUG") != nullptr;
+    const double t0 = now_s();
+    master = read_lp_file(master_file);
+    const double t1 = now_s();
+    blocks.assign((size_t)K, BlockHost());
+    std::vector<std::vector<std::pair<int, double>>> mcols(master.n());
+    for (size_t t = 0; t < master.a_val.size(); ++t) mcols[master.a_col[t]].emplace_back(master.a_row[t], master.a_val[t]);
+    if (readers <= 0) {
+        readers = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        if (const char *e = std::getenv("DWSOLVER_READ_THREADS")) readers = std::max(1, std::atoi(e));
+    }
+    readers = std::max(1, std::min(readers, K));
+    std::vector<std::string> errors((size_t)readers);
+    auto read_some = [&](int t) {
+        try {
+            for (int k = t; k < K; k += readers) {
+                LpModel sub = read_lp_file(subproblem_files[k]);
+                build_block(sub, master, mcols, blocks[k]);
+            }
+        } catch (const std::exception &e) {
+            errors[(size_t)t] = e.what()[0] ? e.what() : "cannot read a subproblem file";
+        }
+    };
+    const double t2 = now_s();
+    std::vector<std::thread> pool;
+    for (int t = 1; t < readers; ++t) pool.emplace_back(read_some, t);
+    read_some(0);
+    for (auto &th : pool) th.join();
+    if (dbg) std::fprintf(stderr, "dwsolver-b200: read master %.3f s, column index %.3f s, %d block files %.3f s with %d reader(s)\n", t1 - t0, t2 - t1, K, now_s() - t2, readers);
+    for (auto &msg : errors) if (!msg.empty()) throw std::runtime_error(msg);
 }
 
 struct Proposal {            // X[k][iter] of the reference (src/dw_phases.c:173-179, 427-433): kept on the device
@@ -438,15 +480,9 @@ int dw_solve(const char *master_file, const char *const *subproblem_files, int n
     // ---- read the problem -------------------------------------------------------------------------
     const int K = num_subproblems;
     LpModel master;
-    std::vector<BlockHost> blocks(K);
+    std::vector<BlockHost> blocks;
     try {
-        master = read_lp_file(master_file);
-        std::vector<std::vector<std::pair<int, double>>> mcols(master.n());
-        for (size_t t = 0; t < master.a_val.size(); ++t) mcols[master.a_col[t]].emplace_back(master.a_row[t], master.a_val[t]);
-        for (int k = 0; k < K; ++k) {
-            LpModel sub = read_lp_file(subproblem_files[k]);
-            build_block(sub, master, mcols, blocks[k]);
-        }
+        read_problem(master_file, subproblem_files, K, 0, master, blocks);
     } catch (const std::exception &e) {
         if (verb >= DW_OUTPUT_QUIET) std::fprintf(stderr, "dwsolver-b200: %s\n", e.what());
         return fail(DW_STATUS_ERR_FILE);
@@ -480,6 +516,32 @@ int dw_solve_blocks(int K, int L, const dwgpu_block_desc *blocks, const double *
     if (opts_in) opt = *opts_in; else dw_options_init(&opt);
     std::memset(&g_stats, 0, sizeof(g_stats));
     return dw_core(K, L, blocks, link_lb, link_ub, nullptr, opt, now_s(), result);
+}
+
+// Test hook (tests/test_host_library.py, no GPU needed): reads a block-angular instance with `readers` threads and
+// returns sizes and order-sensitive checksums of everything the engine would be given.
+// out[0..7] = L, sum m, sum n, nnz(A), nnz(D), checksum(A), checksum(D), checksum(bounds and costs)
+int dwhost_read_problem_digest(const char *master_file, const char *const *subproblem_files, int K, int readers, double *out)
+{
+    try {
+        LpModel master;
+        std::vector<BlockHost> blocks;
+        read_problem(master_file, subproblem_files, K, readers, master, blocks);
+        for (int i = 0; i < 8; ++i) out[i] = 0.0;
+        out[0] = master.m();
+        auto fin = [](double v) { return std::fabs(v) >= 1e29 ? (v > 0 ? 7.0 : -7.0) : v; };
+        for (int k = 0; k < K; ++k) {
+            const BlockHost &b = blocks[(size_t)k];
+            out[1] += b.m; out[2] += b.n; out[3] += (double)b.a_val.size(); out[4] += (double)b.d_val.size();
+            const double w = 1.0 + (k % 97);
+            for (int i = 0; i < b.m; ++i)
+                for (int t = b.a_rowptr[i]; t < b.a_rowptr[i + 1]; ++t) out[5] += w * b.a_val[t] * (1 + (i % 13)) * (1 + (b.a_col[t] % 17));
+            for (size_t t = 0; t < b.d_val.size(); ++t) out[6] += w * b.d_val[t] * (1 + (b.d_row[t] % 13)) * (1 + (b.d_col[t] % 17));
+            for (int i = 0; i < b.m; ++i) out[7] += w * (fin(b.row_lb[i]) + 2 * fin(b.row_ub[i]));
+            for (int j = 0; j < b.n; ++j) out[7] += w * (fin(b.col_lb[j]) + 2 * fin(b.col_ub[j]) + 3 * b.c_file[j] + 5 * b.c_master[j]) * (1 + (j % 11));
+        }
+        return 0;
+    } catch (const std::exception &) { return 1; }
 }
 
 }  // extern "C"

@@ -7,10 +7,11 @@
 // bound forms `l <= x <= u`, `x >= l`, `x <= u`, `x = v`, `x free`, `+-inf[inity]`, `\` comments.
 #include <cctype>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
-#include <fstream>
-#include <sstream>
+#include <cstring>
 #include <stdexcept>
+#include <string_view>
 
 #include "lp_model.h"
 
@@ -18,40 +19,66 @@ namespace dwh {
 namespace {
 
 enum TokKind { T_NUM, T_NAME, T_OP };
-struct Tok {
+struct Tok {                      // `text` points into the file image: no allocation per token
     TokKind kind;
     double num = 0.0;
-    std::string text;
+    std::string_view text;
 };
 
-bool name_start(char c)
-{
-    return std::isalpha((unsigned char)c) || std::string("!\"#$%&()/,;?@_`'{}|~").find(c) != std::string::npos;
-}
-bool name_char(char c) { return name_start(c) || std::isdigit((unsigned char)c) || c == '.'; }
+// character classes of the CPLEX-LP lexer, one table lookup per character
+struct CharClass {
+    unsigned char start[256], body[256];
+    CharClass()
+    {
+        for (int c = 0; c < 256; ++c) {
+            start[c] = std::isalpha(c) || (c && std::strchr("!\"#$%&()/,;?@_`'{}|~", c)) ? 1 : 0;
+            body[c] = start[c] || std::isdigit(c) || c == '.';
+        }
+    }
+};
+const CharClass kChars;
+inline bool name_start(char c) { return kChars.start[(unsigned char)c]; }
+inline bool name_char(char c) { return kChars.body[(unsigned char)c]; }
+inline bool digit(char c) { return c >= '0' && c <= '9'; }
 
 std::vector<Tok> tokenize(const std::string &text)
 {
     std::vector<Tok> toks;
+    toks.reserve(text.size() / 4);
     size_t pos = 0, n = text.size();
     while (pos < n) {
         const char c = text[pos];
         if (c == '\\') { while (pos < n && text[pos] != '\n') ++pos; continue; }     // comment
         if (std::isspace((unsigned char)c)) { ++pos; continue; }
-        if (std::isdigit((unsigned char)c) || (c == '.' && pos + 1 < n && std::isdigit((unsigned char)text[pos + 1]))) {
+        if (digit(c) || (c == '.' && pos + 1 < n && digit(text[pos + 1]))) {
             // number: digits [. digits] [e[+-]digits]  (an exponent needs at least one digit after it)
             size_t e = pos;
-            while (e < n && std::isdigit((unsigned char)text[e])) ++e;
-            if (e < n && text[e] == '.') { ++e; while (e < n && std::isdigit((unsigned char)text[e])) ++e; }
+            while (e < n && digit(text[e])) ++e;
+            bool plain_integer = true;
+            if (e < n && text[e] == '.') { plain_integer = false; ++e; while (e < n && digit(text[e])) ++e; }
             if (e < n && (text[e] == 'e' || text[e] == 'E')) {
                 size_t f = e + 1;
                 if (f < n && (text[f] == '+' || text[f] == '-')) ++f;
-                if (f < n && std::isdigit((unsigned char)text[f])) {
-                    while (f < n && std::isdigit((unsigned char)text[f])) ++f;
+                if (f < n && digit(text[f])) {
+                    while (f < n && digit(text[f])) ++f;
                     e = f;
+                    plain_integer = false;
                 }
             }
-            Tok t; t.kind = T_NUM; t.num = std::strtod(text.substr(pos, e - pos).c_str(), nullptr);
+            Tok t; t.kind = T_NUM; t.text = std::string_view(text.data() + pos, e - pos);
+            if (plain_integer && e - pos <= 15) {            // exact in a double; the common case in LP files
+                long long v = 0;
+                for (size_t i = pos; i < e; ++i) v = v * 10 + (text[i] - '0');
+                t.num = (double)v;
+            } else {
+                // strtod on a bounded copy (on the file image it would also swallow forms the grammar above does
+                // not allow, e.g. hexadecimal)
+                char buf[64];
+                if (e - pos < sizeof buf) {
+                    std::memcpy(buf, text.data() + pos, e - pos); buf[e - pos] = 0;
+                    t.num = std::strtod(buf, nullptr);
+                } else t.num = std::strtod(text.substr(pos, e - pos).c_str(), nullptr);
+            }
             toks.push_back(t);
             pos = e;
             continue;
@@ -59,7 +86,7 @@ std::vector<Tok> tokenize(const std::string &text)
         if (name_start(c)) {
             size_t e = pos + 1;
             while (e < n && name_char(text[e])) ++e;
-            Tok t; t.kind = T_NAME; t.text = text.substr(pos, e - pos);
+            Tok t; t.kind = T_NAME; t.text = std::string_view(text.data() + pos, e - pos);
             toks.push_back(t);
             pos = e;
             continue;
@@ -67,9 +94,9 @@ std::vector<Tok> tokenize(const std::string &text)
         Tok t; t.kind = T_OP;
         if ((c == '<' || c == '>' || c == '=') && pos + 1 < n && (text[pos + 1] == '=' || text[pos + 1] == '<' || text[pos + 1] == '>')
             && !(c == '=' && text[pos + 1] == '=')) {
-            t.text = text.substr(pos, 2); pos += 2;
+            t.text = std::string_view(text.data() + pos, 2); pos += 2;
         } else if (c == '<' || c == '>' || c == '=' || c == '+' || c == '-' || c == ':') {
-            t.text = std::string(1, c); ++pos;
+            t.text = std::string_view(text.data() + pos, 1); ++pos;
         } else {
             throw std::runtime_error("LP syntax error near: " + text.substr(pos, 30));
         }
@@ -78,9 +105,9 @@ std::vector<Tok> tokenize(const std::string &text)
     return toks;
 }
 
-std::string lower(const std::string &s)
+std::string lower(std::string_view s)
 {
-    std::string r = s;
+    std::string r(s);
     for (auto &ch : r) ch = (char)std::tolower((unsigned char)ch);
     return r;
 }
@@ -108,7 +135,7 @@ bool is_sense(const Tok &t)
     return t.kind == T_OP && (t.text == "<=" || t.text == ">=" || t.text == "=<" || t.text == "=>" || t.text == "<" ||
                               t.text == ">" || t.text == "=");
 }
-int sense_dir(const std::string &s)      // -1: <=, +1: >=, 0: =
+int sense_dir(std::string_view s)      // -1: <=, +1: >=, 0: =
 {
     if (s == "<=" || s == "=<" || s == "<") return -1;
     if (s == ">=" || s == "=>" || s == ">") return 1;
@@ -117,8 +144,9 @@ int sense_dir(const std::string &s)      // -1: <=, +1: >=, 0: =
 
 struct Parser {
     LpModel lp;
-    int col(const std::string &name)
+    int col(std::string_view name_view)
     {
+        const std::string name(name_view);          // short names stay in the small-string buffer
         auto it = lp.col_index.find(name);
         if (it != lp.col_index.end()) return it->second;
         const int j = lp.n();
@@ -147,7 +175,7 @@ struct Parser {
                 ++pos;
                 continue;
             }
-            throw std::runtime_error("unexpected token in a linear expression: " + t.text);
+            throw std::runtime_error("unexpected token in a linear expression: " + std::string(t.text));
         }
         constant = have_coef ? sign * coef : 0.0;
         return pos;
@@ -170,7 +198,7 @@ struct Parser {
         size_t pos = 0;
         while (pos < st.size()) {
             std::string name;
-            if (st[pos].kind == T_NAME && pos + 1 < st.size() && is_op(st[pos + 1], ":")) { name = st[pos].text; pos += 2; }
+            if (st[pos].kind == T_NAME && pos + 1 < st.size() && is_op(st[pos + 1], ":")) { name = std::string(st[pos].text); pos += 2; }
             std::vector<std::pair<int, double>> terms;
             double constant = 0.0;
             pos = linear(st, pos, terms, constant);
@@ -211,7 +239,7 @@ struct Parser {
                 }
                 continue;
             }
-            if (st[pos].kind != T_NAME) throw std::runtime_error("bad bounds entry at: " + st[pos].text);
+            if (st[pos].kind != T_NAME) throw std::runtime_error("bad bounds entry at: " + std::string(st[pos].text));
             const int j = col(st[pos].text);
             ++pos;
             if (pos < st.size() && st[pos].kind == T_NAME && lower(st[pos].text) == "free") {
@@ -293,12 +321,17 @@ LpModel parse_lp_text(const std::string &text)
 
 LpModel read_lp_file(const std::string &path)
 {
-    std::ifstream in(path);
-    if (!in) throw std::runtime_error("cannot open LP file " + path);
-    std::stringstream ss;
-    ss << in.rdbuf();
+    std::FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("cannot open LP file " + path);
+    std::string text;
+    char chunk[1 << 16];
+    size_t got;
+    while ((got = std::fread(chunk, 1, sizeof chunk, f)) > 0) text.append(chunk, got);
+    const bool bad = std::ferror(f) != 0;
+    std::fclose(f);
+    if (bad) throw std::runtime_error("cannot read LP file " + path);
     try {
-        return parse_lp_text(ss.str());
+        return parse_lp_text(text);
     } catch (const std::exception &e) {
         throw std::runtime_error(path + ": " + e.what());
     }

@@ -74,6 +74,39 @@ def test_bad_arguments_and_missing_files():
     assert res.status == 2
 
 
+def test_block_files_read_by_several_threads(tmp_path):
+    """the K block files are parsed by a team of host threads (the reference serialises them under
+    glpk_mutex/master_mutex, src/dw_subprob.c:105-111, 203-258); the blocks handed to the engine are the same for
+    any number of readers, and an unreadable block file is still DW_STATUS_ERR_FILE."""
+    L = lib()
+    prob = P.gen_mcf(24, 12, 30, 6, seed=11)
+    paths = write_example(prob, tmp_path)
+    subs = (C.c_char_p * prob.K)(*[s.encode() for s in paths["subs"]])
+    L.dwhost_read_problem_digest.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(C.c_double)]
+    digests = []
+    for readers in (1, 3, 8, 0):
+        out = (C.c_double * 8)()
+        assert L.dwhost_read_problem_digest(paths["master"].encode(), subs, prob.K, readers, out) == 0
+        digests.append(list(out))
+    assert all(d == digests[0] for d in digests)                        # bit-identical, order-sensitive checksums
+    d = digests[0]
+    assert d[0] == prob.L
+    assert d[1] == sum(b.m for b in prob.blocks) and d[2] == sum(b.n for b in prob.blocks)
+    assert d[4] == sum(len(b.d_val) for b in prob.blocks)
+    # a missing block file: every reader count reports it, and dw_solve maps it to DW_STATUS_ERR_FILE
+    bad = [s.encode() for s in paths["subs"]]
+    bad[prob.K // 2] = str(tmp_path / "no_such_block.lp").encode()
+    bad_arr = (C.c_char_p * prob.K)(*bad)
+    for readers in (1, 4):
+        assert L.dwhost_read_problem_digest(paths["master"].encode(), bad_arr, prob.K, readers, (C.c_double * 8)()) == 1
+    o = DwOptions()
+    L.dw_options_init(C.byref(o))
+    o.verbosity = -1
+    res = DwResult()
+    assert L.dw_solve(paths["master"].encode(), bad_arr, prob.K, C.byref(o), C.byref(res)) == 2
+    assert res.status == 2
+
+
 @pytest.mark.parametrize("name", EXAMPLES)
 def test_cpp_lp_reader_matches_package_reader(name, tmp_path):
     L = lib()
