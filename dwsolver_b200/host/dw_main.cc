@@ -26,7 +26,9 @@ static void usage(const char *argv0)
     std::printf(" --write-final-master | --no-write-final-master   (accepted; no file is written)\n");
     std::printf(" --print-timing | --no-timing\n");
     std::printf(" --phase1_max <n>        Max phase I iterations (default 100).\n");
-    std::printf(" --phase2_max <n>        Max phase II iterations (default 3000).\n\n");
+    std::printf(" --phase2_max <n>        Max phase II iterations (default 3000).\n");
+    std::printf(" --write-container <f>   With -g: store the parsed instance in the binary container <f> and exit.\n");
+    std::printf(" --container <f>         Solve the instance stored in container <f> (no guidefile, no LP text).\n\n");
     std::printf("The guide file format:\n  n\n  sub_file_1\n  ...\n  sub_file_n\n  master_file\n  monolithic_file\n  objective_constant\n\n");
 }
 
@@ -42,7 +44,7 @@ int main(int argc, char **argv)
 {
     dw_options_t opt;
     dw_options_init(&opt);
-    std::string guide;
+    std::string guide, container_in, container_out;
     bool skip_mono = false;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
@@ -67,7 +69,15 @@ int main(int argc, char **argv)
         else if (a == "--no-timing") opt.print_timing_data = 0;
         else if (a == "--phase1_max" && i + 1 < argc) opt.max_phase1_iterations = std::atoi(argv[++i]);
         else if (a == "--phase2_max" && i + 1 < argc) opt.max_phase2_iterations = std::atoi(argv[++i]);
+        else if (a == "--write-container" && i + 1 < argc) container_out = argv[++i];
+        else if (a == "--container" && i + 1 < argc) container_in = argv[++i];
         else std::printf("Command line argument %s not recognized. Trying to continue.\n", argv[i]);
+    }
+    if (!container_in.empty()) {                                  // binary container: nothing else to read
+        dw_result_t res;
+        const int rc = dw_solve_container(container_in.c_str(), &opt, &res);
+        dw_result_free(&res);
+        return rc == DW_STATUS_OK ? 0 : rc;
     }
     if (guide.empty()) { usage(argv[0]); return 1; }
     std::ifstream gf(guide);
@@ -91,6 +101,11 @@ int main(int argc, char **argv)
     }
     std::vector<const char *> ptrs(n);
     for (int i = 0; i < n; ++i) ptrs[i] = subs[i].c_str();
+    if (!container_out.empty()) {
+        const int rc = dw_write_container(master.c_str(), ptrs.data(), n, opt.shift, container_out.c_str());
+        if (rc == DW_STATUS_OK && opt.verbosity >= DW_OUTPUT_NORMAL) std::printf("Wrote %s\n", container_out.c_str());
+        return rc == DW_STATUS_OK ? 0 : rc;
+    }
     dw_result_t res;
     const int rc = dw_solve(master.c_str(), ptrs.data(), n, &opt, &res);
     dw_result_free(&res);

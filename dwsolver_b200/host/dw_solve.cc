@@ -125,6 +125,144 @@ void read_problem(const char *master_file, const char *const *subproblem_files, 
     for (auto &msg : errors) if (!msg.empty()) throw std::runtime_error(msg);
 }
 
+// ---- binary block-angular container ---------------------------------------------------------------
+// One file holding exactly what read_problem() produces, so that a second solve of the same instance skips the LP
+// text: little-endian, every array 8-byte aligned, read with one fread and handed to the engine without a copy.
+//   header   : char magic[8] = "DWB200\0\1"; int32 K, L, has_names, 0; double shift (the guidefile's objective
+//              constant); double link_lb[L], link_ub[L]
+//   table    : K x { int32 m, n, a_nnz, d_nnz }
+//   block k  : int32 a_rowptr[m+1], a_col[a_nnz], d_row[d_nnz], d_col[d_nnz], (pad to 8);
+//              double a_val[a_nnz], row_lb[m], row_ub[m], col_lb[n], col_ub[n], c_file[n], c_master[n], d_val[d_nnz]
+//   names    : if has_names, per block n NUL-terminated column names, in column order
+// Bounds are stored the way the engine takes them (no bound = +-DWGPU_INF).
+constexpr char kContainerMagic[8] = {'D', 'W', 'B', '2', '0', '0', 0, 1};
+
+struct ContainerWriter {
+    std::FILE *f;
+    size_t written = 0;
+    bool ok = true;
+    void raw(const void *p, size_t bytes)
+    {
+        if (bytes && std::fwrite(p, 1, bytes, f) != bytes) ok = false;
+        written += bytes;
+    }
+    template <class T> void vec(const std::vector<T> &v) { raw(v.data(), v.size() * sizeof(T)); }
+    void pad8() { static const char zero[8] = {0}; if (written % 8) raw(zero, 8 - written % 8); }
+};
+
+struct ContainerView {               // pointers into `image`
+    std::vector<char> image;
+    int K = 0, L = 0;
+    double shift = 0.0;
+    const double *link_lb = nullptr, *link_ub = nullptr;
+    std::vector<dwgpu_block_desc> desc;
+    std::vector<std::vector<std::string>> names;
+    bool has_names = false;
+};
+
+// throws std::runtime_error on a missing, truncated or foreign file
+void load_container(const char *path, ContainerView &v)
+{
+    std::FILE *f = std::fopen(path, "rb");
+    if (!f) throw std::runtime_error(std::string("cannot open container ") + path);
+    std::fseek(f, 0, SEEK_END);
+    const long size = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    v.image.resize(size > 0 ? (size_t)size : 0);
+    const size_t got = v.image.empty() ? 0 : std::fread(v.image.data(), 1, v.image.size(), f);
+    std::fclose(f);
+    if (got != v.image.size()) throw std::runtime_error(std::string("cannot read container ") + path);
+    const char *base = v.image.data();
+    size_t pos = 0;
+    const size_t end = v.image.size();
+    auto take = [&](size_t bytes) -> const char * {
+        if (bytes > end - pos) throw std::runtime_error(std::string(path) + ": truncated container");
+        const char *p = base + pos;
+        pos += bytes;
+        return p;
+    };
+    if (end < 32 || std::memcmp(take(8), kContainerMagic, 8) != 0)
+        throw std::runtime_error(std::string(path) + ": not a dwsolver-b200 container (or another format version)");
+    const int *hdr = reinterpret_cast<const int *>(take(16));
+    v.K = hdr[0]; v.L = hdr[1]; v.has_names = hdr[2] != 0;
+    if (v.K < 1 || v.L < 0) throw std::runtime_error(std::string(path) + ": bad container header");
+    std::memcpy(&v.shift, take(8), 8);
+    v.link_lb = reinterpret_cast<const double *>(take(sizeof(double) * (size_t)v.L));
+    v.link_ub = reinterpret_cast<const double *>(take(sizeof(double) * (size_t)v.L));
+    const int *table = reinterpret_cast<const int *>(take(16 * (size_t)v.K));
+    v.desc.assign((size_t)v.K, dwgpu_block_desc());
+    for (int k = 0; k < v.K; ++k) {
+        const int m = table[4 * k], n = table[4 * k + 1], an = table[4 * k + 2], dn = table[4 * k + 3];
+        if (m < 0 || n < 0 || an < 0 || dn < 0) throw std::runtime_error(std::string(path) + ": bad block sizes in the container");
+        dwgpu_block_desc &d = v.desc[(size_t)k];
+        d.m = m; d.n = n; d.d_nnz = dn;
+        d.a_rowptr = reinterpret_cast<const int *>(take(4 * ((size_t)m + 1)));
+        d.a_col = reinterpret_cast<const int *>(take(4 * (size_t)an));
+        d.d_row = reinterpret_cast<const int *>(take(4 * (size_t)dn));
+        d.d_col = reinterpret_cast<const int *>(take(4 * (size_t)dn));
+        if (pos % 8) take(8 - pos % 8);
+        auto dbl = [&](size_t cnt) { return reinterpret_cast<const double *>(take(8 * cnt)); };
+        d.a_val = dbl((size_t)an);
+        d.row_lb = dbl((size_t)m); d.row_ub = dbl((size_t)m);
+        d.col_lb = dbl((size_t)n); d.col_ub = dbl((size_t)n);
+        d.c_file = dbl((size_t)n); d.c_master = dbl((size_t)n);
+        d.d_val = dbl((size_t)dn);
+        // the structure the engine indexes with must be sane before it reaches the device
+        if (d.a_rowptr[0] != 0 || d.a_rowptr[m] != an) throw std::runtime_error(std::string(path) + ": corrupt row pointers in the container");
+        for (int i = 0; i < m; ++i) if (d.a_rowptr[i] > d.a_rowptr[i + 1]) throw std::runtime_error(std::string(path) + ": corrupt row pointers in the container");
+        for (int t = 0; t < an; ++t) if (d.a_col[t] < 0 || d.a_col[t] >= n) throw std::runtime_error(std::string(path) + ": column index out of range in the container");
+        for (int t = 0; t < dn; ++t)
+            if (d.d_row[t] < 0 || d.d_row[t] >= v.L || d.d_col[t] < 0 || d.d_col[t] >= n)
+                throw std::runtime_error(std::string(path) + ": linking entry out of range in the container");
+    }
+    if (v.has_names) {
+        v.names.assign((size_t)v.K, {});
+        for (int k = 0; k < v.K; ++k) {
+            v.names[(size_t)k].reserve((size_t)v.desc[(size_t)k].n);
+            for (int j = 0; j < v.desc[(size_t)k].n; ++j) {
+                const void *z = pos < end ? std::memchr(base + pos, 0, end - pos) : nullptr;
+                if (!z) throw std::runtime_error(std::string(path) + ": truncated names in the container");
+                const size_t len = (size_t)(static_cast<const char *>(z) - (base + pos));
+                v.names[(size_t)k].emplace_back(base + pos, len);
+                pos += len + 1;
+            }
+        }
+    }
+}
+
+// order-sensitive digest shared by the two test hooks below (text path and container path must agree bit for bit)
+void digest_blocks(int K, int L, const dwgpu_block_desc *desc, double *out)
+{
+    for (int i = 0; i < 8; ++i) out[i] = 0.0;
+    out[0] = L;
+    auto fin = [](double v) { return std::fabs(v) >= 1e29 ? (v > 0 ? 7.0 : -7.0) : v; };
+    for (int k = 0; k < K; ++k) {
+        const dwgpu_block_desc &b = desc[k];
+        const int an = b.a_rowptr[b.m];
+        out[1] += b.m; out[2] += b.n; out[3] += an; out[4] += b.d_nnz;
+        const double w = 1.0 + (k % 97);
+        for (int i = 0; i < b.m; ++i)
+            for (int t = b.a_rowptr[i]; t < b.a_rowptr[i + 1]; ++t) out[5] += w * b.a_val[t] * (1 + (i % 13)) * (1 + (b.a_col[t] % 17));
+        for (int t = 0; t < b.d_nnz; ++t) out[6] += w * b.d_val[t] * (1 + (b.d_row[t] % 13)) * (1 + (b.d_col[t] % 17));
+        for (int i = 0; i < b.m; ++i) out[7] += w * (fin(b.row_lb[i]) + 2 * fin(b.row_ub[i]));
+        for (int j = 0; j < b.n; ++j) out[7] += w * (fin(b.col_lb[j]) + 2 * fin(b.col_ub[j]) + 3 * b.c_file[j] + 5 * b.c_master[j]) * (1 + (j % 11));
+    }
+}
+
+void describe(std::vector<BlockHost> &blocks, std::vector<dwgpu_block_desc> &desc)
+{
+    desc.assign(blocks.size(), dwgpu_block_desc());
+    for (size_t k = 0; k < blocks.size(); ++k) {
+        BlockHost &b = blocks[k];
+        dwgpu_block_desc &d = desc[k];
+        d.m = b.m; d.n = b.n;
+        d.a_rowptr = b.a_rowptr.data(); d.a_col = b.a_col.data(); d.a_val = b.a_val.data();
+        d.row_lb = b.row_lb.data(); d.row_ub = b.row_ub.data(); d.col_lb = b.col_lb.data(); d.col_ub = b.col_ub.data();
+        d.c_file = b.c_file.data(); d.c_master = b.c_master.data();
+        d.d_nnz = (int)b.d_val.size(); d.d_row = b.d_row.data(); d.d_col = b.d_col.data(); d.d_val = b.d_val.data();
+    }
+}
+
 struct Proposal {            // X[k][iter] of the reference (src/dw_phases.c:173-179, 427-433): kept on the device
     int k, iter;
     long long id;            // dwgpu_history_push id of the copy of x_k
@@ -489,18 +627,10 @@ int dw_solve(const char *master_file, const char *const *subproblem_files, int n
     }
     const int L = master.m();
     g_stats.seconds_read = now_s() - t_begin;
-    std::vector<dwgpu_block_desc> desc(K);
+    std::vector<dwgpu_block_desc> desc;
+    describe(blocks, desc);
     std::vector<std::vector<std::string>> names(K);
-    for (int k = 0; k < K; ++k) {
-        BlockHost &b = blocks[k];
-        dwgpu_block_desc &d = desc[k];
-        d.m = b.m; d.n = b.n;
-        d.a_rowptr = b.a_rowptr.data(); d.a_col = b.a_col.data(); d.a_val = b.a_val.data();
-        d.row_lb = b.row_lb.data(); d.row_ub = b.row_ub.data(); d.col_lb = b.col_lb.data(); d.col_ub = b.col_ub.data();
-        d.c_file = b.c_file.data(); d.c_master = b.c_master.data();
-        d.d_nnz = (int)b.d_val.size(); d.d_row = b.d_row.data(); d.d_col = b.d_col.data(); d.d_val = b.d_val.data();
-        names[k] = b.col_names;
-    }
+    for (int k = 0; k < K; ++k) names[k] = blocks[k].col_names;
     std::vector<double> llb(L), lub(L);
     for (int i = 0; i < L; ++i) { llb[i] = to_engine_bound(master.row_lb[i]); lub[i] = to_engine_bound(master.row_ub[i]); }
     return dw_core(K, L, desc.data(), llb.data(), lub.data(), &names, opt, t_begin, result);
@@ -518,30 +648,101 @@ int dw_solve_blocks(int K, int L, const dwgpu_block_desc *blocks, const double *
     return dw_core(K, L, blocks, link_lb, link_ub, nullptr, opt, now_s(), result);
 }
 
-// Test hook (tests/test_host_library.py, no GPU needed): reads a block-angular instance with `readers` threads and
-// returns sizes and order-sensitive checksums of everything the engine would be given.
-// out[0..7] = L, sum m, sum n, nnz(A), nnz(D), checksum(A), checksum(D), checksum(bounds and costs)
+// Test hooks (tests/test_host_library.py, no GPU needed): sizes and order-sensitive checksums of everything the engine
+// would be given — out[0..7] = L, sum m, sum n, nnz(A), nnz(D), checksum(A), checksum(D), checksum(bounds and costs) —
+// for an instance read from LP text with `readers` threads, and for one loaded from a container.
 int dwhost_read_problem_digest(const char *master_file, const char *const *subproblem_files, int K, int readers, double *out)
 {
     try {
         LpModel master;
         std::vector<BlockHost> blocks;
         read_problem(master_file, subproblem_files, K, readers, master, blocks);
-        for (int i = 0; i < 8; ++i) out[i] = 0.0;
-        out[0] = master.m();
-        auto fin = [](double v) { return std::fabs(v) >= 1e29 ? (v > 0 ? 7.0 : -7.0) : v; };
-        for (int k = 0; k < K; ++k) {
-            const BlockHost &b = blocks[(size_t)k];
-            out[1] += b.m; out[2] += b.n; out[3] += (double)b.a_val.size(); out[4] += (double)b.d_val.size();
-            const double w = 1.0 + (k % 97);
-            for (int i = 0; i < b.m; ++i)
-                for (int t = b.a_rowptr[i]; t < b.a_rowptr[i + 1]; ++t) out[5] += w * b.a_val[t] * (1 + (i % 13)) * (1 + (b.a_col[t] % 17));
-            for (size_t t = 0; t < b.d_val.size(); ++t) out[6] += w * b.d_val[t] * (1 + (b.d_row[t] % 13)) * (1 + (b.d_col[t] % 17));
-            for (int i = 0; i < b.m; ++i) out[7] += w * (fin(b.row_lb[i]) + 2 * fin(b.row_ub[i]));
-            for (int j = 0; j < b.n; ++j) out[7] += w * (fin(b.col_lb[j]) + 2 * fin(b.col_ub[j]) + 3 * b.c_file[j] + 5 * b.c_master[j]) * (1 + (j % 11));
+        std::vector<dwgpu_block_desc> desc;
+        describe(blocks, desc);
+        digest_blocks(K, master.m(), desc.data(), out);
+        return 0;
+    } catch (const std::exception &) { return 1; }
+}
+
+int dwhost_container_digest(const char *container_path, double *out, int *K_out, char *first_name, int first_name_cap)
+{
+    try {
+        ContainerView v;
+        load_container(container_path, v);
+        digest_blocks(v.K, v.L, v.desc.data(), out);
+        if (K_out) *K_out = v.K;
+        if (first_name && first_name_cap > 0) {
+            const std::string nm = v.has_names && !v.names[0].empty() ? v.names[0][0] : std::string();
+            std::snprintf(first_name, (size_t)first_name_cap, "%s", nm.c_str());
         }
         return 0;
     } catch (const std::exception &) { return 1; }
+}
+
+int dw_write_container(const char *master_file, const char *const *subproblem_files, int num_subproblems, double shift,
+                       const char *container_path)
+{
+    if (!master_file || !subproblem_files || num_subproblems < 1 || !container_path) return DW_STATUS_ERR_BAD_ARGS;
+    for (int k = 0; k < num_subproblems; ++k) if (!subproblem_files[k]) return DW_STATUS_ERR_BAD_ARGS;
+    const int K = num_subproblems;
+    LpModel master;
+    std::vector<BlockHost> blocks;
+    try {
+        read_problem(master_file, subproblem_files, K, 0, master, blocks);
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "dwsolver-b200: %s\n", e.what());
+        return DW_STATUS_ERR_FILE;
+    }
+    const int L = master.m();
+    std::FILE *f = std::fopen(container_path, "wb");
+    if (!f) { std::fprintf(stderr, "dwsolver-b200: cannot write %s\n", container_path); return DW_STATUS_ERR_FILE; }
+    ContainerWriter w{f};
+    w.raw(kContainerMagic, 8);
+    const int hdr[4] = {K, L, 1, 0};
+    w.raw(hdr, sizeof hdr);
+    w.raw(&shift, sizeof shift);
+    std::vector<double> llb(L), lub(L);
+    for (int i = 0; i < L; ++i) { llb[i] = to_engine_bound(master.row_lb[i]); lub[i] = to_engine_bound(master.row_ub[i]); }
+    w.vec(llb); w.vec(lub);
+    for (int k = 0; k < K; ++k) {
+        const BlockHost &b = blocks[k];
+        const int t[4] = {b.m, b.n, (int)b.a_val.size(), (int)b.d_val.size()};
+        w.raw(t, sizeof t);
+    }
+    for (int k = 0; k < K; ++k) {
+        const BlockHost &b = blocks[k];
+        w.vec(b.a_rowptr); w.vec(b.a_col); w.vec(b.d_row); w.vec(b.d_col);
+        w.pad8();
+        w.vec(b.a_val); w.vec(b.row_lb); w.vec(b.row_ub); w.vec(b.col_lb); w.vec(b.col_ub); w.vec(b.c_file); w.vec(b.c_master);
+        w.vec(b.d_val);
+    }
+    for (int k = 0; k < K; ++k)
+        for (const std::string &nm : blocks[k].col_names) w.raw(nm.c_str(), nm.size() + 1);
+    const bool closed = std::fclose(f) == 0;
+    if (!w.ok || !closed) { std::fprintf(stderr, "dwsolver-b200: error while writing %s\n", container_path); return DW_STATUS_ERR_FILE; }
+    return DW_STATUS_OK;
+}
+
+int dw_solve_container(const char *container_path, const dw_options_t *opts_in, dw_result_t *result)
+{
+    if (!result) return DW_STATUS_ERR_BAD_ARGS;
+    std::memset(result, 0, sizeof(*result));
+    if (!container_path) { result->status = DW_STATUS_ERR_BAD_ARGS; return DW_STATUS_ERR_BAD_ARGS; }
+    dw_options_t opt;
+    if (opts_in) opt = *opts_in; else dw_options_init(&opt);
+    std::memset(&g_stats, 0, sizeof(g_stats));
+    const double t_begin = now_s();
+    ContainerView v;
+    try {
+        load_container(container_path, v);
+    } catch (const std::exception &e) {
+        if (opt.verbosity >= DW_OUTPUT_QUIET) std::fprintf(stderr, "dwsolver-b200: %s\n", e.what());
+        result->status = DW_STATUS_ERR_FILE;
+        return DW_STATUS_ERR_FILE;
+    }
+    g_stats.seconds_read = now_s() - t_begin;
+    if (opt.shift == 0.0) opt.shift = v.shift;          // an explicit option wins over the stored constant
+    return dw_core(v.K, v.L, v.desc.data(), v.link_lb, v.link_ub, v.has_names ? &v.names : nullptr, opt, t_begin, result);
 }
 
 }  // extern "C"

@@ -84,6 +84,21 @@ struct dwgpu_block_desc;
 int dw_solve_blocks(int K, int L, const struct dwgpu_block_desc *blocks, const double *link_lb, const double *link_ub,
                     const dw_options_t *opts, dw_result_t *result);
 
+
+/* Binary block-angular container (replaces, for repeated solves, the LP-text input path
+ * src/dw_main.c:213-259 -> glp_read_lp at src/dw_subprob.c:105-111 and src/dw_solver.c:192-198, and the by-name
+ * column mapping src/dw_subprob.c:203-258).  dw_write_container() reads the master and block LP files exactly like
+ * dw_solve() and stores the assembled blocks (CSR rows, bounds with the engine's "no bound" value, file and master
+ * costs, COO of D_k in the reference's order, linking-row bounds, column names) in one file; dw_solve_container()
+ * loads it with one read, hands the arrays to the engine without a copy and then runs the same solve as dw_solve()
+ * (same status codes, same relaxed_solution file with the original variable names; opts->shift == 0 means "use the
+ * stored constant").
+ * CLI: `dwsolver -g guidefile --write-container file` converts, `dwsolver --container file` solves. */
+int dw_write_container(const char *master_file, const char *const *subproblem_files, int num_subproblems,
+                       double shift /* the guidefile's objective constant, stored with the instance */,
+                       const char *container_path);
+int dw_solve_container(const char *container_path, const dw_options_t *opts, dw_result_t *result);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,8 +52,14 @@ def write_example(prob, d):
 
 def test_public_api_symbols_and_defaults():
     L = lib()
-    for name in ("dw_options_init", "dw_solve", "dw_result_free", "dw_version", "dw_last_stats"):
-        assert hasattr(L, name)
+    import re
+    header = open(os.path.join(ROOT, "include", "dwsolver.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(dw_[a-z_]+)\s*\(", header))
+    assert {"dw_options_init", "dw_solve", "dw_result_free", "dw_version", "dw_last_stats", "dw_solve_blocks",
+            "dw_write_container", "dw_solve_container"} <= declared
+    for name in declared:                                # every function include/dwsolver.h declares is exported
+        assert hasattr(L, name), name
     o = DwOptions()
     L.dw_options_init(C.byref(o))
     assert (o.verbosity, o.max_phase1_iterations, o.max_phase2_iterations, o.print_relaxed_sol) == (5, 100, 3000, 1)
@@ -105,6 +111,68 @@ def test_block_files_read_by_several_threads(tmp_path):
     res = DwResult()
     assert L.dw_solve(paths["master"].encode(), bad_arr, prob.K, C.byref(o), C.byref(res)) == 2
     assert res.status == 2
+
+
+def _container_api(L):
+    L.dw_write_container.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_double, C.c_char_p]
+    L.dw_solve_container.argtypes = [C.c_char_p, C.POINTER(DwOptions), C.POINTER(DwResult)]
+    L.dwhost_container_digest.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_char_p, C.c_int]
+    L.dwhost_read_problem_digest.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(C.c_double)]
+
+
+@pytest.mark.parametrize("source", ["mcf", "book_dantzig", "web_trick"])
+def test_container_holds_what_the_lp_text_path_reads(source, tmp_path):
+    """the binary container carries bit for bit what the LP-text path (glp_read_lp + the by-name column
+    mapping, src/dw_subprob.c:105-111, 203-258) hands to the engine; damaged files are DW_STATUS_ERR_FILE."""
+    L = lib()
+    _container_api(L)
+    if source == "mcf":
+        prob = P.gen_mcf(24, 12, 30, 6, seed=5)
+    else:
+        prob = load_example(source)
+    paths = write_example(prob, tmp_path)
+    subs = (C.c_char_p * prob.K)(*[s.encode() for s in paths["subs"]])
+    box = str(tmp_path / "instance.dwb").encode()
+    assert L.dw_write_container(paths["master"].encode(), subs, prob.K, 2.5, box) == 0
+    text, packed = (C.c_double * 8)(), (C.c_double * 8)()
+    assert L.dwhost_read_problem_digest(paths["master"].encode(), subs, prob.K, 1, text) == 0
+    k_out, name = C.c_int(0), C.create_string_buffer(256)
+    assert L.dwhost_container_digest(box, packed, C.byref(k_out), name, 256) == 0
+    assert list(text) == list(packed) and k_out.value == prob.K
+    first = name.value.decode()
+    assert first and first in open(paths["subs"][0]).read().split()           # the block's own column names travel
+    # damaged containers: truncated at several places, wrong magic, missing file
+    blob = open(box, "rb").read()
+    for cut in (7, 31, len(blob) // 3, len(blob) - 1):
+        bad = tmp_path / f"cut{cut}.dwb"
+        bad.write_bytes(blob[:cut])
+        assert L.dwhost_container_digest(str(bad).encode(), packed, None, None, 0) == 1
+    (tmp_path / "magic.dwb").write_bytes(b"NOTADWB!" + blob[8:])
+    assert L.dwhost_container_digest(str(tmp_path / "magic.dwb").encode(), packed, None, None, 0) == 1
+    o = DwOptions()
+    L.dw_options_init(C.byref(o))
+    o.verbosity = -1
+    res = DwResult()
+    assert L.dw_solve_container(str(tmp_path / "nope.dwb").encode(), C.byref(o), C.byref(res)) == 2 and res.status == 2
+    assert L.dw_solve_container(str(tmp_path / "cut31.dwb").encode(), C.byref(o), C.byref(res)) == 2
+    assert L.dw_solve_container(None, C.byref(o), C.byref(res)) == 1
+    assert L.dw_write_container(b"/nonexistent/master.lp", subs, prob.K, 0.0, box) == 2
+
+
+def test_cli_writes_a_container(tmp_path):
+    """`dwsolver -g guidefile --write-container f` converts without solving (no GPU involved)"""
+    L = lib()
+    _container_api(L)
+    prob = P.gen_mcf(12, 10, 24, 5, seed=9)
+    paths = write_example(prob, tmp_path)
+    out = subprocess.run([CLI, "-g", paths["guidefile"], "--write-container", "p.dwb", "--quiet"], cwd=tmp_path,
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    packed, text = (C.c_double * 8)(), (C.c_double * 8)()
+    subs = (C.c_char_p * prob.K)(*[s.encode() for s in paths["subs"]])
+    assert L.dwhost_container_digest(str(tmp_path / "p.dwb").encode(), packed, None, None, 0) == 0
+    assert L.dwhost_read_problem_digest(paths["master"].encode(), subs, prob.K, 2, text) == 0
+    assert list(packed) == list(text)
 
 
 @pytest.mark.parametrize("name", EXAMPLES)
@@ -213,6 +281,41 @@ def test_dw_solve_api_on_synthetic_mcf(tmp_path):
             assert res.num_vars > 0 and np.isfinite(res.x[0])
             L.dw_result_free(C.byref(res))
             assert not res.x
+    finally:
+        os.chdir(cwd)
+
+
+@pytest.mark.gpu
+def test_dw_solve_container_matches_dw_solve(tmp_path):
+    """the same instance through LP text and through the binary container: same objective, same master columns, same
+    relaxed_solution file (original variable names), and the stored objective constant is applied"""
+    L = lib()
+    _container_api(L)
+    prob = P.gen_mcf(40, 16, 40, 8, seed=3)
+    paths = write_example(prob, tmp_path)
+    subs = (C.c_char_p * prob.K)(*[s.encode() for s in paths["subs"]])
+    box = str(tmp_path / "instance.dwb").encode()
+    assert L.dw_write_container(paths["master"].encode(), subs, prob.K, 0.0, box) == 0
+    shifted = str(tmp_path / "shifted.dwb").encode()
+    assert L.dw_write_container(paths["master"].encode(), subs, prob.K, 100.0, shifted) == 0
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        o = DwOptions()
+        L.dw_options_init(C.byref(o))
+        o.verbosity = -1
+        r_text, r_box, r_shift = DwResult(), DwResult(), DwResult()
+        assert L.dw_solve(paths["master"].encode(), subs, prob.K, C.byref(o), C.byref(r_text)) == 0
+        sol_text = sorted(open("relaxed_solution").read().splitlines())
+        os.remove("relaxed_solution")
+        assert L.dw_solve_container(box, C.byref(o), C.byref(r_box)) == 0
+        sol_box = sorted(open("relaxed_solution").read().splitlines())
+        assert r_box.objective_value == r_text.objective_value and r_box.num_vars == r_text.num_vars
+        assert sol_box == sol_text and len(sol_box) == sum(b.n for b in prob.blocks)
+        assert L.dw_solve_container(shifted, C.byref(o), C.byref(r_shift)) == 0
+        assert abs(r_shift.objective_value - (r_text.objective_value + 100.0)) <= 1e-9 * (1 + abs(r_text.objective_value))
+        for r in (r_text, r_box, r_shift):
+            L.dw_result_free(C.byref(r))
     finally:
         os.chdir(cwd)
 
