@@ -1,5 +1,6 @@
 """ctypes mirror of the drop-in host library (include/dwsolver.h -> dwsolver_b200/lib/libdwsolver_b200.so):
-the reference's public API dw_solve (LP files) and this build's dw_solve_blocks (in-memory instance)."""
+the reference's public API dw_solve (LP files), this build's dw_solve_blocks (in-memory instance) and the binary
+container pair dw_write_container / dw_solve_container."""
 from __future__ import annotations
 
 import ctypes as C
@@ -45,6 +46,8 @@ def load_library():
         L.dw_solve.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(DwOptions), C.POINTER(DwResult)]
         L.dw_solve_blocks.argtypes = [C.c_int, C.c_int, C.POINTER(E.BlockDesc), c_dp, c_dp, C.POINTER(DwOptions),
                                       C.POINTER(DwResult)]
+        L.dw_write_container.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_double, C.c_char_p]
+        L.dw_solve_container.argtypes = [C.c_char_p, C.POINTER(DwOptions), C.POINTER(DwResult)]
         _LIB = L
     return _LIB
 
@@ -74,6 +77,20 @@ def dw_solve(master_file: str, subproblem_files: Sequence[str], **opts) -> dict:
     subs = (C.c_char_p * len(subproblem_files))(*[s.encode() for s in subproblem_files])
     res = DwResult()
     rc = lib.dw_solve(master_file.encode(), subs, len(subproblem_files), C.byref(_options(**opts)), C.byref(res))
+    return _result(lib, rc, res)
+
+
+def dw_write_container(master_file: str, subproblem_files: Sequence[str], container_path: str, shift: float = 0.0) -> int:
+    """Parse the LP files once and store the assembled instance (include/dwsolver.h); returns the status code."""
+    lib = load_library()
+    subs = (C.c_char_p * len(subproblem_files))(*[s.encode() for s in subproblem_files])
+    return lib.dw_write_container(master_file.encode(), subs, len(subproblem_files), float(shift), container_path.encode())
+
+
+def dw_solve_container(container_path: str, **opts) -> dict:
+    lib = load_library()
+    res = DwResult()
+    rc = lib.dw_solve_container(container_path.encode(), C.byref(_options(**opts)), C.byref(res))
     return _result(lib, rc, res)
 
 
