@@ -12,7 +12,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/dwgpu.h"
@@ -24,6 +27,21 @@
 namespace {
 
 thread_local std::string g_err;
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (device, kernel) pair, not to an engine: a second engine
+// with smaller blocks must not lower the limit under a first one that is still launching (several engines live in one
+// process when dw_solve shards the blocks, DWSOLVER_DEVICES).  The limit only ever grows; launches ask for what they need.
+std::mutex g_attr_mu;
+std::map<std::pair<int, const void *>, int> g_attr_max;
+cudaError_t allow_dynamic_smem(int device, const void *kernel, int bytes)
+{
+    std::lock_guard<std::mutex> lock(g_attr_mu);
+    int &cur = g_attr_max[std::make_pair(device, kernel)];
+    if (bytes <= cur) return cudaSuccess;
+    const cudaError_t rc = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (rc == cudaSuccess) cur = bytes;
+    return rc;
+}
 
 int fail(int code, const std::string &msg)
 {
@@ -145,6 +163,13 @@ extern "C" {
 
 const char *dwgpu_last_error(void) { return g_err.c_str(); }
 const char *dwgpu_version(void) { return "dwgpu 0.2 (sm_100a)"; }
+
+int dwgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 #if DWK_TIMERS
 // profiling builds only (not part of include/dwgpu.h): cycles per kernel phase summed over all CTAs since the last reset
@@ -422,14 +447,11 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(e->d_list_c.upload(e->list_c));
 
     if (!e->list_smem.empty())
-        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)e->smem_dyn));
+        CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_SMEM, 0, 0, false>, (int)e->smem_dyn));
     if (!e->list_a.empty())
-        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 64, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)dwk::smem2_bytes(64, 128)));
+        CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_SMEM, 64, 128, false>, (int)dwk::smem2_bytes(64, 128)));
     if (!e->list_c.empty()) {
-        CUE(cudaFuncSetAttribute(dwk::solve_cluster_kernel<dwk::NT_CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)e->smem_dyn_c));
+        CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_cluster_kernel<dwk::NT_CL>, (int)e->smem_dyn_c));
         if (e->cluster_size > 8)
             CUE(cudaFuncSetAttribute(dwk::solve_cluster_kernel<dwk::NT_CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         // the hardware may not be able to co-schedule a cluster this large with this much shared memory
@@ -449,28 +471,21 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
             e->cluster_size /= 2;
         }
     }
-    CUE(cudaFuncSetAttribute(dwk::order_by_last_iterations_kernel<1024, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(8192 * sizeof(unsigned long long))));
+    CUE(allow_dynamic_smem(e->device, (const void *)dwk::order_by_last_iterations_kernel<1024, 8192>, (int)(8192 * sizeof(unsigned long long))));
     if (const char *nr = std::getenv("DWGPU_NO_REORDER")) e->reorder = std::atoi(nr) == 0;
     if (const char *tg = std::getenv("DWGPU_TG_THREADS")) {
         const int v = std::atoi(tg);
         e->tg_threads = (v == 256 || v == NT_TG_WIDE || v == NT_TG) ? v : 0;
     }
     if (!e->list_g.empty()) {
-        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)e->smem_dyn_g));
-        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_TG, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)e->smem_dyn_g));
-        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_TG_WIDE, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)e->smem_dyn_g));
+        CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_SMEM, 0, 0, true>, (int)e->smem_dyn_g));
+        CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG, 0, 0, true>, (int)e->smem_dyn_g));
+        CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG_WIDE, 0, 0, true>, (int)e->smem_dyn_g));
     }
     if (!e->list_b.empty()) {
-        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_SMEM, 256, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)dwk::smem2_bytes(256, 512, true)));
-        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_TG, 256, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)dwk::smem2_bytes(256, 512, true)));
-        CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)dwk::smem2_bytes(256, 512, true)));
+        CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_SMEM, 256, 512, true>, (int)dwk::smem2_bytes(256, 512, true)));
+        CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG, 256, 512, true>, (int)dwk::smem2_bytes(256, 512, true)));
+        CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true>, (int)dwk::smem2_bytes(256, 512, true)));
     }
 
     dwk::init_kernel<256><<<K, 256, 0, e->stream>>>(e->blocks.p, K);

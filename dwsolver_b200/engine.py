@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "dwgpu_sync", "dwgpu_last_error", "dwgpu_version", "dwgpu_last_kernel_ms", "dwgpu_measure_smem_bandwidth",
     "dwgpu_reset", "dwgpu_initial_solve_device", "dwgpu_initial_solve_packed", "dwgpu_iterate_packed", "dwgpu_pack_gathered",
     "dwgpu_device_record", "dwgpu_pack_gathered_records", "dwgpu_history_push", "dwgpu_history_combine",
-    "dwgpu_initial_solve_mailboxes", "dwgpu_iterate_mailboxes",
+    "dwgpu_initial_solve_mailboxes", "dwgpu_iterate_mailboxes", "dwgpu_device_count",
 ]
 
 

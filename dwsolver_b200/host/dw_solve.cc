@@ -278,16 +278,87 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
     auto fail = [&](int code) { result->status = code; return code; };
     const int verb = opt.verbosity;
     std::vector<dwgpu_block_desc> desc(desc_in, desc_in + K);
-    // ---- GPU engine: replaces pthread_create(subproblem_thread) x K (src/dw_solver.c:154-184) --------
-    dwgpu_options gopt;
-    dwgpu_options_init(&gopt);
-    if (const char *dev = std::getenv("DWSOLVER_DEVICE")) gopt.device = std::atoi(dev);
-    dwgpu_engine *eng = nullptr;
-    if (dwgpu_create(K, L, desc.data(), &gopt, &eng) != 0) {
-        std::fprintf(stderr, "dwsolver-b200: cannot create the GPU engine: %s\n", dwgpu_last_error());
+    // ---- GPU engines: replace pthread_create(subproblem_thread) x K (src/dw_solver.c:154-184) ----------
+    // One engine per device; blocks are sharded statically and contiguously over them: shard g owns
+    // blocks [K g / G, K (g+1) / G).  DWSOLVER_DEVICES = comma-separated CUDA ordinals (a device may be listed more than
+    // once) or "all"; default: one engine on DWSOLVER_DEVICE (or 0).  Per round every shard is driven by its own
+    // host thread; the duals go down to each device and the packed proposals come up from each, no peer traffic.
+    std::vector<int> devices;
+    if (const char *list = std::getenv("DWSOLVER_DEVICES")) {
+        if (std::strcmp(list, "all") == 0) {
+            const int n_dev = dwgpu_device_count();
+            for (int d = 0; d < n_dev; ++d) devices.push_back(d);
+        } else {
+            for (const char *p = list; *p;) {
+                char *endp = nullptr;
+                const long d = std::strtol(p, &endp, 10);
+                if (endp == p) break;
+                devices.push_back((int)d);
+                p = *endp == ',' ? endp + 1 : endp;
+                if (*endp && *endp != ',') break;
+            }
+        }
+    }
+    if (devices.empty()) {
+        const char *dev = std::getenv("DWSOLVER_DEVICE");
+        devices.push_back(dev ? std::atoi(dev) : 0);
+    }
+    if ((int)devices.size() > K) devices.resize((size_t)K);
+    const int G = (int)devices.size();
+    struct Shard {
+        dwgpu_engine *eng = nullptr;
+        int k0 = 0, k1 = 0;          // block range
+        long long x0 = 0, xn = 0;    // its slice of the block-major x vector
+        dwgpu_packed pk;
+        int rc = 0;
+        std::string err;
+        std::vector<int> accepted;   // local block ids accepted this round
+        std::vector<long long> kept_ids;
+    };
+    std::vector<Shard> shards((size_t)G);
+    struct EngineGuard {
+        std::vector<Shard> &s;
+        ~EngineGuard() { for (auto &sh : s) if (sh.eng) dwgpu_destroy(sh.eng); }
+    } guard{shards};
+    {
+        long long xoff = 0;
+        for (int g = 0; g < G; ++g) {
+            Shard &sh = shards[(size_t)g];
+            sh.k0 = (int)((long long)K * g / G); sh.k1 = (int)((long long)K * (g + 1) / G);
+            sh.x0 = xoff;
+            for (int k = sh.k0; k < sh.k1; ++k) xoff += desc[k].n;
+            sh.xn = xoff - sh.x0;
+        }
+    }
+    // run f(shard) on every shard at once (the calls into the engine block until the shard's round is done)
+    auto on_all_shards = [&](auto &&f) {
+        auto body = [&](int g) {
+            Shard &sh = shards[(size_t)g];
+            sh.rc = f(sh);
+            if (sh.rc != 0) sh.err = dwgpu_last_error();       // the error text is per thread
+        };
+        std::vector<std::thread> pool;
+        for (int g = 1; g < G; ++g) pool.emplace_back(body, g);
+        body(0);
+        for (auto &th : pool) th.join();
+        for (auto &sh : shards) if (sh.rc != 0) { std::fprintf(stderr, "dwsolver-b200: %s\n", sh.err.c_str()); return sh.rc; }
+        return 0;
+    };
+    if (on_all_shards([&](Shard &sh) {
+            dwgpu_options gopt;
+            dwgpu_options_init(&gopt);
+            gopt.device = devices[(size_t)(&sh - shards.data())];
+            return dwgpu_create(sh.k1 - sh.k0, L, desc.data() + sh.k0, &gopt, &sh.eng);
+        }) != 0) {
+        std::fprintf(stderr, "dwsolver-b200: cannot create the GPU engine\n");
         return fail(DW_STATUS_ERR_INTERNAL);
     }
-    struct EngineGuard { dwgpu_engine *e; ~EngineGuard() { dwgpu_destroy(e); } } guard{eng};
+    auto shard_of = [&](int k) -> Shard & {
+        int g = (int)(((long long)k * G) / K);                  // close; fix up at the range borders
+        while (k < shards[(size_t)g].k0) --g;
+        while (k >= shards[(size_t)g].k1) ++g;
+        return shards[(size_t)g];
+    };
 
     // ---- restricted master (src/dw_solver.c:247-440) ---------------------------------------------------
     // master LP: GUB working basis (L x L) by default; DWSOLVER_MASTER=dense selects the (L+K)^2 dense inverse
@@ -332,35 +403,39 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
     std::vector<std::pair<int, double>> remembered;              // Phase I: (column, true cost) (:143-144, 163)
     std::vector<double> xbuf;
     int iter = 0;
-    dwgpu_packed pk;
-    std::vector<int> accepted;
-    std::vector<long long> kept_ids;
     auto consume = [&](bool phase_one, int *n_added) -> int {
         int added = 0;
-        accepted.clear();
         const size_t first_new = X.size();
-        for (int k = 0; k < K; ++k) {
-            if (pk.status[k] == DWGPU_UNBND) {
-                std::fprintf(stderr, "dwsolver-b200: subproblem %d is unbounded; unbounded subproblems are not supported (src/dw_phases.c:111-115)\n", k);
-                return DW_STATUS_ERR_UNBOUNDED;
+        for (Shard &sh : shards) {
+            const dwgpu_packed &pk = sh.pk;
+            sh.accepted.clear();
+            for (int k = sh.k0; k < sh.k1; ++k) {
+                const int kl = k - sh.k0;
+                if (pk.status[kl] == DWGPU_UNBND) {
+                    std::fprintf(stderr, "dwsolver-b200: subproblem %d is unbounded; unbounded subproblems are not supported (src/dw_phases.c:111-115)\n", k);
+                    return DW_STATUS_ERR_UNBOUNDED;
+                }
+                if (!(r[k] - pk.obj[kl] > kTolerance)) continue;      // src/dw_phases.c:108, 358
+                std::vector<int> idx;
+                std::vector<double> val;
+                for (int t = pk.colptr[kl]; t < pk.colptr[kl + 1]; ++t) { idx.push_back(pk.ind[t] - 1); val.push_back(pk.val[t]); }
+                idx.push_back(L + k); val.push_back(1.0);
+                const std::string name = "lambda_" + std::to_string(k) + "_" + std::to_string(iter);
+                const int j = add(name, phase_one ? 0.0 : pk.cost[kl], 1.0, idx, val, false);
+                if (phase_one) remembered.emplace_back(j, pk.cost[kl]);
+                Proposal p; p.k = k; p.iter = iter; p.id = -1;
+                X.push_back(p);
+                sh.accepted.push_back(kl);
+                ++added;
             }
-            if (!(r[k] - pk.obj[k] > kTolerance)) continue;      // src/dw_phases.c:108, 358
-            std::vector<int> idx;
-            std::vector<double> val;
-            for (int t = pk.colptr[k]; t < pk.colptr[k + 1]; ++t) { idx.push_back(pk.ind[t] - 1); val.push_back(pk.val[t]); }
-            idx.push_back(L + k); val.push_back(1.0);
-            const std::string name = "lambda_" + std::to_string(k) + "_" + std::to_string(iter);
-            const int j = add(name, phase_one ? 0.0 : pk.cost[k], 1.0, idx, val, false);
-            if (phase_one) remembered.emplace_back(j, pk.cost[k]);
-            Proposal p; p.k = k; p.iter = iter; p.id = -1;
-            X.push_back(p);
-            accepted.push_back(k);
-            ++added;
         }
-        // one device-to-device launch keeps the x_k of every accepted block (no per-column host copies)
-        kept_ids.resize(accepted.size());
-        if (dwgpu_history_push(eng, (int)accepted.size(), accepted.data(), kept_ids.data()) != 0) return DW_STATUS_ERR_INTERNAL;
-        for (size_t t = 0; t < accepted.size(); ++t) X[first_new + t].id = kept_ids[t];
+        // one device-to-device launch per shard keeps the x_k of every accepted block (no per-column host copies)
+        if (on_all_shards([&](Shard &sh) {
+                sh.kept_ids.resize(sh.accepted.size());
+                return dwgpu_history_push(sh.eng, (int)sh.accepted.size(), sh.accepted.data(), sh.kept_ids.data());
+            }) != 0) return DW_STATUS_ERR_INTERNAL;
+        size_t w = first_new;
+        for (Shard &sh : shards) for (size_t t = 0; t < sh.accepted.size(); ++t) X[w++].id = sh.kept_ids[t];
         *n_added = added;
         return 0;
     };
@@ -381,8 +456,10 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
     };
     auto round = [&](bool phase_one) -> int {
         const double t0 = now_s();
-        // with r given the engine ships only the columns the acceptance test below will take
-        const int rc = dwgpu_iterate_packed(eng, pi.data(), phase_one ? 1 : 0, r.data(), &pk);
+        // with r given the engine ships only the columns the acceptance test above will take
+        const int rc = on_all_shards([&](Shard &sh) {
+            return dwgpu_iterate_packed(sh.eng, pi.data(), phase_one ? 1 : 0, r.data() + sh.k0, &sh.pk);
+        });
         g_stats.seconds_subproblems += now_s() - t0;
         return rc;
     };
@@ -390,16 +467,15 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
     // first proposals: cold solve with the file objective, always accepted (r = 1e6) (src/dw_subprob.c:121-122, 184)
     {
         const double t0 = now_s();
-        if (dwgpu_initial_solve_packed(eng, &pk) != 0) {
-            std::fprintf(stderr, "dwsolver-b200: %s\n", dwgpu_last_error());
+        if (on_all_shards([&](Shard &sh) { return dwgpu_initial_solve_packed(sh.eng, &sh.pk); }) != 0)
             return fail(DW_STATUS_ERR_INTERNAL);
-        }
         g_stats.seconds_subproblems += now_s() - t0;
     }
-    for (int k = 0; k < K; ++k)
-        if (pk.status[k] == DWGPU_NOFEAS) {
-            if (verb >= DW_OUTPUT_QUIET) std::printf("Subproblem %d is infeasible.\n", k);
-        }
+    for (Shard &sh : shards)
+        for (int k = sh.k0; k < sh.k1; ++k)
+            if (sh.pk.status[k - sh.k0] == DWGPU_NOFEAS) {
+                if (verb >= DW_OUTPUT_QUIET) std::printf("Subproblem %d is infeasible.\n", k);
+            }
 
     int status = DW_STATUS_OK;
     int added = 0;
@@ -434,7 +510,7 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
             if (mrc != 0) { std::fprintf(stderr, "dwsolver-b200: Phase I master LP failed (code %d)\n", mrc); return fail(DW_STATUS_ERR_INTERNAL); }
             if (std::fabs(M.obj_val()) < kTolerance) { feasible = true; break; }     // :509-514
             if (added == 0) break;                                                   // :516-521
-            if (round(true) != 0) { std::fprintf(stderr, "dwsolver-b200: %s\n", dwgpu_last_error()); return fail(DW_STATUS_ERR_INTERNAL); }
+            if (round(true) != 0) return fail(DW_STATUS_ERR_INTERNAL);
         }
         if (!feasible) {
             if (p1 >= opt.max_phase1_iterations) {
@@ -475,7 +551,7 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
         int p2 = 0;
         bool done = false;
         for (; p2 < opt.max_phase2_iterations && !done; ++p2) {
-            if (round(false) != 0) { std::fprintf(stderr, "dwsolver-b200: %s\n", dwgpu_last_error()); return fail(DW_STATUS_ERR_INTERNAL); }
+            if (round(false) != 0) return fail(DW_STATUS_ERR_INTERNAL);
             int rc = consume(false, &added);
             if (rc) return fail(rc);
             const int mrc = solve_master();
@@ -517,8 +593,8 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
     if (opt.print_relaxed_sol) {
         std::map<std::pair<int, int>, const Proposal *> by_id;
         for (auto &p : X) by_id[{p.k, p.iter}] = &p;
-        std::vector<long long> term_id;
-        std::vector<double> term_w;
+        struct Terms { std::vector<long long> id; std::vector<double> w; };
+        std::vector<Terms> terms((size_t)G);                     // per shard, in master-column order
         for (int j = 0; j < M.cols(); ++j) {                     // every column is scanned (the reference skips the first L)
             const double v = M.col_prim(j);
             if (v == 0.0) continue;
@@ -526,16 +602,19 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
             if (std::sscanf(M.name(j).c_str(), "lambda_%d_%d", &k, &t) != 2) continue;
             auto it = by_id.find({k, t});
             if (it == by_id.end()) continue;
-            term_id.push_back(it->second->id);
-            term_w.push_back(v);
+            Terms &tm = terms[(size_t)(&shard_of(k) - shards.data())];
+            tm.id.push_back(it->second->id);
+            tm.w.push_back(v);
         }
         long long ntot = 0;
         for (int k = 0; k < K; ++k) ntot += desc[k].n;
         std::vector<double> xall((size_t)std::max<long long>(ntot, 1), 0.0);
-        if (dwgpu_history_combine(eng, (int)term_id.size(), term_id.data(), term_w.data(), xall.data()) != 0) {
-            std::fprintf(stderr, "dwsolver-b200: %s\n", dwgpu_last_error());
+        // contiguous shards: every engine's block-major x lands in its own slice of the global one
+        if (on_all_shards([&](Shard &sh) {
+                Terms &tm = terms[(size_t)(&sh - shards.data())];
+                return dwgpu_history_combine(sh.eng, (int)tm.id.size(), tm.id.data(), tm.w.data(), xall.data() + sh.x0);
+            }) != 0)
             return fail(DW_STATUS_ERR_INTERNAL);
-        }
         std::vector<std::vector<double>> xs(K);
         {
             long long off = 0;
@@ -554,8 +633,11 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
         }
     }
 
-    dwgpu_counters cnt;
-    if (dwgpu_get_counters(eng, &cnt) == 0) g_stats.sub_pivots = cnt.pivots + cnt.flips;
+    g_stats.sub_pivots = 0;
+    for (Shard &sh : shards) {
+        dwgpu_counters cnt;
+        if (dwgpu_get_counters(sh.eng, &cnt) == 0) g_stats.sub_pivots += cnt.pivots + cnt.flips;
+    }
     g_stats.dw_iterations = iter;
     g_stats.master_columns = M.cols();
     g_stats.seconds_total = now_s() - t_begin;

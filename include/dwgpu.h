@@ -223,6 +223,9 @@ int  dwgpu_last_kernel_ms(dwgpu_engine *e, float ms[2]);
  * shared-memory path, which MEASURED_PEAKS.json does not carry. */
 int  dwgpu_measure_smem_bandwidth(int device, double *gbps);
 int  dwgpu_sync(dwgpu_engine *e);
+/* Number of CUDA devices this process can use (0 when there is none or the driver is unusable); what
+ * DWSOLVER_DEVICES=all expands to when dw_solve shards the blocks over one engine per device. */
+int  dwgpu_device_count(void);
 const char *dwgpu_last_error(void);
 const char *dwgpu_version(void);
 

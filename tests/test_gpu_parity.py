@@ -479,3 +479,25 @@ def test_host_mailboxes_match_dense_results(force_path):
             same(e2.iterate_mailboxes(pi, t == 0))
     assert e2.counters()["mailbox_bytes"] > 0
     e1.close(); e2.close()
+
+
+def test_two_live_engines_of_different_shapes():
+    """A kernel's dynamic shared-memory limit belongs to the device, not to an engine: an engine created later for
+    smaller blocks must not take it away from one that is still launching (several engines live in one process when
+    dw_solve shards the blocks over DWSOLVER_DEVICES).  The big blocks need more than the 48 KB a kernel gets without
+    the opt-in (61 x 142 doubles of tableau)."""
+    big = P.gen_mcf(4, 60, 140, 8, seed=5)
+    small = P.gen_mcf(5, 6, 12, 3, seed=6)
+    pi = -np.random.default_rng(8).random(big.L) * 10.0
+    solo = engine(big)
+    want0 = [p["obj"] for p in solo.initial()]
+    want1 = [p["obj"] for p in solo.iterate(pi, False)]
+    solo.close()
+    a = engine(big)
+    b = engine(small)                                  # created while `a` is alive, smaller shared-memory need
+    got0 = [p["obj"] for p in a.initial()]
+    assert all(p["status"] == OPT for p in b.initial())
+    got1 = [p["obj"] for p in a.iterate(pi, False)]
+    assert got0 == want0 and got1 == want1             # same kernels, same inputs: bit-identical
+    b.close()
+    a.close()

@@ -320,6 +320,56 @@ def test_dw_solve_container_matches_dw_solve(tmp_path):
         os.chdir(cwd)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["0,0,0", "all", "0,0,0,0,0,0,0"])
+def test_dw_solve_sharded_over_several_engines(devices, tmp_path, monkeypatch):
+    """SURVEY 8e inside the drop-in: DWSOLVER_DEVICES shards the blocks contiguously over one engine per listed
+    device (a device may be listed more than once, so the sharded path also runs on a one-GPU box); every shard is
+    driven by its own host thread.  Same objective, same master columns and the same relaxed_solution as one engine."""
+    L = lib()
+    prob = P.gen_mcf(40, 16, 40, 8, seed=3)
+    paths = write_example(prob, tmp_path)
+    subs = (C.c_char_p * prob.K)(*[s.encode() for s in paths["subs"]])
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        def run():
+            o = DwOptions()
+            L.dw_options_init(C.byref(o))
+            o.verbosity = -1
+            res = DwResult()
+            assert L.dw_solve(paths["master"].encode(), subs, prob.K, C.byref(o), C.byref(res)) == 0
+            out = (res.objective_value, res.num_vars, sorted(open("relaxed_solution").read().splitlines()))
+            L.dw_result_free(C.byref(res))
+            os.remove("relaxed_solution")
+            return out
+        monkeypatch.delenv("DWSOLVER_DEVICES", raising=False)
+        one = run()
+        monkeypatch.setenv("DWSOLVER_DEVICES", devices)
+        many = run()
+        assert abs(many[0] - one[0]) <= 1e-9 * (1 + abs(one[0]))
+        assert many[1] == one[1] and many[2] == one[2]
+    finally:
+        os.chdir(cwd)
+
+
+@pytest.mark.gpu
+def test_dw_solve_sharded_example_with_fewer_blocks_than_devices(golden, tmp_path, monkeypatch):
+    """more listed devices than blocks: the list is cut to K; the reference's book_dantzig objective is reached"""
+    monkeypatch.setenv("DWSOLVER_DEVICES", "0,0,0,0,0,0,0,0")
+    prob = load_example("book_dantzig")
+    from dwsolver_b200.solver import dw_solve
+    paths = write_example(prob, tmp_path)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        r = dw_solve(paths["master"], paths["subs"], verbosity=-1, shift=float(prob.shift or 0.0))
+    finally:
+        os.chdir(cwd)
+    want = golden["objective"]["book_dantzig"]
+    assert r["status"] == 0 and abs(r["objective"] - want) <= 1e-7 * (1 + abs(want))
+
+
 def _gub_case(rng, L, K):
     """a random DW-shaped master: (cols, cost, rhs, lam) — L linking equalities, K convexity rows, 3-6 columns per
     block, one +1 slack and one costly -1 column per linking row"""
