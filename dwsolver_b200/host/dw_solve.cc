@@ -344,6 +344,7 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
         for (auto &sh : shards) if (sh.rc != 0) { std::fprintf(stderr, "dwsolver-b200: %s\n", sh.err.c_str()); return sh.rc; }
         return 0;
     };
+    const double t_create0 = now_s();
     if (on_all_shards([&](Shard &sh) {
             dwgpu_options gopt;
             dwgpu_options_init(&gopt);
@@ -353,6 +354,8 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
         std::fprintf(stderr, "dwsolver-b200: cannot create the GPU engine\n");
         return fail(DW_STATUS_ERR_INTERNAL);
     }
+    const double t_create = now_s() - t_create0;
+    double t_consume = 0.0, t_history = 0.0;
     auto shard_of = [&](int k) -> Shard & {
         int g = (int)(((long long)k * G) / K);                  // close; fix up at the range borders
         while (k < shards[(size_t)g].k0) --g;
@@ -404,6 +407,7 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
     std::vector<double> xbuf;
     int iter = 0;
     auto consume = [&](bool phase_one, int *n_added) -> int {
+        const double t_c0 = now_s();
         int added = 0;
         const size_t first_new = X.size();
         for (Shard &sh : shards) {
@@ -430,12 +434,15 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
             }
         }
         // one device-to-device launch per shard keeps the x_k of every accepted block (no per-column host copies)
+        const double t_h0 = now_s();
         if (on_all_shards([&](Shard &sh) {
                 sh.kept_ids.resize(sh.accepted.size());
                 return dwgpu_history_push(sh.eng, (int)sh.accepted.size(), sh.accepted.data(), sh.kept_ids.data());
             }) != 0) return DW_STATUS_ERR_INTERNAL;
         size_t w = first_new;
         for (Shard &sh : shards) for (size_t t = 0; t < sh.accepted.size(); ++t) X[w++].id = sh.kept_ids[t];
+        t_history += now_s() - t_h0;
+        t_consume += now_s() - t_c0;
         *n_added = added;
         return 0;
     };
@@ -641,6 +648,10 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
     g_stats.dw_iterations = iter;
     g_stats.master_columns = M.cols();
     g_stats.seconds_total = now_s() - t_begin;
+    if (std::getenv("DWSOLVER_DEBUG_TIMING"))
+        std::fprintf(stderr, "dwsolver-b200: %d engine(s) created in %.4f s; columns consumed in %.4f s (of which history push %.4f s); "
+                             "subproblem calls %.4f s, master %.4f s, total %.4f s\n",
+                     G, t_create, t_consume, t_history, g_stats.seconds_subproblems, g_stats.seconds_master, g_stats.seconds_total);
     if (opt.print_timing_data && verb >= DW_OUTPUT_SILENT) {
         std::printf("Total wall time: %.6f s (read %.6f, subproblems on the GPU %.6f, master %.6f); %d DW iterations, %lld subproblem pivots\n",
                     g_stats.seconds_total, g_stats.seconds_read, g_stats.seconds_subproblems, g_stats.seconds_master,
