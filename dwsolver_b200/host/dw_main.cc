@@ -28,7 +28,8 @@ static void usage(const char *argv0)
     std::printf(" --phase1_max <n>        Max phase I iterations (default 100).\n");
     std::printf(" --phase2_max <n>        Max phase II iterations (default 3000).\n");
     std::printf(" --write-container <f>   With -g: store the parsed instance in the binary container <f> and exit.\n");
-    std::printf(" --container <f>         Solve the instance stored in container <f> (no guidefile, no LP text).\n\n");
+    std::printf(" --container <f>         Solve the instance stored in container <f> (no guidefile, no LP text).\n");
+    std::printf(" --devices <list|all>    Shard the subproblems over these CUDA devices, e.g. 0,1,2,3 (default: device 0).\n\n");
     std::printf("The guide file format:\n  n\n  sub_file_1\n  ...\n  sub_file_n\n  master_file\n  monolithic_file\n  objective_constant\n\n");
 }
 
@@ -71,6 +72,7 @@ int main(int argc, char **argv)
         else if (a == "--phase2_max" && i + 1 < argc) opt.max_phase2_iterations = std::atoi(argv[++i]);
         else if (a == "--write-container" && i + 1 < argc) container_out = argv[++i];
         else if (a == "--container" && i + 1 < argc) container_in = argv[++i];
+        else if (a == "--devices" && i + 1 < argc) setenv("DWSOLVER_DEVICES", argv[++i], 1);
         else std::printf("Command line argument %s not recognized. Trying to continue.\n", argv[i]);
     }
     if (!container_in.empty()) {                                  // binary container: nothing else to read
