@@ -1,0 +1,181 @@
+/*
+ * stub_dwgpu.c — TEST DOUBLE of the engine's C ABI (include/dwgpu.h).  TEST INFRASTRUCTURE ONLY.
+ *
+ * It exists so that the host side of the drop-in (dwsolver_b200/host: dw_solve, the Phase I / II loop, the stop
+ * rules, block sharding over several engines, the container path, the command line) can be exercised by the CPU
+ * test-suite on a machine without a GPU.  It implements exactly the ten entry points libdwsolver_b200.so imports,
+ * on top of the CPU oracle (oracle/), and is built by tests/stub_engine/Makefile into tests/_build/lib/ — a private
+ * directory into which the tests COPY the host library and the CLI, so that their `$ORIGIN` run-path finds this
+ * file there instead of the CUDA engine.  Nothing in dwsolver_b200/ or include/ refers to it, it is never installed
+ * next to the product, and the product has no way to select it: dwsolver_b200/lib/libdwgpu.so is the CUDA engine and
+ * fails loudly without a device (tests/test_abi.py).  Results obtained through this file say nothing about the GPU
+ * path; the parity tests proper are the `-m gpu` ones.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/dwgpu.h"
+#include "../../oracle/oracle.h"
+
+struct dwgpu_engine {
+    int K, L;
+    orc_block **blocks;
+    orc_proposal *props;
+    int *n;
+    long long *xoff, ntot;
+    /* packed record (what the CUDA engine keeps in pinned memory) */
+    double *obj, *cost, *val;
+    int *status, *colptr, *ind;
+    /* kept copies of x_k */
+    double *hist;
+    long long hist_used, hist_cap;
+    long long *hist_off;
+    int *hist_block;
+    long long hist_n, hist_slots;
+};
+
+static __thread char g_err[256];
+static int fail(int code, const char *msg) { snprintf(g_err, sizeof g_err, "%s", msg); return code; }
+
+const char *dwgpu_last_error(void) { return g_err; }
+int dwgpu_device_count(void) { return 1; }
+
+void dwgpu_options_init(dwgpu_options *o)
+{
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->clamp_lo_cols = 1; o->max_iter_mult = 50; o->tol_dj = o->tol_bnd = o->tol_piv = 1e-9;
+}
+
+void dwgpu_destroy(dwgpu_engine *e)
+{
+    if (!e) return;
+    for (int k = 0; k < e->K; ++k) {
+        if (e->blocks && e->blocks[k]) orc_block_free(e->blocks[k]);
+        if (e->props) { free(e->props[k].ind); free(e->props[k].val); free(e->props[k].x); }
+    }
+    free(e->blocks); free(e->props); free(e->n); free(e->xoff);
+    free(e->obj); free(e->cost); free(e->val); free(e->status); free(e->colptr); free(e->ind);
+    free(e->hist); free(e->hist_off); free(e->hist_block);
+    free(e);
+}
+
+int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *opt, dwgpu_engine **out)
+{
+    (void)opt;
+    if (K < 1 || L < 0 || !bd || !out) return fail(DWGPU_E_ARGS, "bad arguments");
+    if (getenv("DWSTUB_FAIL_CREATE")) return fail(DWGPU_E_CUDA, "stub engine: creation failure requested by the test");
+    dwgpu_engine *e = calloc(1, sizeof *e);
+    if (!e) return fail(DWGPU_E_NOMEM, "out of memory");
+    e->K = K; e->L = L;
+    e->blocks = calloc((size_t)K, sizeof *e->blocks);
+    e->props = calloc((size_t)K, sizeof *e->props);
+    e->n = calloc((size_t)K, sizeof *e->n);
+    e->xoff = calloc((size_t)K + 1, sizeof *e->xoff);
+    e->obj = calloc((size_t)K, sizeof(double)); e->cost = calloc((size_t)K, sizeof(double));
+    e->status = calloc((size_t)K, sizeof(int)); e->colptr = calloc((size_t)K + 1, sizeof(int));
+    e->ind = calloc((size_t)K * (size_t)(L > 0 ? L : 1), sizeof(int));
+    e->val = calloc((size_t)K * (size_t)(L > 0 ? L : 1), sizeof(double));
+    for (int k = 0; k < K; ++k) {
+        const dwgpu_block_desc *b = &bd[k];
+        e->n[k] = b->n;
+        e->xoff[k + 1] = e->xoff[k] + b->n;
+        e->blocks[k] = orc_block_new(b->m, b->n, b->a_rowptr, b->a_col, b->a_val, b->row_lb, b->row_ub, b->col_lb, b->col_ub,
+                                     b->c_file, b->c_master, L, b->d_nnz, b->d_row, b->d_col, b->d_val);
+        e->props[k].ind = calloc((size_t)(L > 0 ? L : 1) + 1, sizeof(int));
+        e->props[k].val = calloc((size_t)(L > 0 ? L : 1) + 1, sizeof(double));
+        e->props[k].x = calloc((size_t)(b->n > 0 ? b->n : 1), sizeof(double));
+        if (!e->blocks[k] || !e->props[k].ind || !e->props[k].val || !e->props[k].x) { dwgpu_destroy(e); return fail(DWGPU_E_NOMEM, "out of memory"); }
+    }
+    e->ntot = e->xoff[K];
+    *out = e;
+    return 0;
+}
+
+/* src/dw_phases.c:108, 358 through the engine's packed record: with r given only the columns the master will accept
+ * are shipped (dwsolver_b200/csrc/pack.cuh) */
+static void pack(dwgpu_engine *e, const double *r, dwgpu_packed *out)
+{
+    int nnz = 0;
+    for (int k = 0; k < e->K; ++k) {
+        const orc_proposal *p = &e->props[k];
+        e->obj[k] = p->obj; e->cost[k] = p->new_obj_coeff; e->status[k] = p->status;
+        e->colptr[k] = nnz;
+        if (r && !(r[k] - p->obj > 1e-6)) continue;
+        for (int t = 0; t < p->len; ++t) { e->ind[nnz] = p->ind[t]; e->val[nnz] = p->val[t]; ++nnz; }
+    }
+    e->colptr[e->K] = nnz;
+    if (out) {
+        out->obj = e->obj; out->cost = e->cost; out->status = e->status; out->colptr = e->colptr;
+        out->ind = e->ind; out->val = e->val; out->nnz = nnz;
+    }
+}
+
+int dwgpu_initial_solve_packed(dwgpu_engine *e, dwgpu_packed *out)
+{
+    if (!e) return fail(DWGPU_E_ARGS, "bad arguments");
+    orc_batch(e->blocks, e->props, e->K, NULL, 0, 1, 2);
+    pack(e, NULL, out);
+    return 0;
+}
+
+int dwgpu_iterate_packed(dwgpu_engine *e, const double *pi, int phase_one, const double *r, dwgpu_packed *out)
+{
+    if (!e || (e->L > 0 && !pi)) return fail(DWGPU_E_ARGS, "bad arguments");
+    if (getenv("DWSTUB_FAIL_ITERATE")) return fail(DWGPU_E_CUDA, "stub engine: round failure requested by the test");
+    orc_batch(e->blocks, e->props, e->K, pi, phase_one, 0, 2);
+    pack(e, r, out);
+    return 0;
+}
+
+int dwgpu_history_push(dwgpu_engine *e, int count, const int *blocks, long long *ids_out)
+{
+    if (!e || count < 0 || (count > 0 && (!blocks || !ids_out))) return fail(DWGPU_E_ARGS, "bad arguments");
+    for (int i = 0; i < count; ++i) {
+        const int k = blocks[i];
+        if (k < 0 || k >= e->K) return fail(DWGPU_E_ARGS, "block index out of range");
+        if (e->hist_used + e->n[k] > e->hist_cap) {
+            e->hist_cap = 2 * (e->hist_used + e->n[k]) + 2 * e->ntot;
+            e->hist = realloc(e->hist, sizeof(double) * (size_t)e->hist_cap);
+        }
+        if (e->hist_n == e->hist_slots) {
+            e->hist_slots = 2 * e->hist_slots + 64;
+            e->hist_off = realloc(e->hist_off, sizeof(long long) * (size_t)e->hist_slots);
+            e->hist_block = realloc(e->hist_block, sizeof(int) * (size_t)e->hist_slots);
+        }
+        if (!e->hist || !e->hist_off || !e->hist_block) return fail(DWGPU_E_NOMEM, "out of memory");
+        memcpy(e->hist + e->hist_used, e->props[k].x, sizeof(double) * (size_t)e->n[k]);
+        ids_out[i] = e->hist_n;
+        e->hist_off[e->hist_n] = e->hist_used; e->hist_block[e->hist_n] = k; ++e->hist_n;
+        e->hist_used += e->n[k];
+    }
+    return 0;
+}
+
+int dwgpu_history_combine(dwgpu_engine *e, int nterms, const long long *ids, const double *weights, double *x_out)
+{
+    if (!e || nterms < 0 || !x_out || (nterms > 0 && (!ids || !weights))) return fail(DWGPU_E_ARGS, "bad arguments");
+    for (long long j = 0; j < e->ntot; ++j) x_out[j] = 0.0;
+    for (int t = 0; t < nterms; ++t) {
+        if (ids[t] < 0 || ids[t] >= e->hist_n) return fail(DWGPU_E_ARGS, "unknown history id");
+        const int k = e->hist_block[ids[t]];
+        const double *src = e->hist + e->hist_off[ids[t]];
+        double *dst = x_out + e->xoff[k];
+        for (int j = 0; j < e->n[k]; ++j) dst[j] = fma(weights[t], src[j], dst[j]);
+    }
+    return 0;
+}
+
+int dwgpu_get_counters(dwgpu_engine *e, dwgpu_counters *c)
+{
+    if (!e || !c) return fail(DWGPU_E_ARGS, "bad arguments");
+    memset(c, 0, sizeof *c);
+    for (int k = 0; k < e->K; ++k) {
+        long p = 0, f = 0, rf = 0;
+        orc_block_counters(e->blocks[k], &p, &f, &rf);
+        c->pivots += p; c->flips += f; c->rebuilds += rf;
+    }
+    return 0;
+}

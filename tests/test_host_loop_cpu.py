@@ -1,0 +1,127 @@
+"""The host side of the drop-in on a machine WITHOUT a GPU: dw_solve's Phase I / Phase II loop, stop rules, block
+sharding over several engines, the container path and the command line (dwsolver_b200/host), run against a TEST
+DOUBLE of the engine ABI (tests/stub_engine/stub_dwgpu.c: the ten entry points the host library imports, on the CPU
+oracle).  The double lives in tests/_build/ next to COPIES of the host library and of the CLI — their $ORIGIN
+run-path finds it there; the product's own lib/ directory only ever holds the CUDA engine, which has no CPU
+fallback (tests/test_abi.py).  What these tests pin is the host logic; the subproblem numerics are the oracle's, and
+the GPU engine is compared with that oracle in tests/test_gpu_parity.py (-m gpu), where the same CLI checks run
+against the real engine (tests/test_host_library.py).
+
+Everything goes through the CLI in a child process: a second libdwgpu.so cannot be loaded into a Python process that
+may already hold the real one.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import EXAMPLES, ROOT, load_example
+from dwsolver_b200 import problem as P
+
+BUILD = os.path.join(ROOT, "tests", "_build")
+CLI = os.path.join(BUILD, "bin", "dwsolver")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def stub_build():
+    out = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "stub_engine")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    ldd = subprocess.run(["ldd", CLI], capture_output=True, text=True).stdout
+    assert os.path.join("tests", "_build") in ldd.split("libdwgpu.so")[1].splitlines()[0]     # the double, not the engine
+
+
+def run(cwd, *args, env=None):
+    e = dict(os.environ)
+    e.pop("DWSOLVER_DEVICES", None)
+    e.update(env or {})
+    return subprocess.run([CLI, *args], cwd=str(cwd), capture_output=True, text=True, timeout=600, env=e)
+
+
+def banner(out):
+    lines = [ln for ln in out.stdout.splitlines() if "Master objective value" in ln]
+    assert lines, out.stdout + out.stderr
+    return lines[-1].split("=")[1].strip()
+
+
+def solution(cwd):
+    return dict(ln.split("\t") for ln in open(os.path.join(str(cwd), "relaxed_solution")).read().splitlines())
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_examples_through_the_cli(name, golden, tmp_path):
+    """tests/dw-tests.sh of the reference: objective banner (and its %e literal), sorted relaxed_solution (%f)"""
+    P.write_block_angular(load_example(name), str(tmp_path))
+    out = run(tmp_path, "-g", "guidefile")
+    assert out.returncode == 0, out.stderr
+    want = golden["objective"][name]
+    assert abs(float(banner(out)) - want) <= 1e-6 * (1 + abs(want))
+    if name in golden["objective_literal"]:
+        assert banner(out) == golden["objective_literal"][name]
+    sol = golden["relaxed_solution"].get(name)
+    if sol:
+        rs = solution(tmp_path)
+        for nm, v in sol.items():
+            assert "%f" % (float(rs[nm]) + 0.0) == "%f" % v, (nm, rs[nm], v)
+
+
+@pytest.mark.parametrize("devices", ["0,0,0", "all", "0,0,0,0,0,0,0"])
+def test_sharded_solve_equals_single_engine(devices, tmp_path):
+    """SURVEY 8e inside dw_solve: contiguous shards, one host thread per shard and round — same banner, same
+    relaxed_solution as one engine (per-block results do not depend on the shard a block sits in)"""
+    prob = P.gen_mcf(40, 16, 40, 8, seed=3)
+    P.write_block_angular(prob, str(tmp_path))
+    one = run(tmp_path, "-g", "guidefile")
+    sol_one = solution(tmp_path)
+    os.remove(tmp_path / "relaxed_solution")
+    many = run(tmp_path, "-g", "guidefile", "--devices", devices)
+    assert one.returncode == 0 and many.returncode == 0, one.stderr + many.stderr
+    assert banner(one) == banner(many)
+    assert solution(tmp_path) == sol_one and len(sol_one) == sum(b.n for b in prob.blocks)
+    # against the monolithic LP
+    from highs_util import solve_monolithic
+    ref = solve_monolithic(prob)["objective"]
+    assert abs(float(banner(many)) - ref) <= 1e-6 * (1 + abs(ref))
+
+
+def test_more_devices_than_blocks(golden, tmp_path):
+    P.write_block_angular(load_example("book_dantzig"), str(tmp_path))
+    out = run(tmp_path, "-g", "guidefile", env={"DWSOLVER_DEVICES": "0,0,0,0,0,0,0,0"})
+    assert out.returncode == 0 and banner(out) == golden["objective_literal"]["book_dantzig"]
+
+
+@pytest.mark.parametrize("name", ["four_sea", "book_lasdon"])
+def test_container_solve_equals_text_solve(name, tmp_path):
+    P.write_block_angular(load_example(name), str(tmp_path))
+    text = run(tmp_path, "-g", "guidefile")
+    sol_text = solution(tmp_path)
+    os.remove(tmp_path / "relaxed_solution")
+    assert run(tmp_path, "-g", "guidefile", "--write-container", "p.dwb", "--quiet").returncode == 0
+    box = run(tmp_path, "--container", "p.dwb")
+    assert text.returncode == 0 and box.returncode == 0, text.stderr + box.stderr
+    assert banner(text) == banner(box) and solution(tmp_path) == sol_text      # original variable names travel
+    assert run(tmp_path, "--container", "missing.dwb", "--quiet").returncode == 2   # DW_STATUS_ERR_FILE
+
+
+def test_engine_failures_become_status_99(tmp_path):
+    """the CUDA layer never exits the process: a failing dwgpu_create / dwgpu_iterate_packed comes back as
+    DW_STATUS_ERR_INTERNAL with the engine's message on stderr (error conventions)"""
+    P.write_block_angular(load_example("web_trick"), str(tmp_path))
+    out = run(tmp_path, "-g", "guidefile", "--quiet", env={"DWSTUB_FAIL_CREATE": "1"})
+    assert out.returncode == 99 and "creation failure requested" in out.stderr
+    out = run(tmp_path, "-g", "guidefile", "--quiet", env={"DWSTUB_FAIL_ITERATE": "1"})
+    assert out.returncode == 99 and "round failure requested" in out.stderr
+    out = run(tmp_path, "-g", "guidefile", "--quiet", "--devices", "0,0", env={"DWSTUB_FAIL_ITERATE": "1"})
+    assert out.returncode == 99
+
+
+def test_iteration_limits_and_missing_files(tmp_path):
+    prob = P.gen_mcf(24, 12, 30, 6, seed=11)
+    P.write_block_angular(prob, str(tmp_path))
+    full = run(tmp_path, "-g", "guidefile", "--quiet")
+    assert full.returncode == 0
+    assert run(tmp_path, "-g", "guidefile", "--quiet", "--phase2_max", "1").returncode == 5    # DW_STATUS_ERR_PHASE2_LIMIT
+    assert run(tmp_path, "-g", "guidefile", "--quiet", "--phase1_max", "1").returncode == 4    # DW_STATUS_ERR_PHASE1_LIMIT
+    os.remove(tmp_path / "sub3.lp")
+    assert run(tmp_path, "-g", "guidefile", "--quiet").returncode == 2                         # DW_STATUS_ERR_FILE
+    assert run(tmp_path, "-g", "no_such_guidefile").returncode == 1
