@@ -125,3 +125,31 @@ def test_iteration_limits_and_missing_files(tmp_path):
     os.remove(tmp_path / "sub3.lp")
     assert run(tmp_path, "-g", "guidefile", "--quiet").returncode == 2                         # DW_STATUS_ERR_FILE
     assert run(tmp_path, "-g", "no_such_guidefile").returncode == 1
+
+
+def _tiny_block(lb, ub, c):
+    return P.Block(m=1, n=1, a_rowptr=np.array([0, 1], np.int32), a_col=np.array([0], np.int32), a_val=np.array([1.0]),
+                   row_lb=np.array([-np.inf]), row_ub=np.array([100.0]), col_lb=np.array([lb]), col_ub=np.array([ub]),
+                   c_file=np.array([c]), c_master=np.array([c]), d_row=np.array([0], np.int32),
+                   d_col=np.zeros(1, np.int32), d_val=np.array([1.0]))
+
+
+@pytest.mark.parametrize("case,want_rc", [("infeasible", 3), ("feasible", 0), ("unbounded", 6)])
+def test_status_codes(case, want_rc, tmp_path):
+    """src/dw_solver.h:88-97 — infeasible linking row -> DW_STATUS_ERR_INFEASIBLE with the reference's message
+    (src/dw_solver.c:516-521); a block unbounded below -> DW_STATUS_ERR_UNBOUNDED (src/dw_phases.c:111-115)"""
+    if case == "unbounded":
+        blocks, ub = [_tiny_block(-np.inf, 5.0, 1.0)], 3.0              # min x, x free below
+    else:
+        blocks = [_tiny_block(1.0, 5.0, 1.0), _tiny_block(1.0, 5.0, 1.0)]   # x1, x2 >= 1 and x1 + x2 <= ub
+        ub = 1.0 if case == "infeasible" else 3.0
+    prob = P.BlockAngularLP(K=len(blocks), L=1, blocks=blocks, link_lb=np.array([-np.inf]), link_ub=np.array([ub]))
+    P.write_block_angular(prob, str(tmp_path))
+    out = run(tmp_path, "-g", "guidefile", "--quiet" if case != "feasible" else "--output-normal")
+    assert out.returncode == want_rc, out.stdout + out.stderr
+    if case == "infeasible":
+        assert "Problem is infeasible." in out.stdout
+    if case == "unbounded":
+        assert "unbounded" in out.stderr
+    if case == "feasible":
+        assert abs(float(banner(out)) - 2.0) <= 1e-9
