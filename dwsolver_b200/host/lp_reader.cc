@@ -25,6 +25,15 @@ struct Tok {                      // `text` points into the file image: no alloc
     std::string_view text;
 };
 
+struct TokSpan {                  // a section's tokens: a window into the token array, no copy
+    const Tok *b = nullptr;
+    size_t n = 0;
+    size_t size() const { return n; }
+    const Tok &operator[](size_t i) const { return b[i]; }
+    const Tok *begin() const { return b; }
+    const Tok *end() const { return b + n; }
+};
+
 // character classes of the CPLEX-LP lexer, one table lookup per character
 struct CharClass {
     unsigned char start[256], body[256];
@@ -146,19 +155,17 @@ struct Parser {
     LpModel lp;
     int col(std::string_view name_view)
     {
-        const std::string name(name_view);          // short names stay in the small-string buffer
-        auto it = lp.col_index.find(name);
-        if (it != lp.col_index.end()) return it->second;
-        const int j = lp.n();
-        lp.col_index.emplace(name, j);
-        lp.col_names.push_back(name);
+        // one hash per lookup; short names stay in the small-string buffer
+        auto ins = lp.col_index.try_emplace(std::string(name_view), lp.n());
+        if (!ins.second) return ins.first->second;
+        lp.col_names.push_back(ins.first->first);
         lp.obj.push_back(0.0);
         lp.col_lb.push_back(0.0);
         lp.col_ub.push_back(kInf);
-        return j;
+        return lp.n() - 1;
     }
     // [+|-] [coef] name ... until a sense operator, the end, or the label of the next row
-    size_t linear(const std::vector<Tok> &st, size_t pos, std::vector<std::pair<int, double>> &terms, double &constant)
+    size_t linear(const TokSpan &st, size_t pos, std::vector<std::pair<int, double>> &terms, double &constant)
     {
         double sign = 1.0, coef = 0.0;
         bool have_coef = false;
@@ -181,7 +188,7 @@ struct Parser {
         return pos;
     }
     // optional signs, then a number or inf[inity]
-    bool value(const std::vector<Tok> &st, size_t &pos, double &v)
+    bool value(const TokSpan &st, size_t &pos, double &v)
     {
         size_t p = pos;
         double sgn = 1.0;
@@ -193,7 +200,7 @@ struct Parser {
         }
         return false;
     }
-    void rows(const std::vector<Tok> &st)
+    void rows(const TokSpan &st)
     {
         size_t pos = 0;
         while (pos < st.size()) {
@@ -216,7 +223,7 @@ struct Parser {
             for (auto &t : terms) { lp.a_row.push_back(i); lp.a_col.push_back(t.first); lp.a_val.push_back(t.second); }
         }
     }
-    void bounds(const std::vector<Tok> &st)
+    void bounds(const TokSpan &st)
     {
         size_t pos = 0;
         while (pos < st.size()) {
@@ -263,33 +270,40 @@ LpModel parse_lp_text(const std::string &text)
 {
     const std::vector<Tok> toks = tokenize(text);
     // split into sections ("subject to" / "such that" are two words; a keyword followed by ':' is a label)
-    std::vector<std::pair<Section, std::vector<Tok>>> secs;
+    std::vector<std::pair<Section, TokSpan>> secs;
     Section cur = S_NONE;
-    std::vector<Tok> buf;
+    size_t sec_begin = 0;
+    auto close = [&](size_t end) {
+        if (cur != S_NONE) { TokSpan sp; sp.b = toks.data() + sec_begin; sp.n = end - sec_begin; secs.emplace_back(cur, sp); }
+    };
     for (size_t i = 0; i < toks.size();) {
         Section sec = S_NONE;
         size_t adv = 1;
-        if (toks[i].kind == T_NAME && !(i + 1 < toks.size() && is_op(toks[i + 1], ":"))) {
+        // every keyword is at most 9 characters long and starts with one of m s b g i e (any case): almost every
+        // name token of a large model is dismissed by this test without building a lower-case copy
+        if (toks[i].kind == T_NAME && toks[i].text.size() <= 9 && std::strchr("mMsSbBgGiIeE", toks[i].text[0]) &&
+            !(i + 1 < toks.size() && is_op(toks[i + 1], ":"))) {
             const std::string w = lower(toks[i].text);
             if ((w == "subject" || w == "such") && i + 1 < toks.size() && toks[i + 1].kind == T_NAME &&
                 (lower(toks[i + 1].text) == "to" || lower(toks[i + 1].text) == "that")) { sec = S_ROWS; adv = 2; }
             else sec = section_of(w);
         }
         if (sec != S_NONE) {
-            if (cur != S_NONE) secs.emplace_back(cur, buf);
-            cur = sec; buf.clear();
+            close(i);
+            cur = sec;
             i += adv;
-            if (sec == S_END) break;
+            sec_begin = i;
+            if (sec == S_END) { cur = S_NONE; break; }
             continue;
         }
-        buf.push_back(toks[i]);
         ++i;
+        if (i == toks.size()) close(i);
     }
-    if (cur != S_NONE) secs.emplace_back(cur, buf);
 
     Parser P;
+    P.lp.col_index.reserve(toks.size() / 4);          // about one new name per four tokens in a wide model
     for (auto &sc : secs) {
-        const std::vector<Tok> &st = sc.second;
+        const TokSpan &st = sc.second;
         switch (sc.first) {
         case S_OBJ:
         case S_OBJMAX: {
@@ -316,7 +330,7 @@ LpModel parse_lp_text(const std::string &text)
         default: break;
         }
     }
-    return P.lp;
+    return std::move(P.lp);
 }
 
 LpModel read_lp_file(const std::string &path)
