@@ -153,3 +153,61 @@ def test_status_codes(case, want_rc, tmp_path):
         assert "unbounded" in out.stderr
     if case == "feasible":
         assert abs(float(banner(out)) - 2.0) <= 1e-9
+
+
+_LIB_API_CHILD = r"""
+import ctypes as C, math, os, sys
+sys.path.insert(0, {root!r})
+from dwsolver_b200.solver import DwOptions, DwResult
+L = C.CDLL({lib!r})
+L.dw_version.restype = C.c_char_p
+L.dw_solve.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(DwOptions), C.POINTER(DwResult)]
+master, subs = {master!r}.encode(), [s.encode() for s in {subs!r}]
+arr = (C.c_char_p * len(subs))(*subs)
+o = DwOptions(); L.dw_options_init(C.byref(o))
+# T1 defaults (tests/test_lib_api.c:74-94)
+assert (o.verbosity, o.max_phase1_iterations, o.max_phase2_iterations, o.rounding_flag, o.integerize_flag) == (5, 100, 3000, 0, 0)
+assert abs(o.mip_gap - 0.01) < 1e-10 and o.shift == 0.0 and o.print_relaxed_sol == 1 and o.perturb == 0
+# T2/T3 solve and free (:96-125)
+o.verbosity = -1
+res = DwResult()
+rc = L.dw_solve(master, arr, len(subs), C.byref(o), C.byref(res))
+assert rc == 0 and res.status == 0 and res.num_vars > 0 and bool(res.x) and math.isfinite(res.objective_value)
+first = res.objective_value
+L.dw_result_free(C.byref(res))
+assert not res.x and res.num_vars == 0
+# T4 NULL master (:127-139)
+res = DwResult()
+assert L.dw_solve(None, arr, len(subs), C.byref(o), C.byref(res)) == 1 and not res.x
+# T5 version (:144-150)
+assert L.dw_version().startswith(b"dwsolver")
+# T6 silent verbosity prints nothing (:157-190), T7 custom mip_gap (:195-213)
+o.verbosity = -1; o.mip_gap = 0.05
+res = DwResult()
+assert L.dw_solve(master, arr, len(subs), C.byref(o), C.byref(res)) == 0 and res.objective_value == first
+L.dw_result_free(C.byref(res))
+# T8 NULL options = defaults (:218-240); a fourth solve in one process reaches the same optimum
+res = DwResult()
+assert L.dw_solve(master, arr, len(subs), None, C.byref(res)) == 0 and res.objective_value == first
+L.dw_result_free(C.byref(res))
+print("LIBAPI-OK %.10g" % first)
+"""
+
+
+def test_library_api_like_the_reference(golden, tmp_path):
+    """tests/test_lib_api.c of the reference (tests 1-8: defaults, solve + free, NULL master, version, silent
+    verbosity, custom mip_gap, NULL options, four dw_solve calls in one process) on the host library, in a child
+    process whose libdwgpu.so is the test double"""
+    import sys
+    paths = P.write_block_angular(load_example("book_bertsimas"), str(tmp_path))
+    code = _LIB_API_CHILD.format(root=ROOT, lib=os.path.join(BUILD, "lib", "libdwsolver_b200.so"),
+                                 master=paths["master"], subs=paths["subs"])
+    out = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.splitlines()
+    assert lines[-1].startswith("LIBAPI-OK")
+    want = golden["objective"]["book_bertsimas"]
+    assert abs(float(lines[-1].split()[1]) - want) <= 1e-7 * (1 + abs(want))
+    # T6: with verbosity -1 (silent) the only solve that printed is the NULL-options one (default verbosity 5)
+    silent_part = out.stdout.split("####")[0]
+    assert "Master objective" not in silent_part
