@@ -211,3 +211,34 @@ def test_library_api_like_the_reference(golden, tmp_path):
     # T6: with verbosity -1 (silent) the only solve that printed is the NULL-options one (default verbosity 5)
     silent_part = out.stdout.split("####")[0]
     assert "Master objective" not in silent_part
+
+
+REFERENCE_EXAMPLES = "/root/reference/examples"
+# tests/dw-tests.sh of the reference, run for run: (example directory, guidefile, how it is judged)
+DW_TESTS_SH = [("book_bertsimas", "guidefile", "solution"), ("book_lasdon", "guidefile", "solution"),
+               ("web_mitchell", "guidefile", "solution"), ("web_trick", "guidefile", "-4.000000e+01"),
+               ("four_sea", "guidefile", "1.200000e+01"), ("book_dantzig", "guidefile", "6.357895e+01"),
+               ("single_sub", "guidefile", "solution"), ("one_iter", "guidefile", "-6.000000e+00"),
+               ("neg_y", "guidefile", "solution")]
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_EXAMPLES), reason="the reference tree is only present in the build container")
+@pytest.mark.parametrize("example,guide,judge", DW_TESTS_SH)
+def test_reference_test_script_on_the_reference_files(example, guide, judge, tmp_path):
+    """The reference's own acceptance script (tests/dw-tests.sh:11-160) on the reference's own input files — guidefile
+    and CPLEX-LP text exactly as they lie under examples/ (copied to a scratch directory, the tree is read-only), through
+    this build's CLI: `sort relaxed_solution | diff -w -B ex_relaxed_solution -` for the five solution-judged runs,
+    the last `Master objective value` banner literal for the other four."""
+    import shutil
+    work = tmp_path / example
+    shutil.copytree(os.path.join(REFERENCE_EXAMPLES, example), work)
+    if judge == "solution":
+        out = run(work, "--no-write-final-master", "--quiet", "-g", guide)
+        assert out.returncode == 0, out.stdout + out.stderr
+        got = sorted(open(work / "relaxed_solution").read().splitlines())
+        norm = lambda lines: [" ".join(ln.split()) for ln in lines if ln.strip()]          # diff -w -B
+        assert norm(got) == norm(open(work / "ex_relaxed_solution").read().splitlines())
+    else:
+        out = run(work, "-g", guide)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert judge in [ln for ln in out.stdout.splitlines() if "Master objective value" in ln][-1]
