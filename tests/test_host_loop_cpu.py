@@ -242,3 +242,19 @@ def test_reference_test_script_on_the_reference_files(example, guide, judge, tmp
         out = run(work, "-g", guide)
         assert out.returncode == 0, out.stdout + out.stderr
         assert judge in [ln for ln in out.stdout.splitlines() if "Master objective value" in ln][-1]
+
+
+def test_random_instances_match_highs_through_the_host_loop():
+    """profiles/stress_dw.py — 24 random block-angular instances (multicommodity flow of two sizes, dense blocks) through
+    dw_solve_blocks against the HiGHS optimum of the monolithic LP, 1e-7 relative — with the host library bound to the
+    engine test double (child process; the stress script itself is what `-m gpu` runs against the real engine)"""
+    import sys
+    code = ("import sys, runpy\n"
+            f"sys.path.insert(0, {ROOT!r})\n"
+            "import dwsolver_b200.solver as S\n"
+            f"S.LIB_PATH = {os.path.join(BUILD, 'lib', 'libdwsolver_b200.so')!r}\n"
+            "sys.argv = ['stress_dw.py', '24']\n"
+            f"runpy.run_path({os.path.join(ROOT, 'profiles', 'stress_dw.py')!r}, run_name='__main__')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "24 / 24 instances match HiGHS" in out.stdout
