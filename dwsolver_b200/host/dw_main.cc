@@ -23,7 +23,7 @@ static void usage(const char *argv0)
     std::printf(" -p, --perturb           (ignored)\n");
     std::printf(" --verbose | --output-all | -n, --output-normal | -q, --quiet | --silent\n");
     std::printf(" --skip-monolithic-read  Guide file has no monolithic entry.\n");
-    std::printf(" --write-final-master | --no-write-final-master   (accepted; no file is written)\n");
+    std::printf(" --write-final-master | --no-write-final-master   Write the final master to done.cpxlp (default: no).\n");
     std::printf(" --print-timing | --no-timing\n");
     std::printf(" --phase1_max <n>        Max phase I iterations (default 100).\n");
     std::printf(" --phase2_max <n>        Max phase II iterations (default 3000).\n");

@@ -270,10 +270,69 @@ struct Proposal {            // X[k][iter] of the reference (src/dw_phases.c:173
 
 }  // namespace
 
+// The final restricted master as CPLEX-LP text, `done.cpxlp` (src/dw_solver.c:749-753: glp_write_lp of master_lp after
+// Phase II — "solving this on its own later will provide the optimal value").  Rows: the linking rows under their
+// original names, all equalities by now (src/dw_solver.c:321-419), then sub<k>_convexity = 1 (:262-265); columns: the
+// slack / surplus columns and every lambda ever accepted, lambdas bounded by 1 and of integer kind like the
+// reference's (src/dw_phases.c:393-400).
+static bool write_final_master(const char *path, const IMaster &M, int L, int K, double obj_const,
+                               const std::vector<std::string> *link_names)
+{
+    std::FILE *f = std::fopen(path, "w");
+    if (!f) return false;
+    auto row_name = [&](int i) {
+        if (i >= L) return "sub" + std::to_string(i - L + 1) + "_convexity";
+        if (link_names && i < (int)link_names->size() && !(*link_names)[(size_t)i].empty()) return (*link_names)[(size_t)i];
+        return "r_" + std::to_string(i + 1);
+    };
+    const int n = M.cols();
+    std::fprintf(f, "\\* Problem: master *\\\n\n");
+    if (obj_const != 0.0) std::fprintf(f, "\\* Objective constant (not part of the LP text): %.15g *\\\n\n", obj_const);
+    std::fprintf(f, "Minimize\n obj:");
+    int on_line = 0;
+    bool any = false;
+    for (int j = 0; j < n; ++j) {
+        const double c = M.cost(j);
+        if (c == 0.0) continue;
+        std::fprintf(f, " %c %.15g %s", c < 0 ? '-' : '+', std::fabs(c), M.name(j).c_str());
+        any = true;
+        if (++on_line % 4 == 0) std::fprintf(f, "\n");
+    }
+    if (!any && n > 0) std::fprintf(f, " + 0 %s", M.name(0).c_str());
+    std::fprintf(f, "\n\nSubject To\n");
+    // by rows: gather every column's entries
+    std::vector<std::vector<std::pair<int, double>>> rows((size_t)(L + K));
+    for (int j = 0; j < n; ++j) {
+        const std::vector<int> &ix = M.col_idx(j);
+        const std::vector<double> &vv = M.col_val(j);
+        for (size_t t = 0; t < ix.size(); ++t) if (vv[t] != 0.0) rows[(size_t)ix[t]].emplace_back(j, vv[t]);
+    }
+    for (int i = 0; i < L + K; ++i) {
+        std::fprintf(f, " %s:", row_name(i).c_str());
+        on_line = 0;
+        if (rows[(size_t)i].empty() && n > 0) std::fprintf(f, " + 0 %s", M.name(0).c_str());
+        for (auto &e : rows[(size_t)i]) {
+            std::fprintf(f, " %c %.15g %s", e.second < 0 ? '-' : '+', std::fabs(e.second), M.name(e.first).c_str());
+            if (++on_line % 4 == 0) std::fprintf(f, "\n");
+        }
+        std::fprintf(f, " = %.15g\n", M.rhs(i));
+    }
+    std::fprintf(f, "\nBounds\n");
+    std::vector<int> lambdas;
+    for (int j = 0; j < n; ++j)
+        if (M.name(j).compare(0, 7, "lambda_") == 0) { std::fprintf(f, " 0 <= %s <= 1\n", M.name(j).c_str()); lambdas.push_back(j); }
+    if (!lambdas.empty()) {
+        std::fprintf(f, "\nGenerals\n");
+        for (int j : lambdas) std::fprintf(f, " %s\n", M.name(j).c_str());
+    }
+    std::fprintf(f, "\nEnd\n");
+    return std::fclose(f) == 0;
+}
+
 // The solve proper, on in-memory blocks (what both dw_solve and dw_solve_blocks end up calling).
 static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *link_lb, const double *link_ub,
                    const std::vector<std::vector<std::string>> *names, const dw_options_t &opt, double t_begin,
-                   dw_result_t *result)
+                   dw_result_t *result, const std::vector<std::string> *link_names = nullptr)
 {
     auto fail = [&](int code) { result->status = code; return code; };
     const int verb = opt.verbosity;
@@ -589,6 +648,13 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
         std::printf("################################################\n");
     }
 
+    if (opt.print_final_master) {                            // src/dw_solver.c:749-753
+        if (verb >= DW_OUTPUT_NORMAL) std::printf("%-40s ", "Printing final master to done.cpxlp...");
+        const bool ok = write_final_master("done.cpxlp", M, L, K, opt.shift, link_names);
+        if (verb >= DW_OUTPUT_NORMAL) std::printf("%s\n", ok ? "DONE!" : "FAILED");
+        if (!ok && verb >= DW_OUTPUT_QUIET) std::fprintf(stderr, "dwsolver-b200: cannot write done.cpxlp\n");
+    }
+
     // ---- results (src/dw_solver.c:877-889) ---------------------------------------------------------------------
     result->objective_value = M.obj_val();
     result->num_vars = M.cols();
@@ -726,7 +792,7 @@ int dw_solve(const char *master_file, const char *const *subproblem_files, int n
     for (int k = 0; k < K; ++k) names[k] = blocks[k].col_names;
     std::vector<double> llb(L), lub(L);
     for (int i = 0; i < L; ++i) { llb[i] = to_engine_bound(master.row_lb[i]); lub[i] = to_engine_bound(master.row_ub[i]); }
-    return dw_core(K, L, desc.data(), llb.data(), lub.data(), &names, opt, t_begin, result);
+    return dw_core(K, L, desc.data(), llb.data(), lub.data(), &names, opt, t_begin, result, &master.row_names);
 }
 
 int dw_solve_blocks(int K, int L, const dwgpu_block_desc *blocks, const double *link_lb, const double *link_ub,

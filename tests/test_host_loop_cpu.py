@@ -258,3 +258,30 @@ def test_random_instances_match_highs_through_the_host_loop():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "24 / 24 instances match HiGHS" in out.stdout
+
+
+@pytest.mark.parametrize("name", ["book_dantzig", "four_sea", "web_mitchell"])
+def test_final_master_file_solves_to_the_same_optimum(name, golden, tmp_path):
+    """--write-final-master (src/dw_solver.c:749-753): done.cpxlp holds the final restricted master — the original
+    linking-row names, sub<k>_convexity rows, every accepted lambda — and "solving this on its own later will provide
+    the optimal value": read back with the package's LP reader and solved by HiGHS it gives the banner's objective"""
+    import scipy.sparse as sp
+    from scipy.optimize import linprog
+    prob = load_example(name)
+    P.write_block_angular(prob, str(tmp_path))
+    out = run(tmp_path, "-g", "guidefile", "--write-final-master")
+    assert out.returncode == 0 and "Printing final master to done.cpxlp" in out.stdout
+    lp = P.read_lp(str(tmp_path / "done.cpxlp"))
+    assert lp.m == prob.L + prob.K and lp.row_names[prob.L:] == [f"sub{k + 1}_convexity" for k in range(prob.K)]
+    assert sum(nm.startswith("lambda_") for nm in lp.col_names) >= prob.K
+    A = sp.csr_matrix((lp.a_vals, (lp.a_rows, lp.a_cols)), shape=(lp.m, lp.n))
+    assert np.array_equal(lp.row_lb, lp.row_ub)                                   # all rows are equalities by now
+    res = linprog(lp.obj, A_eq=A, b_eq=lp.row_ub, bounds=list(zip(lp.col_lb, [None if not np.isfinite(u) else u for u in lp.col_ub])),
+                  method="highs")
+    assert res.status == 0
+    want = golden["objective"][name]
+    assert abs(res.fun + float(prob.shift or 0.0) - want) <= 1e-7 * (1 + abs(want))
+    assert abs(float(banner(out)) - want) <= 1e-6 * (1 + abs(want))
+    # without the flag nothing is written
+    os.remove(tmp_path / "done.cpxlp")
+    assert run(tmp_path, "-g", "guidefile", "--quiet").returncode == 0 and not os.path.exists(tmp_path / "done.cpxlp")
