@@ -20,7 +20,7 @@ static void usage(const char *argv0)
     std::printf(" -i, --integerize        (not supported by the GPU build; ignored)\n");
     std::printf(" -e, --sub-int-enforce   (not supported by the GPU build; ignored)\n");
     std::printf(" -r, --round             (not supported by the GPU build; ignored)\n");
-    std::printf(" -p, --perturb           (ignored)\n");
+    std::printf(" -p, --perturb           Perturb the linking right-hand sides against degeneracy during the solve.\n");
     std::printf(" --verbose | --output-all | -n, --output-normal | -q, --quiet | --silent\n");
     std::printf(" --skip-monolithic-read  Guide file has no monolithic entry.\n");
     std::printf(" --write-final-master | --no-write-final-master   Write the final master to done.cpxlp (default: no).\n");

@@ -457,6 +457,9 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
         }
     }
     for (int k = 0; k < K; ++k) M.set_rhs(L + k, 1.0);
+    // --perturb: every linking right-hand side is moved by 1e-8 * (1-based row index) against degeneracy
+    // (src/dw_solver.c:427-431) and moved back after Phase II (:701-707)
+    if (opt.perturb) for (int i = 0; i < L; ++i) M.set_rhs(i, M.rhs(i) + 1e-8 * (i + 1));
     const bool need_phase1 = L > 0;
 
     // ---- per-round plumbing ---------------------------------------------------------------------------
@@ -641,6 +644,16 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
             banner();
         }
         if (!done && status == DW_STATUS_OK && p2 >= opt.max_phase2_iterations) status = DW_STATUS_ERR_PHASE2_LIMIT;
+    }
+    if (opt.perturb) {                                           // src/dw_solver.c:701-724
+        for (int i = 0; i < L; ++i) M.set_rhs(i, M.rhs(i) - 1e-8 * (i + 1));
+        const double t0 = now_s();
+        const int mrc = M.solve();
+        g_stats.seconds_master += now_s() - t0;
+        if (mrc != 0 && status == DW_STATUS_OK) {
+            std::fprintf(stderr, "dwsolver-b200: master LP failed after the perturbation was removed (code %d)\n", mrc);
+            return fail(DW_STATUS_ERR_INTERNAL);
+        }
     }
     if (verb >= DW_OUTPUT_NORMAL) {                              // src/dw_solver.c:721
         std::printf("################################################\n");

@@ -285,3 +285,14 @@ def test_final_master_file_solves_to_the_same_optimum(name, golden, tmp_path):
     # without the flag nothing is written
     os.remove(tmp_path / "done.cpxlp")
     assert run(tmp_path, "-g", "guidefile", "--quiet").returncode == 0 and not os.path.exists(tmp_path / "done.cpxlp")
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_perturbed_solve_reaches_the_same_optimum(name, golden, tmp_path):
+    """-p / --perturb (src/dw_solver.c:427-431, 701-724): linking right-hand sides moved by 1e-8 * i during the solve,
+    moved back and the master re-solved at the end — the final banner is the unperturbed optimum"""
+    P.write_block_angular(load_example(name), str(tmp_path))
+    out = run(tmp_path, "-g", "guidefile", "--perturb")
+    assert out.returncode == 0, out.stdout + out.stderr
+    want = golden["objective"][name]
+    assert abs(float(banner(out)) - want) <= 1e-6 * (1 + abs(want))
