@@ -8,7 +8,8 @@
  * directory into which the tests COPY the host library and the CLI, so that their `$ORIGIN` run-path finds this
  * file there instead of the CUDA engine.  Nothing in dwsolver_b200/ or include/ refers to it, it is never installed
  * next to the product, and the product has no way to select it: dwsolver_b200/lib/libdwgpu.so is the CUDA engine and
- * fails loudly without a device (tests/test_abi.py).  Results obtained through this file say nothing about the GPU
+ * fails loudly without a device (tests/test_abi.py).  dwgpu_create() here refuses to work unless the test-suite
+ * announces itself (DWSOLVER_TEST_DOUBLE=tests-only).  Results obtained through this file say nothing about the GPU
  * path; the parity tests proper are the `-m gpu` ones.
  */
 #include <math.h>
@@ -66,6 +67,9 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
 {
     (void)opt;
     if (K < 1 || L < 0 || !bd || !out) return fail(DWGPU_E_ARGS, "bad arguments");
+    /* refuses to work anywhere but under the test-suite, which announces itself */
+    if (!getenv("DWSOLVER_TEST_DOUBLE") || strcmp(getenv("DWSOLVER_TEST_DOUBLE"), "tests-only") != 0)
+        return fail(DWGPU_E_STATE, "this libdwgpu.so is the test double of tests/stub_engine, not the CUDA engine");
     if (getenv("DWSTUB_FAIL_CREATE")) return fail(DWGPU_E_CUDA, "stub engine: creation failure requested by the test");
     dwgpu_engine *e = calloc(1, sizeof *e);
     if (!e) return fail(DWGPU_E_NOMEM, "out of memory");

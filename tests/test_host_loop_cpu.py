@@ -32,7 +32,7 @@ def stub_build():
 
 
 def run(cwd, *args, env=None):
-    e = dict(os.environ)
+    e = dict(os.environ, DWSOLVER_TEST_DOUBLE="tests-only")      # the double refuses to run unannounced
     e.pop("DWSOLVER_DEVICES", None)
     e.update(env or {})
     return subprocess.run([CLI, *args], cwd=str(cwd), capture_output=True, text=True, timeout=600, env=e)
@@ -113,6 +113,13 @@ def test_engine_failures_become_status_99(tmp_path):
     assert out.returncode == 99 and "round failure requested" in out.stderr
     out = run(tmp_path, "-g", "guidefile", "--quiet", "--devices", "0,0", env={"DWSTUB_FAIL_ITERATE": "1"})
     assert out.returncode == 99
+
+
+def test_the_double_refuses_to_run_unannounced(tmp_path):
+    P.write_block_angular(load_example("single_sub"), str(tmp_path))
+    env = {k: v for k, v in os.environ.items() if k != "DWSOLVER_TEST_DOUBLE"}
+    out = subprocess.run([CLI, "-g", "guidefile", "--quiet"], cwd=str(tmp_path), capture_output=True, text=True, env=env)
+    assert out.returncode == 99 and "test double" in out.stderr
 
 
 def test_iteration_limits_and_missing_files(tmp_path):
@@ -202,7 +209,8 @@ def test_library_api_like_the_reference(golden, tmp_path):
     paths = P.write_block_angular(load_example("book_bertsimas"), str(tmp_path))
     code = _LIB_API_CHILD.format(root=ROOT, lib=os.path.join(BUILD, "lib", "libdwsolver_b200.so"),
                                  master=paths["master"], subs=paths["subs"])
-    out = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    out = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, DWSOLVER_TEST_DOUBLE="tests-only"))
     assert out.returncode == 0, out.stdout + out.stderr
     lines = out.stdout.splitlines()
     assert lines[-1].startswith("LIBAPI-OK")
@@ -255,7 +263,8 @@ def test_random_instances_match_highs_through_the_host_loop():
             f"S.LIB_PATH = {os.path.join(BUILD, 'lib', 'libdwsolver_b200.so')!r}\n"
             "sys.argv = ['stress_dw.py', '24']\n"
             f"runpy.run_path({os.path.join(ROOT, 'profiles', 'stress_dw.py')!r}, run_name='__main__')\n")
-    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, DWSOLVER_TEST_DOUBLE="tests-only"))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "24 / 24 instances match HiGHS" in out.stdout
 
