@@ -56,14 +56,15 @@ int main(int argc, char **argv)
         else if (a == "-e" || a == "--sub-int-enforce") opt.enforce_sub_integrality = 1;
         else if (a == "-r" || a == "--round") opt.rounding_flag = 1;
         else if (a == "-p" || a == "--perturb") opt.perturb = 1;
-        else if (a == "--mip-gap" && i + 1 < argc) opt.mip_gap = std::atof(argv[++i]);
+        else if ((a == "--mip-gap" || a == "--mip_gap") && i + 1 < argc) opt.mip_gap = std::atof(argv[++i]);
         else if (a == "--verbose") opt.verbosity = DW_OUTPUT_VERBOSE;
         else if (a == "--output-all") opt.verbosity = DW_OUTPUT_ALL;
         else if (a == "-n" || a == "--output-normal") opt.verbosity = DW_OUTPUT_NORMAL;
         else if (a == "-q" || a == "--quiet") opt.verbosity = DW_OUTPUT_QUIET;
         else if (a == "--silent") opt.verbosity = DW_OUTPUT_SILENT;
         else if (a == "--skip-monolithic-read") skip_mono = true;
-        else if (a == "--write-bases" || a == "--write-int-probs") { /* accepted, nothing written */ }
+        else if (a == "--write-bases" || a == "--write-int-probs")        // src/dw_main.c:171-174
+            std::fprintf(stderr, "Warning: %s is not supported by this build; option ignored.\n", a.c_str());
         else if (a == "--write-final-master") opt.print_final_master = 1;
         else if (a == "--no-write-final-master") opt.print_final_master = 0;
         else if (a == "--print-timing") opt.print_timing_data = 1;
