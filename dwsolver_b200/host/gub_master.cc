@@ -112,6 +112,7 @@ void GubMaster::link_minus_key(int j, std::vector<double> &w) const
 void GubMaster::refactor()
 {
     const int L = L_, n = cols();
+    pend_n_ = 0;                      // a fresh inverse of the current basis supersedes every pending update
     winv_.assign((size_t)L * L, 0.0);
     for (int r = 0; r < L; ++r) { winv_[(size_t)r * L + r] = 1.0; pos_var_[r] = -(r + 1); }
     std::vector<double> w(L), alpha(L);
@@ -252,6 +253,29 @@ int GubMaster::solve()
     }
     ThreadTeam &team = *team_;
     const int T = team.size();
+    // Optional blocked updates of the working inverse (DWSOLVER_MASTER_BLOCK = k, 2..64; default off): a column
+    // replacement W^-1 -= u v' is kept as a pending pair instead of being swept over the L x L array (that sweep is
+    // bound by L2 bandwidth: 1 MB per iteration at L = 256), FTRAN, the duals and the pivot row fold the pending pairs
+    // in at O(kL), and every k-th replacement applies them all in ONE pass over the array.  Same mathematics, other
+    // rounding: the pivot sequence differs from the unblocked solver's.
+    int block_k = 0;
+    if (const char *e = std::getenv("DWSOLVER_MASTER_BLOCK")) block_k = std::max(0, std::min(64, std::atoi(e)));
+    if (block_k == 1) block_k = 0;
+    if (block_k > 0 && (int)pend_u_.size() < block_k * L) { pend_u_.assign((size_t)block_k * L, 0.0); pend_v_.assign((size_t)block_k * L, 0.0); }
+    auto flush = [&]() {
+        if (pend_n_ == 0) return;
+        team.run([&](int member, int members) {
+            const int r0 = L * member / members, r1 = L * (member + 1) / members;
+            for (int r = r0; r < r1; ++r) {
+                double *row = &winv_[(size_t)r * L];
+                for (int j = 0; j < pend_n_; ++j) {
+                    const double a = pend_u_[(size_t)j * L + r];
+                    if (a != 0.0) axpy(L, -a, &pend_v_[(size_t)j * L], row);
+                }
+            }
+        });
+        pend_n_ = 0;
+    };
     std::vector<double> pi(L), ct(L), y(L), wq(L), wn(L), u(L), rpc(L);
     std::vector<double> wk(K, 0.0), rate(K, 0.0);
     std::vector<long long> rate_stamp(K, -1), best_stamp(K, -1);
@@ -318,6 +342,11 @@ int GubMaster::solve()
                     axpy(c1 - c0, ct[r], &winv_[(size_t)r * L + c0], pi.data() + c0);
                 }
             });
+            for (int j = 0; j < pend_n_; ++j) {              // true inverse = winv_ - sum_j u_j v_j'
+                double sj = 0.0;
+                for (int r = 0; r < L; ++r) sj += pend_u_[(size_t)j * L + r] * ct[r];
+                if (sj != 0.0) axpy(L, -sj, &pend_v_[(size_t)j * L], pi.data());
+            }
             pi_valid = true;
         }
         last_phase1 = phase1;
@@ -453,6 +482,11 @@ int GubMaster::solve()
                 y[r] = s;
             }
         });
+        for (int j = 0; j < pend_n_; ++j) {
+            double sj = 0.0;
+            for (size_t t = 0; t < wq_nz.size(); ++t) sj += pend_v_[(size_t)j * L + wq_nz[t]] * wq[wq_nz[t]];
+            if (sj != 0.0) axpy(L, -sj, &pend_u_[(size_t)j * L], y.data());
+        }
         t_ftran += tick() - t0; t0 = tick();
         // d x_key(s) / d theta = sum_{r in s} y_r - [s == set(q)]
         touched.clear();
@@ -508,6 +542,7 @@ int GubMaster::solve()
         }
         t_ratio += tick() - t0; t0 = tick();
         // ---- basis change
+        if (leave_key >= 0) flush();          // the two key-changing updates below work on the rows themselves
         if (leave_key >= 0 && leave_key == sq) {
             // the key of the entering column's own block leaves: the entering column becomes the key.  The block's
             // other basic columns change from a_i - a_old to a_i - a_q:  W' = W (I - y 1_R'),  Sherman-Morrison.
@@ -582,6 +617,27 @@ int GubMaster::solve()
             if (std::fabs(piv) < 1e-12) { refactor(); compute_values(); since_refactor = 0; pi_valid = false; scan_keys = true; ++iters_; continue; }
             const double inv = 1.0 / piv;
             double *rp = &winv_[(size_t)r * L];
+            if (block_k > 0) {
+                // pending form: v = (true row r) / piv, u = y - e_r; the true row r afterwards equals v
+                for (int i = 0; i < L; ++i) rpc[i] = rp[i];
+                for (int j = 0; j < pend_n_; ++j) {
+                    const double a = pend_u_[(size_t)j * L + r];
+                    if (a != 0.0) axpy(L, -a, &pend_v_[(size_t)j * L], rpc.data());
+                }
+                scale(L, inv, rpc.data());
+                double *pu = &pend_u_[(size_t)pend_n_ * L], *pv = &pend_v_[(size_t)pend_n_ * L];
+                for (int i = 0; i < L; ++i) { pu[i] = y[i]; pv[i] = rpc[i]; }
+                pu[r] = piv - 1.0;
+                ++pend_n_;
+                if (vleave >= 0) stat_[vleave] = NONBASIC;
+                pos_var_[r] = q;
+                stat_[q] = NONKEY;
+                xn_[r] = theta;
+                if (leave_key < 0 && !phase1 && pi_valid) axpy(L, dq, rpc.data(), pi.data());
+                else pi_valid = false;
+                ++since_refactor;
+                if (pend_n_ >= block_k) flush();
+            } else {
             for (int i = 0; i < L; ++i) rpc[i] = rp[i] * inv;      // the scaled pivot row, handed to every row owner
             team.run([&](int member, int members) {
                 const int r0 = L * member / members, r1 = L * (member + 1) / members;
@@ -601,6 +657,7 @@ int GubMaster::solve()
             if (leave_key < 0 && !phase1 && pi_valid) axpy(L, dq, rp, pi.data());
             else pi_valid = false;
             ++since_refactor;
+            }
         }
         t_update += tick() - t0;
         ++iters_;
@@ -609,6 +666,7 @@ int GubMaster::solve()
         if (theta <= 1e-11) { if (++degen_run > 500) bland = true; }
         else { degen_run = 0; bland = false; }
     }
+    flush();
     if (std::getenv("DWSOLVER_MASTER_DEBUG"))
         std::fprintf(stderr, "gub master: status %d, %lld iterations (%lld degenerate, %lld trivial key swaps, %lld key hand-overs), %lld full pricing passes, %d columns\n",
                      status, iters_ - it_begin, n_degen, n_trivial, n_keyswap, n_full, cols());

@@ -64,6 +64,9 @@ private:
     std::vector<int> key_;              // per block: key column, -1: none yet
     std::vector<int> pos_var_;          // working-basis position -> column (>= 0) or -(row+1) for a logical
     std::vector<double> winv_;          // L x L
+    // pending rank-1 updates of winv_ (blocked updates, DWSOLVER_MASTER_BLOCK): true inverse = winv_ - sum_j u_j v_j'
+    std::vector<double> pend_u_, pend_v_;
+    int pend_n_ = 0;
     std::vector<double> xn_, xkey_, x_, y_;
     bool factor_valid_ = false, vals_valid_ = false, crashed_ = false;
     double c0_ = 0.0, obj_ = 0.0;
