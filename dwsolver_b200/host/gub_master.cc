@@ -25,6 +25,28 @@ DWH_CLONES void scale(int n, double a, double *x)
 {
     for (int i = 0; i < n; ++i) x[i] *= a;
 }
+// row -= sum_j coef[j] * V[j][:], j = 0..k-1 in this order for every element (what k successive axpy calls compute), in
+// one pass over the row: a chunk of the row stays in registers while the k pending vectors stream through it
+DWH_CLONES void apply_pending(int n, int k, const double *coef, const double *V, int ldv, double *row)
+{
+    constexpr int kChunk = 32;
+    int i = 0;
+    for (; i + kChunk <= n; i += kChunk) {
+        double acc[kChunk];
+        for (int t = 0; t < kChunk; ++t) acc[t] = row[i + t];
+        for (int j = 0; j < k; ++j) {
+            const double a = coef[j];
+            const double *v = V + (size_t)j * ldv + i;
+            for (int t = 0; t < kChunk; ++t) acc[t] -= a * v[t];
+        }
+        for (int t = 0; t < kChunk; ++t) row[i + t] = acc[t];
+    }
+    for (; i < n; ++i) {
+        double s = row[i];
+        for (int j = 0; j < k; ++j) s -= coef[j] * V[(size_t)j * ldv + i];
+        row[i] = s;
+    }
+}
 constexpr double kTolDj = 1e-9, kTolBnd = 1e-9, kTolPiv = 1e-9, kTolTie = 1e-12;
 constexpr double kInfD = std::numeric_limits<double>::infinity();
 constexpr int kRefactorEvery = 2000;     // counted in iterations that changed the working inverse (a refactorisation
@@ -266,12 +288,11 @@ int GubMaster::solve()
         if (pend_n_ == 0) return;
         team.run([&](int member, int members) {
             const int r0 = L * member / members, r1 = L * (member + 1) / members;
+            double coef[64];
             for (int r = r0; r < r1; ++r) {
-                double *row = &winv_[(size_t)r * L];
-                for (int j = 0; j < pend_n_; ++j) {
-                    const double a = pend_u_[(size_t)j * L + r];
-                    if (a != 0.0) axpy(L, -a, &pend_v_[(size_t)j * L], row);
-                }
+                bool any = false;
+                for (int j = 0; j < pend_n_; ++j) { coef[j] = pend_u_[(size_t)j * L + r]; any |= coef[j] != 0.0; }
+                if (any) apply_pending(L, pend_n_, coef, pend_v_.data(), L, &winv_[(size_t)r * L]);
             }
         });
         pend_n_ = 0;

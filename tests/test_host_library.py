@@ -395,8 +395,11 @@ def _gub_case(rng, L, K):
     return cols, np.array(cost), rhs, lam
 
 
-def test_gub_master_thread_team_is_deterministic(monkeypatch):
-    """L = 144 linking rows: large enough for the master's thread team (host/thread_team.h).  One, three and eight
+@pytest.mark.parametrize("block", [0, 8])
+def test_gub_master_thread_team_is_deterministic(block, monkeypatch):
+    """(block = 8: the same with blocked updates of the working inverse, DWSOLVER_MASTER_BLOCK — pending rank-1 pairs
+    folded into FTRAN, duals and pivot rows, applied in one pass every 8 column replacements.)
+    L = 144 linking rows: large enough for the master's thread team (host/thread_team.h).  One, three and eight
     members must walk the SAME simplex path — equal iteration counts and bit-equal primal and dual vectors — and
     reach the HiGHS optimum."""
     L_ = lib()
@@ -418,6 +421,7 @@ def test_gub_master_thread_team_is_deterministic(monkeypatch):
         colptr[j + 1] = len(idx)
     idx = np.array(idx, np.int32); val = np.array(val)
     seen = []
+    monkeypatch.setenv("DWSOLVER_MASTER_BLOCK", str(block))
     for threads in (1, 3, 8):
         monkeypatch.setenv("DWSOLVER_MASTER_THREADS", str(threads))
         x, y = np.zeros(n), np.zeros(m)
@@ -432,6 +436,12 @@ def test_gub_master_thread_team_is_deterministic(monkeypatch):
     assert seen[0][0] > L                                   # a real solve, not a crash basis that happened to be optimal
     for other in seen[1:]:
         assert other[0] == seen[0][0] and np.array_equal(other[1], seen[0][1]) and np.array_equal(other[2], seen[0][2])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_gub_master_with_blocked_updates_matches_highs(seed, monkeypatch):
+    monkeypatch.setenv("DWSOLVER_MASTER_BLOCK", str(2 + 3 * (seed % 4)))       # k = 2, 5, 8, 11
+    test_gub_master_matches_highs(10 + 6 * seed)                               # L = 14 ... 56
 
 
 @pytest.mark.parametrize("seed", range(8))
