@@ -275,12 +275,13 @@ int GubMaster::solve()
     }
     ThreadTeam &team = *team_;
     const int T = team.size();
-    // Optional blocked updates of the working inverse (DWSOLVER_MASTER_BLOCK = k, 2..64; default off): a column
+    // Blocked updates of the working inverse (k = 8 once the L x L array has outgrown the L1 cache, L >= 128;
+    // DWSOLVER_MASTER_BLOCK = k, 2..64, overrides and 0 switches them off): a column
     // replacement W^-1 -= u v' is kept as a pending pair instead of being swept over the L x L array (that sweep is
     // bound by L2 bandwidth: 1 MB per iteration at L = 256), FTRAN, the duals and the pivot row fold the pending pairs
     // in at O(kL), and every k-th replacement applies them all in ONE pass over the array.  Same mathematics, other
-    // rounding: the pivot sequence differs from the unblocked solver's.
-    int block_k = 0;
+    // rounding: the pivot sequence differs from the unblocked solver's (config B: 249 088 iterations against 246 554).
+    int block_k = L >= 128 ? 8 : 0;      // measured at L = 256: k = 8 beats 4, 6, 12 and 16 (profiles/README.md)
     if (const char *e = std::getenv("DWSOLVER_MASTER_BLOCK")) block_k = std::max(0, std::min(64, std::atoi(e)));
     if (block_k == 1) block_k = 0;
     if (block_k > 0 && (int)pend_u_.size() < block_k * L) { pend_u_.assign((size_t)block_k * L, 0.0); pend_v_.assign((size_t)block_k * L, 0.0); }
