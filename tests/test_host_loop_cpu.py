@@ -305,3 +305,16 @@ def test_perturbed_solve_reaches_the_same_optimum(name, golden, tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     want = golden["objective"][name]
     assert abs(float(banner(out)) - want) <= 1e-6 * (1 + abs(want))
+
+
+@pytest.mark.parametrize("block", ["default", "0"])
+def test_wide_master_against_highs(block, tmp_path):
+    """128 linking rows: the master's working inverse is updated in blocks of 8 by default (host/gub_master.cc);
+    DWSOLVER_MASTER_BLOCK=0 is the unblocked solver — both reach the HiGHS optimum of the monolithic LP"""
+    from highs_util import solve_monolithic
+    prob = P.gen_mcf(48, 128, 300, 128, seed=21)
+    P.write_block_angular(prob, str(tmp_path))
+    out = run(tmp_path, "-g", "guidefile", env={} if block == "default" else {"DWSOLVER_MASTER_BLOCK": block})
+    assert out.returncode == 0, out.stdout + out.stderr
+    ref = solve_monolithic(prob)["objective"]
+    assert abs(float(banner(out)) - ref) <= 1e-6 * (1 + abs(ref))
