@@ -21,6 +21,7 @@
 #include "../../include/dwgpu.h"
 #include "simplex_cta.cuh"
 #include "simplex_smem.cuh"
+#include "simplex_warp.cuh"
 #include "pack.cuh"
 #include "simplex_cluster.cuh"
 
@@ -108,7 +109,12 @@ struct dwgpu_engine {
     int cluster_size = 1;              // CTAs per block on the cluster path (list_c)
     size_t smem_dyn_c = 0;
     size_t smem_dyn_g = 0;
-    int tg_threads = 0;                // 0: by shard size; DWGPU_TG_THREADS=64|128|256 forces one
+    int tg_threads = 0;                // 0: 128-thread CTAs; DWGPU_TG_THREADS=32 (one warp per block)|64|128|256 forces one
+    size_t smem_dyn_w = 0;             // warp kernel, generic shapes (list_g)
+    bool warp_ok_g = false;            // every block of list_g fits the warp kernel
+    DevBuf<int> redo_list, redo_count; // blocks the warp kernel handed over to the CTA kernel this round
+    DevBuf<unsigned char> redo_moved;
+    int warp_bail_after = 0;           // test hook (DWGPU_WARP_BAIL_AFTER): hand over after this many basis changes
     bool reorder = true;
     size_t smem_dyn = 0;
     int max_smem_optin = 0;
@@ -215,6 +221,7 @@ void dwgpu_destroy(dwgpu_engine *e)
     e->gcolptr.release();
     e->r_dev.release();
     e->counters.release(); e->last_iters.release();
+    e->redo_list.release(); e->redo_count.release(); e->redo_moved.release();
     if (e->h_pi) cudaFreeHost(e->h_pi);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -293,7 +300,11 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         if (path == 1 && b.m == 64 && b.n == 128) e->list_a.push_back(k);
         else if (path == 1) { e->list_smem.push_back(k); e->smem_dyn = std::max(e->smem_dyn, dwk::smem2_bytes(b.m, b.n)); }
         else if (path == 3 && b.m == 256 && b.n == 512) e->list_b.push_back(k);
-        else if (path == 3) { e->list_g.push_back(k); e->smem_dyn_g = std::max(e->smem_dyn_g, dwk::smem2_bytes(b.m, b.n, true)); }
+        else if (path == 3) {
+            e->list_g.push_back(k);
+            e->smem_dyn_g = std::max(e->smem_dyn_g, dwk::smem2_bytes(b.m, b.n, true));
+            e->smem_dyn_w = std::max(e->smem_dyn_w, dwk::warp_smem_bytes(b.m, b.n));
+        }
         else if (path == 4) { e->list_c.push_back(k); e->smem_dyn_c = std::max(e->smem_dyn_c, dwk::cl_smem_bytes(b.m, b.n)); }
         else e->list_gmem.push_back(k);
     }
@@ -475,7 +486,20 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     if (const char *nr = std::getenv("DWGPU_NO_REORDER")) e->reorder = std::atoi(nr) == 0;
     if (const char *tg = std::getenv("DWGPU_TG_THREADS")) {
         const int v = std::atoi(tg);
-        e->tg_threads = (v == 256 || v == NT_TG_WIDE || v == NT_TG) ? v : 0;
+        e->tg_threads = (v == 256 || v == NT_TG_WIDE || v == NT_TG || v == 32) ? v : 0;
+    }
+    if (const char *ba = std::getenv("DWGPU_WARP_BAIL_AFTER")) e->warp_bail_after = std::max(0, std::atoi(ba));
+    // warp kernel: 16-bit variable ids, at least 4 blocks per SM
+    e->warp_ok_g = !e->list_g.empty() && e->smem_dyn_w <= smem_cap / 4;
+    for (int k : e->list_g) if (e->m[k] + e->n[k] >= 65535) e->warp_ok_g = false;
+    if (!e->list_g.empty() || !e->list_b.empty()) {
+        CUE(e->redo_list.alloc(K)); CUE(e->redo_count.alloc(1)); CUE(e->redo_moved.alloc(K));
+        CUE(cudaMemset(e->redo_count.p, 0, sizeof(int)));
+        CUE(cudaMemset(e->redo_moved.p, 0, (size_t)K));
+        if (e->warp_ok_g)
+            CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_warp_kernel<0, 0>, (int)e->smem_dyn_w));
+        if (!e->list_b.empty())
+            CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_warp_kernel<256, 512>, (int)dwk::warp_smem_bytes(256, 512)));
     }
     if (!e->list_g.empty()) {
         CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_SMEM, 0, 0, true>, (int)e->smem_dyn_g));
@@ -559,39 +583,45 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
     if (!e->list_g.empty() || !e->list_b.empty()) {
         const bool own_events = !e->ev_used[1];
         if (own_events) CU(cudaEventRecord(e->ev[0], st));
-        auto threads_for = [&](size_t nblocks) {
-            if (e->tg_threads) return e->tg_threads;
-            // 128-thread CTAs, 4 per SM: measured best at every shard size once the sweeps maintain the row masks
-            // themselves (config B, 8192 blocks: 33.1 ms per step against 34.0 ms with 64-thread CTAs at 6 per SM,
-            // 37.3 ms at 3 per SM / 168 registers, 34.7 ms at 5 per SM / 96 registers); DWGPU_TG_THREADS overrides
-            (void)nblocks;
-            return NT_TG_WIDE;
+        // Kernel choice for the HBM-tableau blocks.  Default: the CTA kernel with 128 threads, 4 per SM.
+        // DWGPU_TG_THREADS = 64 | 256 picks another CTA width; DWGPU_TG_THREADS = 32 runs ONE WARP per block
+        // (simplex_warp.cuh, 10 blocks per SM resident) followed by the CTA kernel over the blocks the warps handed over
+        // (normally none: the second launch reads the list length on the device and its CTAs exit at once).  Measured on
+        // config B (profiles/r2a_warp_kernel.md): the warp kernel needs 30 % fewer instructions per basis change but a
+        // single warp's dependent chain is 3x longer, so 10 resident blocks do not beat 4 CTAs (40.1 vs 33.1 ms a step).
+        const dwk::Continuation none{nullptr, nullptr};
+        auto cta_launch = [&](bool spec_b, const int *list, unsigned nb, int nt, const dwk::Continuation &cn) {
+            const size_t sm = spec_b ? dwk::smem2_bytes(256, 512, true) : e->smem_dyn_g;
+            if (spec_b) {
+                if (nt == 256) dwk::solve_smem_kernel<NT_SMEM, 256, 512, true><<<nb, NT_SMEM, sm, st>>>(e->blocks.p, list, (int)nb, P, cn);
+                else if (nt == NT_TG) dwk::solve_smem_kernel<NT_TG, 256, 512, true><<<nb, NT_TG, sm, st>>>(e->blocks.p, list, (int)nb, P, cn);
+                else dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true><<<nb, NT_TG_WIDE, sm, st>>>(e->blocks.p, list, (int)nb, P, cn);
+            } else {
+                if (nt == 256) dwk::solve_smem_kernel<NT_SMEM, 0, 0, true><<<nb, NT_SMEM, sm, st>>>(e->blocks.p, list, (int)nb, P, cn);
+                else if (nt == NT_TG) dwk::solve_smem_kernel<NT_TG, 0, 0, true><<<nb, NT_TG, sm, st>>>(e->blocks.p, list, (int)nb, P, cn);
+                else dwk::solve_smem_kernel<NT_TG_WIDE, 0, 0, true><<<nb, NT_TG_WIDE, sm, st>>>(e->blocks.p, list, (int)nb, P, cn);
+            }
+            e->last_launches++;
+            return cudaGetLastError();
         };
-        if (!e->list_b.empty()) {
-            const unsigned nb = (unsigned)e->list_b.size();
-            const size_t sm = dwk::smem2_bytes(256, 512, true);
-            const int nt = threads_for(nb);
-            if (nt == 256)
-                dwk::solve_smem_kernel<NT_SMEM, 256, 512, true><<<nb, NT_SMEM, sm, st>>>(e->blocks.p, e->d_list_b.p, (int)nb, P);
-            else if (nt == NT_TG_WIDE)
-                dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true><<<nb, NT_TG_WIDE, sm, st>>>(e->blocks.p, e->d_list_b.p, (int)nb, P);
+        auto run_list = [&](bool spec_b, const int *list, unsigned nb, bool warp_fits) -> cudaError_t {
+            const bool warp = warp_fits && e->tg_threads == 32;
+            if (!warp) return cta_launch(spec_b, list, nb, e->tg_threads == 32 ? 0 : e->tg_threads, none);
+            cudaError_t rc = cudaMemsetAsync(e->redo_count.p, 0, sizeof(int), st);
+            if (rc != cudaSuccess) return rc;
+            dwk::WarpExtra X{e->redo_list.p, e->redo_count.p, e->redo_moved.p, e->warp_bail_after};
+            if (spec_b)
+                dwk::solve_warp_kernel<256, 512><<<nb, 32, dwk::warp_smem_bytes(256, 512), st>>>(e->blocks.p, list, (int)nb, P, X);
             else
-                dwk::solve_smem_kernel<NT_TG, 256, 512, true><<<nb, NT_TG, sm, st>>>(e->blocks.p, e->d_list_b.p, (int)nb, P);
-            CU(cudaGetLastError());
+                dwk::solve_warp_kernel<0, 0><<<nb, 32, e->smem_dyn_w, st>>>(e->blocks.p, list, (int)nb, P, X);
             e->last_launches++;
-        }
-        if (!e->list_g.empty()) {
-            const unsigned nb = (unsigned)e->list_g.size();
-            const int nt = threads_for(nb);
-            if (nt == 256)
-                dwk::solve_smem_kernel<NT_SMEM, 0, 0, true><<<nb, NT_SMEM, e->smem_dyn_g, st>>>(e->blocks.p, e->d_list_g.p, (int)nb, P);
-            else if (nt == NT_TG_WIDE)
-                dwk::solve_smem_kernel<NT_TG_WIDE, 0, 0, true><<<nb, NT_TG_WIDE, e->smem_dyn_g, st>>>(e->blocks.p, e->d_list_g.p, (int)nb, P);
-            else
-                dwk::solve_smem_kernel<NT_TG, 0, 0, true><<<nb, NT_TG, e->smem_dyn_g, st>>>(e->blocks.p, e->d_list_g.p, (int)nb, P);
-            CU(cudaGetLastError());
-            e->last_launches++;
-        }
+            rc = cudaGetLastError();
+            if (rc != cudaSuccess) return rc;
+            const dwk::Continuation cn{e->redo_count.p, e->redo_moved.p};
+            return cta_launch(spec_b, e->redo_list.p, nb, 0, cn);
+        };
+        if (!e->list_b.empty()) CU(run_list(true, e->d_list_b.p, (unsigned)e->list_b.size(), true));
+        if (!e->list_g.empty()) CU(run_list(false, e->d_list_g.p, (unsigned)e->list_g.size(), e->warp_ok_g));
         CU(cudaEventRecord(e->ev[1], st));
         e->ev_used[1] = true;
     }
@@ -599,13 +629,13 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         CU(cudaEventRecord(e->ev[2], st));
         if (!e->list_a.empty()) {
             dwk::solve_smem_kernel<NT_SMEM, 64, 128, false><<<(unsigned)e->list_a.size(), NT_SMEM, dwk::smem2_bytes(64, 128), st>>>(
-                e->blocks.p, e->d_list_a.p, (int)e->list_a.size(), P);
+                e->blocks.p, e->d_list_a.p, (int)e->list_a.size(), P, dwk::Continuation{nullptr, nullptr});
             CU(cudaGetLastError());
             e->last_launches++;
         }
         if (!e->list_smem.empty()) {
             dwk::solve_smem_kernel<NT_SMEM, 0, 0, false><<<(unsigned)e->list_smem.size(), NT_SMEM, e->smem_dyn, st>>>(
-                e->blocks.p, e->d_list_smem.p, (int)e->list_smem.size(), P);
+                e->blocks.p, e->d_list_smem.p, (int)e->list_smem.size(), P, dwk::Continuation{nullptr, nullptr});
             CU(cudaGetLastError());
             e->last_launches++;
         }

@@ -120,6 +120,13 @@ __host__ __device__ inline size_t smem2_bytes(int m, int n, bool tg = false)
 
 enum { K_NONE = 0, K_PIVOT = 1, K_FAIL = 2, K_REDO = 3 };
 
+// Second launch of a round over the blocks the warp kernel (simplex_warp.cuh) handed over: the list length is read
+// on the device, and a block that had already moved must not take the "nothing changed" exit.
+struct Continuation {
+    const int *dyn_count;           // nullptr: the launch covers `count` blocks
+    const unsigned char *moved;     // by block id; nullptr: none
+};
+
 // tableau accessors: global-memory tableaux (TG) bypass L1 (.cg) — rows are streamed once per basis
 // change and the strided column read touches one sector per row, so L1 only adds thrash
 template <bool TG> __device__ __forceinline__ double ld_t(const double *p) { return TG ? __ldcg(p) : *p; }
@@ -1062,7 +1069,7 @@ __device__ __forceinline__ unsigned masked_cells(const Sm3 &c, int nl)
 // (blocks too large for one CTA's shared memory, config B class); the decision/sweep code is shared.
 template <int NT, int MC, int NC, bool TG>
 __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC) : 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
-                                                          SolveParams P)
+                                                          SolveParams P, Continuation CN)
 {
     extern __shared__ __align__(16) char smem_raw[];
     __shared__ Scratch<NT> scr;
@@ -1071,6 +1078,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
     __shared__ __align__(8) uint64_t bar;
     __shared__ int s_kind, s_changed;
     if ((int)blockIdx.x >= count) return;
+    if (CN.dyn_count != nullptr && (int)blockIdx.x >= *CN.dyn_count) return;
     phase_init();
     const int k = list[blockIdx.x];
     const BlockDev &B = blocks[k];      // fields are fetched where they are used (read-only, cached)
@@ -1118,7 +1126,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
         if (t_bytes) bulk_g2s(c.T, B.T, t_bytes, &bar);
         if (k_bytes) bulk_g2s(c.rmask, B.rmask, k_bytes, &bar);
         bulk_g2s(pst, B.beta, p_bytes, &bar);
-        s_changed = 0;
+        s_changed = (CN.moved != nullptr && CN.moved[k]) ? 1 : 0;
     }
     // priced objective while the copies fly (same arithmetic as the generic kernel / reference)
     // (four columns per thread at a time, every level of the CSC walk issued as one batch of read-only

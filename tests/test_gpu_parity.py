@@ -140,10 +140,10 @@ def test_dense_blocks_global_path(force_path):
     eng.close()
 
 
-@pytest.mark.parametrize("threads", [64, 128, 256])
+@pytest.mark.parametrize("threads", [32, 64, 128, 256])
 def test_mcf_config_b_shape_global_tableau_kernel(threads, monkeypatch):
-    """256 x 512 blocks take the specialised global-tableau kernel (path 3); the engine picks 64- or
-    128-thread CTAs by shard size, DWGPU_TG_THREADS forces each instantiation here."""
+    """256 x 512 blocks take the specialised global-tableau kernels (path 3): one warp per block by default
+    (DWGPU_TG_THREADS=32), or the CTA kernel with 64 / 128 / 256 threads; each instantiation is forced here."""
     from oracle import oracle as O
     monkeypatch.setenv("DWGPU_TG_THREADS", str(threads))
     prob = P.gen_mcf(48, 256, 512, 256, 8192001)
@@ -418,7 +418,33 @@ def test_device_history_push_and_combine():
     eng.close()
 
 
-@pytest.mark.parametrize("threads", [64, 128])
+@pytest.mark.parametrize("bail_after", [1, 3, 17])
+@pytest.mark.parametrize("shape", ["B", "dense", "generic"])
+def test_warp_kernel_hands_over_to_cta_kernel(shape, bail_after, monkeypatch):
+    """The warp-per-block kernel hands a block over to the CTA kernel of the same round (redo list, second launch) when
+    it meets something it does not do itself.  DWGPU_WARP_BAIL_AFTER forces the hand-over after that many basis changes
+    of a solve, mid-phase-1 or mid-phase-2: the state image it leaves must be one the CTA kernel can continue from."""
+    from oracle import oracle as O
+    monkeypatch.setenv("DWGPU_WARP_BAIL_AFTER", str(bail_after))
+    monkeypatch.setenv("DWGPU_TG_THREADS", "32")
+    if shape == "B":
+        prob = P.gen_mcf(40, 256, 512, 256, 8192001)
+    elif shape == "dense":
+        prob = P.gen_dense(5, 150, 300, 12, 64001, dens_a=0.05)
+    else:
+        prob = P.gen_mcf(24, 37, 91, 16, 4242)
+    eng = engine(prob, force_path=3)
+    orc = O.OracleBlocks(prob)
+    rng = np.random.default_rng(23)
+    compare_round(prob, eng.initial(), orc.initial(8), None, False, initial=True)
+    for t in range(3):
+        pi = -rng.random(prob.L) * 15.0 * (t + 1)
+        compare_round(prob, eng.iterate(pi, t == 0), orc.iterate(pi, t == 0, 8), pi, t == 0)
+    assert eng.last_launch_count() >= 2
+    eng.close()
+
+
+@pytest.mark.parametrize("threads", [32, 64, 128])
 @pytest.mark.parametrize("shape", ["B", "dense", "generic"])
 def test_path3_reads_only_masked_cells(shape, threads, monkeypatch):
     """Path 3 leaves its tableaux un-zeroed: a cell exists only if its row's item mask says so.  With the arena
