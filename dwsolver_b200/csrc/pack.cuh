@@ -62,6 +62,9 @@ __device__ __forceinline__ int shipped_len(const PackSrc &s, int k)
     const PackBlk b = pack_block(s, k);
     int ln = b.len[0];
     if (s.r != nullptr && !(s.r[k] - b.obj[0] > s.accept_tol)) ln = 0;
+    // a block that did not reach an optimum (1: iteration limit / numerical failure, 4: infeasible) proposes nothing;
+    // an unbounded one (6) keeps its record — the host reports it (dw_solve.cc, consume)
+    if (s.r != nullptr && (b.status[0] == 1 || b.status[0] == 4)) ln = 0;
     return ln;
 }
 

@@ -251,6 +251,7 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
     std::vector<std::pair<int, double>> remembered;              // Phase I: (column, true cost) (:143-144, 163)
     std::vector<double> xbuf;
     int iter = 0;
+    bool warned_nofeas = false;
     auto consume = [&](bool phase_one, int *n_added) -> int {
         const double t_c0 = now_s();
         int added = 0;
@@ -263,6 +264,18 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
                 if (pk.status[kl] == DWGPU_UNBND) {
                     std::fprintf(stderr, "dwsolver-b200: subproblem %d is unbounded; unbounded subproblems are not supported (src/dw_phases.c:111-115)\n", k);
                     return DW_STATUS_ERR_UNBOUNDED;
+                }
+                // The reference never looks at glp_simplex's return code (src/dw_subprob.c:329) because GLPK practically
+                // never fails there; this engine's kernels have real failure exits (iteration limit, singular rebuild).
+                // A block that did not reach an optimum must not become a lambda column: its x_k need not even be feasible.
+                if (pk.status[kl] == DWGPU_UNDEF) {
+                    std::fprintf(stderr, "dwsolver-b200: subproblem %d did not reach an optimum (engine status %d)\n", k, pk.status[kl]);
+                    return DW_STATUS_ERR_INTERNAL;
+                }
+                if (pk.status[kl] == DWGPU_NOFEAS) {
+                    if (!warned_nofeas && verb >= DW_OUTPUT_QUIET) std::printf("Subproblem %d is infeasible.\n", k);
+                    warned_nofeas = true;
+                    continue;                                          // no point of the block exists: nothing to propose
                 }
                 if (!(r[k] - pk.obj[kl] > kTolerance)) continue;      // src/dw_phases.c:108, 358
                 std::vector<int> idx;
@@ -327,6 +340,7 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
         for (int k = sh.k0; k < sh.k1; ++k)
             if (sh.pk.status[k - sh.k0] == DWGPU_NOFEAS) {
                 if (verb >= DW_OUTPUT_QUIET) std::printf("Subproblem %d is infeasible.\n", k);
+                warned_nofeas = true;
             }
 
     int status = DW_STATUS_OK;
@@ -601,37 +615,6 @@ int dw_solve_blocks(int K, int L, const dwgpu_block_desc *blocks, const double *
     if (opts_in) opt = *opts_in; else dw_options_init(&opt);
     std::memset(&g_stats, 0, sizeof(g_stats));
     return dw_core(K, L, blocks, link_lb, link_ub, nullptr, opt, now_s(), result);
-}
-
-// Test hooks (tests/test_host_library.py, no GPU needed): sizes and order-sensitive checksums of everything the engine
-// would be given — out[0..7] = L, sum m, sum n, nnz(A), nnz(D), checksum(A), checksum(D), checksum(bounds and costs) —
-// for an instance read from LP text with `readers` threads, and for one loaded from a container.
-int dwhost_read_problem_digest(const char *master_file, const char *const *subproblem_files, int K, int readers, double *out)
-{
-    try {
-        LpModel master;
-        std::vector<BlockHost> blocks;
-        read_problem(master_file, subproblem_files, K, readers, master, blocks);
-        std::vector<dwgpu_block_desc> desc;
-        describe(blocks, desc);
-        digest_blocks(K, master.m(), desc.data(), out);
-        return 0;
-    } catch (const std::exception &) { return 1; }
-}
-
-int dwhost_container_digest(const char *container_path, double *out, int *K_out, char *first_name, int first_name_cap)
-{
-    try {
-        ContainerView v;
-        load_container(container_path, v);
-        digest_blocks(v.K, v.L, v.desc.data(), out);
-        if (K_out) *K_out = v.K;
-        if (first_name && first_name_cap > 0) {
-            const std::string nm = v.has_names && !v.names[0].empty() ? v.names[0][0] : std::string();
-            std::snprintf(first_name, (size_t)first_name_cap, "%s", nm.c_str());
-        }
-        return 0;
-    } catch (const std::exception &) { return 1; }
 }
 
 int dw_write_container(const char *master_file, const char *const *subproblem_files, int num_subproblems, double shift,

@@ -80,7 +80,7 @@ class ProductMaster(HighsMaster):
         import os
         here = os.path.dirname(os.path.abspath(__file__))
         self.C = C
-        self.lib = C.CDLL(os.path.join(here, "..", "dwsolver_b200", "lib", "libdwsolver_b200.so"))
+        self.lib = C.CDLL(os.path.join(here, "..", "dwsolver_b200", "lib", "libdwhost_testhooks.so"))   # tests/host_hooks
         self.lib.dwhost_im_new.restype = C.c_void_p
         self.lib.dwhost_im_new.argtypes = [C.c_int, C.c_int, C.c_int]
         self.lib.dwhost_im_free.argtypes = [C.c_void_p]

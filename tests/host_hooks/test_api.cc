@@ -1,12 +1,16 @@
-// test_api.cc — C entry points that let the (Python) test-suite exercise the host pieces in isolation:
+// test_api.cc — TEST-ONLY library (libdwhost_testhooks.so, never linked into the product): C entry points that let the
+// (Python) test-suite exercise the host pieces in isolation:
 // the LP reader against the package's own reader, the master LP solver against HiGHS.
 #include <cstring>
 #include <stdexcept>
 #include <vector>
 
-#include "lp_model.h"
-#include "gub_master.h"
-#include "master_lp.h"
+#include "../../dwsolver_b200/host/lp_model.h"
+#include "../../dwsolver_b200/host/gub_master.h"
+#include "../../dwsolver_b200/host/master_lp.h"
+#include "../../dwsolver_b200/host/instance.h"
+#include <cstdio>
+#include <string>
 
 extern "C" {
 
@@ -123,6 +127,37 @@ void dwhost_im_primal(void *h, double *x)
 {
     dwh::IMaster *M = static_cast<dwh::IMaster *>(h);
     for (int j = 0; j < M->cols(); ++j) x[j] = M->col_prim(j);
+}
+
+// Test hooks (tests/test_host_library.py, no GPU needed): sizes and order-sensitive checksums of everything the engine
+// would be given — out[0..7] = L, sum m, sum n, nnz(A), nnz(D), checksum(A), checksum(D), checksum(bounds and costs) —
+// for an instance read from LP text with `readers` threads, and for one loaded from a container.
+int dwhost_read_problem_digest(const char *master_file, const char *const *subproblem_files, int K, int readers, double *out)
+{
+    try {
+        dwh::LpModel master;
+        std::vector<dwh::BlockHost> blocks;
+        dwh::read_problem(master_file, subproblem_files, K, readers, master, blocks);
+        std::vector<dwgpu_block_desc> desc;
+        dwh::describe(blocks, desc);
+        dwh::digest_blocks(K, master.m(), desc.data(), out);
+        return 0;
+    } catch (const std::exception &) { return 1; }
+}
+
+int dwhost_container_digest(const char *container_path, double *out, int *K_out, char *first_name, int first_name_cap)
+{
+    try {
+        dwh::ContainerView v;
+        dwh::load_container(container_path, v);
+        dwh::digest_blocks(v.K, v.L, v.desc.data(), out);
+        if (K_out) *K_out = v.K;
+        if (first_name && first_name_cap > 0) {
+            const std::string nm = v.has_names && !v.names[0].empty() ? v.names[0][0] : std::string();
+            std::snprintf(first_name, (size_t)first_name_cap, "%s", nm.c_str());
+        }
+        return 0;
+    } catch (const std::exception &) { return 1; }
 }
 
 }  // extern "C"

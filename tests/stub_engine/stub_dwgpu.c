@@ -29,6 +29,7 @@ struct dwgpu_engine {
     /* packed record (what the CUDA engine keeps in pinned memory) */
     double *obj, *cost, *val;
     int *status, *colptr, *ind;
+    int packed_rounds;              /* packed rounds served so far (failure injection) */
     /* kept copies of x_k */
     double *hist;
     long long hist_used, hist_cap;
@@ -107,10 +108,21 @@ static void pack(dwgpu_engine *e, const double *r, dwgpu_packed *out)
         const orc_proposal *p = &e->props[k];
         e->obj[k] = p->obj; e->cost[k] = p->new_obj_coeff; e->status[k] = p->status;
         e->colptr[k] = nnz;
-        if (r && !(r[k] - p->obj > 1e-6)) continue;
+        /* failure injection: DWSTUB_STATUS="<round>:<block>:<status>" makes one block report that status in that
+           packed round (0 = the initial solve) with an attractive objective, as a kernel failure exit would */
+        if (getenv("DWSTUB_STATUS")) {
+            int rd = -1, bk = -1, st = 0;
+            if (sscanf(getenv("DWSTUB_STATUS"), "%d:%d:%d", &rd, &bk, &st) == 3 && rd == e->packed_rounds && bk == k) {
+                e->status[k] = st;
+                e->obj[k] = -1e9;
+            }
+        }
+        if (r && (e->status[k] == DWGPU_UNDEF || e->status[k] == DWGPU_NOFEAS)) continue;
+        if (r && !(r[k] - e->obj[k] > 1e-6)) continue;
         for (int t = 0; t < p->len; ++t) { e->ind[nnz] = p->ind[t]; e->val[nnz] = p->val[t]; ++nnz; }
     }
     e->colptr[e->K] = nnz;
+    e->packed_rounds++;
     if (out) {
         out->obj = e->obj; out->cost = e->cost; out->status = e->status; out->colptr = e->colptr;
         out->ind = e->ind; out->val = e->val; out->nnz = nnz;

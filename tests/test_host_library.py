@@ -20,6 +20,7 @@ from conftest import EXAMPLES, ROOT, load_example
 from dwsolver_b200 import problem as P
 
 LIB = os.path.join(ROOT, "dwsolver_b200", "lib", "libdwsolver_b200.so")
+HOOKS = os.path.join(ROOT, "dwsolver_b200", "lib", "libdwhost_testhooks.so")      # dwhost_* test entry points (tests/host_hooks)
 CLI = os.path.join(ROOT, "dwsolver_b200", "bin", "dwsolver")
 c_dp, c_ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
 
@@ -42,6 +43,19 @@ def lib():
     L.dw_version.restype = C.c_char_p
     L.dw_solve.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(DwOptions), C.POINTER(DwResult)]
     return L
+
+
+_HOOKS = None
+
+
+def hooks():
+    """the test-only entry points (tests/host_hooks/test_api.cc), a library of their own next to the product's"""
+    global _HOOKS
+    if _HOOKS is None:
+        if not os.path.exists(HOOKS):
+            pytest.fail(f"{HOOKS} is missing: run __graft_entry__.build()")
+        _HOOKS = C.CDLL(HOOKS)
+    return _HOOKS
 
 
 def write_example(prob, d):
@@ -88,11 +102,11 @@ def test_block_files_read_by_several_threads(tmp_path):
     prob = P.gen_mcf(24, 12, 30, 6, seed=11)
     paths = write_example(prob, tmp_path)
     subs = (C.c_char_p * prob.K)(*[s.encode() for s in paths["subs"]])
-    L.dwhost_read_problem_digest.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(C.c_double)]
+    hooks().dwhost_read_problem_digest.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(C.c_double)]
     digests = []
     for readers in (1, 3, 8, 0):
         out = (C.c_double * 8)()
-        assert L.dwhost_read_problem_digest(paths["master"].encode(), subs, prob.K, readers, out) == 0
+        assert hooks().dwhost_read_problem_digest(paths["master"].encode(), subs, prob.K, readers, out) == 0
         digests.append(list(out))
     assert all(d == digests[0] for d in digests)                        # bit-identical, order-sensitive checksums
     d = digests[0]
@@ -104,7 +118,7 @@ def test_block_files_read_by_several_threads(tmp_path):
     bad[prob.K // 2] = str(tmp_path / "no_such_block.lp").encode()
     bad_arr = (C.c_char_p * prob.K)(*bad)
     for readers in (1, 4):
-        assert L.dwhost_read_problem_digest(paths["master"].encode(), bad_arr, prob.K, readers, (C.c_double * 8)()) == 1
+        assert hooks().dwhost_read_problem_digest(paths["master"].encode(), bad_arr, prob.K, readers, (C.c_double * 8)()) == 1
     o = DwOptions()
     L.dw_options_init(C.byref(o))
     o.verbosity = -1
@@ -116,8 +130,8 @@ def test_block_files_read_by_several_threads(tmp_path):
 def _container_api(L):
     L.dw_write_container.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_double, C.c_char_p]
     L.dw_solve_container.argtypes = [C.c_char_p, C.POINTER(DwOptions), C.POINTER(DwResult)]
-    L.dwhost_container_digest.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_char_p, C.c_int]
-    L.dwhost_read_problem_digest.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(C.c_double)]
+    hooks().dwhost_container_digest.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_char_p, C.c_int]
+    hooks().dwhost_read_problem_digest.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(C.c_double)]
 
 
 @pytest.mark.parametrize("source", ["mcf", "book_dantzig", "web_trick"])
@@ -135,9 +149,9 @@ def test_container_holds_what_the_lp_text_path_reads(source, tmp_path):
     box = str(tmp_path / "instance.dwb").encode()
     assert L.dw_write_container(paths["master"].encode(), subs, prob.K, 2.5, box) == 0
     text, packed = (C.c_double * 8)(), (C.c_double * 8)()
-    assert L.dwhost_read_problem_digest(paths["master"].encode(), subs, prob.K, 1, text) == 0
+    assert hooks().dwhost_read_problem_digest(paths["master"].encode(), subs, prob.K, 1, text) == 0
     k_out, name = C.c_int(0), C.create_string_buffer(256)
-    assert L.dwhost_container_digest(box, packed, C.byref(k_out), name, 256) == 0
+    assert hooks().dwhost_container_digest(box, packed, C.byref(k_out), name, 256) == 0
     assert list(text) == list(packed) and k_out.value == prob.K
     first = name.value.decode()
     assert first and first in open(paths["subs"][0]).read().split()           # the block's own column names travel
@@ -146,9 +160,9 @@ def test_container_holds_what_the_lp_text_path_reads(source, tmp_path):
     for cut in (7, 31, len(blob) // 3, len(blob) - 1):
         bad = tmp_path / f"cut{cut}.dwb"
         bad.write_bytes(blob[:cut])
-        assert L.dwhost_container_digest(str(bad).encode(), packed, None, None, 0) == 1
+        assert hooks().dwhost_container_digest(str(bad).encode(), packed, None, None, 0) == 1
     (tmp_path / "magic.dwb").write_bytes(b"NOTADWB!" + blob[8:])
-    assert L.dwhost_container_digest(str(tmp_path / "magic.dwb").encode(), packed, None, None, 0) == 1
+    assert hooks().dwhost_container_digest(str(tmp_path / "magic.dwb").encode(), packed, None, None, 0) == 1
     o = DwOptions()
     L.dw_options_init(C.byref(o))
     o.verbosity = -1
@@ -170,8 +184,8 @@ def test_cli_writes_a_container(tmp_path):
     assert out.returncode == 0, out.stderr
     packed, text = (C.c_double * 8)(), (C.c_double * 8)()
     subs = (C.c_char_p * prob.K)(*[s.encode() for s in paths["subs"]])
-    assert L.dwhost_container_digest(str(tmp_path / "p.dwb").encode(), packed, None, None, 0) == 0
-    assert L.dwhost_read_problem_digest(paths["master"].encode(), subs, prob.K, 2, text) == 0
+    assert hooks().dwhost_container_digest(str(tmp_path / "p.dwb").encode(), packed, None, None, 0) == 0
+    assert hooks().dwhost_read_problem_digest(paths["master"].encode(), subs, prob.K, 2, text) == 0
     assert list(packed) == list(text)
 
 
@@ -183,7 +197,7 @@ def test_cpp_lp_reader_matches_package_reader(name, tmp_path):
     for path in [paths["master"]] + paths["subs"]:
         ref = P.read_lp(path)
         dims = (C.c_int * 3)()
-        assert L.dwhost_lp_dims(path.encode(), dims) == 0
+        assert hooks().dwhost_lp_dims(path.encode(), dims) == 0
         m, n, nnz = dims[0], dims[1], dims[2]
         assert (m, n, nnz) == (ref.m, ref.n, len(ref.a_vals))
         obj, lb, ub = np.zeros(n), np.zeros(n), np.zeros(n)
@@ -193,7 +207,7 @@ def test_cpp_lp_reader_matches_package_reader(name, tmp_path):
         mx = C.c_int(0)
         d = lambda a: a.ctypes.data_as(c_dp)
         i = lambda a: a.ctypes.data_as(c_ip)
-        assert L.dwhost_lp_read(path.encode(), d(obj), d(lb), d(ub), d(rlb), d(rub), i(ar), i(ac), d(av), names,
+        assert hooks().dwhost_lp_read(path.encode(), d(obj), d(lb), d(ub), d(rlb), d(rub), i(ar), i(ac), d(av), names,
                                 len(names), C.byref(mx)) == 0
         assert names.value.decode().split("\n")[:-1] == list(ref.col_names)
         assert np.array_equal(obj, ref.obj) and np.array_equal(lb, ref.col_lb) and np.array_equal(ub, ref.col_ub)
@@ -221,7 +235,7 @@ def test_master_lp_matches_highs(seed):
         obj, its = C.c_double(0), C.c_longlong(0)
         cp = A.indptr.astype(np.int32)
         ix = A.indices.astype(np.int32)
-        rc = L.dwhost_master_solve(m, n, cp.ctypes.data_as(c_ip), ix.ctypes.data_as(c_ip), A.data.ctypes.data_as(c_dp),
+        rc = hooks().dwhost_master_solve(m, n, cp.ctypes.data_as(c_ip), ix.ctypes.data_as(c_ip), A.data.ctypes.data_as(c_dp),
                                    cost.ctypes.data_as(c_dp), ub.ctypes.data_as(c_dp), rhs.ctypes.data_as(c_dp), n_first,
                                    x.ctypes.data_as(c_dp), y.ctypes.data_as(c_dp), C.byref(obj), C.byref(its))
         assert rc == 0
@@ -426,7 +440,7 @@ def test_gub_master_thread_team_is_deterministic(block, monkeypatch):
         monkeypatch.setenv("DWSOLVER_MASTER_THREADS", str(threads))
         x, y = np.zeros(n), np.zeros(m)
         obj, its = C.c_double(0), C.c_longlong(0)
-        rc = L_.dwhost_gub_solve(L, K, n, colptr.ctypes.data_as(c_ip), idx.ctypes.data_as(c_ip), val.ctypes.data_as(c_dp),
+        rc = hooks().dwhost_gub_solve(L, K, n, colptr.ctypes.data_as(c_ip), idx.ctypes.data_as(c_ip), val.ctypes.data_as(c_dp),
                                  cost.ctypes.data_as(c_dp), rhs.ctypes.data_as(c_dp), 0, x.ctypes.data_as(c_dp),
                                  y.ctypes.data_as(c_dp), C.byref(obj), C.byref(its))
         assert rc == 0
@@ -495,7 +509,7 @@ def test_gub_master_matches_highs(seed):
                 continue
         x, y = np.zeros(n), np.zeros(m)
         obj, its = C.c_double(0), C.c_longlong(0)
-        rc = L_.dwhost_gub_solve(L, K, n, colptr.ctypes.data_as(c_ip), idx.ctypes.data_as(c_ip), val.ctypes.data_as(c_dp),
+        rc = hooks().dwhost_gub_solve(L, K, n, colptr.ctypes.data_as(c_ip), idx.ctypes.data_as(c_ip), val.ctypes.data_as(c_dp),
                                  cost.ctypes.data_as(c_dp), rhs.ctypes.data_as(c_dp), n_first, x.ctypes.data_as(c_dp),
                                  y.ctypes.data_as(c_dp), C.byref(obj), C.byref(its))
         assert rc == 0

@@ -115,6 +115,21 @@ def test_engine_failures_become_status_99(tmp_path):
     assert out.returncode == 99
 
 
+def test_a_block_that_did_not_reach_an_optimum_never_becomes_a_column(tmp_path):
+    """the kernels have real failure exits (status 1: iteration limit / numerical failure; 4: infeasible).
+    A block reporting one mid-run — with an attractive objective, so that the acceptance test r_k - obj_k > 1e-6 would
+    take it — must not enter the master: status 1 ends the solve with DW_STATUS_ERR_INTERNAL, status 4 is skipped."""
+    P.write_block_angular(load_example("web_trick"), str(tmp_path))
+    ref = run(tmp_path, "-g", "guidefile")
+    assert ref.returncode == 0
+    for rd in (1, 2):
+        out = run(tmp_path, "-g", "guidefile", "--quiet", env={"DWSTUB_STATUS": f"{rd}:0:1"})
+        assert out.returncode == 99 and "did not reach an optimum" in out.stderr, (rd, out.returncode, out.stderr)
+    out = run(tmp_path, "-g", "guidefile", env={"DWSTUB_STATUS": "2:0:4"})
+    assert out.returncode == 0 and "Subproblem 0 is infeasible." in out.stdout
+    assert float(banner(out)) >= float(banner(ref)) - 1e-9      # built from real proposals only: never below the optimum
+
+
 def test_the_double_refuses_to_run_unannounced(tmp_path):
     P.write_block_angular(load_example("single_sub"), str(tmp_path))
     env = {k: v for k, v in os.environ.items() if k != "DWSOLVER_TEST_DOUBLE"}

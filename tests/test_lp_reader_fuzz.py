@@ -13,6 +13,7 @@ from conftest import ROOT
 from dwsolver_b200 import problem as P
 
 LIB = os.path.join(ROOT, "dwsolver_b200", "lib", "libdwsolver_b200.so")
+HOOKS = os.path.join(ROOT, "dwsolver_b200", "lib", "libdwhost_testhooks.so")      # dwhost_* test entry points (tests/host_hooks)
 c_dp, c_ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
 
 
@@ -91,7 +92,7 @@ def read_with_host_library(L, path):
 
 
 def test_lp_reader_agrees_with_the_python_reader_on_odd_formatting(tmp_path):
-    L = C.CDLL(LIB)
+    L = C.CDLL(HOOKS)
     rng = np.random.default_rng(20261020)
     path = str(tmp_path / "f.lp")
     inf = lambda a: np.where(np.abs(a) >= 1e300, np.copysign(np.inf, a), a)
