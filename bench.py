@@ -152,6 +152,93 @@ def cpu_replay(prob_sample, pis, phases, threads):
     return c[0] + c[1], dt, t_setup
 
 
+_CPU_DW_CHILD = r"""
+import json, os, sys, tempfile
+sys.path.insert(0, {root!r})
+import dwsolver_b200.solver as S
+from dwsolver_b200 import problem as P
+S.LIB_PATH = {lib!r}
+prob = P.make_config({tag!r})
+os.chdir(tempfile.mkdtemp())
+r = S.dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=0)
+st = r["stats"]
+print(json.dumps(dict(seconds=st["seconds_total"], subproblem_seconds=st["seconds_subproblems"],
+                      master_seconds=st["seconds_master"], dw_rounds=st["dw_iterations"], status=r["status"],
+                      objective=r["objective"])))
+"""
+
+
+def cpu_dw_time_to_optimal(tag, threads):
+    """DW time-to-optimal of the whole instance on the host cores: the SAME host loop and master LP as the GPU arm
+    (libdwsolver_b200.so), with the engine ABI served by the CPU oracle (tests/stub_engine: pthreads + oracle/ — the
+    stand-in for the reference's pthreads + GLPK workers, GLPK being absent).  The reference's own timer is the
+    monotonic clock around the same region (src/dw_solver.c:117-124, 729-744).  Runs in a child process whose
+    library path resolves libdwgpu.so to the test double; built on demand (it never travels: .gpurunignore)."""
+    try:
+        for d in ("oracle", os.path.join("tests", "stub_engine")):
+            mk = subprocess.run(["make", "-C", os.path.join(ROOT, d)], capture_output=True, text=True, timeout=600)
+            if mk.returncode != 0:
+                return {"error": f"make -C {d}: {mk.stderr[-300:]}"}
+        lib = os.path.join(ROOT, "tests", "_build", "lib", "libdwsolver_b200.so")
+        code = _CPU_DW_CHILD.format(root=ROOT, lib=lib, tag=tag)
+        env = dict(os.environ, DWSOLVER_TEST_DOUBLE="tests-only", DWSTUB_THREADS=str(threads))
+        for k_ in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "DWSOLVER_DEVICES"):
+            env.pop(k_, None)
+        ch = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=1200)
+        lines_ = [ln for ln in ch.stdout.splitlines() if ln.startswith("{")]
+        if ch.returncode != 0 or not lines_:
+            return {"error": f"child exit {ch.returncode}: {(ch.stderr or ch.stdout)[-300:]}"}
+        out = json.loads(lines_[-1])
+        out["cores"] = threads
+        out["api"] = ("dw_solve_blocks of the same host library and master LP, subproblems by the CPU oracle on "
+                      f"{threads} pthreads (engine test double; NOT GLPK)")
+        return out
+    except Exception as exc:                         # the bench line must not die on the optional part
+        return {"error": str(exc)}
+
+
+def highs_block_sample(prob, pis, phases, blocks=8, budget_s=8.0):
+    """A second, stronger stated CPU baseline: every sampled block solved from scratch with HiGHS (scipy,
+    dual simplex, one thread) at every recorded (pi, phase) — a production sparse revised simplex, but without the
+    warm start the reference's workers have.  Reports block-solves/s and HiGHS' own iteration count per second."""
+    try:
+        import scipy.sparse as sp
+        from scipy.optimize import linprog
+    except Exception as exc:
+        return {"error": f"scipy unavailable: {exc}"}
+    solves, nit, secs = 0, 0, 0.0
+    t_begin = time.perf_counter()
+    for b in prob.blocks[:blocks]:
+        A = sp.csr_matrix((b.a_val, b.a_col, b.a_rowptr), shape=(b.m, b.n))
+        eq = b.row_lb == b.row_ub
+        up = ~eq & np.isfinite(b.row_ub)
+        lo = ~eq & np.isfinite(b.row_lb)
+        A_ub = sp.vstack([A[up], -A[lo]]) if (up.any() or lo.any()) else None
+        b_ub = np.concatenate([b.row_ub[up], -b.row_lb[lo]]) if A_ub is not None else None
+        A_eq, b_eq = (A[eq], b.row_ub[eq]) if eq.any() else (None, None)
+        ub = P.effective_col_ub(b)
+        bounds = list(zip(np.where(np.isfinite(b.col_lb), b.col_lb, None), np.where(np.isfinite(ub), ub, None)))
+        for r in range(-1, len(phases)):
+            if r < 0:
+                d = b.c_file
+            else:
+                y = np.zeros(b.n)
+                np.add.at(y, b.d_col, pis[r][b.d_row] * b.d_val)
+                d = (0.0 if phases[r] else b.c_master) - y
+            t0 = time.perf_counter()
+            res = linprog(d, A_ub=A_ub, b_ub=b_ub, A_eq=A_eq, b_eq=b_eq, bounds=bounds, method="highs-ds")
+            secs += time.perf_counter() - t0
+            solves += 1
+            nit += int(getattr(res, "nit", 0) or 0)
+            if time.perf_counter() - t_begin > budget_s:
+                break
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    return {"block_solves_per_s": solves / secs if secs > 0 else None, "iterations_per_s": nit / secs if secs > 0 else None,
+            "cores": 1, "solves": solves, "seconds": secs, "kind": "HiGHS dual simplex via scipy.optimize.linprog, cold start per solve",
+            "sample": f"first {blocks} blocks (or as many as fit {budget_s:.0f} s), cold solve + every recorded round"}
+
+
 def tto_child(tag):
     """DW time-to-optimal of the whole instance through the drop-in library (include/dwsolver.h), in a process of its
     own: dw_solve_blocks() shards the blocks over the devices named in DWSOLVER_DEVICES.  Prints one JSON line."""
@@ -205,7 +292,9 @@ def main():
             print(json.dumps({"impl": "reference", "unavailable": "config C: the CPU oracle (dense tableau, Dantzig pricing) "
                               "does not finish a 2048x4096 block in minutes; GLPK (the reference's LP engine) is absent"}))
             return
-        sample_k = min(K_total, args.cpu_blocks or (32 * cores if m <= 64 else 8 * cores))
+        # every step replays the trajectory on ALL blocks of the instance (config B on 16 host threads: ~3 s a step), so
+        # the arm runs on the same config as ours; --cpu-blocks bounds it if a box is too slow for that
+        sample_k = min(K_total, args.cpu_blocks or K_total)
         prob = P.make_config(args.config, block_range=range(sample_k))
         piv_total, t_total = 0, 0.0
         for step in range(W + S):
@@ -214,15 +303,19 @@ def main():
                 piv_total += piv
                 t_total += dt
         v = piv_total / t_total if t_total > 0 else 0.0
-        sample = f"first {sample_k} of {K_total} blocks per step, full trajectory ({R} rounds), {cores} pthreads"
+        sample = (f"all {K_total} blocks" if sample_k == K_total else f"first {sample_k} of {K_total} blocks") + \
+                 f" per step, full trajectory ({R} rounds), {cores} pthreads"
+        tto = None if args.no_time_to_optimal else cpu_dw_time_to_optimal(args.config, cores)
+        highs = highs_block_sample(prob, pis, phases)
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": S,
             "warmup": W, "ms_per_step": 1e3 * t_total / max(S, 1), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "sample": sample},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "note": cpu_note},
+                             "note": cpu_note, "highs": highs},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "dw_time_to_optimal": tto,
         }))
         return
 
@@ -337,11 +430,15 @@ def main():
                 exchange_up(); up_to_host()                        # proposals up (NCCL) + D2H on rank 0
 
     # ---- one step, device only: duals already in HBM, results stay in HBM
-    def step_dev(kern_acc=None):
+    def step_dev(kern_acc=None, cnt_acc=None):
         eng.reset(sptr)
+        if cnt_acc is not None:
+            cnt_acc.append(count())
         eng.initial_solve_device(sptr)
         if kern_acc is not None:
             kern_acc.append(eng.last_kernel_ms())
+        if cnt_acc is not None:
+            cnt_acc.append(count())
         if dist is not None:
             exchange_up()
         for r in range(R):
@@ -354,6 +451,8 @@ def main():
                 eng.iterate_device(pis_dev[r].data_ptr(), phases[r], sptr)
             if kern_acc is not None:
                 kern_acc.append(eng.last_kernel_ms())
+            if cnt_acc is not None:
+                cnt_acc.append(count())
 
     def count():
         c = eng.counters()
@@ -413,14 +512,16 @@ def main():
         t_dev = sum(ev0[i].elapsed_time(ev1[i]) for i in range(W, W + S)) * 1e-3
     # kernel-only time of the dominant kernel: separate pass with a sync after every launch (the
     # per-launch events live inside the engine), same work, not part of `value`
+    cnt_by_launch = None
     for step in range(0 if single else 2):
-        kern = []
+        kern, cacc = [], []
         flush_buf.fill_(1)
         barrier()
         c0 = count()
-        step_dev(kern)
+        step_dev(kern, cacc)
         torch.cuda.synchronize()
         kcnt = count() - c0
+        cnt_by_launch = np.diff(np.array(cacc), axis=0)          # counters of each launch (this rank)
     kern = np.array(kern)
     dom = 0 if kern[:, 0].sum() >= kern[:, 1].sum() else 1
     k_time = float(kern[:, dom].sum()) * 1e-3
@@ -471,9 +572,11 @@ def main():
             peak_src = "of fallback (B200_PROFILING.md)"
         bound = "hbm"
     achieved = alg_bytes / k_time / 1e9 if k_time > 0 else 0.0
+    # N > 1: bytes are summed over the ranks and the time is the slowest rank's, so the denominator is N GPUs' peak
+    peak_all = peak * world
     kname = {("A", True): "dwk::solve_smem_kernel<256,64,128,false>", ("B", False): "dwk::solve_smem_kernel<128,256,512,true>",
              ("C", False): "dwk::solve_cluster_kernel<512>"}
-    traffic, traffic_note = None, None
+    traffic, traffic_note, tr = None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             tr = json.load(fh).get(args.config)
@@ -482,21 +585,55 @@ def main():
             traffic_note = f"{tr['which_launch']}; {tr['source']}"
     except (OSError, ValueError, KeyError):
         pass
-    roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_note": traffic_note,
+
+    def touched_bytes(c):          # c = [pivots, flips, rebuilds, rows, cells, price_cells, mailbox]
+        return c[4] * 16.0 + c[0] * 8.0 * (m + n) + c[5] * 8.0
+
+    per_launch = None
+    if cnt_by_launch is not None and len(cnt_by_launch) == len(kern):
+        per_launch = [{"ms": round(float(kern[i, dom]), 4), "basis_changes": int(cnt_by_launch[i][0]),
+                       "cells_swept": int(cnt_by_launch[i][4]), "price_cells": int(cnt_by_launch[i][5]),
+                       "touched_bytes": int(touched_bytes(cnt_by_launch[i]) + (state_bytes / n_launch if on_smem else 0.0))}
+                      for i in range(len(kern))]
+    # the launch the ncu DRAM capture refers to, so that `traffic` and algorithmic bytes can be divided like for like
+    traffic_launch = None
+    if tr and per_launch and world == 1 and isinstance(tr.get("launch_index"), int) and tr["launch_index"] < len(per_launch):
+        pl = per_launch[tr["launch_index"]]
+        traffic_launch = dict(pl, index=tr["launch_index"], dram_bytes=traffic,
+                              touched_GBps=pl["touched_bytes"] / (pl["ms"] * 1e-3) / 1e9 if pl["ms"] > 0 else None,
+                              dram_GBps=traffic / (pl["ms"] * 1e-3) / 1e9 if pl["ms"] > 0 else None,
+                              touched_frac=pl["touched_bytes"] / (pl["ms"] * 1e-3) / 1e9 / peak if pl["ms"] > 0 else None,
+                              dram_frac=traffic / (pl["ms"] * 1e-3) / 1e9 / peak if pl["ms"] > 0 else None)
+    # second denominator for the HBM-tableau path: what the memory system sustains for THIS access pattern (scattered
+    # 32-byte items of a few rows of a random 1 MB tableau, read + write) — profiles/microbench/random_sector.cu
+    wall = None
+    if not on_smem and args.config == "B":
+        try:
+            with open(os.path.join(ROOT, "profiles", "pattern_wall.json")) as fh:
+                wj = json.load(fh)
+            wall = {"GBps": wj["pivot_pattern_GBps"], "source": wj["source"],
+                    "frac_touched": achieved / (wj["pivot_pattern_GBps"] * world)}
+            if traffic_launch and traffic_launch.get("dram_GBps"):
+                wall["frac_dram_of_traffic_launch"] = traffic_launch["dram_GBps"] / wj["pivot_pattern_GBps"]
+        except (OSError, ValueError, KeyError):
+            pass
+    roofline = {"bound": bound, "achieved": achieved, "peak": peak_all, "unit": "GB/s",
+                "frac": achieved / peak_all if peak_all else None, "traffic": traffic, "traffic_note": traffic_note,
+                "peak_per_gpu": peak, "n_gpus": world,
                 "algorithmic_bytes_per_launch": alg_bytes / n_launch,
                 "kernel": kname.get((args.config, on_smem), "dwk::solve_kernel<false,1024>"),
                 "bytes_definition": "touched: 16 B per rewritten tableau double + 8(m+n) per basis change + 8 B per tableau double read for price rows"
                                     + (" + 16mn state image per block-launch" if on_smem else ""),
                 "dense_equivalent_GBps": dense_bytes / k_time / 1e9 if k_time > 0 else None,
-                "dense_equivalent_frac": dense_bytes / k_time / 1e9 / peak if k_time > 0 and peak else None,
+                "dense_equivalent_frac": dense_bytes / k_time / 1e9 / peak_all if k_time > 0 and peak_all else None,
                 "kernel_ms_per_launch": 1e3 * k_time / n_launch, "launches_per_step": n_launch,
                 "kernel_share_of_solve_kernels": k_share,
                 "kernel_ms_by_launch": [round(float(v), 4) for v in kern[:, dom]],
+                "per_launch": per_launch, "traffic_launch": traffic_launch, "pattern_wall": wall,
                 "bytes_per_basis_change_dense": bpp, "basis_changes_per_step": float(kcnt[0]),
                 "rows_swept_per_basis_change": float(kcnt[3] / max(kcnt[0], 1.0)),
                 "cells_rewritten_per_basis_change": float(kcnt[4] / max(kcnt[0], 1.0)),
-                "state_bytes_per_step": state_bytes, "peak_source": peak_src}
+                "state_bytes_per_step": state_bytes, "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else "")}
 
     # ---------------- DW time-to-optimal through the drop-in host library (N = 1) ----------------
     # the other half of BASELINE.json's metric: the whole solve (Phase I + II, own GUB master, reconstruction)
@@ -538,7 +675,15 @@ def main():
             piv += p_; secs += dt; reps += 1
         cpu = {"value": piv / secs if secs > 0 else None, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {sample_k} of {K_total} blocks, full trajectory ({R} rounds) x {reps} replays, "
-                         f"{cores} pthreads", "seconds": secs, "note": cpu_note}
+                         f"{cores} pthreads", "seconds": secs, "note": cpu_note,
+               "highs": highs_block_sample(sub, pis, phases)}
+        # the other half of the metric on the same host cores: DW time-to-optimal with CPU subproblems (same host loop,
+        # same master LP) — the ratio to the GPU arm's is reported, not optimised for
+        if tto is not None and "error" not in tto and not args.no_time_to_optimal:
+            cpu_tto = cpu_dw_time_to_optimal(args.config, cores)
+            tto["cpu_arm"] = cpu_tto
+            if "error" not in cpu_tto and tto.get("seconds"):
+                tto["speedup_vs_cpu_arm"] = cpu_tto["seconds"] / tto["seconds"]
 
     out = {
         "metric": METRIC, "value": (dev_cnt[0] + dev_cnt[1]) / t_dev if t_dev > 0 else 0.0, "unit": UNIT,

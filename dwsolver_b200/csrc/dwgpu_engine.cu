@@ -116,6 +116,7 @@ struct dwgpu_engine {
     DevBuf<unsigned char> redo_moved;
     int warp_bail_after = 0;           // test hook (DWGPU_WARP_BAIL_AFTER): hand over after this many basis changes
     bool reorder = true;
+    bool have_proposals = false;       // a round has written every block's proposal since create / reset
     size_t smem_dyn = 0;
     int max_smem_optin = 0;
     // device arenas
@@ -534,6 +535,10 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
     P.pi = d_pi; P.phase_one = phase_one; P.initial = initial;
     P.max_iter_mult = e->opt.max_iter_mult;
     P.no_dual_start = e->opt.no_dual_start;
+    // the "nothing moved" exit of the kernels rewrites only obj/status and relies on the previous proposal of
+    // the block still standing in the result arrays; after create / reset there is none until a round has written it
+    P.force_full = (!initial && !e->have_proposals) ? 1 : 0;
+    e->have_proposals = true;
     P.dbg = e->d_dbg;
     P.tol_dj = e->opt.tol_dj; P.tol_bnd = e->opt.tol_bnd; P.tol_piv = e->opt.tol_piv;
     P.obj = e->obj.p; P.cost = e->cost.p; P.status = e->status.p; P.len = e->len.p;
@@ -866,6 +871,8 @@ int dwgpu_reset(dwgpu_engine *e, void *stream)
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     dwk::init_kernel<256><<<e->K, 256, 0, st>>>(e->blocks.p, e->K);
     CU(cudaGetLastError());
+    e->have_proposals = false;
+    e->mail_valid = false;
     return 0;
 }
 

@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
                 if (v >= m) c.rowp[v - m] = c.beta[i]; else aux[v] = c.beta[i];
             }
             __syncthreads();
-            if (!changed && n_reb == 0 && !P.initial) { status = 5; break; }
+            if (!changed && n_reb == 0 && !P.initial && !P.force_full) { status = 5; break; }
             double worst = 0.0;
             for (int i = tid; i < m; i += NT) {
                 double s = 0.0;
@@ -866,7 +866,7 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
         }
         __syncthreads();
     }
-    const bool moved = changed || n_reb != 0 || P.initial != 0 || status != 5;
+    const bool moved = changed || n_reb != 0 || P.initial != 0 || P.force_full != 0 || status != 5;
     // swept rows: every thread counted the non-zeros of the columns it scanned (replicated), so rank 0's
     // block-wide sum is the cluster-wide number
     const double rows_total = block_sum<NT>((double)n_rows, sh.scr);

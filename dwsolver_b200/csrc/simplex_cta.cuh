@@ -58,6 +58,8 @@ struct SolveParams {
     int initial;        // cold solve with the block file's own objective (dw_subprob.c:121)
     int max_iter_mult;
     int no_dual_start;  // cluster path: skip the dual-simplex repair of an infeasible start
+    int force_full;     // no proposal of this engine state exists yet (first round after create / reset without an
+                        // initial solve): a block that needs no pivot must still write its whole proposal
     double tol_dj, tol_bnd, tol_piv;
     double *obj, *cost; // K
     int *status, *len;  // K

@@ -1323,7 +1323,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
         // ---- K_NONE
         if (infeasible) { status = 4; break; }
         // nothing moved since the last optimal solve of this block: x_k is still what B.x holds
-        if (!s_changed && n_reb == 0 && !P.initial) { status = 5; x_in_rowp = false; break; }
+        if (!s_changed && n_reb == 0 && !P.initial && !P.force_full) { status = 5; x_in_rowp = false; break; }
         phase(8);
         // claimed optimal: x into rowp, auxiliary values into colq
         for (int j = tid; j < n; j += NT) {
@@ -1409,7 +1409,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
     // ---- epilogue
     __syncthreads();
     phase(10);
-    const bool changed = s_changed != 0 || n_reb != 0 || P.initial != 0 || status != 5;
+    const bool changed = s_changed != 0 || n_reb != 0 || P.initial != 0 || P.force_full != 0 || status != 5;
     if (status != 5) {
         for (int j = tid; j < n; j += NT) {
             const int v = c.nbv[j];

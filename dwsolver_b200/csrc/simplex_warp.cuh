@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(32, DWK_W_OCC) solve_warp_kernel(const BlockDe
         // ---- K_NONE
         if (infeasible) { status = 4; break; }
         // nothing moved since the last optimal solve of this block: x_k is still what B.x holds
-        if ((n_piv + n_flip) == 0 && !P.initial) { status = 5; x_in_scr = false; break; }
+        if ((n_piv + n_flip) == 0 && !P.initial && !P.force_full) { status = 5; x_in_scr = false; break; }
         // claimed optimal: x into scr, auxiliary values into colv (by variable id)
         for (int j = lane; j < n; j += 32) {
             const int v = c.nbv[j];
@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(32, DWK_W_OCC) solve_warp_kernel(const BlockDe
         }
         return;
     }
-    const bool changed = moved || P.initial != 0 || status != 5;
+    const bool changed = moved || P.initial != 0 || P.force_full != 0 || status != 5;
     if (status != 5) {
         for (int j = lane; j < n; j += 32) {
             const int v = c.nbv[j];

@@ -101,6 +101,14 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
 
 /* src/dw_phases.c:108, 358 through the engine's packed record: with r given only the columns the master will accept
  * are shipped (dwsolver_b200/csrc/pack.cuh) */
+/* worker threads of a round: 2 in the test-suite; bench.py's CPU arm sets DWSTUB_THREADS to the host's core count */
+static int stub_threads(void)
+{
+    const char *t = getenv("DWSTUB_THREADS");
+    const int n = t ? atoi(t) : 2;
+    return n < 1 ? 1 : n;
+}
+
 static void pack(dwgpu_engine *e, const double *r, dwgpu_packed *out)
 {
     int nnz = 0;
@@ -132,7 +140,7 @@ static void pack(dwgpu_engine *e, const double *r, dwgpu_packed *out)
 int dwgpu_initial_solve_packed(dwgpu_engine *e, dwgpu_packed *out)
 {
     if (!e) return fail(DWGPU_E_ARGS, "bad arguments");
-    orc_batch(e->blocks, e->props, e->K, NULL, 0, 1, 2);
+    orc_batch(e->blocks, e->props, e->K, NULL, 0, 1, stub_threads());
     pack(e, NULL, out);
     return 0;
 }
@@ -141,7 +149,7 @@ int dwgpu_iterate_packed(dwgpu_engine *e, const double *pi, int phase_one, const
 {
     if (!e || (e->L > 0 && !pi)) return fail(DWGPU_E_ARGS, "bad arguments");
     if (getenv("DWSTUB_FAIL_ITERATE")) return fail(DWGPU_E_CUDA, "stub engine: round failure requested by the test");
-    orc_batch(e->blocks, e->props, e->K, pi, phase_one, 0, 2);
+    orc_batch(e->blocks, e->props, e->K, pi, phase_one, 0, stub_threads());
     pack(e, r, out);
     return 0;
 }

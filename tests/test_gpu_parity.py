@@ -507,6 +507,29 @@ def test_host_mailboxes_match_dense_results(force_path):
     e1.close(); e2.close()
 
 
+@pytest.mark.parametrize("force_path", [0, 2, 3, 4])
+def test_first_round_after_create_or_reset_without_initial_solve(force_path):
+    """a priced round right after dwgpu_create() or dwgpu_reset() — no initial solve in between — must
+    return complete proposals even for blocks that are already optimal at the all-logical basis (their "nothing moved"
+    exit would otherwise leave an empty or stale column and cost).  Columns get non-zero lower bounds so that x != 0."""
+    from oracle import oracle as O
+    prob = P.gen_mcf(24, 16, 40, 8, seed=5)
+    for b in prob.blocks:
+        b.col_lb = b.col_lb + 0.25
+    rng = np.random.default_rng(9)
+    pi0 = rng.random(prob.L) * 1e-3            # tiny positive duals: most blocks stay at their bounds
+    pi1 = -rng.random(prob.L) * 7.0
+    eng = engine(prob, force_path=force_path)
+    orc = O.OracleBlocks(prob)
+    compare_round(prob, eng.iterate(pi0, False), orc.iterate(pi0, False, 8), pi0, False)
+    compare_round(prob, eng.iterate(pi1, False), orc.iterate(pi1, False, 8), pi1, False)
+    eng.reset()
+    orc = O.OracleBlocks(prob)
+    compare_round(prob, eng.iterate(pi1, True), orc.iterate(pi1, True, 8), pi1, True)
+    compare_round(prob, eng.iterate(pi0, False), orc.iterate(pi0, False, 8), pi0, False)
+    eng.close()
+
+
 def test_two_live_engines_of_different_shapes():
     """A kernel's dynamic shared-memory limit belongs to the device, not to an engine: an engine created later for
     smaller blocks must not take it away from one that is still launching (several engines live in one process when
