@@ -229,6 +229,34 @@ int  dwgpu_device_count(void);
 const char *dwgpu_last_error(void);
 const char *dwgpu_version(void);
 
+/* ---- the restricted master on the device -------------------------------------------------------
+ * Replaces the reference's glp_simplex(master_lp) calls (src/dw_phases.c:219, 450; src/dw_solver.c:561-562) for
+ * large instances: a primal-dual interior-point solve (Mehrotra predictor-corrector) of
+ *     min c'x   s.t.   A x = b,  x >= 0,
+ * where rows 0..L-1 are the linking rows (all turned into equalities with explicit slack / artificial columns, as
+ * src/dw_solver.c:321-419 does) and rows L..L+K-1 the convexity rows; a column has at most ONE entry in the
+ * convexity rows, with coefficient 1 (its block).  The method works on an L x L system per iteration, formed with
+ * FP64 tensor-core MMAs from all master columns (csrc/master_ipm.cu).  Columns are added in CSC form over all L+K
+ * rows; set_costs / set_coef / del_cols mirror glp_set_obj_coef / glp_set_mat_col / glp_del_cols.
+ * dwgpu_master_solve: *status = 0 optimal to `tol` (relative primal and dual infeasibility and duality gap),
+ *   3 = not converged within max_iter iterations (a solve whose best iterate is within 100 tol counts as optimal: the
+ *   FP64 normal equations lose accuracy in the last iterations; dwgpu_master_quality says what was reached).  dwgpu_master_get: objective c'x, dual objective b'y, the L+K row
+ *   duals y (the pi and r_k of src/dw_support.c:142-152), the column values x, iterations and device seconds of the
+ *   last solve (any pointer may be NULL). */
+typedef struct dwgpu_master dwgpu_master;
+int  dwgpu_master_create(int device, int L, int K, dwgpu_master **out);
+void dwgpu_master_destroy(dwgpu_master *m);
+int  dwgpu_master_set_rhs(dwgpu_master *m, const double *b /* L+K */);
+int  dwgpu_master_add_cols(dwgpu_master *m, int ncols, const int *colptr, const int *rows, const double *vals, const double *cost);
+int  dwgpu_master_set_costs(dwgpu_master *m, int first, int count, const double *cost);
+int  dwgpu_master_set_coef(dwgpu_master *m, int col, int pos, double v);
+int  dwgpu_master_del_cols(dwgpu_master *m, const char *flag /* one per column, non-zero = delete */);
+int  dwgpu_master_cols(const dwgpu_master *m);
+int  dwgpu_master_solve(dwgpu_master *m, double tol, int max_iter, int *status);
+int  dwgpu_master_get(dwgpu_master *m, double *obj, double *dual_obj, double *y, double *x, int *iterations, double *seconds);
+int  dwgpu_master_quality(dwgpu_master *m, double *pinf, double *dinf, double *gap);
+const char *dwgpu_master_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -152,6 +152,8 @@ class IpmMaster(HighsMaster):
         self.last = res
         if res["status"] != 0:
             print("  !! ipm did not converge", res["iters"])
+            import pickle
+            pickle.dump(dict(AL=AL, blk=blk, cost=cost, rhs=self.rhs, L=L, K=K), open("/tmp/ipm_fail.pkl", "wb"))
         return dict(obj=res["obj"], x=res["x"], pi=res["yL"].copy(), r=res["yK"].copy())
 
 
