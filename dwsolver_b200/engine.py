@@ -30,6 +30,10 @@ ABI_SYMBOLS = [
     "dwgpu_reset", "dwgpu_initial_solve_device", "dwgpu_initial_solve_packed", "dwgpu_iterate_packed", "dwgpu_pack_gathered",
     "dwgpu_device_record", "dwgpu_pack_gathered_records", "dwgpu_history_push", "dwgpu_history_combine",
     "dwgpu_initial_solve_mailboxes", "dwgpu_iterate_mailboxes", "dwgpu_device_count",
+    # the restricted master on the device (dwsolver_b200/master.py)
+    "dwgpu_master_create", "dwgpu_master_destroy", "dwgpu_master_set_rhs", "dwgpu_master_add_cols",
+    "dwgpu_master_set_costs", "dwgpu_master_set_coef", "dwgpu_master_del_cols", "dwgpu_master_cols",
+    "dwgpu_master_solve", "dwgpu_master_get", "dwgpu_master_quality", "dwgpu_master_last_error",
 ]
 
 

@@ -30,6 +30,7 @@
 #include "instance.h"
 #include "lp_model.h"
 #include "gub_master.h"
+#include "ipm_master.h"
 #include "master_lp.h"
 
 namespace {
@@ -207,10 +208,19 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
 
     // ---- restricted master (src/dw_solver.c:247-440) ---------------------------------------------------
     // master LP: GUB working basis (L x L) by default; DWSOLVER_MASTER=dense selects the (L+K)^2 dense inverse
+    // Large instances (K L >= 2^18, e.g. config B's 8192 x 256): the interior-point master on the device
+    // (ipm_master.h; DWSOLVER_MASTER=ipm forces it, =gub the simplex) — ~25 parallel iterations per master instead of
+    // tens of thousands of simplex pivots.
     const char *mk = std::getenv("DWSOLVER_MASTER");
     std::unique_ptr<IMaster> master_lp;
-    if (mk && std::strcmp(mk, "dense") == 0) master_lp.reset(new MasterLP(L + K));
-    else master_lp.reset(new GubMaster(L, K));
+    const bool want_ipm = mk ? std::strcmp(mk, "ipm") == 0 : ((long long)K * L >= (1LL << 18));
+    if (want_ipm && L > 0) master_lp.reset(IpmMaster::create(devices[0], L, K));
+    const bool ipm_master = (bool)master_lp;
+    if (!master_lp) {
+        if (mk && std::strcmp(mk, "dense") == 0) master_lp.reset(new MasterLP(L + K));
+        else master_lp.reset(new GubMaster(L, K));
+    }
+    if (std::getenv("DWSOLVER_DEBUG_TIMING")) std::fprintf(stderr, "dwsolver-b200: master LP solver: %s\n", ipm_master ? "interior point on the device" : "simplex on the host");
     IMaster &M = *master_lp;
     std::vector<int> art_col(L, -1);
     std::vector<char> is_art;

@@ -203,3 +203,20 @@ int dwgpu_get_counters(dwgpu_engine *e, dwgpu_counters *c)
     }
     return 0;
 }
+
+/* ---- the device-resident master (dwgpu_master_*): not part of the test double — creation fails, so the host loop
+ * keeps its simplex master (dwsolver_b200/host/ipm_master.cc) ---- */
+int dwgpu_master_create(int device, int L, int K, dwgpu_master **out) { (void)device; (void)L; (void)K; if (out) *out = NULL; return DWGPU_E_CUDA; }
+void dwgpu_master_destroy(dwgpu_master *m) { (void)m; }
+int dwgpu_master_set_rhs(dwgpu_master *m, const double *b) { (void)m; (void)b; return DWGPU_E_STATE; }
+int dwgpu_master_add_cols(dwgpu_master *m, int n, const int *cp, const int *r, const double *v, const double *c)
+{ (void)m; (void)n; (void)cp; (void)r; (void)v; (void)c; return DWGPU_E_STATE; }
+int dwgpu_master_set_costs(dwgpu_master *m, int f, int n, const double *c) { (void)m; (void)f; (void)n; (void)c; return DWGPU_E_STATE; }
+int dwgpu_master_set_coef(dwgpu_master *m, int c, int p, double v) { (void)m; (void)c; (void)p; (void)v; return DWGPU_E_STATE; }
+int dwgpu_master_del_cols(dwgpu_master *m, const char *f) { (void)m; (void)f; return DWGPU_E_STATE; }
+int dwgpu_master_cols(const dwgpu_master *m) { (void)m; return 0; }
+int dwgpu_master_solve(dwgpu_master *m, double tol, int it, int *st) { (void)m; (void)tol; (void)it; (void)st; return DWGPU_E_STATE; }
+int dwgpu_master_get(dwgpu_master *m, double *o, double *d, double *y, double *x, int *it, double *s)
+{ (void)m; (void)o; (void)d; (void)y; (void)x; (void)it; (void)s; return DWGPU_E_STATE; }
+int dwgpu_master_quality(dwgpu_master *m, double *p, double *d, double *g) { (void)m; (void)p; (void)d; (void)g; return DWGPU_E_STATE; }
+const char *dwgpu_master_last_error(void) { return "the engine test double has no device master"; }
