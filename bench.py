@@ -657,8 +657,8 @@ def main():
             tto = {"seconds": st_["seconds_total"], "first_call_seconds": first_, "subproblem_seconds": st_["seconds_subproblems"],
                    "master_seconds": st_["seconds_master"], "dw_rounds": st_["dw_iterations"], "status": r_["status"],
                    "objective": r_["objective"], "objective_of_recorded_run": dw_objective,
-                   "api": "dw_solve_blocks (include/dwsolver.h): GPU subproblems + this build's GUB master (a team of 4 host threads "
-                          "for the dense L x L work when the host has >= 12 cores, else one)"}
+                   "api": "dw_solve_blocks (include/dwsolver.h): GPU subproblems + this build's master LP — the device-resident "
+                          "interior-point master (csrc/master_ipm.cu) when K L >= 2^18 (config B), else the host GUB simplex"}
         except Exception as exc:                     # the bench line must not die on the optional part
             tto = {"error": str(exc)}
 
@@ -728,7 +728,7 @@ def main():
                     tto["objective_of_recorded_run"] = dw_objective
                     tto["api"] = (f"dw_solve_blocks (include/dwsolver.h) in a child process, DWSOLVER_DEVICES={env['DWSOLVER_DEVICES']}: "
                                   "one engine per GPU over a contiguous block range, one host thread per shard and round, "
-                                  "this build's GUB master on the host; second call of the process (first_call_seconds beside it)")
+                                  "this build's master LP (device interior point when K L >= 2^18, else host GUB simplex); second call of the process (first_call_seconds beside it)")
                 else:
                     tto = {"error": f"child exit {ch.returncode}: {(ch.stderr or ch.stdout)[-300:]}"}
             except Exception as exc:                 # the bench line must not die on the optional part

@@ -173,7 +173,7 @@ __global__ void k_syrk_reduce(int L, int npairs, int nchunks, const double *part
     int bi = 0;
     while ((bi + 1) * (bi + 2) / 2 <= p) ++bi;
     const int bj = p - bi * (bi + 1) / 2;
-    for (int e = threadIdx.x; e < SY_T * SY_T; e += blockDim.x) {
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < SY_T * SY_T; e += gridDim.y * blockDim.x) {
         double s = 0.0;
         for (int c = 0; c < nchunks; ++c) s += part[((size_t)c * npairs + p) * (SY_T * SY_T) + e];
         const int i = bi * SY_T + e / SY_T, j = bj * SY_T + e % SY_T;
@@ -183,10 +183,10 @@ __global__ void k_syrk_reduce(int L, int npairs, int nchunks, const double *part
 }
 
 // ---- Cholesky of S (lower triangle, in place), one CTA, panels of 32 columns factored in shared memory ------------
-constexpr int CH_P = 32;
+constexpr int CH_P = 32, CH_LD = CH_P + 1;        // panel width and its shared-memory pitch (odd: no bank conflicts)
 __global__ void __launch_bounds__(1024) k_cholesky(int L, double *S, double reg_rel)
 {
-    extern __shared__ double pan[];          // (L - p0) x CH_P, row-major
+    extern __shared__ double pan[];          // (L - p0) x CH_P, row-major with pitch CH_LD
     __shared__ double red[32];
     __shared__ double s_reg;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -201,28 +201,28 @@ __global__ void __launch_bounds__(1024) k_cholesky(int L, double *S, double reg_
     }
     for (int p0 = 0; p0 < L; p0 += CH_P) {
         const int pw = min(CH_P, L - p0), rows = L - p0;
-        for (int e = tid; e < rows * pw; e += nt) { const int r = e / pw, c = e - r * pw; pan[r * CH_P + c] = S[(size_t)(p0 + r) * L + p0 + c]; }
+        for (int e = tid; e < rows * pw; e += nt) { const int r = e / pw, c = e - r * pw; pan[r * CH_LD + c] = S[(size_t)(p0 + r) * L + p0 + c]; }
         __syncthreads();
         for (int k = 0; k < pw; ++k) {
-            const double dkk = pan[k * CH_P + k];
+            const double dkk = pan[k * CH_LD + k];
             const double piv = dkk > 0.0 ? sqrt(dkk) : 1e150;       // a non-positive pivot: the direction is dropped
             __syncthreads();
-            for (int r = k + tid; r < rows; r += nt) pan[r * CH_P + k] = (r == k) ? piv : pan[r * CH_P + k] / piv;
+            for (int r = k + tid; r < rows; r += nt) pan[r * CH_LD + k] = (r == k) ? piv : pan[r * CH_LD + k] / piv;
             __syncthreads();
             // update the panel columns right of k
             for (int e = tid; e < (rows - k - 1) * (pw - k - 1); e += nt) {
                 const int r = k + 1 + e / (pw - k - 1), c = k + 1 + e % (pw - k - 1);
-                if (r >= c) pan[r * CH_P + c] -= pan[r * CH_P + k] * pan[c * CH_P + k];
+                if (r >= c) pan[r * CH_LD + c] -= pan[r * CH_LD + k] * pan[c * CH_LD + k];
             }
             __syncthreads();
         }
-        for (int e = tid; e < rows * pw; e += nt) { const int r = e / pw, c = e - r * pw; if (r >= c) S[(size_t)(p0 + r) * L + p0 + c] = pan[r * CH_P + c]; }
+        for (int e = tid; e < rows * pw; e += nt) { const int r = e / pw, c = e - r * pw; if (r >= c) S[(size_t)(p0 + r) * L + p0 + c] = pan[r * CH_LD + c]; }
         // trailing update: S[i][j] -= sum_k pan[i][k] pan[j][k], i >= j >= p0 + pw
         const int t0 = pw, tn = rows - pw;
         for (int e = tid; e < tn * tn; e += nt) {
             const int ri = e / tn, rj = e - ri * tn;
             if (ri < rj) continue;
-            const double *pi_ = pan + (t0 + ri) * CH_P, *pj_ = pan + (t0 + rj) * CH_P;
+            const double *pi_ = pan + (t0 + ri) * CH_LD, *pj_ = pan + (t0 + rj) * CH_LD;
             double s = 0.0;
 #pragma unroll 8
             for (int k = 0; k < pw; ++k) s += pi_[k] * pj_[k];
@@ -576,7 +576,7 @@ int dwgpu_master_create(int device, int L, int K, dwgpu_master **out)
     if (e == cudaSuccess) e = cudaMallocHost((void **)&m->h_scal, sizeof(double) * SC_COUNT);
     if (e != cudaSuccess) { delete m; return mfail(DWGPU_E_CUDA, cudaGetErrorString(e)); }
     // shared-memory needs of the one-CTA kernels
-    const int pan_bytes = (int)(sizeof(double) * (size_t)L * CH_P);
+    const int pan_bytes = (int)(sizeof(double) * (size_t)L * CH_LD);
     if (pan_bytes > 48 * 1024) {
         e = cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, pan_bytes);
         if (e != cudaSuccess) { cudaFreeHost(m->h_scal); cudaStreamDestroy(m->st); delete m; return mfail(DWGPU_E_ARGS, "too many linking rows for the device master"); }
@@ -732,14 +732,14 @@ int dwgpu_master_solve(dwgpu_master *m, double tol, int max_iter, int *status_ou
     const int chunk = std::max(SY_KS, ((n + 147) / 148 + SY_KS - 1) / SY_KS * SY_KS);       // ~one wave of CTAs per tile pair row
     const int nchunks = (n + chunk - 1) / chunk;
     MCU(m->Spart.need((size_t)nchunks * npairs * SY_T * SY_T));
-    const size_t pan_bytes = sizeof(double) * (size_t)L * CH_P, y_bytes = sizeof(double) * (size_t)L;
+    const size_t pan_bytes = sizeof(double) * (size_t)L * CH_LD, y_bytes = sizeof(double) * (size_t)L;
     double *scal = m->scal.p, *part = m->part.p;
 
     auto factor = [&]() -> cudaError_t {     // d -> delta, abar, Bt, S = Bt'Bt, Cholesky
         k_block_prep<<<K, 128, sizeof(double) * L, st>>>(L, blkptr, blkcols, colptr, rowidx, val, m->d.p, m->delta.p, m->abar.p);
         k_build_bt<<<n, 64, 0, st>>>(L, colptr, rowidx, val, blk, m->d.p, m->abar.p, m->Bt.p);
         k_syrk_dmma<<<dim3(npairs, nchunks), 256, 0, st>>>(L, n, chunk, m->Bt.p, m->Spart.p);
-        k_syrk_reduce<<<npairs, 256, 0, st>>>(L, npairs, nchunks, m->Spart.p, m->S.p);
+        k_syrk_reduce<<<dim3(npairs, 16), 256, 0, st>>>(L, npairs, nchunks, m->Spart.p, m->S.p);
         k_cholesky<<<1, 1024, pan_bytes, st>>>(L, m->S.p, 1e-14);
         return cudaGetLastError();
     };

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <limits>
 
 namespace dwh {
@@ -105,6 +106,8 @@ int IpmMaster::solve()
     if (fallback_) return solve_fallback();
     const int n = cols();
     int rc = 0;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
     if (rebuild_) {
         std::vector<char> all((size_t)std::max(dwgpu_master_cols(h_), 1), 1);
         if (dwgpu_master_cols(h_) > 0) rc = dwgpu_master_del_cols(h_, all.data());
@@ -118,6 +121,7 @@ int IpmMaster::solve()
     }
     if (rc) { std::fprintf(stderr, "dwsolver-b200: device master: %s; the simplex master takes over\n", dwgpu_master_last_error()); return solve_fallback(); }
     synced_ = n; rebuild_ = false;
+    const double t_push = now();
     const char *te = std::getenv("DWSOLVER_IPM_TOL");
     const double tol = te ? std::atof(te) : 1e-9;
     int st = 3;
@@ -132,6 +136,7 @@ int IpmMaster::solve()
                      rc ? dwgpu_master_last_error() : "iteration limit");
         return solve_fallback();
     }
+    const double t_solved = now();
     double pobj = 0.0, dobj = 0.0, secs = 0.0;
     int its = 0;
     x_.assign((size_t)n, 0.0);
@@ -162,6 +167,9 @@ int IpmMaster::solve()
     obj_ = pobj + c0_;
     changed_ = false;
     last_status_ = 0;
+    if (std::getenv("DWSOLVER_DEBUG_TIMING"))
+        std::fprintf(stderr, "dwsolver-b200: device master: %d columns, %d iterations, quality %.1e/%.1e/%.1e; push %.4f s, solve call %.4f s (device %.4f s), duals %.4f s\n",
+                     n, its, pinf, dinf, gap, t_push - t_begin, t_solved - t_push, secs, now() - t_solved);
     return 0;
 }
 
