@@ -371,26 +371,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    rec_t = gath = None
-    if dist is not None:   # every rank receives every shard's result record; rank 0 is the consumer
-        rec_ptr, rec_bytes = eng.device_record()
-        rec_t = torch.as_tensor(Cai(rec_ptr, (rec_bytes,), "|u1"), device=dev)
-        gath = torch.empty(world * rec_bytes, dtype=torch.uint8, device=dev)
+    up_props = None
+    if dist is not None:
+        # Multi-GPU plumbing from the C layer (include/dwgpu.h): an NCCL communicator per engine and the up-link buffer in
+        # rank 0's HBM that every rank's kernels store into over NVLink peer memory (CUDA IPC mapping).  torch.distributed
+        # only carries the 128-byte NCCL id and the 64-byte IPC handle, the barriers and the timing reductions.
+        box = [E.Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.comm_init(box[0], world, rank)
+        box = [None]
+        if rank == 0:
+            handle, up_props = eng.uplink_create(K_total)
+            box = [handle]
+        dist.broadcast_object_list(box, src=0)
+        eng.uplink_attach(None if rank == 0 else box[0], K_total, my_range.start)
     pi_pin = torch.zeros(L, dtype=torch.float64).pin_memory()
     pi_dev = torch.zeros(L, dtype=torch.float64, device=dev)
     pis_dev = torch.from_numpy(pis).to(dev)
 
-    def exchange_up():
-        SH.proposals_up_record(dist, rec_t, gath)            # one NCCL all-gather per round
-
     def up_to_host():
-        # rank 0: the gathered proposals of all ranks, packed by the engine into its pinned record
+        # rank 0: every rank's proposals are in its up-link buffer; packed by the engine into its pinned record
         if rank == 0:
-            pk = eng.pack_gathered_records(world, gath.data_ptr(), sptr)
+            pk = eng.pack_gathered_struct(K_total, up_props, sptr)        # synchronises the stream
             d2h[0] += 8 + K_total * (8 + 8 + 4) + (K_total + 1) * 4 + pk["nnz"] * 12
             launches[0] += 2
             last_status[0] = np.array(pk["status"])
-        torch.cuda.synchronize()
 
     launches = [0]
     d2h = [0]
@@ -417,36 +422,34 @@ def main():
             last_status[0] = np.array(mb["status"])
             # (d2h bytes: the device counter mailbox_bytes, read outside the timed region)
         else:
-            eng.initial_solve_device(sptr)
+            eng.round_comm(0, False, True, sptr)                    # cold solve; proposals land in rank 0's HBM
             launches[0] += eng.last_launch_count()
-            exchange_up(); up_to_host()
+            up_to_host()
             for r in range(R):
                 if rank == 0:
                     pi_pin.copy_(torch.from_numpy(pis[r]))
                     pi_dev.copy_(pi_pin, non_blocking=True)
-                SH.duals_down(dist, pi_dev, src=0)                  # duals down (NCCL)
-                eng.iterate_device(pi_dev.data_ptr(), phases[r], sptr)
+                eng.round_comm(pi_dev.data_ptr(), phases[r], False, sptr)   # NCCL duals down, solve + NVLink up-link, close
                 launches[0] += eng.last_launch_count()
-                exchange_up(); up_to_host()                        # proposals up (NCCL) + D2H on rank 0
+                up_to_host()                                        # rank 0: pack + D2H of what the master would read
 
     # ---- one step, device only: duals already in HBM, results stay in HBM
     def step_dev(kern_acc=None, cnt_acc=None):
         eng.reset(sptr)
         if cnt_acc is not None:
             cnt_acc.append(count())
-        eng.initial_solve_device(sptr)
+        if dist is not None:
+            eng.round_comm(0, False, True, sptr)
+        else:
+            eng.initial_solve_device(sptr)
         if kern_acc is not None:
             kern_acc.append(eng.last_kernel_ms())
         if cnt_acc is not None:
             cnt_acc.append(count())
-        if dist is not None:
-            exchange_up()
         for r in range(R):
             if dist is not None:
                 pi_dev.copy_(pis_dev[r])
-                SH.duals_down(dist, pi_dev, src=0)
-                eng.iterate_device(pi_dev.data_ptr(), phases[r], sptr)
-                exchange_up()
+                eng.round_comm(pi_dev.data_ptr(), phases[r], False, sptr)
             else:
                 eng.iterate_device(pis_dev[r].data_ptr(), phases[r], sptr)
             if kern_acc is not None:
@@ -693,15 +696,15 @@ def main():
                    "passes": "single pass: value = pivots / summed CUDA-event time of the solve kernels of the e2e pass" if single
                    else "separate e2e and device-resident passes",
                    "parallelism": f"blocks sharded over {world} GPU(s)" +
-                   ("; pi broadcast + one all-gather of the result records over NCCL every round" if world > 1 else ""),
+                   ("; per round: ncclBroadcast of pi, kernels store proposals into rank 0's HBM over NVLink peer memory, one-int ncclAllReduce closes the round (dwgpu_round_comm)" if world > 1 else ""),
                    "dw_objective_of_trajectory": dw_objective},
         "e2e": {"value": (e2e_cnt[0] + e2e_cnt[1]) / e2e_time if e2e_time > 0 else 0.0, "unit": UNIT,
                 "h2d_bytes_per_step": 8 * L * R,
                 "d2h_bytes_per_step": int(e2e_cnt[6] / max(S, 1)) if world == 1 else d2h[0],
                 "api": "dwgpu_initial_solve_mailboxes + dwgpu_iterate_mailboxes (host pi in; the kernels store every block's "
                        "proposal into pinned host mailboxes, d2h = bytes stored, device counter)"
-                       if world == 1 else "per rank dwgpu_iterate_device; NCCL broadcast of pi, ONE all-gather of the result records, "
-                                          "dwgpu_pack_gathered_records into rank 0's pinned record",
+                       if world == 1 else "per rank dwgpu_round_comm (NCCL duals down, NVLink peer-memory up-link into rank 0's HBM); "
+                                          "rank 0: host pi in, dwgpu_pack_gathered into its pinned record every round",
                 "ms_per_step": 1e3 * e2e_time / S},
         "gpu_launches": launches[0] * S,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "dw_time_to_optimal": tto,

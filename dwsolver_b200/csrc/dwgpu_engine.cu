@@ -6,6 +6,8 @@
 // (/root/reference/src/dw_subprob.h:44-94); here it is the (T, beta, head, nbv, vstat)
 // arrays that stay resident in HBM between rounds.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -96,6 +98,8 @@ inline double norm_bound(double v, bool upper)
 
 }  // namespace
 
+extern "C" void dwgpu_comm_release(struct dwgpu_engine *e);
+
 struct dwgpu_engine {
     int K = 0, L = 0, device = 0;
     dwgpu_options opt{};
@@ -117,6 +121,18 @@ struct dwgpu_engine {
     int warp_bail_after = 0;           // test hook (DWGPU_WARP_BAIL_AFTER): hand over after this many basis changes
     bool reorder = true;
     bool have_proposals = false;       // a round has written every block's proposal since create / reset
+    // multi-GPU: the up-link lives in rank 0's HBM (one mailbox per block of the WHOLE instance); every rank's kernels
+    // store their blocks' proposals straight into it over NVLink peer memory (CUDA IPC mapping), NCCL carries the duals
+    // down and closes the round
+    char *uplink_base = nullptr;       // rank 0: owned allocation; other ranks: IPC mapping
+    bool uplink_owned = false;
+    int uplink_K = 0, uplink_first = 0;
+    dwk::MailDst uplink{};             // this rank's window (pointers already offset by its first block)
+    dwk::MailDst uplink_all{};         // the whole buffer (rank 0 reads it)
+    bool uplink_valid = false;         // the previous round wrote the window
+    ncclComm_t comm = nullptr;
+    int comm_world = 0, comm_rank = 0;
+    DevBuf<int> comm_flag;
     size_t smem_dyn = 0;
     int max_smem_optin = 0;
     // device arenas
@@ -171,6 +187,160 @@ extern "C" {
 const char *dwgpu_last_error(void) { return g_err.c_str(); }
 const char *dwgpu_version(void) { return "dwgpu 0.2 (sm_100a)"; }
 
+
+static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int initial, cudaStream_t st, bool mail, const dwk::MailDst *direct);
+
+// ---- multi-GPU: NCCL from the C layer (replaces the reference's cond-broadcast of the duals and its
+// semaphore/queue up-link, src/dw_phases.c:338-350, 526-548 and src/dw_subprob.c:417-427) --------------------------
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+// NCCL is bound at run time: a single-GPU user of libdwgpu.so needs no NCCL at all, and a process that already
+// carries one (PyTorch's) shares it — dlopen by soname returns the loaded copy
+int nccl_api()
+{
+    std::lock_guard<std::mutex> lock(g_nccl_mu);
+    if (g_nccl.lib) return 0;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(DWGPU_E_STATE, std::string("NCCL is not available: ") + dlerror());
+#define NSYM(field, name) g_nccl.field = (decltype(g_nccl.field))dlsym(h, name); if (!g_nccl.field) return fail(DWGPU_E_STATE, "NCCL symbol missing: " name);
+    NSYM(GetUniqueId, "ncclGetUniqueId") NSYM(CommInitRank, "ncclCommInitRank") NSYM(CommDestroy, "ncclCommDestroy")
+    NSYM(Broadcast, "ncclBroadcast") NSYM(AllReduce, "ncclAllReduce") NSYM(GetErrorString, "ncclGetErrorString")
+#undef NSYM
+    g_nccl.lib = h;
+    return 0;
+}
+#define NC(call)                                                                                  \
+    do {                                                                                          \
+        ncclResult_t r_ = (call);                                                                 \
+        if (r_ != ncclSuccess) return fail(DWGPU_E_CUDA, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
+    } while (0)
+}  // namespace
+
+void dwgpu_comm_release(dwgpu_engine *e)
+{
+    if (e && e->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(e->comm); e->comm = nullptr; }
+}
+
+int dwgpu_comm_unique_id(void *id128)
+{
+    if (!id128) return fail(DWGPU_E_ARGS, "id buffer is NULL");
+    if (int rc = nccl_api()) return rc;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    NC(g_nccl.GetUniqueId((ncclUniqueId *)id128));
+    return 0;
+}
+
+int dwgpu_comm_init(dwgpu_engine *e, const void *id128, int world, int rank)
+{
+    if (!e || !id128 || world < 1 || rank < 0 || rank >= world) return fail(DWGPU_E_ARGS, "bad arguments");
+    if (int rc = nccl_api()) return rc;
+    CU(cudaSetDevice(e->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    NC(g_nccl.CommInitRank(&e->comm, world, id, rank));
+    e->comm_world = world; e->comm_rank = rank;
+    CU(e->comm_flag.alloc(2));
+    CU(cudaMemset(e->comm_flag.p, 0, 2 * sizeof(int)));
+    return 0;
+}
+
+// Rank 0 allocates one mailbox per block of the whole instance in its HBM and publishes a CUDA IPC handle (64 bytes,
+// sent to the other ranks by whatever the host uses for its rendezvous).
+int dwgpu_uplink_create(dwgpu_engine *e, int K_total, void *ipc_handle64, dwgpu_proposals *dev_out)
+{
+    if (!e || K_total < e->K || !ipc_handle64) return fail(DWGPU_E_ARGS, "bad arguments");
+    CU(cudaSetDevice(e->device));
+    const size_t K = (size_t)K_total, KL = K * (size_t)e->L;
+    const size_t bytes = sizeof(double) * (2 * K + KL) + sizeof(int) * (2 * K + KL) + 64;
+    CU(cudaMalloc((void **)&e->uplink_base, bytes));
+    CU(cudaMemset(e->uplink_base, 0, bytes));
+    e->uplink_owned = true;
+    e->uplink_K = K_total;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, e->uplink_base));
+    std::memcpy(ipc_handle64, &h, sizeof(h));
+    double *dd = (double *)e->uplink_base;
+    int *ii = (int *)(dd + 2 * K + KL);
+    e->uplink_all = dwk::MailDst{dd, dd + K, dd + 2 * K, ii, ii + K, ii + 2 * K};
+    if (dev_out) {
+        dev_out->obj = e->uplink_all.obj; dev_out->cost = e->uplink_all.cost; dev_out->val = e->uplink_all.val;
+        dev_out->status = e->uplink_all.status; dev_out->len = e->uplink_all.len; dev_out->ind = e->uplink_all.ind; dev_out->x = nullptr;
+    }
+    return 0;
+}
+
+// Every rank (rank 0 too, with ipc_handle64 = NULL): this engine's blocks are blocks k_first .. k_first + K - 1 of the
+// instance; from now on dwgpu_round_comm() makes the kernels store their proposals into that window of rank 0's buffer.
+int dwgpu_uplink_attach(dwgpu_engine *e, const void *ipc_handle64, int K_total, int k_first)
+{
+    if (!e || K_total < 1 || k_first < 0 || k_first + e->K > K_total) return fail(DWGPU_E_ARGS, "bad arguments");
+    CU(cudaSetDevice(e->device));
+    if (ipc_handle64) {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, ipc_handle64, sizeof(h));
+        void *p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        e->uplink_base = (char *)p;
+        e->uplink_owned = false;
+        e->uplink_K = K_total;
+    } else if (!e->uplink_base || e->uplink_K != K_total) return fail(DWGPU_E_STATE, "rank 0 attaches after dwgpu_uplink_create");
+    const size_t K = (size_t)K_total, KL = K * (size_t)e->L;
+    double *dd = (double *)e->uplink_base;
+    int *ii = (int *)(dd + 2 * K + KL);
+    e->uplink_all = dwk::MailDst{dd, dd + K, dd + 2 * K, ii, ii + K, ii + 2 * K};
+    const size_t f = (size_t)k_first;
+    e->uplink = dwk::MailDst{dd + f, dd + K + f, dd + 2 * K + f * e->L, ii + f, ii + K + f, ii + 2 * K + f * e->L};
+    e->uplink_first = k_first;
+    e->uplink_valid = false;
+    return 0;
+}
+
+// One DW round of a sharded instance, everything enqueued on ONE stream with no host step in between:
+//   duals down   ncclBroadcast of pi (L doubles, root = rank 0)                       [skipped for the initial solve]
+//   solve        this rank's blocks; the kernels' epilogues store each block's proposal into rank 0's up-link buffer
+//                over NVLink (a block that did not move rewrites 12 bytes)
+//   close        a one-int ncclAllReduce: when it completes on rank 0, every rank's stores have landed
+int dwgpu_round_comm(dwgpu_engine *e, double *pi_dev, int phase_one, int initial, void *stream)
+{
+    if (!e || !e->initialised) return fail(DWGPU_E_STATE, "engine not initialised");
+    if (!e->comm || !e->uplink_base) return fail(DWGPU_E_STATE, "dwgpu_comm_init / dwgpu_uplink_attach first");
+    if (!initial && e->L > 0 && !pi_dev) return fail(DWGPU_E_ARGS, "pi_dev is NULL");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    if (!initial && e->L > 0) NC(g_nccl.Broadcast(pi_dev, pi_dev, (size_t)e->L, ncclDouble, 0, e->comm, st));
+    const bool direct = e->uplink_valid;
+    int rc = launch_round(e, pi_dev, phase_one ? 1 : 0, initial ? 1 : 0, st, false, &e->uplink);
+    if (rc) return rc;
+    dwk::PackSrc s;
+    std::memset(&s, 0, sizeof(s));
+    s.obj = e->obj.p; s.cost = e->cost.p; s.val = e->val.p; s.status = e->status.p; s.len = e->len.p; s.ind = e->ind.p;
+    s.K = e->K; s.L = e->L;
+    auto copy = [&](const int *list, size_t count) -> cudaError_t {
+        if (!count) return cudaSuccess;
+        dwk::mailbox_copy_kernel<256><<<(unsigned)((count + 7) / 8), 256, 0, st>>>(s, list, (int)count, e->uplink, e->counters.p);
+        e->last_launches++;
+        return cudaGetLastError();
+    };
+    // kernels that do not write mailboxes themselves (legacy, cluster) and the first round after a reset: copied
+    if (!direct) CU(copy(nullptr, (size_t)e->K));
+    else { CU(copy(e->d_list_gmem.p, e->list_gmem.size())); CU(copy(e->d_list_c.p, e->list_c.size())); }
+    e->uplink_valid = true;
+    NC(g_nccl.AllReduce(e->comm_flag.p, e->comm_flag.p + 1, 1, ncclInt, ncclSum, e->comm, st));
+    return 0;
+}
+
 int dwgpu_device_count(void)
 {
     int n = 0;
@@ -213,6 +383,9 @@ void dwgpu_destroy(dwgpu_engine *e)
     e->a_ci.release(); e->dc_ptr.release(); e->dc_row.release(); e->dr_ptr.release();
     e->dr_col.release(); e->blocks.release(); e->d_list_smem.release();
     e->d_list_gmem.release(); e->d_list_a.release(); e->d_list_g.release(); e->d_list_b.release(); e->d_list_c.release(); e->pi.release(); e->rec.release(); e->colptr.release();
+    if (e->uplink_base) { if (e->uplink_owned) cudaFree(e->uplink_base); else cudaIpcCloseMemHandle(e->uplink_base); }
+    e->comm_flag.release();
+    if (e->comm) dwgpu_comm_release(e);
     if (e->h_pack) cudaFreeHost(e->h_pack);
     if (e->h_mail) cudaFreeHost(e->h_mail);
     if (e->h_r) cudaFreeHost(e->h_r);
@@ -522,10 +695,15 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
 #undef CUE
 }
 
-static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int initial, cudaStream_t st, bool mail = false)
+static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int initial, cudaStream_t st, bool mail = false,
+                        const dwk::MailDst *direct = nullptr)
 {
     dwk::SolveParams P;
-    if (mail && e->mail_valid) {
+    if (direct) {         // the kernels' epilogues store into this window (multi-GPU up-link in rank 0's HBM)
+        P.m_obj = direct->obj; P.m_cost = direct->cost; P.m_val = direct->val;
+        P.m_status = direct->status; P.m_len = direct->len; P.m_ind = direct->ind;
+        e->mail_valid = false;
+    } else if (mail && e->mail_valid) {
         P.m_obj = e->mail_dev.obj; P.m_cost = e->mail_dev.cost; P.m_val = e->mail_dev.val;
         P.m_status = e->mail_dev.status; P.m_len = e->mail_dev.len; P.m_ind = e->mail_dev.ind;
     } else {
@@ -547,8 +725,14 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
     // longest-processing-time-first inside each list (DWGPU_NO_REORDER=1 keeps the natural order)
     if (!initial && e->reorder) {
         auto order = [&](DevBuf<int> &d, size_t n) -> cudaError_t {
-            if (n < 2048 || n > 8192) return cudaSuccess;          // pays off from ~3 waves of CTAs on
-            if (n <= 4096)
+            // pays off whenever a launch is more than one wave of CTAs deep (592 resident 128-thread CTAs): multi-GPU
+            // shards of 1024 blocks are 1.7 waves, where the long poles of an unordered launch end up in the tail
+            if (n < 600 || n > 8192) return cudaSuccess;
+            if (n <= 1024)
+                dwk::order_by_last_iterations_kernel<1024, 1024><<<1, 1024, 1024 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p);
+            else if (n <= 2048)
+                dwk::order_by_last_iterations_kernel<1024, 2048><<<1, 1024, 2048 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p);
+            else if (n <= 4096)
                 dwk::order_by_last_iterations_kernel<1024, 4096><<<1, 1024, 4096 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p);
             else
                 dwk::order_by_last_iterations_kernel<1024, 8192><<<1, 1024, 8192 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p);
@@ -873,6 +1057,7 @@ int dwgpu_reset(dwgpu_engine *e, void *stream)
     CU(cudaGetLastError());
     e->have_proposals = false;
     e->mail_valid = false;
+    e->uplink_valid = false;
     return 0;
 }
 

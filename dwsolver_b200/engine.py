@@ -34,6 +34,9 @@ ABI_SYMBOLS = [
     "dwgpu_master_create", "dwgpu_master_destroy", "dwgpu_master_set_rhs", "dwgpu_master_add_cols",
     "dwgpu_master_set_costs", "dwgpu_master_set_coef", "dwgpu_master_del_cols", "dwgpu_master_cols",
     "dwgpu_master_solve", "dwgpu_master_get", "dwgpu_master_quality", "dwgpu_master_last_error",
+    # multi-GPU rounds from the C layer: NCCL + the NVLink peer-memory up-link
+    "dwgpu_comm_unique_id", "dwgpu_comm_init", "dwgpu_comm_release", "dwgpu_uplink_create", "dwgpu_uplink_attach",
+    "dwgpu_round_comm",
 ]
 
 
@@ -106,6 +109,13 @@ def load_library():
         L.dwgpu_pack_gathered.argtypes = [C.c_void_p, C.c_int, C.POINTER(Proposals), C.c_void_p, C.c_void_p,
                                           C.POINTER(Packed)]
         L.dwgpu_device_record.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.dwgpu_comm_unique_id.argtypes = [C.c_void_p]
+        L.dwgpu_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        L.dwgpu_comm_release.argtypes = [C.c_void_p]
+        L.dwgpu_comm_release.restype = None
+        L.dwgpu_uplink_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Proposals)]
+        L.dwgpu_uplink_attach.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        L.dwgpu_round_comm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.dwgpu_pack_gathered_records.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Packed)]
         L.dwgpu_history_push.argtypes = [C.c_void_p, C.c_int, c_ip, C.POINTER(C.c_longlong)]
         L.dwgpu_history_combine.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), c_dp, c_dp]
@@ -303,6 +313,42 @@ class Engine:
         _check(self._lib.dwgpu_history_combine(self._h, len(ids), ids.ctypes.data_as(C.POINTER(C.c_longlong)),
                                                w.ctypes.data_as(c_dp), x.ctypes.data_as(c_dp)), "dwgpu_history_combine")
         return x
+
+    # ---- multi-GPU rounds from the C layer (include/dwgpu.h: dwgpu_comm_*, dwgpu_uplink_*, dwgpu_round_comm) ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        _check(lib.dwgpu_comm_unique_id(buf), "dwgpu_comm_unique_id")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, world: int, rank: int):
+        _check(self._lib.dwgpu_comm_init(self._h, C.c_char_p(unique_id), world, rank), "dwgpu_comm_init")
+
+    def uplink_create(self, K_total: int):
+        """rank 0: returns (64-byte CUDA IPC handle, Proposals struct of device arrays over all K_total blocks)"""
+        h = C.create_string_buffer(64)
+        p = Proposals()
+        _check(self._lib.dwgpu_uplink_create(self._h, K_total, h, C.byref(p)), "dwgpu_uplink_create")
+        return h.raw, p
+
+    def uplink_attach(self, handle: Optional[bytes], K_total: int, k_first: int):
+        _check(self._lib.dwgpu_uplink_attach(self._h, C.c_char_p(handle) if handle is not None else None, K_total, k_first),
+               "dwgpu_uplink_attach")
+
+    def round_comm(self, d_pi_ptr: int, phase_one: bool, initial: bool, stream: int = 0):
+        _check(self._lib.dwgpu_round_comm(self._h, C.c_void_p(d_pi_ptr) if d_pi_ptr else None, 1 if phase_one else 0,
+                                          1 if initial else 0, C.c_void_p(stream) if stream else None), "dwgpu_round_comm")
+
+    def pack_gathered_struct(self, K_total: int, props: "Proposals", stream: int = 0, r_dev_ptr: int = 0) -> dict:
+        """dwgpu_pack_gathered on a Proposals struct of device arrays (what uplink_create returned)"""
+        pk = Packed()
+        _check(self._lib.dwgpu_pack_gathered(self._h, K_total, C.byref(props), C.c_void_p(r_dev_ptr) if r_dev_ptr else None,
+                                             C.c_void_p(stream) if stream else None, C.byref(pk)), "dwgpu_pack_gathered")
+        n = int(pk.nnz)
+        return dict(nnz=n, status=np.ctypeslib.as_array(pk.status, shape=(K_total,)),
+                    obj=np.ctypeslib.as_array(pk.obj, shape=(K_total,)),
+                    colptr=np.ctypeslib.as_array(pk.colptr, shape=(K_total + 1,)))
 
     def iterate_device(self, d_pi_ptr: int, phase_one: bool, stream: int = 0):
         _check(self._lib.dwgpu_iterate_device(self._h, C.c_void_p(d_pi_ptr), int(bool(phase_one)),

@@ -229,6 +229,26 @@ int  dwgpu_device_count(void);
 const char *dwgpu_last_error(void);
 const char *dwgpu_version(void);
 
+/* ---- multi-GPU rounds from the C layer --------------------------------------------------------------
+ * One process (or host thread) per GPU, each with an engine over its contiguous block range.  Replaces the reference's
+ * cond-broadcast of the duals and its semaphore / queue up-link (src/dw_phases.c:338-350, 526-548;
+ * src/dw_subprob.c:417-427):
+ *   dwgpu_comm_unique_id / dwgpu_comm_init   an NCCL communicator per engine (NCCL is bound at run time by soname);
+ *   dwgpu_uplink_create (rank 0)             one mailbox per block of the WHOLE instance in rank 0's HBM + a 64-byte
+ *                                            CUDA IPC handle for the other ranks; dev_out = the arrays (obj, cost,
+ *                                            status, len: K_total; ind, val: K_total x L, block-major) for
+ *                                            dwgpu_pack_gathered();
+ *   dwgpu_uplink_attach (every rank)         maps the buffer (NULL handle on rank 0) and selects this rank's window;
+ *   dwgpu_round_comm                         ncclBroadcast of pi from rank 0 -> solve kernels whose epilogues store the
+ *                                            proposals into rank 0's buffer over NVLink peer memory (only what moved)
+ *                                            -> a one-int ncclAllReduce that closes the round; all on one stream. */
+int  dwgpu_comm_unique_id(void *id128);
+int  dwgpu_comm_init(dwgpu_engine *e, const void *id128, int world, int rank);
+void dwgpu_comm_release(dwgpu_engine *e);
+int  dwgpu_uplink_create(dwgpu_engine *e, int K_total, void *ipc_handle64, dwgpu_proposals *dev_out);
+int  dwgpu_uplink_attach(dwgpu_engine *e, const void *ipc_handle64, int K_total, int k_first);
+int  dwgpu_round_comm(dwgpu_engine *e, double *pi_dev, int phase_one, int initial, void *stream);
+
 /* ---- the restricted master on the device -------------------------------------------------------
  * Replaces the reference's glp_simplex(master_lp) calls (src/dw_phases.c:219, 450; src/dw_solver.c:561-562) for
  * large instances: a primal-dual interior-point solve (Mehrotra predictor-corrector) of

@@ -530,6 +530,34 @@ def test_first_round_after_create_or_reset_without_initial_solve(force_path):
     eng.close()
 
 
+def test_results_do_not_depend_on_how_the_blocks_are_sharded():
+    """a 1-, 2-, 4- or 8-GPU run must give every block bit-identical results (the reference is
+    nondeterministic here: its master consumes proposals in completion order, src/dw_phases.c:344-348).  A block's
+    solve depends on nothing but its own state and the duals, so an engine over ALL blocks and engines over 2, 4 and 8
+    contiguous shards (what each rank of a multi-GPU run owns; here on one device) must agree bit for bit — objective,
+    column, cost and x — through a cold solve and priced rounds, whatever the launch order inside a shard."""
+    prob = P.gen_mcf(64, 256, 512, 256, 8192001)
+    rng = np.random.default_rng(77)
+    pis = [-rng.random(prob.L) * 12.0 * (t + 1) for t in range(3)]
+
+    def run(shards):
+        out = []
+        bounds = [prob.K * g // shards for g in range(shards + 1)]
+        engs = [engine(prob, block_range=range(bounds[g], bounds[g + 1])) for g in range(shards)]
+        rounds = [[p for e in engs for p in e.initial()]]
+        for t, pi in enumerate(pis):
+            rounds.append([p for e in engs for p in e.iterate(pi, t == 0)])
+        for e in engs:
+            e.close()
+        for props in rounds:
+            out.append([(p["status"], p["obj"], p["cost"], p["ind"].tobytes(), p["val"].tobytes(), p["x"].tobytes()) for p in props])
+        return out
+
+    whole = run(1)
+    for shards in (2, 4, 8):
+        assert run(shards) == whole, shards
+
+
 def test_two_live_engines_of_different_shapes():
     """A kernel's dynamic shared-memory limit belongs to the device, not to an engine: an engine created later for
     smaller blocks must not take it away from one that is still launching (several engines live in one process when
