@@ -10,6 +10,8 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +19,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -81,11 +84,36 @@ struct DevBuf {
         if (e != cudaSuccess || h.empty()) return e;
         return cudaMemcpy(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice);
     }
+    template <typename H>
+    cudaError_t upload_buf(const H &h)
+    {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpy(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice);
+    }
     void release()
     {
         if (p) cudaFree(p);
         p = nullptr;
     }
+};
+
+// plain uninitialised host array (malloc), vector-like enough for the staging code and DevBuf::upload
+template <typename T>
+struct HostBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    explicit HostBuf(size_t count) : n(count) { p = (T *)std::malloc(sizeof(T) * std::max<size_t>(count, 1)); }
+    ~HostBuf() { std::free(p); }
+    HostBuf(const HostBuf &) = delete;
+    HostBuf &operator=(const HostBuf &) = delete;
+    bool ok() const { return p != nullptr; }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
 };
 
 inline double norm_bound(double v, bool upper)
@@ -428,6 +456,10 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         }                                                                                     \
     } while (0)
 
+    const bool timing = std::getenv("DWGPU_DEBUG_TIMING") != nullptr;
+    auto stamp = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double ts[8]; int nts = 0;
+    ts[nts++] = stamp();
     CUE(cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, opt.device));
     CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     for (auto &ev : e->ev) CUE(cudaEventCreate(&ev));
@@ -502,12 +534,18 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     }
     e->ntot = e->xoff[K];
 
+    ts[nts++] = stamp();
     // ---- host staging of the static data
-    std::vector<double> h_bnd(2 * v_off[K]), h_av(a_off[K]), h_dcv(d_off[K]), h_drv(d_off[K]),
-        h_cf(e->ntot), h_cm(e->ntot);
-    std::vector<int> h_arp(arp_off[K]), h_aci(a_off[K]), h_dcp(dcp_off[K]), h_dcr(d_off[K]), h_drp(drp_off[K]),
-        h_drc(d_off[K]);
-    for (int k = 0; k < K; ++k) {
+    // (uninitialised buffers: a zero-filling std::vector would touch every page from this one thread first — 100 MB at
+    //  config B — before the staging team gets to write it)
+    HostBuf<double> h_bnd(2 * v_off[K]), h_av(a_off[K]), h_dcv(d_off[K]), h_drv(d_off[K]), h_cf(e->ntot), h_cm(e->ntot);
+    HostBuf<int> h_arp(arp_off[K]), h_aci(a_off[K]), h_dcp(dcp_off[K]), h_dcr(d_off[K]), h_drp(drp_off[K]), h_drc(d_off[K]);
+    if (!h_bnd.ok() || !h_av.ok() || !h_dcv.ok() || !h_drv.ok() || !h_cf.ok() || !h_cm.ok() || !h_arp.ok() || !h_aci.ok() ||
+        !h_dcp.ok() || !h_dcr.ok() || !h_drp.ok() || !h_drc.ok()) { fail(DWGPU_E_NOMEM, "host staging buffers"); return bail(DWGPU_E_NOMEM); }
+    // (one block's slices are written by one thread: the K blocks are staged by a small team of host threads — at config B
+    //  this loop was 0.16 s of a 0.22 s engine creation, itself 40 % of a 0.56 s DW solve)
+    std::atomic<int> stage_err{0};
+    auto stage_block = [&](int k) {
         const dwgpu_block_desc &b = bd[k];
         const int m = b.m, n = b.n;
         double *lo = h_bnd.data() + 2 * v_off[k], *up = lo + (m + n);
@@ -523,7 +561,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         const int nnz = m > 0 ? b.a_rowptr[m] : 0;
         for (int i = 0; i <= m; ++i) h_arp[arp_off[k] + i] = m > 0 ? b.a_rowptr[i] : 0;
         for (int p = 0; p < nnz; ++p) {
-            if (b.a_col[p] < 0 || b.a_col[p] >= n) { fail(DWGPU_E_ARGS, "A column index out of range"); return bail(DWGPU_E_ARGS); }
+            if (b.a_col[p] < 0 || b.a_col[p] >= n) { stage_err = 1; return; }
             h_aci[a_off[k] + p] = b.a_col[p];
             h_av[a_off[k] + p] = b.a_val[p];
         }
@@ -531,8 +569,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         int *cp = h_dcp.data() + dcp_off[k], *rp = h_drp.data() + drp_off[k];
         std::fill(cp, cp + n + 1, 0); std::fill(rp, rp + L + 1, 0);
         for (int t = 0; t < b.d_nnz; ++t) {
-            if (b.d_row[t] < 0 || b.d_row[t] >= L || b.d_col[t] < 0 || b.d_col[t] >= n)
-                { fail(DWGPU_E_ARGS, "D index out of range"); return bail(DWGPU_E_ARGS); }
+            if (b.d_row[t] < 0 || b.d_row[t] >= L || b.d_col[t] < 0 || b.d_col[t] >= n) { stage_err = 2; return; }
             cp[b.d_col[t] + 1]++; rp[b.d_row[t] + 1]++;
         }
         for (int j = 0; j < n; ++j) cp[j + 1] += cp[j];
@@ -543,8 +580,19 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
             h_dcr[d_off[k] + a] = b.d_row[t]; h_dcv[d_off[k] + a] = b.d_val[t];
             h_drc[d_off[k] + r] = b.d_col[t]; h_drv[d_off[k] + r] = b.d_val[t];
         }
+    };
+    {
+        const int nthreads = (int)std::max(1u, std::min(16u, std::min(std::thread::hardware_concurrency(), (unsigned)((K + 255) / 256))));
+        std::atomic<int> next{0};
+        auto worker = [&]() { for (int k; (k = next.fetch_add(1)) < K && !stage_err;) stage_block(k); };
+        std::vector<std::thread> team;
+        try { for (int t = 1; t < nthreads; ++t) team.emplace_back(worker); } catch (...) {}
+        worker();
+        for (auto &th : team) th.join();
     }
+    if (stage_err) { fail(DWGPU_E_ARGS, stage_err == 1 ? "A column index out of range" : "D index out of range"); return bail(DWGPU_E_ARGS); }
 
+    ts[nts++] = stamp();
     // ---- device arenas
     CUE(e->T.alloc(t_off[K]));
     // Test hook: fill the tableau arena with NaN bit patterns before the first initialisation.  Path 3 never zeroes its
@@ -552,11 +600,11 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     if (std::getenv("DWGPU_POISON_TABLEAU")) CUE(cudaMemset(e->T.p, 0xFF, sizeof(double) * (size_t)t_off[K]));
     CUE(e->pst.alloc(pst_off[K]));
     CUE(cudaMemset(e->pst.p, 0, std::max<long long>(pst_off[K], 1)));
-    CUE(e->bnd.upload(h_bnd));
-    CUE(e->a_rp.upload(h_arp)); CUE(e->a_ci.upload(h_aci)); CUE(e->a_v.upload(h_av));
-    CUE(e->dc_ptr.upload(h_dcp)); CUE(e->dc_row.upload(h_dcr)); CUE(e->dc_val.upload(h_dcv));
-    CUE(e->dr_ptr.upload(h_drp)); CUE(e->dr_col.upload(h_drc)); CUE(e->dr_val.upload(h_drv));
-    CUE(e->c_file.upload(h_cf)); CUE(e->c_master.upload(h_cm));
+    CUE(e->bnd.upload_buf(h_bnd));
+    CUE(e->a_rp.upload_buf(h_arp)); CUE(e->a_ci.upload_buf(h_aci)); CUE(e->a_v.upload_buf(h_av));
+    CUE(e->dc_ptr.upload_buf(h_dcp)); CUE(e->dc_row.upload_buf(h_dcr)); CUE(e->dc_val.upload_buf(h_dcv));
+    CUE(e->dr_ptr.upload_buf(h_drp)); CUE(e->dr_col.upload_buf(h_drc)); CUE(e->dr_val.upload_buf(h_drv));
+    CUE(e->c_file.upload_buf(h_cf)); CUE(e->c_master.upload_buf(h_cm));
     CUE(e->x.alloc(e->ntot));
     CUE(e->dsave.alloc(e->ntot)); CUE(e->cssave.alloc(e->ntot)); CUE(e->dflag.alloc(K));
     CUE(cudaMemset(e->dflag.p, 0, sizeof(int) * (size_t)K));
@@ -564,6 +612,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(e->rmask.alloc((size_t)rm_off[K]));
     CUE(cudaMemset(e->rmask.p, 0, sizeof(unsigned) * std::max<size_t>((size_t)rm_off[K], 1)));
     CUE(e->pi.alloc(L));
+    ts[nts++] = stamp();
     {
         const size_t KL = (size_t)K * L;
         const size_t nd = 2 * (size_t)K + KL, ni = 2 * (size_t)K + KL;
@@ -603,6 +652,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(cudaMemset(e->x.p, 0, sizeof(double) * std::max<long long>(e->ntot, 1)));
     CUE(cudaMallocHost((void **)&e->h_pi, sizeof(double) * std::max(L, 1)));
 
+    ts[nts++] = stamp();
     std::vector<dwk::BlockDev> hb(K);
     for (int k = 0; k < K; ++k) {
         dwk::BlockDev &B = hb[k];
@@ -686,9 +736,14 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true>, (int)dwk::smem2_bytes(256, 512, true)));
     }
 
+    ts[nts++] = stamp();
     dwk::init_kernel<256><<<K, 256, 0, e->stream>>>(e->blocks.p, K);
     CUE(cudaGetLastError());
     CUE(cudaStreamSynchronize(e->stream));
+    ts[nts++] = stamp();
+    if (timing)
+        std::fprintf(stderr, "dwgpu_create: sizes %.4f s, host staging %.4f s, arenas + uploads %.4f s, pinned records %.4f s, descriptors + attributes %.4f s, init kernel %.4f s\n",
+                     ts[1] - ts[0], ts[2] - ts[1], ts[3] - ts[2], ts[4] - ts[3], ts[5] - ts[4], ts[6] - ts[5]);
     e->initialised = true;
     *out = e;
     return 0;

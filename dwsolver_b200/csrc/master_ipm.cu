@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(1024) k_cholesky(int L, double *S, double reg_
     extern __shared__ double pan[];          // (L - p0) x CH_P, row-major with pitch CH_LD
     __shared__ double red[32];
     __shared__ double s_reg;
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     {
         double tr = 0.0;
         for (int i = tid; i < L; i += nt) tr += S[(size_t)i * L + i];
@@ -203,52 +203,94 @@ __global__ void __launch_bounds__(1024) k_cholesky(int L, double *S, double reg_
         const int pw = min(CH_P, L - p0), rows = L - p0;
         for (int e = tid; e < rows * pw; e += nt) { const int r = e / pw, c = e - r * pw; pan[r * CH_LD + c] = S[(size_t)(p0 + r) * L + p0 + c]; }
         __syncthreads();
-        for (int k = 0; k < pw; ++k) {
-            const double dkk = pan[k * CH_LD + k];
-            const double piv = dkk > 0.0 ? sqrt(dkk) : 1e150;       // a non-positive pivot: the direction is dropped
-            __syncthreads();
-            for (int r = k + tid; r < rows; r += nt) pan[r * CH_LD + k] = (r == k) ? piv : pan[r * CH_LD + k] / piv;
-            __syncthreads();
-            // update the panel columns right of k
-            for (int e = tid; e < (rows - k - 1) * (pw - k - 1); e += nt) {
-                const int r = k + 1 + e / (pw - k - 1), c = k + 1 + e % (pw - k - 1);
-                if (r >= c) pan[r * CH_LD + c] -= pan[r * CH_LD + k] * pan[c * CH_LD + k];
+        // (a) the pw x pw diagonal block: one warp, lane = row, warp-synchronous
+        //     (measured: register-resident variants of (a) and (b) need > 64 registers, i.e. 256-thread CTAs, and lose more
+        //      in the trailing update than they gain here: 0.58 ms against 0.36 ms per factorisation)
+        if (tid < 32) {
+            for (int k = 0; k < pw; ++k) {
+                const double dkk = pan[k * CH_LD + k];
+                const double piv = dkk > 0.0 ? sqrt(dkk) : 1e150;       // a non-positive pivot: the direction is dropped
+                __syncwarp();
+                double lrk = 0.0;
+                if (lane >= k && lane < pw) { lrk = (lane == k) ? piv : pan[lane * CH_LD + k] / piv; pan[lane * CH_LD + k] = lrk; }
+                __syncwarp();
+                if (lane > k && lane < pw)
+                    for (int c = k + 1; c <= lane; ++c) pan[lane * CH_LD + c] -= lrk * pan[c * CH_LD + k];
+                __syncwarp();
             }
-            __syncthreads();
         }
+        __syncthreads();
+        // (b) the rows below it: L21 = A21 L11^-T, one thread per row (forward substitution along the row)
+        for (int r = pw + tid; r < rows; r += nt) {
+            double *row = pan + r * CH_LD;
+            for (int c = 0; c < pw; ++c) {
+                double v = row[c];
+                const double *lc = pan + c * CH_LD;
+                for (int k = 0; k < c; ++k) v -= row[k] * lc[k];
+                row[c] = v / lc[c];
+            }
+        }
+        __syncthreads();
         for (int e = tid; e < rows * pw; e += nt) { const int r = e / pw, c = e - r * pw; if (r >= c) S[(size_t)(p0 + r) * L + p0 + c] = pan[r * CH_LD + c]; }
-        // trailing update: S[i][j] -= sum_k pan[i][k] pan[j][k], i >= j >= p0 + pw
+        // (c) trailing update: S[i][j] -= sum_k pan[i][k] pan[j][k], i >= j >= p0 + pw.  4 x 4 register tiles (8 shared loads
+        // per 16 FMAs: the plain dot-product form is bound by shared-memory bandwidth); a tile's rows are TT apart so that
+        // neighbouring threads read neighbouring panel rows (pitch 33: conflict-free)
         const int t0 = pw, tn = rows - pw;
-        for (int e = tid; e < tn * tn; e += nt) {
-            const int ri = e / tn, rj = e - ri * tn;
-            if (ri < rj) continue;
-            const double *pi_ = pan + (t0 + ri) * CH_LD, *pj_ = pan + (t0 + rj) * CH_LD;
-            double s = 0.0;
-#pragma unroll 8
-            for (int k = 0; k < pw; ++k) s += pi_[k] * pj_[k];
-            S[(size_t)(p0 + t0 + ri) * L + p0 + t0 + rj] -= s;
+        const int TT = (tn + 3) / 4;
+        for (int e = tid; e < TT * TT; e += nt) {
+            const int ti = e / TT, tj = e - ti * TT;
+            double acc[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+            const double *pa[4], *pb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                pa[u] = pan + (t0 + min(ti + u * TT, tn - 1)) * CH_LD;
+                pb[u] = pan + (t0 + min(tj + u * TT, tn - 1)) * CH_LD;
+            }
+            for (int k = 0; k < pw; ++k) {
+                double a[4], b[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { a[u] = pa[u][k]; b[u] = pb[u][k]; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) acc[u][v] += a[u] * b[v];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int ri = ti + u * TT, rj = tj + v * TT;
+                    if (ri < tn && rj < tn && ri >= rj) S[(size_t)(p0 + t0 + ri) * L + p0 + t0 + rj] -= acc[u][v];
+                }
         }
         __syncthreads();
     }
 }
 
-// x = (L L')^-1 b for the factor stored in the lower triangle of S; one CTA; b and x in global, work in shared
+// x = (L L')^-1 b for the factor stored in the lower triangle of S; one CTA; b and x in global, work in shared.
+// Each 32 x 32 diagonal block is staged in shared memory before its 32 dependent steps (one warp); the off-diagonal
+// part of a panel is applied by all threads.
 __global__ void __launch_bounds__(1024) k_chol_solve(int L, const double *S, const double *b, double *x)
 {
-    extern __shared__ double y[];
+    extern __shared__ double y[];            // L
+    __shared__ double dg[CH_P][CH_LD];
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < L; i += nt) y[i] = b[i];
-    __syncthreads();
     // forward: L y = b, panel by panel
     for (int p0 = 0; p0 < L; p0 += CH_P) {
         const int pw = min(CH_P, L - p0);
+        for (int e = tid; e < pw * pw; e += nt) { const int r = e / pw, c = e - r * pw; dg[r][c] = S[(size_t)(p0 + r) * L + p0 + c]; }
+        __syncthreads();
         if (tid < 32) {
             for (int k = 0; k < pw; ++k) {
-                const double yk = y[p0 + k] / S[(size_t)(p0 + k) * L + p0 + k];
+                const double yk = y[p0 + k] / dg[k][k];
                 __syncwarp();
-                if (tid == 0) y[p0 + k] = yk;
-                const int r = p0 + k + 1 + tid;
-                if (r < p0 + pw) y[r] -= S[(size_t)r * L + p0 + k] * yk;
+                if (tid == k) y[p0 + k] = yk;
+                if (tid > k && tid < pw) y[p0 + tid] -= dg[tid][k] * yk;
                 __syncwarp();
             }
         }
@@ -264,13 +306,14 @@ __global__ void __launch_bounds__(1024) k_chol_solve(int L, const double *S, con
     // backward: L' x = y
     for (int p1 = ((L - 1) / CH_P) * CH_P; p1 >= 0; p1 -= CH_P) {
         const int pw = min(CH_P, L - p1);
+        for (int e = tid; e < pw * pw; e += nt) { const int r = e / pw, c = e - r * pw; dg[r][c] = S[(size_t)(p1 + r) * L + p1 + c]; }
+        __syncthreads();
         if (tid < 32) {
             for (int k = pw - 1; k >= 0; --k) {
-                const double xk = y[p1 + k] / S[(size_t)(p1 + k) * L + p1 + k];
+                const double xk = y[p1 + k] / dg[k][k];
                 __syncwarp();
-                if (tid == 0) y[p1 + k] = xk;
-                const int r = p1 + tid;
-                if (tid < k) y[r] -= S[(size_t)(p1 + k) * L + r] * xk;
+                if (tid == k) y[p1 + k] = xk;
+                if (tid < k) y[p1 + tid] -= dg[k][tid] * xk;
                 __syncwarp();
             }
         }
@@ -735,12 +778,29 @@ int dwgpu_master_solve(dwgpu_master *m, double tol, int max_iter, int *status_ou
     const size_t pan_bytes = sizeof(double) * (size_t)L * CH_LD, y_bytes = sizeof(double) * (size_t)L;
     double *scal = m->scal.p, *part = m->part.p;
 
+    // per-phase device times (DWGPU_MASTER_DEBUG=2): events around the pieces of one factorisation / solve
+    const bool ptime = std::getenv("DWGPU_MASTER_DEBUG") && std::atoi(std::getenv("DWGPU_MASTER_DEBUG")) >= 2;
+    cudaEvent_t pe[8];
+    float pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (ptime) for (auto &e_ : pe) cudaEventCreate(&e_);
+    auto mark = [&](int i) { if (ptime) cudaEventRecord(pe[i], st); };
+    auto collect = [&](int n_marks) {
+        if (!ptime) return;
+        cudaEventSynchronize(pe[n_marks - 1]);
+        for (int i = 0; i + 1 < n_marks; ++i) { float ms_ = 0.f; cudaEventElapsedTime(&ms_, pe[i], pe[i + 1]); pacc[i] += ms_; }
+    };
     auto factor = [&]() -> cudaError_t {     // d -> delta, abar, Bt, S = Bt'Bt, Cholesky
+        mark(0);
         k_block_prep<<<K, 128, sizeof(double) * L, st>>>(L, blkptr, blkcols, colptr, rowidx, val, m->d.p, m->delta.p, m->abar.p);
         k_build_bt<<<n, 64, 0, st>>>(L, colptr, rowidx, val, blk, m->d.p, m->abar.p, m->Bt.p);
+        mark(1);
         k_syrk_dmma<<<dim3(npairs, nchunks), 256, 0, st>>>(L, n, chunk, m->Bt.p, m->Spart.p);
+        mark(2);
         k_syrk_reduce<<<dim3(npairs, 16), 256, 0, st>>>(L, npairs, nchunks, m->Spart.p, m->S.p);
+        mark(3);
         k_cholesky<<<1, 1024, pan_bytes, st>>>(L, m->S.p, 1e-14);
+        mark(4);
+        collect(5);
         return cudaGetLastError();
     };
     // solves (A D A') [dyL; dyK] = [rL + A_L h ; rK + E h] given h (and rcs for the primal step when wanted)
@@ -839,6 +899,10 @@ int dwgpu_master_solve(dwgpu_master *m, double tol, int max_iter, int *status_ou
         k_update<<<std::min(1024, (n + L + K + 255) / 256), 256, 0, st>>>(n, L, K, scal, m->x.p, m->s.p, m->dx.p, m->ds.p, m->yL.p, m->dyL.p,
                                                                           m->yK.p, m->dyK.p);
         MCU(cudaGetLastError());
+    }
+    if (ptime) {
+        std::fprintf(stderr, "    ipm phases (ms over %d factorisations): prep+build %.2f, syrk %.2f, reduce %.2f, cholesky %.2f\n", it, pacc[0], pacc[1], pacc[2], pacc[3]);
+        for (auto &e_ : pe) cudaEventDestroy(e_);
     }
     if (!std::isfinite(best_merit)) return mfail(DWGPU_E_STATE, "the interior-point master produced no finite iterate");
     if (status != 0 && best_merit <= 1e2 * tol) status = 0;      // converged as far as FP64 normal equations go: accepted,
