@@ -424,6 +424,8 @@ def main():
         else:
             eng.round_comm(0, False, True, sptr)                    # cold solve; proposals land in rank 0's HBM
             launches[0] += eng.last_launch_count()
+            if kern_acc is not None:
+                kern_acc.append(eng.last_kernel_ms())
             up_to_host()
             for r in range(R):
                 if rank == 0:
@@ -431,6 +433,8 @@ def main():
                     pi_dev.copy_(pi_pin, non_blocking=True)
                 eng.round_comm(pi_dev.data_ptr(), phases[r], False, sptr)   # NCCL duals down, solve + NVLink up-link, close
                 launches[0] += eng.last_launch_count()
+                if kern_acc is not None:
+                    kern_acc.append(eng.last_kernel_ms())
                 up_to_host()                                        # rank 0: pack + D2H of what the master would read
 
     # ---- one step, device only: duals already in HBM, results stay in HBM
@@ -463,7 +467,7 @@ def main():
                          c["mailbox_bytes"]], dtype=np.float64)
 
     # =========================== e2e ===========================
-    single = args.single_pass and dist is None
+    single = args.single_pass
     e2e_time, e2e_cnt = 0.0, np.zeros(7)
     sp_kern, sp_kcnt, sp_ksum = [], np.zeros(7), 0.0
     sp_clocks = ClockSampler(local_rank) if single else None
