@@ -158,6 +158,18 @@ struct dwgpu_engine {
     dwk::MailDst uplink{};             // this rank's window (pointers already offset by its first block)
     dwk::MailDst uplink_all{};         // the whole buffer (rank 0 reads it)
     bool uplink_valid = false;         // the previous round wrote the window
+    // several dual vectors per round (dwgpu_iterate_multi)
+    DevBuf<double> Dt;                 // dense D_k' (n x L) of the blocks whose D_k is dense enough for the pricing GEMM
+    std::vector<int> list_dense;       // those blocks
+    DevBuf<int> d_list_dense;
+    DevBuf<double> multi_pi, multi_cs; // P x L dual vectors, P x ntot priced costs
+    int multi_P = 0;                   // capacity of the above and of the pinned records below
+    const double *cs_pre_now = nullptr; // priced costs of the vector the next launch_round solves for (nullptr: kernels price)
+    char *h_mpack = nullptr, *d_mpack = nullptr;
+    std::vector<dwk::PackDst> mpk_dev, mpk_host;
+    DevBuf<long long> hp_src, hp_dst;  // history push: persistent index staging (no cudaMalloc per round)
+    DevBuf<int> hp_len;
+    size_t hp_cap = 0;
     ncclComm_t comm = nullptr;
     int comm_world = 0, comm_rank = 0;
     DevBuf<int> comm_flag;
@@ -413,6 +425,9 @@ void dwgpu_destroy(dwgpu_engine *e)
     e->d_list_gmem.release(); e->d_list_a.release(); e->d_list_g.release(); e->d_list_b.release(); e->d_list_c.release(); e->pi.release(); e->rec.release(); e->colptr.release();
     if (e->uplink_base) { if (e->uplink_owned) cudaFree(e->uplink_base); else cudaIpcCloseMemHandle(e->uplink_base); }
     e->comm_flag.release();
+    e->Dt.release(); e->d_list_dense.release(); e->multi_pi.release(); e->multi_cs.release();
+    e->hp_src.release(); e->hp_dst.release(); e->hp_len.release();
+    if (e->h_mpack) cudaFreeHost(e->h_mpack);
     if (e->comm) dwgpu_comm_release(e);
     if (e->h_pack) cudaFreeHost(e->h_pack);
     if (e->h_mail) cudaFreeHost(e->h_mail);
@@ -652,6 +667,17 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(cudaMemset(e->x.p, 0, sizeof(double) * std::max<long long>(e->ntot, 1)));
     CUE(cudaMallocHost((void **)&e->h_pi, sizeof(double) * std::max(L, 1)));
 
+    // blocks whose D_k is dense enough (>= 1/8 of L x n) to price several dual vectors with one FP64 tensor-core GEMM;
+    // only the cluster path (large blocks) uses it — a network block's D_k has a handful of entries per column
+    std::vector<long long> dt_off(K, -1);
+    {
+        long long dt_tot = 0;
+        for (int k = 0; k < K; ++k)
+            if (e->path[k] == 4 && L > 0 && (long long)bd[k].d_nnz * 8 >= (long long)L * bd[k].n) {
+                dt_off[k] = dt_tot; dt_tot += (long long)L * bd[k].n; e->list_dense.push_back(k);
+            }
+        if (dt_tot > 0) { CUE(e->Dt.alloc((size_t)dt_tot)); CUE(e->d_list_dense.upload(e->list_dense)); }
+    }
     ts[nts++] = stamp();
     std::vector<dwk::BlockDev> hb(K);
     for (int k = 0; k < K; ++k) {
@@ -672,6 +698,8 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         B.ws = e->ws.p + ws_off[k];
         B.rmask = e->path[k] == 3 ? e->rmask.p + rm_off[k] : nullptr;
         B.rwd = dwk::rmask_words(B.n);
+        B.xoff = e->xoff[k];
+        B.Dt = dt_off[k] >= 0 ? e->Dt.p + dt_off[k] : nullptr;
     }
     CUE(e->blocks.upload(hb));
     CUE(e->d_list_smem.upload(e->list_smem));
@@ -737,6 +765,10 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     }
 
     ts[nts++] = stamp();
+    if (!e->list_dense.empty()) {
+        dwk::densify_dt_kernel<<<(unsigned)e->list_dense.size(), 1024, 0, e->stream>>>(e->blocks.p, e->d_list_dense.p, (int)e->list_dense.size());
+        CUE(cudaGetLastError());
+    }
     dwk::init_kernel<256><<<K, 256, 0, e->stream>>>(e->blocks.p, K);
     CUE(cudaGetLastError());
     CUE(cudaStreamSynchronize(e->stream));
@@ -770,6 +802,7 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
     P.no_dual_start = e->opt.no_dual_start;
     // the "nothing moved" exit of the kernels rewrites only obj/status and relies on the previous proposal of
     // the block still standing in the result arrays; after create / reset there is none until a round has written it
+    P.cs_pre = e->cs_pre_now;
     P.force_full = (!initial && !e->have_proposals) ? 1 : 0;
     e->have_proposals = true;
     P.dbg = e->d_dbg;
@@ -1206,15 +1239,119 @@ int dwgpu_history_push(dwgpu_engine *e, int count, const int *blocks, long long 
         e->hist_block.push_back(k);
         e->hist_used += e->n[k];
     }
-    DevBuf<long long> d_src, d_dst;
-    DevBuf<int> d_len;
-    CU(d_src.upload(src)); CU(d_dst.upload(dst)); CU(d_len.upload(len));
-    dwk::history_push_kernel<<<(unsigned)count, 256, 0, st>>>(e->x.p, e->hist.p, d_src.p, d_dst.p, d_len.p, count);
+    // index lists through persistent device staging (grow-only): no cudaMalloc / cudaFree per round
+    if ((size_t)count > e->hp_cap) {
+        e->hp_src.release(); e->hp_dst.release(); e->hp_len.release();
+        e->hp_cap = (size_t)std::max(count * 2, e->K);
+        CU(e->hp_src.alloc(e->hp_cap)); CU(e->hp_dst.alloc(e->hp_cap)); CU(e->hp_len.alloc(e->hp_cap));
+    }
+    CU(cudaMemcpyAsync(e->hp_src.p, src.data(), sizeof(long long) * (size_t)count, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->hp_dst.p, dst.data(), sizeof(long long) * (size_t)count, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->hp_len.p, len.data(), sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, st));
+    dwk::history_push_kernel<<<(unsigned)count, 256, 0, st>>>(e->x.p, e->hist.p, e->hp_src.p, e->hp_dst.p, e->hp_len.p, count);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(st));
-    d_src.release(); d_dst.release(); d_len.release();
+    CU(cudaStreamSynchronize(st));          // the pageable host lists above are read by the copies
     return 0;
 }
+
+// Several dual vectors per round (the reference prices ONE vector per round, src/dw_phases.c:358-437): for
+// p = 0 .. P-1 every block is priced with Pi[p] and re-solved from the basis the previous vector left, its proposal packed
+// into record p and its x_k kept in the device history (ids_out[p * K + k]); one synchronisation at the end.  Blocks with
+// a dense D_k (cluster path) get their P priced cost vectors from one FP64 tensor-core GEMM up front.
+int dwgpu_iterate_multi(dwgpu_engine *e, const double *Pi, int P, int phase_one, dwgpu_packed *out, long long *ids_out)
+{
+    if (!e || !e->initialised) return fail(DWGPU_E_STATE, "engine not initialised");
+    if (P < 1 || P > 32 || !out || (e->L > 0 && !Pi)) return fail(DWGPU_E_ARGS, "1 <= P <= 32 dual vectors, out = P records");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const size_t K = (size_t)e->K, KL = K * (size_t)e->L, L = (size_t)e->L;
+    const size_t rec_stride = (e->pack_bytes + 63) & ~(size_t)63;        // records start 64-byte aligned
+    if (P > e->multi_P) {
+        CU(cudaStreamSynchronize(st));
+        e->multi_pi.release(); e->multi_cs.release();
+        if (e->h_mpack) { cudaFreeHost(e->h_mpack); e->h_mpack = nullptr; }
+        CU(e->multi_pi.alloc((size_t)P * std::max<size_t>(L, 1)));
+        if (!e->list_dense.empty()) CU(e->multi_cs.alloc((size_t)P * (size_t)e->ntot));
+        CU(cudaHostAlloc((void **)&e->h_mpack, rec_stride * (size_t)P, cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer((void **)&e->d_mpack, e->h_mpack, 0));
+        std::memset(e->h_mpack, 0, rec_stride * (size_t)P);
+        e->mpk_dev.assign((size_t)P, dwk::PackDst{}); e->mpk_host.assign((size_t)P, dwk::PackDst{});
+        auto carve = [&](char *base, dwk::PackDst &d) {
+            d.nnz = (long long *)base;
+            double *dd = (double *)(base + sizeof(double));
+            d.obj = dd; d.cost = dd + K; d.val = dd + 2 * K;
+            int *ii = (int *)(dd + 2 * K + KL);
+            d.status = ii; d.colptr = ii + K; d.ind = ii + 2 * K + 1;
+        };
+        for (int p = 0; p < P; ++p) {
+            carve(e->d_mpack + rec_stride * (size_t)p, e->mpk_dev[(size_t)p]);
+            carve(e->h_mpack + rec_stride * (size_t)p, e->mpk_host[(size_t)p]);
+        }
+        e->multi_P = P;
+    }
+    if (L > 0) CU(cudaMemcpyAsync(e->multi_pi.p, Pi, sizeof(double) * (size_t)P * L, cudaMemcpyHostToDevice, st));
+    if (!e->list_dense.empty() && L > 0) {
+        int nmax = 0;
+        for (int k : e->list_dense) nmax = std::max(nmax, e->n[k]);
+        const size_t sm = sizeof(double) * 32 * (L + 4);
+        CU(allow_dynamic_smem(e->device, (const void *)dwk::price_multi_dmma_kernel, (int)sm));
+        dwk::price_multi_dmma_kernel<<<dim3((unsigned)e->list_dense.size(), (unsigned)((nmax + 63) / 64)), 256, sm, st>>>(
+            e->blocks.p, e->d_list_dense.p, e->multi_pi.p, P, phase_one ? 1 : 0, e->ntot, e->multi_cs.p);
+        CU(cudaGetLastError());
+    }
+    // history room for P copies of every block's x
+    if (ids_out) {
+        const long long need = (long long)P * e->ntot;
+        if (e->hist_used + need > e->hist_cap) {
+            long long cap = std::max<long long>(2 * e->hist_cap, e->hist_used + need);
+            DevBuf<double> bigger;
+            CU(bigger.alloc((size_t)cap));
+            if (e->hist_used > 0)
+                CU(cudaMemcpyAsync(bigger.p, e->hist.p, sizeof(double) * (size_t)e->hist_used, cudaMemcpyDeviceToDevice, st));
+            CU(cudaStreamSynchronize(st));
+            e->hist.release();
+            e->hist = bigger;
+            e->hist_cap = cap;
+        }
+    }
+    int launches = 0;
+    for (int p = 0; p < P; ++p) {
+        e->cs_pre_now = e->list_dense.empty() ? nullptr : e->multi_cs.p + (size_t)p * (size_t)e->ntot;
+        const int rc = launch_round(e, e->multi_pi.p + (size_t)p * L, phase_one ? 1 : 0, 0, st);
+        e->cs_pre_now = nullptr;
+        if (rc) return rc;
+        launches += e->last_launches;
+        dwk::PackSrc s;
+        std::memset(&s, 0, sizeof(s));
+        s.obj = e->obj.p; s.cost = e->cost.p; s.val = e->val.p; s.status = e->status.p; s.len = e->len.p; s.ind = e->ind.p;
+        s.K = e->K; s.L = e->L; s.accept_tol = 1e-6;
+        dwk::pack_scan_kernel<1024><<<1, 1024, 0, st>>>(s, e->colptr.p, e->mpk_dev[(size_t)p]);
+        CU(cudaGetLastError());
+        dwk::pack_copy_kernel<256><<<(unsigned)((e->K + 7) / 8), 256, 0, st>>>(s, e->colptr.p, e->mpk_dev[(size_t)p]);
+        CU(cudaGetLastError());
+        launches += 2;
+        if (ids_out) {           // x of all blocks is one contiguous array: one device-to-device copy keeps it
+            CU(cudaMemcpyAsync(e->hist.p + e->hist_used, e->x.p, sizeof(double) * (size_t)e->ntot, cudaMemcpyDeviceToDevice, st));
+            for (int k = 0; k < e->K; ++k) {
+                ids_out[(size_t)p * K + k] = (long long)e->hist_off.size();
+                e->hist_off.push_back(e->hist_used + e->xoff[k]);
+                e->hist_block.push_back(k);
+            }
+            e->hist_used += e->ntot;
+        }
+    }
+    e->last_launches = launches;
+    CU(cudaStreamSynchronize(st));
+    for (int p = 0; p < P; ++p) {
+        const dwk::PackDst &h = e->mpk_host[(size_t)p];
+        out[p].obj = h.obj; out[p].cost = h.cost; out[p].status = h.status; out[p].colptr = h.colptr;
+        out[p].ind = h.ind; out[p].val = h.val; out[p].nnz = h.nnz[0];
+    }
+    return 0;
+}
+
+/* number of blocks whose pricing runs through the multi-vector FP64 tensor-core GEMM */
+int dwgpu_dense_pricing_blocks(dwgpu_engine *e) { return e ? (int)e->list_dense.size() : 0; }
 
 int dwgpu_history_combine(dwgpu_engine *e, int nterms, const long long *ids, const double *weights, double *x_out)
 {

@@ -190,6 +190,65 @@ __global__ void __launch_bounds__(NT) order_by_last_iterations_kernel(int *list,
     for (int e = threadIdx.x; e < count; e += NT) list[e] = (int)(0xffffffffu - (unsigned)(key[e] & 0xffffffffull));
 }
 
+// ---- multi-vector pricing: cs_p = (phase_one ? 0 : c_k) - D_k' pi_p for P dual vectors at once ---------
+// For a block whose D_k is dense enough (config C: 25 % of 256 x 4096) this is a real FP64 contraction
+// Y (n x P) = Dt (n x L) . Pi' (L x P), done with FP64 tensor-core MMAs (mma.sync m8n8k4 f64 -> DMMA).  The reference
+// prices one vector at a time with a COO loop (src/dw_subprob.c:291-293 -> src/dw_blas.c:106-122).
+__global__ void densify_dt_kernel(const BlockDev *blocks, const int *list, int count)
+{
+    const int e = blockIdx.x;
+    if (e >= count) return;
+    const BlockDev &B = blocks[list[e]];
+    double *Dt = const_cast<double *>(B.Dt);
+    const int n = B.n, L = B.L;
+    for (size_t t = threadIdx.x; t < (size_t)n * L; t += blockDim.x) Dt[t] = 0.0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x)
+        for (int t = B.dc_ptr[j]; t < B.dc_ptr[j + 1]; ++t) Dt[(size_t)j * L + B.dc_row[t]] += B.dc_val[t];
+}
+
+// grid (dense blocks, ceil(n / 64)); 8 warps, warp w prices rows [64 bx + 8 w, +8) for all P vectors (P <= 32, padded to
+// a multiple of 8 with zero vectors in shared memory).  out[p * ntot + xoff + j] = base_j - sum_i Dt[j][i] Pi[p][i].
+__global__ void __launch_bounds__(256) price_multi_dmma_kernel(const BlockDev *blocks, const int *list, const double *Pi, int P,
+                                                               int phase_one, long long ntot, double *out)
+{
+    extern __shared__ double spi[];              // [32][L + 4]: Pi rows, zero beyond P
+    const BlockDev &B = blocks[list[blockIdx.x]];
+    const int n = B.n, L = B.L, ldp = L + 4;
+    for (int e = threadIdx.x; e < 32 * L; e += 256) { const int p = e / L, i = e - p * L; spi[p * ldp + i] = p < P ? Pi[(size_t)p * L + i] : 0.0; }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, ar = lane >> 2, ak = lane & 3;
+    const int j0 = blockIdx.y * 64 + warp * 8;
+    if (j0 >= n) return;
+    const int jr = min(j0 + ar, n - 1);
+    const double *drow = B.Dt + (size_t)jr * L;
+    double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    const int PT = (P + 7) / 8;
+    for (int k0 = 0; k0 < L; k0 += 4) {
+        const double a = (k0 + ak < L) ? __ldg(drow + k0 + ak) : 0.0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (t < PT) {
+                const double b = (k0 + ak < L) ? spi[(t * 8 + ar) * ldp + k0 + ak] : 0.0;
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(a), "d"(b));
+            }
+        }
+    }
+    // C[row = ar][col = 2 ak + {0,1}] of p-tile t  ->  vector p = 8 t + 2 ak + {0,1}, column j0 + ar
+    const int j = j0 + ar;
+    if (j < n) {
+        const double base = phase_one ? 0.0 : __ldg(B.c_master + j);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int p = t * 8 + 2 * ak + h;
+                if (t < PT && p < P) out[(size_t)p * ntot + B.xoff + j] = base - acc[t][h];
+            }
+    }
+}
+
 // ---- device-resident proposal history (see dwgpu_history_push / _combine in include/dwgpu.h) -------------
 // one CTA per listed block: hist[dst[i] ..) <- x[src[i] ..)
 __global__ void __launch_bounds__(256) history_push_kernel(const double *x, double *hist, const long long *src,

@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(NT, 1) solve_cluster_kernel(const BlockDev *bl
         c.dvx[j] = 1.0f;
         double cj;
         if (P.initial) cj = B.c_file[j];
+        else if (P.cs_pre != nullptr && B.Dt != nullptr) cj = __ldg(P.cs_pre + B.xoff + j);     // priced by the multi-vector GEMM
         else {
             double y = 0.0;
             for (int e = B.dc_ptr[j]; e < B.dc_ptr[j + 1]; ++e)

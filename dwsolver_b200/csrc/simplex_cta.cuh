@@ -50,6 +50,8 @@ struct BlockDev {
     unsigned *rmask;        // path 3: per row, one bit per 32-byte item of T that may be non-zero (nullptr: none)
     int rwd;                // 32-bit words per row of rmask
     int pad2;
+    long long xoff;         // offset of this block's columns in the engine-wide column arrays (x, cs_pre)
+    const double *Dt;       // dense D_k transposed, n x L row-major (blocks whose D_k is dense enough for the pricing GEMM; else nullptr)
 };
 
 struct SolveParams {
@@ -58,6 +60,8 @@ struct SolveParams {
     int initial;        // cold solve with the block file's own objective (dw_subprob.c:121)
     int max_iter_mult;
     int no_dual_start;  // cluster path: skip the dual-simplex repair of an infeasible start
+    const double *cs_pre; // priced costs d = (phase_one ? 0 : c_k) - D_k' pi of ALL columns (engine-wide, BlockDev::xoff), computed by
+                        // the multi-vector pricing GEMM (pack.cuh: price_multi_dmma_kernel) for blocks with a dense D_k; nullptr: none
     int force_full;     // no proposal of this engine state exists yet (first round after create / reset without an
                         // initial solve): a block that needs no pivot must still write its whole proposal
     double tol_dj, tol_bnd, tol_piv;

@@ -37,6 +37,8 @@ ABI_SYMBOLS = [
     # multi-GPU rounds from the C layer: NCCL + the NVLink peer-memory up-link
     "dwgpu_comm_unique_id", "dwgpu_comm_init", "dwgpu_comm_release", "dwgpu_uplink_create", "dwgpu_uplink_attach",
     "dwgpu_round_comm",
+    # several dual vectors per round
+    "dwgpu_iterate_multi", "dwgpu_dense_pricing_blocks",
 ]
 
 
@@ -116,6 +118,8 @@ def load_library():
         L.dwgpu_uplink_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Proposals)]
         L.dwgpu_uplink_attach.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         L.dwgpu_round_comm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.dwgpu_iterate_multi.argtypes = [C.c_void_p, c_dp, C.c_int, C.c_int, C.POINTER(Packed), C.POINTER(C.c_longlong)]
+        L.dwgpu_dense_pricing_blocks.argtypes = [C.c_void_p]
         L.dwgpu_pack_gathered_records.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Packed)]
         L.dwgpu_history_push.argtypes = [C.c_void_p, C.c_int, c_ip, C.POINTER(C.c_longlong)]
         L.dwgpu_history_combine.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), c_dp, c_dp]
@@ -349,6 +353,20 @@ class Engine:
         return dict(nnz=n, status=np.ctypeslib.as_array(pk.status, shape=(K_total,)),
                     obj=np.ctypeslib.as_array(pk.obj, shape=(K_total,)),
                     colptr=np.ctypeslib.as_array(pk.colptr, shape=(K_total + 1,)))
+
+    def iterate_multi(self, Pi, phase_one: bool, keep_history: bool = True):
+        """dwgpu_iterate_multi: Pi is P x L; returns (list of P packed-record dicts, P x K history ids or None)"""
+        Pi = np.ascontiguousarray(Pi, np.float64).reshape(-1, max(self.L, 1))
+        P = Pi.shape[0]
+        recs = (Packed * P)()
+        ids = np.zeros((P, self.K), np.int64) if keep_history else None
+        _check(self._lib.dwgpu_iterate_multi(self._h, Pi.ctypes.data_as(c_dp), P, 1 if phase_one else 0, recs,
+                                             ids.ctypes.data_as(C.POINTER(C.c_longlong)) if keep_history else None),
+               "dwgpu_iterate_multi")
+        return [self._packed_views(recs[p]) for p in range(P)], ids
+
+    def dense_pricing_blocks(self) -> int:
+        return int(self._lib.dwgpu_dense_pricing_blocks(self._h))
 
     def iterate_device(self, d_pi_ptr: int, phase_one: bool, stream: int = 0):
         _check(self._lib.dwgpu_iterate_device(self._h, C.c_void_p(d_pi_ptr), int(bool(phase_one)),

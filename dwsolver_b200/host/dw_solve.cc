@@ -157,6 +157,8 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
         std::string err;
         std::vector<int> accepted;   // local block ids accepted this round
         std::vector<long long> kept_ids;
+        std::vector<dwgpu_packed> mpk;       // several dual vectors per round: one record per vector
+        std::vector<long long> mids;         // and the history ids of every block's x_k of every pass
     };
     std::vector<Shard> shards((size_t)G);
     struct EngineGuard {
@@ -262,13 +264,22 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
     std::vector<double> xbuf;
     int iter = 0;
     bool warned_nofeas = false;
+    // DWSOLVER_MULTI=P (2..8): Phase II rounds price every block with P dual vectors — the master's duals and P-1 points
+    // between them and the previous round's duals — and offer all the proposals to the master (the reference
+    // prices one vector per round, src/dw_phases.c:358-437).  multi_now says whether the round just run was such a round.
+    int multiP = 1;
+    if (const char *mp = std::getenv("DWSOLVER_MULTI")) multiP = std::max(1, std::min(8, std::atoi(mp)));
+    std::vector<double> pi_prev;
+    bool multi_now = false;
     auto consume = [&](bool phase_one, int *n_added) -> int {
         const double t_c0 = now_s();
         int added = 0;
         const size_t first_new = X.size();
+        const int passes = multi_now ? multiP : 1;
+        for (Shard &sh : shards) sh.accepted.clear();
+        for (int pass = 0; pass < passes; ++pass)
         for (Shard &sh : shards) {
-            const dwgpu_packed &pk = sh.pk;
-            sh.accepted.clear();
+            const dwgpu_packed &pk = multi_now ? sh.mpk[(size_t)pass] : sh.pk;
             for (int k = sh.k0; k < sh.k1; ++k) {
                 const int kl = k - sh.k0;
                 if (pk.status[kl] == DWGPU_UNBND) {
@@ -287,28 +298,39 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
                     warned_nofeas = true;
                     continue;                                          // no point of the block exists: nothing to propose
                 }
-                if (!(r[k] - pk.obj[kl] > kTolerance)) continue;      // src/dw_phases.c:108, 358
+                // the acceptance test compares with the reduced cost AT THE MASTER'S DUALS: for the pass priced with them
+                // that is the subproblem optimum itself (src/dw_phases.c:108, 358), for the other passes it is recomputed
+                double dred = pk.obj[kl];
+                if (pass > 0) {
+                    dred = pk.cost[kl];
+                    for (int t = pk.colptr[kl]; t < pk.colptr[kl + 1]; ++t) dred -= pi[pk.ind[t] - 1] * pk.val[t];
+                }
+                if (!(r[k] - dred > kTolerance)) continue;
                 std::vector<int> idx;
                 std::vector<double> val;
                 for (int t = pk.colptr[kl]; t < pk.colptr[kl + 1]; ++t) { idx.push_back(pk.ind[t] - 1); val.push_back(pk.val[t]); }
                 idx.push_back(L + k); val.push_back(1.0);
-                const std::string name = "lambda_" + std::to_string(k) + "_" + std::to_string(iter);
+                const int tag = iter + 100000 * pass;                   // unique per (round, pass)
+                const std::string name = "lambda_" + std::to_string(k) + "_" + std::to_string(tag);
                 const int j = add(name, phase_one ? 0.0 : pk.cost[kl], 1.0, idx, val, false);
                 if (phase_one) remembered.emplace_back(j, pk.cost[kl]);
-                Proposal p; p.k = k; p.iter = iter; p.id = -1;
+                Proposal p; p.k = k; p.iter = tag; p.id = multi_now ? sh.mids[(size_t)pass * (size_t)(sh.k1 - sh.k0) + kl] : -1;
                 X.push_back(p);
-                sh.accepted.push_back(kl);
+                if (!multi_now) sh.accepted.push_back(kl);
                 ++added;
             }
         }
-        // one device-to-device launch per shard keeps the x_k of every accepted block (no per-column host copies)
+        // one device-to-device launch per shard keeps the x_k of every accepted block (no per-column host copies);
+        // a multi-vector round kept every pass's x_k on the device already
         const double t_h0 = now_s();
-        if (on_all_shards([&](Shard &sh) {
-                sh.kept_ids.resize(sh.accepted.size());
-                return dwgpu_history_push(sh.eng, (int)sh.accepted.size(), sh.accepted.data(), sh.kept_ids.data());
-            }) != 0) return DW_STATUS_ERR_INTERNAL;
-        size_t w = first_new;
-        for (Shard &sh : shards) for (size_t t = 0; t < sh.accepted.size(); ++t) X[w++].id = sh.kept_ids[t];
+        if (!multi_now) {
+            if (on_all_shards([&](Shard &sh) {
+                    sh.kept_ids.resize(sh.accepted.size());
+                    return dwgpu_history_push(sh.eng, (int)sh.accepted.size(), sh.accepted.data(), sh.kept_ids.data());
+                }) != 0) return DW_STATUS_ERR_INTERNAL;
+            size_t w = first_new;
+            for (Shard &sh : shards) for (size_t t = 0; t < sh.accepted.size(); ++t) X[w++].id = sh.kept_ids[t];
+        }
         t_history += now_s() - t_h0;
         t_consume += now_s() - t_c0;
         *n_added = added;
@@ -331,10 +353,27 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
     };
     auto round = [&](bool phase_one) -> int {
         const double t0 = now_s();
-        // with r given the engine ships only the columns the acceptance test above will take
-        const int rc = on_all_shards([&](Shard &sh) {
-            return dwgpu_iterate_packed(sh.eng, pi.data(), phase_one ? 1 : 0, r.data() + sh.k0, &sh.pk);
-        });
+        int rc;
+        multi_now = multiP > 1 && !phase_one && L > 0 && (int)pi_prev.size() == L;
+        if (multi_now) {
+            // pass 0: the master's duals; pass p: a point p / P of the way back to the previous round's duals
+            std::vector<double> Pi((size_t)multiP * L);
+            for (int p = 0; p < multiP; ++p) {
+                const double a = (double)p / multiP;
+                for (int i = 0; i < L; ++i) Pi[(size_t)p * L + i] = (1.0 - a) * pi[i] + a * pi_prev[i];
+            }
+            rc = on_all_shards([&](Shard &sh) {
+                sh.mpk.resize((size_t)multiP);
+                sh.mids.resize((size_t)multiP * (size_t)(sh.k1 - sh.k0));
+                return dwgpu_iterate_multi(sh.eng, Pi.data(), multiP, 0, sh.mpk.data(), sh.mids.data());
+            });
+        } else {
+            // with r given the engine ships only the columns the acceptance test above will take
+            rc = on_all_shards([&](Shard &sh) {
+                return dwgpu_iterate_packed(sh.eng, pi.data(), phase_one ? 1 : 0, r.data() + sh.k0, &sh.pk);
+            });
+        }
+        if (!phase_one && L > 0) pi_prev.assign(pi.begin(), pi.begin() + L);
         g_stats.seconds_subproblems += now_s() - t0;
         return rc;
     };

@@ -205,6 +205,16 @@ int  dwgpu_fetch_x(dwgpu_engine *e, int k, double *x);
 int  dwgpu_history_push(dwgpu_engine *e, int count, const int *blocks, long long *ids_out);
 int  dwgpu_history_combine(dwgpu_engine *e, int nterms, const long long *ids, const double *weights, double *x_out);
 
+/* Several dual vectors per round (multi-column pricing; the reference prices one vector per round,
+ * src/dw_phases.c:358-437, src/dw_subprob.c:291-329).  Pi holds P (1..32) dual vectors of L doubles each; for p = 0..P-1
+ * every block is priced with Pi[p] and re-solved from the basis the previous vector left; out[p] is the packed record of
+ * that pass (every column shipped; valid until the next call) and ids_out (NULL, or P*K entries) receives the history id
+ * of every block's x_k of that pass (as dwgpu_history_push would return).  Blocks whose D_k is dense enough — at least
+ * 1/8 of L x n, cluster path — get all P priced cost vectors from ONE FP64 tensor-core GEMM D_k' [pi_0 .. pi_P-1]
+ * (dwgpu_dense_pricing_blocks says how many blocks that is). */
+int  dwgpu_iterate_multi(dwgpu_engine *e, const double *Pi, int P, int phase_one, dwgpu_packed *out, long long *ids_out);
+int  dwgpu_dense_pricing_blocks(dwgpu_engine *e);
+
 int  dwgpu_get_counters(dwgpu_engine *e, dwgpu_counters *total);
 /* per-block pivots+flips of the LAST round (K long longs) — load-balance diagnostics */
 int  dwgpu_get_block_iterations(dwgpu_engine *e, long long *iters);

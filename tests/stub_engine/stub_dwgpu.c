@@ -30,6 +30,10 @@ struct dwgpu_engine {
     double *obj, *cost, *val;
     int *status, *colptr, *ind;
     int packed_rounds;              /* packed rounds served so far (failure injection) */
+    /* records of a multi-vector round */
+    int multi_P;
+    double *m_obj, *m_cost, *m_val;
+    int *m_status, *m_colptr, *m_ind;
     /* kept copies of x_k */
     double *hist;
     long long hist_used, hist_cap;
@@ -61,6 +65,7 @@ void dwgpu_destroy(dwgpu_engine *e)
     free(e->blocks); free(e->props); free(e->n); free(e->xoff);
     free(e->obj); free(e->cost); free(e->val); free(e->status); free(e->colptr); free(e->ind);
     free(e->hist); free(e->hist_off); free(e->hist_block);
+    free(e->m_obj); free(e->m_cost); free(e->m_val); free(e->m_status); free(e->m_colptr); free(e->m_ind);
     free(e);
 }
 
@@ -203,6 +208,39 @@ int dwgpu_get_counters(dwgpu_engine *e, dwgpu_counters *c)
     }
     return 0;
 }
+
+/* several dual vectors per round (include/dwgpu.h: dwgpu_iterate_multi): P oracle passes, one packed record each
+ * (every column shipped), every block's x_k of every pass kept in the history */
+int dwgpu_iterate_multi(dwgpu_engine *e, const double *Pi, int P, int phase_one, dwgpu_packed *out, long long *ids_out)
+{
+    if (!e || P < 1 || P > 32 || !out || (e->L > 0 && !Pi)) return fail(DWGPU_E_ARGS, "bad arguments");
+    const size_t K = (size_t)e->K, KL = K * (size_t)(e->L > 0 ? e->L : 1);
+    if (P > e->multi_P) {
+        e->m_obj = realloc(e->m_obj, sizeof(double) * K * (size_t)P); e->m_cost = realloc(e->m_cost, sizeof(double) * K * (size_t)P);
+        e->m_status = realloc(e->m_status, sizeof(int) * K * (size_t)P); e->m_colptr = realloc(e->m_colptr, sizeof(int) * (K + 1) * (size_t)P);
+        e->m_ind = realloc(e->m_ind, sizeof(int) * KL * (size_t)P); e->m_val = realloc(e->m_val, sizeof(double) * KL * (size_t)P);
+        if (!e->m_obj || !e->m_cost || !e->m_status || !e->m_colptr || !e->m_ind || !e->m_val) return fail(DWGPU_E_NOMEM, "out of memory");
+        e->multi_P = P;
+    }
+    for (int p = 0; p < P; ++p) {
+        orc_batch(e->blocks, e->props, e->K, Pi + (size_t)p * (size_t)e->L, phase_one, 0, stub_threads());
+        dwgpu_packed one;
+        pack(e, NULL, &one);
+        memcpy(e->m_obj + K * (size_t)p, e->obj, sizeof(double) * K); memcpy(e->m_cost + K * (size_t)p, e->cost, sizeof(double) * K);
+        memcpy(e->m_status + K * (size_t)p, e->status, sizeof(int) * K); memcpy(e->m_colptr + (K + 1) * (size_t)p, e->colptr, sizeof(int) * (K + 1));
+        memcpy(e->m_ind + KL * (size_t)p, e->ind, sizeof(int) * (size_t)one.nnz); memcpy(e->m_val + KL * (size_t)p, e->val, sizeof(double) * (size_t)one.nnz);
+        out[p].obj = e->m_obj + K * (size_t)p; out[p].cost = e->m_cost + K * (size_t)p; out[p].status = e->m_status + K * (size_t)p;
+        out[p].colptr = e->m_colptr + (K + 1) * (size_t)p; out[p].ind = e->m_ind + KL * (size_t)p; out[p].val = e->m_val + KL * (size_t)p;
+        out[p].nnz = one.nnz;
+        if (ids_out)
+            for (int k = 0; k < e->K; ++k) {
+                const int rc = dwgpu_history_push(e, 1, &k, &ids_out[(size_t)p * K + (size_t)k]);
+                if (rc) return rc;
+            }
+    }
+    return 0;
+}
+int dwgpu_dense_pricing_blocks(dwgpu_engine *e) { (void)e; return 0; }
 
 /* ---- the device-resident master (dwgpu_master_*): not part of the test double — creation fails, so the host loop
  * keeps its simplex master (dwsolver_b200/host/ipm_master.cc) ---- */

@@ -558,6 +558,52 @@ def test_results_do_not_depend_on_how_the_blocks_are_sharded():
         assert run(shards) == whole, shards
 
 
+@pytest.mark.parametrize("kind", ["mcf_B_shape", "dense_cluster"])
+def test_several_dual_vectors_per_round(kind):
+    """SURVEY 8f-4, dwgpu_iterate_multi: P dual vectors priced and solved in one call, one packed record and one kept
+    x_k per vector and block.  Every pass must reach the oracle's optimum for ITS vector (the optimum does not depend
+    on the basis the previous vector left), ship the exact D_k x_k column, and the kept x_k must be that pass's.
+    `dense_cluster`: blocks whose D_k is 25 % dense on the cluster path get their P priced cost vectors from ONE FP64
+    tensor-core GEMM (price_multi_dmma_kernel) instead of P sparse walks — summation order differs from the
+    reference's COO loop, so its objective is compared at 1e-9 like everything else."""
+    from oracle import oracle as O
+    if kind == "mcf_B_shape":
+        prob = P.gen_mcf(24, 256, 512, 256, 8192001)
+        eng = engine(prob)
+        assert eng.dense_pricing_blocks() == 0
+    else:
+        prob = P.gen_dense(4, 96, 200, 24, 64001, dens_a=0.05, dens_d=0.25)
+        eng = engine(prob, force_path=4, cluster_size=2)
+        assert eng.dense_pricing_blocks() == prob.K
+    orc = O.OracleBlocks(prob)
+    compare_round(prob, eng.initial(), orc.initial(8), None, False, initial=True)
+    rng = np.random.default_rng(5)
+    for P_ in (3, 17):
+        Pi = -rng.random((P_, prob.L)) * 9.0
+        recs, ids = eng.iterate_multi(Pi, False)
+        assert len(recs) == P_ and ids.shape == (P_, prob.K)
+        for p in range(P_):
+            op = orc.iterate(Pi[p], False, 8)
+            rec = recs[p]
+            # the kept x_k of pass p: one term of weight 1 per block
+            x_all = eng.history_combine(ids[p], np.ones(prob.K))
+            off = 0
+            for k, b in enumerate(prob.blocks):
+                assert rec["status"][k] == OPT and op[k]["status"] == OPT
+                assert abs(rec["obj"][k] - op[k]["obj"]) <= 1e-9 * (1 + abs(op[k]["obj"])), (kind, p, k)
+                x = x_all[off:off + b.n]
+                off += b.n
+                assert residual(b, x) <= 1e-9
+                yc = np.zeros(prob.L)
+                for r_, c_, v_ in zip(b.d_row, b.d_col, b.d_val):
+                    yc[r_] += x[c_] * v_
+                nz = np.nonzero(yc != 0.0)[0]
+                lo, hi = rec["colptr"][k], rec["colptr"][k + 1]
+                assert np.array_equal(rec["ind"][lo:hi], nz + 1) and np.array_equal(rec["val"][lo:hi], yc[nz])
+                assert abs(rec["cost"][k] - b.c_master @ x) <= 1e-12 * (1 + abs(rec["cost"][k]))
+    eng.close()
+
+
 def test_two_live_engines_of_different_shapes():
     """A kernel's dynamic shared-memory limit belongs to the device, not to an engine: an engine created later for
     smaller blocks must not take it away from one that is still launching (several engines live in one process when

@@ -130,6 +130,21 @@ def test_a_block_that_did_not_reach_an_optimum_never_becomes_a_column(tmp_path):
     assert float(banner(out)) >= float(banner(ref)) - 1e-9      # built from real proposals only: never below the optimum
 
 
+@pytest.mark.parametrize("name", ["book_dantzig", "four_sea", "web_trick", "book_bertsimas"])
+@pytest.mark.parametrize("P_", [2, 4])
+def test_several_dual_vectors_per_round_reach_the_same_optimum(name, P_, golden, tmp_path):
+    """with DWSOLVER_MULTI=P every Phase II round prices the blocks with P dual vectors (the master's duals
+    and points between them and the previous round's) through dwgpu_iterate_multi and offers all proposals to the
+    master, accepted by their reduced cost at the master's duals.  Same optimum as the one-vector loop."""
+    P.write_block_angular(load_example(name), str(tmp_path))
+    ref = run(tmp_path, "-g", "guidefile")
+    out = run(tmp_path, "-g", "guidefile", env={"DWSOLVER_MULTI": str(P_)})
+    assert ref.returncode == 0 and out.returncode == 0, out.stderr
+    want = golden["objective"][name]
+    assert abs(float(banner(out)) - want) <= 1e-6 * (1 + abs(want))
+    assert abs(float(banner(out)) - float(banner(ref))) <= 1e-9 * (1 + abs(want))
+
+
 def test_the_double_refuses_to_run_unannounced(tmp_path):
     P.write_block_angular(load_example("single_sub"), str(tmp_path))
     env = {k: v for k, v in os.environ.items() if k != "DWSOLVER_TEST_DOUBLE"}
