@@ -322,7 +322,6 @@ def main():
     # ---------------- our arm ----------------
     import torch
     from dwsolver_b200 import engine as E
-    from dwsolver_b200 import sharding as SH
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
@@ -333,7 +332,7 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
-    my_range = SH.shard_range(K_total, world, rank)
+    my_range = P.shard_range(K_total, world, rank)
     K_loc = len(my_range)
     prob = P.make_config(args.config, block_range=my_range)
     bpp = algorithmic_bytes_per_pivot(m, n)

@@ -781,3 +781,12 @@ def make_config(tag: str, K: Optional[int] = None, block_range: Optional[range] 
         p.blocks = [p.blocks[k] for k in block_range]
         p.K = len(p.blocks)
     return p
+
+
+def shard_range(K: int, world: int, rank: int) -> range:
+    """Static contiguous block range of a rank: rank g of G owns blocks [g K / G, (g + 1) K / G).
+    K must divide evenly (it does for every BASELINE.json configuration at 1, 2, 4 and 8 GPUs)."""
+    if K % world:
+        raise ValueError(f"{K} blocks do not divide over {world} ranks")
+    per = K // world
+    return range(rank * per, (rank + 1) * per)

@@ -1,7 +1,7 @@
-"""N>1 host logic on CPU: 2 gloo ranks shard the blocks, run rounds with duals-down / proposals-up
-(dwsolver_b200/sharding.py) and must reproduce the single-process result exactly.  The per-rank
-subproblem side is the CPU oracle here (no GPU in this suite); bench.py uses the same functions with
-the CUDA engine over NCCL."""
+"""N>1 host logic on CPU: 2 gloo ranks shard the blocks (dwsolver_b200.problem.shard_range), run rounds with duals
+down / proposals up and must reproduce the single-process result exactly.  The per-rank subproblem side is the CPU
+oracle here (no GPU in this suite) and the exchange is gloo; on GPUs the same round is dwgpu_round_comm (include/dwgpu.h):
+ncclBroadcast of the duals, proposals stored into rank 0's up-link buffer at the rank's block offset."""
 import os
 import socket
 
@@ -12,7 +12,34 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from dwsolver_b200 import problem as P
-from dwsolver_b200 import sharding as S
+
+
+class S:
+    """the round of SURVEY.md §8e restated over torch.distributed (test infrastructure)"""
+    RECORD_FIELDS = ("obj", "cost", "status", "len", "ind", "val")
+    shard_range = staticmethod(P.shard_range)
+
+    @staticmethod
+    def duals_down(dist_, pi_tensor, src=0):
+        dist_.broadcast(pi_tensor, src=src)
+        return pi_tensor
+
+    @staticmethod
+    def proposals_up(dist_, local, gathered):
+        """every rank's records land at its block offset of the K_total-wide arrays (rank-major = block order)"""
+        for f in S.RECORD_FIELDS:
+            dist_.all_gather_into_tensor(gathered[f].view(-1), local[f].reshape(-1))
+        return gathered
+
+    @staticmethod
+    def alloc_gathered(torch_, K_total, L_, device):
+        return {"obj": torch_.empty(K_total, dtype=torch_.float64, device=device),
+                "cost": torch_.empty(K_total, dtype=torch_.float64, device=device),
+                "status": torch_.empty(K_total, dtype=torch_.int32, device=device),
+                "len": torch_.empty(K_total, dtype=torch_.int32, device=device),
+                "ind": torch_.empty((K_total, L_), dtype=torch_.int32, device=device),
+                "val": torch_.empty((K_total, L_), dtype=torch_.float64, device=device)}
+
 
 K, NODES, COLS, L, SEED = 8, 8, 20, 4, 5
 
