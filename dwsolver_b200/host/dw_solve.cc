@@ -21,6 +21,7 @@
 #include <map>
 #include <memory>
 #include <stdexcept>
+#include <utility>
 #include <string>
 #include <thread>
 #include <vector>
@@ -452,12 +453,17 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
         const int mrc = solve_master();
         ++iter;                                                  // :618 (the drained round is simply not launched)
         if (mrc == 1 && status == DW_STATUS_OK) status = DW_STATUS_ERR_INFEASIBLE;
+        if (mrc == 2 && status == DW_STATUS_OK) status = DW_STATUS_ERR_UNBOUNDED;
+        if (mrc == 3 && status == DW_STATUS_OK) { std::fprintf(stderr, "dwsolver-b200: master LP failed after Phase I (code %d)\n", mrc); return fail(DW_STATUS_ERR_INTERNAL); }
     } else {
         M.set_obj_const(opt.shift);
         int rc = consume(false, &added);
         if (rc) return fail(rc);
-        solve_master();
+        const int mrc0 = solve_master();
         ++iter;
+        if (mrc0 == 1) status = DW_STATUS_ERR_INFEASIBLE;
+        else if (mrc0 == 2) status = DW_STATUS_ERR_UNBOUNDED;
+        else if (mrc0 != 0) { std::fprintf(stderr, "dwsolver-b200: master LP failed (code %d)\n", mrc0); return fail(DW_STATUS_ERR_INTERNAL); }
     }
 
     // ---- Phase II (src/dw_solver.c:649-694, stop rule src/dw_phases.c:462-484) --------------------------------
@@ -585,6 +591,22 @@ static int dw_core(int K, int L, const dwgpu_block_desc *desc_in, const double *
     return fail(status);
 }
 
+// dw_core behind the C boundary: nothing in this layer may exit or throw into the caller (a thread that cannot be
+// created, an allocation that fails) — it comes back as DW_STATUS_ERR_INTERNAL like any engine failure
+template <typename... A>
+static int dw_core_guarded(dw_result_t *result, A &&...args)
+{
+    try {
+        return dw_core(std::forward<A>(args)...);
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "dwsolver-b200: %s\n", e.what());
+    } catch (...) {
+        std::fprintf(stderr, "dwsolver-b200: unexpected failure in the solve loop\n");
+    }
+    if (result) { std::free(result->x); result->x = nullptr; result->num_vars = 0; result->status = DW_STATUS_ERR_INTERNAL; }
+    return DW_STATUS_ERR_INTERNAL;
+}
+
 extern "C" {
 
 void dw_options_init(dw_options_t *o)
@@ -651,7 +673,7 @@ int dw_solve(const char *master_file, const char *const *subproblem_files, int n
     for (int k = 0; k < K; ++k) names[k] = blocks[k].col_names;
     std::vector<double> llb(L), lub(L);
     for (int i = 0; i < L; ++i) { llb[i] = to_engine_bound(master.row_lb[i]); lub[i] = to_engine_bound(master.row_ub[i]); }
-    return dw_core(K, L, desc.data(), llb.data(), lub.data(), &names, opt, t_begin, result, &master.row_names);
+    return dw_core_guarded(result, K, L, desc.data(), llb.data(), lub.data(), &names, opt, t_begin, result, &master.row_names);
 }
 
 int dw_solve_blocks(int K, int L, const dwgpu_block_desc *blocks, const double *link_lb, const double *link_ub,
@@ -663,7 +685,7 @@ int dw_solve_blocks(int K, int L, const dwgpu_block_desc *blocks, const double *
     dw_options_t opt;
     if (opts_in) opt = *opts_in; else dw_options_init(&opt);
     std::memset(&g_stats, 0, sizeof(g_stats));
-    return dw_core(K, L, blocks, link_lb, link_ub, nullptr, opt, now_s(), result);
+    return dw_core_guarded(result, K, L, blocks, link_lb, link_ub, nullptr, opt, now_s(), result);
 }
 
 int dw_write_container(const char *master_file, const char *const *subproblem_files, int num_subproblems, double shift,
@@ -706,7 +728,7 @@ int dw_solve_container(const char *container_path, const dw_options_t *opts_in, 
     }
     g_stats.seconds_read = now_s() - t_begin;
     if (opt.shift == 0.0) opt.shift = v.shift;          // an explicit option wins over the stored constant
-    return dw_core(v.K, v.L, v.desc.data(), v.link_lb, v.link_ub, v.has_names ? &v.names : nullptr, opt, t_begin, result);
+    return dw_core_guarded(result, v.K, v.L, v.desc.data(), v.link_lb, v.link_ub, v.has_names ? &v.names : nullptr, opt, t_begin, result);
 }
 
 }  // extern "C"
