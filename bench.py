@@ -656,11 +656,15 @@ def main():
                     # twice: the first call of a process also pays one-off costs of the CUDA runtime (lazy kernel loading,
                     # the first pinned allocations: 0.03 - 0.8 s depending on the box); both are reported
                     first_ = dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=0)["stats"]["seconds_total"]
-                    r_ = dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=0)
+                    # warm calls: three of them, the fastest is reported and all are listed (a single warm call can catch
+                    # a one-off allocator or driver hiccup that is several times a 25 ms solve at config A)
+                    warm_ = [dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=0) for _ in range(3)]
+                    r_ = min(warm_, key=lambda q: q["stats"]["seconds_total"])
                 finally:
                     os.chdir(cwd)
             st_ = r_["stats"]
-            tto = {"seconds": st_["seconds_total"], "first_call_seconds": first_, "subproblem_seconds": st_["seconds_subproblems"],
+            tto = {"seconds": st_["seconds_total"], "first_call_seconds": first_,
+                   "warm_call_seconds": [q["stats"]["seconds_total"] for q in warm_], "subproblem_seconds": st_["seconds_subproblems"],
                    "master_seconds": st_["seconds_master"], "dw_rounds": st_["dw_iterations"], "status": r_["status"],
                    "objective": r_["objective"], "objective_of_recorded_run": dw_objective,
                    "api": "dw_solve_blocks (include/dwsolver.h): GPU subproblems + this build's master LP — the device-resident "
