@@ -621,6 +621,13 @@ def main():
                     "frac_touched": achieved / (wj["pivot_pattern_GBps"] * world)}
             if traffic_launch and traffic_launch.get("dram_GBps"):
                 wall["frac_dram_of_traffic_launch"] = traffic_launch["dram_GBps"] / wj["pivot_pattern_GBps"]
+            # the same wall as a RATE OF 32-BYTE SECTOR OPERATIONS at L2 (what the microbenchmark saturates): the captured
+            # launch's lts sector reads + writes (ncu) over its live duration
+            if traffic_launch and tr.get("lts_sectors_per_launch") and traffic_launch["ms"] > 0:
+                rate = tr["lts_sectors_per_launch"] / (traffic_launch["ms"] * 1e-3)
+                wall["l2_sector_ops_per_s_of_traffic_launch"] = rate
+                wall["sector_ops_wall_per_s"] = wj["pivot_pattern_sector_ops_per_s"]
+                wall["frac_sector_ops_of_traffic_launch"] = rate / wj["pivot_pattern_sector_ops_per_s"]
         except (OSError, ValueError, KeyError):
             pass
     roofline = {"bound": bound, "achieved": achieved, "peak": peak_all, "unit": "GB/s",
