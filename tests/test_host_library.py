@@ -547,6 +547,51 @@ def test_dw_solve_blocks_config_a_both_masters(monkeypatch, tmp_path):
     assert b["status"] == 0 and abs(b["objective"] - want) <= 1e-7 * (1 + abs(want))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["mcf", "examples", "infeasible"])
+def test_dw_solve_with_the_device_master(case, monkeypatch, tmp_path, golden):
+    """DWSOLVER_MASTER=ipm: the restricted master solved by the device-resident interior-point method
+    (csrc/master_ipm.cu behind host/ipm_master.cc) through the whole drop-in loop — Phase I with artificials, Phase II,
+    reconstruction from the (non-vertex) master solution.  Same optimum as the simplex master to 1e-7, and the
+    reconstructed x written to relaxed_solution is feasible for every block and every linking row and attains it."""
+    from dwsolver_b200.solver import dw_solve_blocks
+    monkeypatch.chdir(tmp_path)
+    if case == "infeasible":
+        # x1 >= 1, x2 >= 1, x1 + x2 <= 1: the device master cannot converge on an infeasible Phase II master; the simplex
+        # master takes over and reports it
+        monkeypatch.setenv("DWSOLVER_MASTER", "ipm")
+        inf = P.BlockAngularLP(K=2, L=1, blocks=[_tiny_block(1.0, 5.0, 1.0), _tiny_block(1.0, 5.0, 1.0)],
+                               link_lb=np.array([-np.inf]), link_ub=np.array([1.0]))
+        assert dw_solve_blocks(inf, verbosity=-1, print_relaxed_sol=0)["status"] == 3
+        return
+    probs = [P.gen_mcf(96, 64, 128, 32, 1024001)] if case == "mcf" else [load_example(n) for n in ("book_dantzig", "four_sea", "web_trick", "book_lasdon")]
+    for prob in probs:
+        monkeypatch.setenv("DWSOLVER_MASTER", "gub")
+        ref = dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=0)
+        monkeypatch.setenv("DWSOLVER_MASTER", "ipm")
+        out = dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=1)
+        assert ref["status"] == 0 and out["status"] == 0
+        assert abs(out["objective"] - ref["objective"]) <= 1e-7 * (1 + abs(ref["objective"])), (out["objective"], ref["objective"])
+        # the reconstruction: relaxed_solution names the variables x_<k>_<j>
+        xs = [np.zeros(b.n) for b in prob.blocks]
+        for line in open(tmp_path / "relaxed_solution"):
+            nm, v = line.split()
+            _, k, j = nm.split("_")
+            xs[int(k)][int(j)] = float(v)
+        link = np.zeros(prob.L)
+        total = float(getattr(prob, "shift", 0.0) or 0.0)
+        for b, x in zip(prob.blocks, xs):
+            act = sp.csr_matrix((b.a_val, b.a_col, b.a_rowptr), shape=(b.m, b.n)) @ x
+            ub = P.effective_col_ub(b)
+            tol = 2e-5          # relaxed_solution prints %f (six decimals)
+            assert (act >= b.row_lb - tol * (1 + np.abs(act))).all() and (act <= b.row_ub + tol * (1 + np.abs(act))).all()
+            assert (x >= b.col_lb - tol).all() and (x <= ub + tol).all()
+            np.add.at(link, b.d_row, x[b.d_col] * b.d_val)
+            total += float(b.c_master @ x)
+        assert (link >= prob.link_lb - 1e-3 * (1 + np.abs(link))).all() and (link <= prob.link_ub + 1e-3 * (1 + np.abs(link))).all()
+        assert abs(total - out["objective"]) <= 1e-4 * (1 + abs(out["objective"]))
+
+
 def _tiny_block(lb, ub, c, d_rows=(0,), d_vals=(1.0,)):
     z = np.zeros(0)
     return P.Block(m=1, n=1, a_rowptr=np.array([0, 1], np.int32), a_col=np.array([0], np.int32), a_val=np.array([1.0]),
