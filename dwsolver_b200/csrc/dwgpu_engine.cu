@@ -218,6 +218,11 @@ struct dwgpu_engine {
     long long solves = 0;
     int last_launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // gmem start/end, smem start/end
+    // A round (or a reset) may run on a caller's stream; everything that READS the engine's device arrays afterwards runs on
+    // e->stream.  ev_done is recorded behind the last launch on whichever stream it used and the readers wait for it, so a
+    // fetch right after dwgpu_iterate_device(..., other_stream) is ordered without the caller synchronising.
+    cudaEvent_t ev_done = nullptr;
+    bool ev_done_pending = false;
     bool ev_used[2] = {false, false};
     bool initialised = false;
 };
@@ -429,6 +434,7 @@ void dwgpu_destroy(dwgpu_engine *e)
     e->hp_src.release(); e->hp_dst.release(); e->hp_len.release();
     if (e->h_mpack) cudaFreeHost(e->h_mpack);
     if (e->comm) dwgpu_comm_release(e);
+    if (e->ev_done) cudaEventDestroy(e->ev_done);
     if (e->h_pack) cudaFreeHost(e->h_pack);
     if (e->h_mail) cudaFreeHost(e->h_mail);
     if (e->h_r) cudaFreeHost(e->h_r);
@@ -478,6 +484,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, opt.device));
     CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     for (auto &ev : e->ev) CUE(cudaEventCreate(&ev));
+    CUE(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
 
     // ---- sizes and offsets
     e->m.resize(K); e->n.resize(K); e->xoff.resize(K + 1); e->path.resize(K);
@@ -920,13 +927,23 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         e->ev_used[0] = true;
     }
     e->solves += e->K;
+    if (st != e->stream && e->ev_done) { CU(cudaEventRecord(e->ev_done, st)); e->ev_done_pending = true; }
     return 0;
+}
+
+// orders e->stream behind the last round / reset that ran on another stream
+static cudaError_t after_last_round(dwgpu_engine *e)
+{
+    if (!e->ev_done_pending) return cudaSuccess;
+    e->ev_done_pending = false;
+    return cudaStreamWaitEvent(e->stream, e->ev_done, 0);
 }
 
 int dwgpu_fetch_results(dwgpu_engine *e, dwgpu_proposals *o)
 {
     if (!e) return fail(DWGPU_E_ARGS, "engine is NULL");
     CU(cudaSetDevice(e->device));
+    CU(after_last_round(e));
     cudaStream_t st = e->stream;
     if (e->h_dbg) {
         cudaError_t se = cudaStreamSynchronize(st);
@@ -958,6 +975,7 @@ static int pack_round(dwgpu_engine *e, const double *r, dwgpu_packed *out)
 {
     if (!out) return fail(DWGPU_E_ARGS, "out is NULL");
     cudaStream_t st = e->stream;
+    CU(after_last_round(e));
     dwk::PackSrc s;
     s.obj = e->obj.p; s.cost = e->cost.p; s.val = e->val.p;
     s.status = e->status.p; s.len = e->len.p; s.ind = e->ind.p;
@@ -1146,6 +1164,7 @@ int dwgpu_reset(dwgpu_engine *e, void *stream)
     e->have_proposals = false;
     e->mail_valid = false;
     e->uplink_valid = false;
+    if (st != e->stream && e->ev_done) { CU(cudaEventRecord(e->ev_done, st)); e->ev_done_pending = true; }
     return 0;
 }
 
@@ -1200,6 +1219,7 @@ int dwgpu_fetch_x(dwgpu_engine *e, int k, double *x)
 {
     if (!e || !x || k < 0 || k >= e->K) return fail(DWGPU_E_ARGS, "bad arguments");
     CU(cudaSetDevice(e->device));
+    CU(after_last_round(e));
     CU(cudaStreamSynchronize(e->stream));
     if (e->n[k] > 0)
         CU(cudaMemcpy(x, e->x.p + e->xoff[k], sizeof(double) * e->n[k], cudaMemcpyDeviceToHost));
@@ -1211,6 +1231,7 @@ int dwgpu_history_push(dwgpu_engine *e, int count, const int *blocks, long long 
     if (!e || count < 0 || (count > 0 && (!blocks || !ids_out))) return fail(DWGPU_E_ARGS, "bad arguments");
     if (count == 0) return 0;
     CU(cudaSetDevice(e->device));
+    CU(after_last_round(e));
     cudaStream_t st = e->stream;
     long long need = 0;
     for (int i = 0; i < count; ++i) {
@@ -1394,6 +1415,7 @@ int dwgpu_get_counters(dwgpu_engine *e, dwgpu_counters *t)
 {
     if (!e || !t) return fail(DWGPU_E_ARGS, "NULL argument");
     CU(cudaSetDevice(e->device));
+    CU(after_last_round(e));
     CU(cudaStreamSynchronize(e->stream));
     std::vector<unsigned long long> h((size_t)e->K * 8);
     CU(cudaMemcpy(h.data(), e->counters.p, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
@@ -1414,6 +1436,7 @@ int dwgpu_get_block_iterations(dwgpu_engine *e, long long *iters)
 {
     if (!e || !iters) return fail(DWGPU_E_ARGS, "NULL argument");
     CU(cudaSetDevice(e->device));
+    CU(after_last_round(e));
     CU(cudaStreamSynchronize(e->stream));
     CU(cudaMemcpy(iters, e->last_iters.p, sizeof(long long) * e->K, cudaMemcpyDeviceToHost));
     return 0;

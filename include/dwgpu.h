@@ -186,6 +186,10 @@ int  dwgpu_initial_solve_device(dwgpu_engine *e, void *stream);
  * the engine's own stream).  Asynchronous; results stay on the device, see
  * dwgpu_device_results().  d_pi must stay valid until the stream reaches the end of the call. */
 int  dwgpu_iterate_device(dwgpu_engine *e, const double *d_pi, int phase_one, void *stream);
+/* Stream contract: a round or reset enqueued on a caller's stream is followed by an event; every entry point that reads
+ * the engine's device arrays afterwards (fetch_*, history_*, get_*, *_packed) makes the engine's own stream wait for it,
+ * so no synchronisation by the caller is needed between e.g. dwgpu_iterate_device(e, pi, phase, stream) and
+ * dwgpu_fetch_results(e, &out). */
 
 /* Device-resident result arrays of the last round (same layout as dwgpu_proposals). */
 int  dwgpu_device_results(dwgpu_engine *e, dwgpu_proposals *dev_ptrs);
