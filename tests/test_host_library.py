@@ -624,12 +624,16 @@ def test_dw_solve_blocks_status_codes(monkeypatch, tmp_path):
 
 
 @pytest.mark.gpu
-def test_random_instances_match_highs(monkeypatch, tmp_path):
+@pytest.mark.parametrize("master", ["auto", "ipm"])
+def test_random_instances_match_highs(master, monkeypatch, tmp_path):
     """twelve random block-angular instances (network and dense blocks, all three small-block kernel paths) through
-    dw_solve_blocks against the HiGHS optimum of the monolithic LP (profiles/stress_dw.py runs more of them)"""
+    dw_solve_blocks against the HiGHS optimum of the monolithic LP (profiles/stress_dw.py runs more of them) — with the
+    master the library picks by size (the host simplex at these sizes) and with the device interior-point master forced"""
     from dwsolver_b200.solver import dw_solve_blocks
     from highs_util import solve_monolithic
     monkeypatch.chdir(tmp_path)
+    if master == "ipm":
+        monkeypatch.setenv("DWSOLVER_MASTER", "ipm")
     rng = np.random.default_rng(77)
     for t in range(12):
         if t % 3 == 0:
