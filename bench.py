@@ -18,7 +18,8 @@ work.  The master LP itself is outside the hot path.
   cpu_baseline   the CPU oracle ("port": pthreads + our restatement, NOT GLPK — GLPK is neither in the
             reference tree nor on the box) replaying the same trajectory on a bounded sample of blocks
 
-`--impl reference` times that CPU arm alone with all host threads and prints the same line shape.
+`--impl reference` times that CPU arm alone with all host threads (the whole instance per step) and prints the same line
+shape plus the CPU arm's DW time-to-optimal (same host loop and master LP, oracle subproblems) and a per-block HiGHS sample.
 Launch:  python bench.py [--gpus N --steps K --warmup W]   (N>1: via torch.distributed.run)
 """
 from __future__ import annotations
