@@ -627,6 +627,47 @@ def test_several_dual_vectors_per_round(kind):
     eng.close()
 
 
+def test_round_through_the_c_layer_communicator_single_rank():
+    """SURVEY 8e from the C layer, as far as one GPU can show it: an NCCL communicator of size one (dwgpu_comm_init), the
+    up-link buffer in this rank's HBM (dwgpu_uplink_create / _attach) and rounds through dwgpu_round_comm — ncclBroadcast of
+    pi, solve kernels whose epilogues store the proposals into the up-link window, closing ncclAllReduce — must hand the
+    master, via dwgpu_pack_gathered, exactly what the single-engine API returns.  (2/4/8 ranks: bench.py --gpus N.)"""
+    import torch
+    from dwsolver_b200.engine import Engine
+    prob = P.gen_mcf(48, 256, 512, 256, 8192001)
+    ref = engine(prob)
+    eng = engine(prob, fetch_x=False)
+    eng.comm_init(Engine.comm_unique_id(), 1, 0)
+    _, up = eng.uplink_create(prob.K)
+    eng.uplink_attach(None, prob.K, 0)
+    rng = np.random.default_rng(12)
+    pis = [None] + [-rng.random(prob.L) * 10.0 * (t + 1) for t in range(3)]
+    pi_dev = torch.zeros(prob.L, dtype=torch.float64, device="cuda")
+    for t, pi in enumerate(pis):
+        if pi is None:
+            want = ref.initial()
+            eng.round_comm(0, False, True)
+        else:
+            want = ref.iterate(pi, t == 1)
+            pi_dev.copy_(torch.from_numpy(pi))
+            torch.cuda.synchronize()
+            eng.round_comm(pi_dev.data_ptr(), t == 1, False)
+        got = eng.pack_gathered(prob.K, {f: C_addr(getattr(up, f)) for f in ("obj", "cost", "val", "status", "len", "ind")})
+        for k in range(prob.K):
+            w = want[k]
+            assert got["status"][k] == w["status"] == OPT
+            assert got["obj"][k] == w["obj"] and got["cost"][k] == w["cost"]
+            lo, hi = got["colptr"][k], got["colptr"][k + 1]
+            assert np.array_equal(got["ind"][lo:hi], w["ind"]) and np.array_equal(got["val"][lo:hi], w["val"])
+    eng.close()
+    ref.close()
+
+
+def C_addr(ptr):
+    import ctypes as C
+    return C.cast(ptr, C.c_void_p).value
+
+
 def test_two_live_engines_of_different_shapes():
     """A kernel's dynamic shared-memory limit belongs to the device, not to an engine: an engine created later for
     smaller blocks must not take it away from one that is still launching (several engines live in one process when
