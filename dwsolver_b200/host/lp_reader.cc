@@ -281,8 +281,15 @@ LpModel parse_lp_text(const std::string &text)
         size_t adv = 1;
         // every keyword is at most 9 characters long and starts with one of m s b g i e (any case): almost every
         // name token of a large model is dismissed by this test without building a lower-case copy
+        // ... and, like glp_read_lp, only a word that BEGINS A LINE can be a section keyword: a column that happens to be
+        // called st, end, bin, int, ... inside an objective or constraint line is a column
+        auto begins_line = [&](const Tok &t) {
+            const char *p0 = text.data(), *p = t.text.data();
+            while (p > p0 && (p[-1] == ' ' || p[-1] == '\t' || p[-1] == '\r')) --p;
+            return p == p0 || p[-1] == '\n';
+        };
         if (toks[i].kind == T_NAME && toks[i].text.size() <= 9 && std::strchr("mMsSbBgGiIeE", toks[i].text[0]) &&
-            !(i + 1 < toks.size() && is_op(toks[i + 1], ":"))) {
+            !(i + 1 < toks.size() && is_op(toks[i + 1], ":")) && begins_line(toks[i])) {
             const std::string w = lower(toks[i].text);
             if ((w == "subject" || w == "such") && i + 1 < toks.size() && toks[i + 1].kind == T_NAME &&
                 (lower(toks[i + 1].text) == "to" || lower(toks[i + 1].text) == "that")) { sec = S_ROWS; adv = 2; }

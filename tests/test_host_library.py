@@ -45,6 +45,17 @@ def lib():
     return L
 
 
+def test_lp_reader_keywords_only_at_line_start(tmp_path):
+    """glp_read_lp recognises section keywords only at the start of a line; columns named like keywords
+    (st, end, bin, int, general, bounds) inside an objective or constraint line are columns."""
+    path = tmp_path / "kw.lp"
+    path.write_text("Minimize\n obj: 2 st + 3 end + bin - int + 5 general\nSubject To\n c1: st + end + bin >= 1\n"
+                    " c2: int + general - bounds <= 4\nBounds\n 0 <= st <= 7\n end <= 3\n bounds free\nEnd\n")
+    dims = (C.c_int * 3)()
+    assert hooks().dwhost_lp_dims(str(path).encode(), dims) == 0
+    assert list(dims) == [2, 6, 6]                       # 2 rows, 6 columns, 6 non-zeros
+
+
 _HOOKS = None
 
 
