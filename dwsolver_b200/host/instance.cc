@@ -60,6 +60,10 @@ void read_problem(const char *master_file, const char *const *subproblem_files, 
     const bool dbg = std::getenv("DWSOLVER_READ_DEBUG") != nullptr;
     const double t0 = now_s();
     master = read_lp_file(master_file);
+    // Objective direction: the reference leaves a file's Maximize in its glp_prob and glp_simplex honours it — for a block
+    // that would MAXIMISE the reduced cost the master asks it to minimise (src/dw_subprob.c:320-329).  Neither is a
+    // Dantzig-Wolfe run; this library says so instead of silently minimising.
+    if (master.maximize) throw std::runtime_error(std::string("the master file ") + master_file + " has a Maximize objective: only minimisation is supported");
     const double t1 = now_s();
     blocks.assign((size_t)K, BlockHost());
     std::vector<std::vector<std::pair<int, double>>> mcols(master.n());
@@ -74,6 +78,7 @@ void read_problem(const char *master_file, const char *const *subproblem_files, 
         try {
             for (int k = t; k < K; k += readers) {
                 LpModel sub = read_lp_file(subproblem_files[k]);
+                if (sub.maximize) throw std::runtime_error(std::string("the subproblem file ") + subproblem_files[k] + " has a Maximize objective: only minimisation is supported");
                 build_block(sub, master, mcols, blocks[k]);
             }
         } catch (const std::exception &e) {
