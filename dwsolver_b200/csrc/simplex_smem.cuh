@@ -774,6 +774,15 @@ __device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, i
                     const int j = (int)c.acol[e] * IW;
 #pragma unroll
                     for (int u = 0; u < IW; ++u) rw2[j + u] = make_double2(v[t][u].x * inv, v[t][u].y * inv);
+#if DWK_TIMERS
+                    {   // packing statistics of the pivot row: non-zero doubles per 32-byte item the sweep moves
+                        int nzd = 0;
+#pragma unroll
+                        for (int u = 0; u < IW; ++u) nzd += (v[t][u].x != 0.0) + (v[t][u].y != 0.0);
+                        atomicAdd(&g_phase[12], (unsigned long long)nzd);
+                        atomicAdd(&g_phase[13], 1ull);
+                    }
+#endif
                 }
             }
             __syncthreads();

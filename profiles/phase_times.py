@@ -47,12 +47,14 @@ for r in range(len(phases)):
     v = grab(); total += v; rows.append(("round %d" % r, v, sum(eng.last_kernel_ms())))
 print("%-10s %9s %12s  " % ("launch", "ms", "Mcycles") + "  ".join("%2d" % i for i in range(12)))
 for name, v, ms in rows:
-    cyc = v[:15].sum()
+    cyc = v[:12].sum()
     if cyc == 0:
         continue
     print("%-10s %9.3f %12.1f  " % (name, ms, cyc / 1e6) + "  ".join("%2.0f" % (100 * x / cyc) for x in v[:12]))
-cyc = total[:15].sum()
+cyc = total[:12].sum()
 print("\ntotal CTA cycles %.3e over %d CTAs" % (cyc, total[15]))
 for i in range(12):
     print("  %2d %-28s %6.2f %%" % (i, NAMES[i], 100 * total[i] / cyc))
+if total[13] > 0:
+    print("pivot rows fetched inside the sweep: %.0f items of 32 B, %.2f non-zero doubles per item (4 = perfectly packed)" % (total[13], total[12] / total[13]))
 eng.close()
