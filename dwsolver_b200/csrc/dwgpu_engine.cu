@@ -27,6 +27,7 @@
 #include "simplex_cta.cuh"
 #include "simplex_smem.cuh"
 #include "simplex_warp.cuh"
+#include "simplex_sparse.cuh"
 #include "pack.cuh"
 #include "simplex_cluster.cuh"
 
@@ -146,6 +147,16 @@ struct dwgpu_engine {
     bool warp_ok_g = false;            // every block of list_g fits the warp kernel
     DevBuf<int> redo_list, redo_count; // blocks the warp kernel handed over to the CTA kernel this round
     DevBuf<unsigned char> redo_moved;
+    // path 5 (simplex_sparse.cuh): packed tableau in shared memory.  Hand-over lists of a round: [0] probe -> solve launch,
+    // [1] small heap -> large heap, [2] -> dense path-3 kernel
+    std::vector<int> list_s;
+    DevBuf<int> d_list_s, sp_lists, sp_counts, spflag;
+    DevBuf<unsigned char> sp_moved, sp_reb;
+    DevBuf<unsigned long long> sp_stats;   // hand-over / re-pack counters (dwgpu_debug_sparse_stats)
+    int sp_nt = 256;                   // threads of the solve kernel (DWGPU_SPARSE_THREADS = 128 | 256)
+    int sp_H0 = 0, sp_H1 = 0;          // heap doubles of the two solve launches
+    size_t sp_smem0 = 0, sp_smem1 = 0, sp_smem_probe = 0;
+    bool sp_probe = true;              // DWGPU_SPARSE_PROBE=0: every round goes straight to the solve launch
     int warp_bail_after = 0;           // test hook (DWGPU_WARP_BAIL_AFTER): hand over after this many basis changes
     bool reorder = true;
     bool have_proposals = false;       // a round has written every block's proposal since create / reset
@@ -404,6 +415,22 @@ int dwgpu_debug_phases(unsigned long long *out16, int reset)
 }
 #endif
 
+// path 5 diagnostics (not part of include/dwgpu.h): [0] blocks moved small -> large heap, [1] -> dense path (heap), [2] -> dense
+// path (residual check), [3] heap re-packs, [4] batched sweeps, [5] union-size checks, [6] blocks finished by the probe launch,
+// [7] blocks the probe passed on; [8] heap doubles of the small launch, [9] of the large one
+extern "C" int dwgpu_debug_sparse_stats(dwgpu_engine *e, unsigned long long *out10, int reset)
+{
+    if (!e || !out10) return 1;
+    for (int i = 0; i < 10; ++i) out10[i] = 0;
+    if (e->list_s.empty()) return 0;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(out10, e->sp_stats.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    out10[8] = (unsigned long long)e->sp_H0; out10[9] = (unsigned long long)e->sp_H1;
+    if (reset && cudaMemset(e->sp_stats.p, 0, 8 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+    return 0;
+}
+
 void dwgpu_options_init(dwgpu_options *o)
 {
     if (!o) return;
@@ -445,6 +472,7 @@ void dwgpu_destroy(dwgpu_engine *e)
     e->r_dev.release();
     e->counters.release(); e->last_iters.release();
     e->redo_list.release(); e->redo_count.release(); e->redo_moved.release();
+    e->d_list_s.release(); e->sp_lists.release(); e->sp_counts.release(); e->spflag.release(); e->sp_moved.release(); e->sp_reb.release(); e->sp_stats.release();
     if (e->h_pi) cudaFreeHost(e->h_pi);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -495,6 +523,12 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     e->xoff[0] = 0;
     int n_cluster_blocks = 0;
     const size_t smem_cap = (size_t)e->max_smem_optin - 2048;   // static scratch + reserve
+    // path 5 is opt-in (DWGPU_SPARSE=1 or force_path = 5): measured slower than path 3 on config B
+    bool sparse_on = false;
+    if (const char *sv = std::getenv("DWGPU_SPARSE")) sparse_on = std::atoi(sv) != 0;
+    if (opt.force_path == 5) sparse_on = true;
+    if (const char *sv = std::getenv("DWGPU_SPARSE_THREADS")) e->sp_nt = std::atoi(sv) == 128 ? 128 : 256;
+    if (const char *sv = std::getenv("DWGPU_SPARSE_PROBE")) e->sp_probe = std::atoi(sv) != 0;
     for (int k = 0; k < K; ++k) {
         const dwgpu_block_desc &b = bd[k];
         if (b.m < 0 || b.n < 0 || b.d_nnz < 0 || (b.m > 0 && !b.a_rowptr))
@@ -504,6 +538,16 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         const bool fits_g = dwk::smem2_bytes(b.m, b.n, true) <= smem_cap / 2;   // at least 2 CTAs per SM
         const bool fits_c = dwk::cl_smem_bytes(b.m, b.n) <= smem_cap && b.m >= 1 && b.m < 65535 && b.n < 65535;
         int path = fits ? 1 : (fits_g ? 3 : (fits_c ? 4 : 2));
+        // path 5: blocks of the path-3 class whose constraint matrix is sparse enough for the packed tableau to live in
+        // shared memory (its fill is watched at run time; a block that outgrows the heaps moves to path 3 for good)
+        const int nnz_a = b.m > 0 ? b.a_rowptr[b.m] : 0;
+        // (the initial image, rows with their slack, must fill at most half of the small heap)
+        const long long sp_fixed = (long long)dwk::sp_solve_bytes(b.m, b.n, e->sp_nt, 0);
+        const long long sp_h0 = (((long long)smem_cap - 4096) / 2 - sp_fixed) / (long long)sizeof(double);
+        const bool fits_s = fits_g && sparse_on && b.m >= 1 && b.m <= dwk::SP_MAX_M && b.n >= 1 && b.n <= dwk::SP_MAX_N &&
+                            2 * (nnz_a + nnz_a / 4 + 4LL * b.m) <= sp_h0;
+        if (path == 3 && fits_s) path = 5;
+        if (opt.force_path == 5 && fits_s && !fits) path = 5;
         if (opt.force_path == 2) path = 2;
         if (opt.force_path == 3 && fits_g) path = 3;
         if (opt.force_path == 4 && fits_c) path = 4;
@@ -514,9 +558,15 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         ldg[k] = path == 1 ? dwk::smem2_ld(b.n) : ((b.n + 3) & ~3);
         if (path == 4) n_cluster_blocks++;
         const int nnz = b.m > 0 ? b.a_rowptr[b.m] : 0;
-        t_off[k + 1] = t_off[k] + (long long)b.m * ldg[k];
+        long long t_cells = (long long)b.m * ldg[k];
+        if (path == 5) {       // the slot holds the dense image (path-3 fall-back) or the packed one with the largest heap
+            const long long img = (long long)((dwk::sp_heap_pos(b.m, b.n) + 15) / 8) + (long long)(smem_cap / sizeof(double)) + 2;
+            t_cells = std::max(t_cells, img);
+            t_cells = (t_cells + 1) & ~1LL;
+        }
+        t_off[k + 1] = t_off[k] + t_cells;
         pst_off[k + 1] = pst_off[k] + (long long)dwk::pst_bytes(b.m, b.n);
-        rm_off[k + 1] = rm_off[k] + (path == 3 ? (long long)(dwk::rmask_bytes(b.m, b.n) / sizeof(unsigned)) : 0);
+        rm_off[k + 1] = rm_off[k] + ((path == 3 || path == 5) ? (long long)(dwk::rmask_bytes(b.m, b.n) / sizeof(unsigned)) : 0);
         r_off[k + 1] = r_off[k] + b.m;
         e->xoff[k + 1] = e->xoff[k] + b.n;
         v_off[k + 1] = v_off[k] + b.m + b.n;
@@ -534,7 +584,25 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
             e->smem_dyn_w = std::max(e->smem_dyn_w, dwk::warp_smem_bytes(b.m, b.n));
         }
         else if (path == 4) { e->list_c.push_back(k); e->smem_dyn_c = std::max(e->smem_dyn_c, dwk::cl_smem_bytes(b.m, b.n)); }
+        else if (path == 5) {
+            e->list_s.push_back(k);
+            e->smem_dyn_g = std::max(e->smem_dyn_g, dwk::smem2_bytes(b.m, b.n, true));     // the dense fall-back runs the generic path-3 kernel
+            e->sp_smem_probe = std::max(e->sp_smem_probe, dwk::sp_probe_bytes(b.m, b.n));
+            e->sp_smem0 = std::max(e->sp_smem0, dwk::sp_solve_bytes(b.m, b.n, e->sp_nt, 0));   // without the heap for now
+        }
         else e->list_gmem.push_back(k);
+    }
+    if (!e->list_s.empty()) {
+        // heap sizes: the small launch keeps two CTAs per SM, the large one takes all the shared memory of an SM
+        const size_t fixed = e->sp_smem0;
+        const size_t cap0 = (smem_cap - 4096) / 2, cap1 = smem_cap;
+        e->sp_H0 = (int)((cap0 - fixed) / sizeof(double)) & ~1;
+        e->sp_H1 = (int)((cap1 - fixed) / sizeof(double)) & ~1;
+        // test hooks: smaller heaps force the hand-overs (small heap -> large heap -> dense path 3)
+        if (const char *hv = std::getenv("DWGPU_SPARSE_H0")) e->sp_H0 = std::max(64, std::min(e->sp_H0, std::atoi(hv))) & ~1;
+        if (const char *hv = std::getenv("DWGPU_SPARSE_H1")) e->sp_H1 = std::max(64, std::min(e->sp_H1, std::atoi(hv))) & ~1;
+        e->sp_smem0 = fixed + sizeof(double) * (size_t)e->sp_H0;
+        e->sp_smem1 = fixed + sizeof(double) * (size_t)e->sp_H1;
     }
     // cluster path: G CTAs (one per SM) per block, the largest power of two that keeps every block of
     // the shard co-resident (148 SMs / blocks), 16 at most (non-portable size); reserved[0] overrides
@@ -550,7 +618,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         const dwgpu_block_desc &b = bd[k];
         long long w = 0;
         if (e->path[k] == 2) w = (long long)((dwk::vec_bytes(b.m, b.n) + 15) / 16 * 2);
-        if (e->path[k] == 3) w = (long long)((b.n + 1) & ~1);      // priced costs cs[n]
+        if (e->path[k] == 3 || e->path[k] == 5) w = (long long)((b.n + 1) & ~1);      // priced costs cs[n]
         if (e->path[k] == 4) w = (long long)dwk::cl_ws_doubles(b.n, e->cluster_size);
         ws_off[k + 1] = ws_off[k] + w;
     }
@@ -633,6 +701,14 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(e->ws.alloc(ws_off[K]));
     CUE(e->rmask.alloc((size_t)rm_off[K]));
     CUE(cudaMemset(e->rmask.p, 0, sizeof(unsigned) * std::max<size_t>((size_t)rm_off[K], 1)));
+    if (!e->list_s.empty()) {
+        CUE(e->spflag.alloc(K)); CUE(cudaMemset(e->spflag.p, 0, sizeof(int) * (size_t)K));
+        CUE(e->sp_lists.alloc(3 * (size_t)K)); CUE(e->sp_counts.alloc(4));
+        CUE(cudaMemset(e->sp_counts.p, 0, sizeof(int) * 4));
+        CUE(e->sp_moved.alloc(K)); CUE(e->sp_reb.alloc(K));
+        CUE(cudaMemset(e->sp_moved.p, 0, (size_t)K)); CUE(cudaMemset(e->sp_reb.p, 0, (size_t)K));
+        CUE(e->sp_stats.alloc(8)); CUE(cudaMemset(e->sp_stats.p, 0, sizeof(unsigned long long) * 8));
+    }
     CUE(e->pi.alloc(L));
     ts[nts++] = stamp();
     {
@@ -703,7 +779,9 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         B.x = e->x.p + e->xoff[k];
         B.dsave = e->dsave.p + e->xoff[k]; B.cssave = e->cssave.p + e->xoff[k]; B.dflag = e->dflag.p + k;
         B.ws = e->ws.p + ws_off[k];
-        B.rmask = e->path[k] == 3 ? e->rmask.p + rm_off[k] : nullptr;
+        B.rmask = (e->path[k] == 3 || e->path[k] == 5) ? e->rmask.p + rm_off[k] : nullptr;
+        B.sparse = e->path[k] == 5 ? 1 : 0;
+        B.spflag = e->path[k] == 5 ? e->spflag.p + k : nullptr;
         B.rwd = dwk::rmask_words(B.n);
         B.xoff = e->xoff[k];
         B.Dt = dt_off[k] >= 0 ? e->Dt.p + dt_off[k] : nullptr;
@@ -715,7 +793,13 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     CUE(e->d_list_g.upload(e->list_g));
     CUE(e->d_list_b.upload(e->list_b));
     CUE(e->d_list_c.upload(e->list_c));
+    CUE(e->d_list_s.upload(e->list_s));
 
+    if (!e->list_s.empty()) {
+        CUE(allow_dynamic_smem(e->device, (const void *)dwk::probe_sparse_kernel<128>, (int)e->sp_smem_probe));
+        CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_sparse_kernel<128>, (int)e->sp_smem1));
+        CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_sparse_kernel<256>, (int)e->sp_smem1));
+    }
     if (!e->list_smem.empty())
         CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_SMEM, 0, 0, false>, (int)e->smem_dyn));
     if (!e->list_a.empty())
@@ -760,7 +844,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         if (!e->list_b.empty())
             CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_warp_kernel<256, 512>, (int)dwk::warp_smem_bytes(256, 512)));
     }
-    if (!e->list_g.empty()) {
+    if (!e->list_g.empty() || !e->list_s.empty()) {
         CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_SMEM, 0, 0, true>, (int)e->smem_dyn_g));
         CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG, 0, 0, true>, (int)e->smem_dyn_g));
         CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG_WIDE, 0, 0, true>, (int)e->smem_dyn_g));
@@ -835,6 +919,7 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
             return cudaGetLastError();
         };
         CU(order(e->d_list_b, e->list_b.size())); CU(order(e->d_list_g, e->list_g.size()));
+        CU(order(e->d_list_s, e->list_s.size()));
         CU(order(e->d_list_a, e->list_a.size())); CU(order(e->d_list_smem, e->list_smem.size()));
     }
     // large blocks first: they are the long poles
@@ -864,6 +949,44 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         e->ev_used[1] = true;
         e->last_launches++;
     }
+    if (!e->list_s.empty()) {
+        // path 5: [probe ->] solve (small heap, 2 CTAs per SM) -> solve (large heap) -> dense path-3 kernel; every
+        // launch after the first reads the length of its list on the device (normally 0 for the last two)
+        const bool own_events = !e->ev_used[1];
+        if (own_events) CU(cudaEventRecord(e->ev[0], st));
+        const unsigned nb = (unsigned)e->list_s.size();
+        const int K_ = e->K;
+        int *l0 = e->sp_lists.p, *l1 = l0 + K_, *l2 = l1 + K_;
+        int *c0 = e->sp_counts.p, *c1 = c0 + 1, *c2 = c0 + 2;
+        CU(cudaMemsetAsync(e->sp_counts.p, 0, sizeof(int) * 4, st));
+        const bool probe = e->sp_probe && !initial && !P.force_full;
+        const int *solve_list = e->d_list_s.p;
+        const int *solve_count = nullptr;
+        if (probe) {
+            dwk::SparseRound R{nullptr, 0, l0, c0, l2, c2, e->sp_moved.p, e->sp_reb.p, e->sp_stats.p};
+            dwk::probe_sparse_kernel<128><<<nb, 128, e->sp_smem_probe, st>>>(e->blocks.p, e->d_list_s.p, (int)nb, P, R);
+            CU(cudaGetLastError());
+            e->last_launches++;
+            solve_list = l0; solve_count = c0;
+        }
+        auto solve = [&](const int *list, const int *cnt, int use_moved, int *nl, int *nc, int level, int H, size_t sm) {
+            dwk::SparseRound R{cnt, use_moved, nl, nc, l2, c2, e->sp_moved.p, e->sp_reb.p, e->sp_stats.p};
+            if (e->sp_nt == 128) dwk::solve_sparse_kernel<128><<<nb, 128, sm, st>>>(e->blocks.p, list, (int)nb, P, R, level, H);
+            else dwk::solve_sparse_kernel<256><<<nb, 256, sm, st>>>(e->blocks.p, list, (int)nb, P, R, level, H);
+            e->last_launches++;
+            return cudaGetLastError();
+        };
+        CU(solve(solve_list, solve_count, 0, l1, c1, 0, e->sp_H0, e->sp_smem0));
+        CU(solve(l1, c1, 1, l2, c2, 1, e->sp_H1, e->sp_smem1));
+        {
+            const dwk::Continuation cn{c2, e->sp_moved.p, e->sp_reb.p};
+            dwk::solve_smem_kernel<NT_TG_WIDE, 0, 0, true><<<nb, NT_TG_WIDE, e->smem_dyn_g, st>>>(e->blocks.p, l2, (int)nb, P, cn);
+            CU(cudaGetLastError());
+            e->last_launches++;
+        }
+        CU(cudaEventRecord(e->ev[1], st));
+        e->ev_used[1] = true;
+    }
     if (!e->list_g.empty() || !e->list_b.empty()) {
         const bool own_events = !e->ev_used[1];
         if (own_events) CU(cudaEventRecord(e->ev[0], st));
@@ -873,7 +996,7 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         // (normally none: the second launch reads the list length on the device and its CTAs exit at once).  Measured on
         // config B (profiles/r2a_warp_kernel.md): the warp kernel needs 30 % fewer instructions per basis change but a
         // single warp's dependent chain is 3x longer, so 10 resident blocks do not beat 4 CTAs (40.1 vs 33.1 ms a step).
-        const dwk::Continuation none{nullptr, nullptr};
+        const dwk::Continuation none{nullptr, nullptr, nullptr};
         auto cta_launch = [&](bool spec_b, const int *list, unsigned nb, int nt, const dwk::Continuation &cn) {
             const size_t sm = spec_b ? dwk::smem2_bytes(256, 512, true) : e->smem_dyn_g;
             if (spec_b) {
@@ -901,7 +1024,7 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
             e->last_launches++;
             rc = cudaGetLastError();
             if (rc != cudaSuccess) return rc;
-            const dwk::Continuation cn{e->redo_count.p, e->redo_moved.p};
+            const dwk::Continuation cn{e->redo_count.p, e->redo_moved.p, nullptr};
             return cta_launch(spec_b, e->redo_list.p, nb, 0, cn);
         };
         if (!e->list_b.empty()) CU(run_list(true, e->d_list_b.p, (unsigned)e->list_b.size(), true));
@@ -913,13 +1036,13 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         CU(cudaEventRecord(e->ev[2], st));
         if (!e->list_a.empty()) {
             dwk::solve_smem_kernel<NT_SMEM, 64, 128, false><<<(unsigned)e->list_a.size(), NT_SMEM, dwk::smem2_bytes(64, 128), st>>>(
-                e->blocks.p, e->d_list_a.p, (int)e->list_a.size(), P, dwk::Continuation{nullptr, nullptr});
+                e->blocks.p, e->d_list_a.p, (int)e->list_a.size(), P, dwk::Continuation{nullptr, nullptr, nullptr});
             CU(cudaGetLastError());
             e->last_launches++;
         }
         if (!e->list_smem.empty()) {
             dwk::solve_smem_kernel<NT_SMEM, 0, 0, false><<<(unsigned)e->list_smem.size(), NT_SMEM, e->smem_dyn, st>>>(
-                e->blocks.p, e->d_list_smem.p, (int)e->list_smem.size(), P, dwk::Continuation{nullptr, nullptr});
+                e->blocks.p, e->d_list_smem.p, (int)e->list_smem.size(), P, dwk::Continuation{nullptr, nullptr, nullptr});
             CU(cudaGetLastError());
             e->last_launches++;
         }

@@ -28,7 +28,7 @@ constexpr double BIG = 1e30;
 
 struct BlockDev {
     int m, n, L, ldg;
-    int pad0, pad1;
+    int sparse, pad1;       // sparse: the block starts on path 5 (packed tableau image at T, simplex_sparse.cuh)
     double *T;              // m x ldg (global, persistent between rounds)
     double *beta;           // m
     int *head;              // m
@@ -52,6 +52,7 @@ struct BlockDev {
     int pad2;
     long long xoff;         // offset of this block's columns in the engine-wide column arrays (x, cs_pre)
     const double *Dt;       // dense D_k transposed, n x L row-major (blocks whose D_k is dense enough for the pricing GEMM; else nullptr)
+    int *spflag;            // path 5: 0 = T holds the packed image, 1 = the block moved to the dense layout of path 3 (nullptr: not a path-5 block)
 };
 
 struct SolveParams {
@@ -628,6 +629,8 @@ __global__ void __launch_bounds__(NT) solve_kernel(const BlockDev *blocks, const
     for (int v = tid; v < m + n; v += NT) B.vstat[v] = c.vstat[v];
 }
 
+template <int NT> __device__ void sp_init_image(const BlockDev &B);     // simplex_sparse.cuh
+
 // initial state: all-logical basis, structurals at a finite bound (GLPK's "standard" basis
 // after glp_read_lp), T = A_k, beta = A_k x_N
 template <int NT>
@@ -644,7 +647,9 @@ __global__ void __launch_bounds__(NT) init_kernel(const BlockDev *blocks, int K)
         B.vstat[v] = v < B.m ? ST_BASIC : initial_stat(B.lo[v], B.up[v]);
     if (threadIdx.x == 0) B.dflag[0] = 0;
     __syncthreads();
-    if (B.rmask != nullptr) {
+    if (B.sparse) {
+        sp_init_image<NT>(B);        // path 5: packed image (simplex_sparse.cuh)
+    } else if (B.rmask != nullptr) {
         // Path 3 reads a tableau cell only through its row's item mask, so only the 32-byte items that hold an
         // entry of A_k are written (whole items: their other cells are real zeros) and the rest of the 1 MB
         // row-major image is left as it is — the reset of config B writes 0.7 GB instead of zeroing 8.6 GB.

@@ -125,6 +125,8 @@ enum { K_NONE = 0, K_PIVOT = 1, K_FAIL = 2, K_REDO = 3 };
 struct Continuation {
     const int *dyn_count;           // nullptr: the launch covers `count` blocks
     const unsigned char *moved;     // by block id; nullptr: none
+    const unsigned char *reb;       // by block id: the tableau in HBM is not valid, rebuild it from A_k for the basis of the
+                                    // state image before anything else (blocks handed over by path 5); nullptr: none
 };
 
 // tableau accessors: global-memory tableaux (TG) bypass L1 (.cg) — rows are streamed once per basis
@@ -1194,10 +1196,12 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
     const int degen_limit = 100 + (m + n) / 2;
     const int dflag_in = B.dflag[0];
     const bool use_saved = dflag_in > 0 && dflag_in < 32;
+    bool reb_now = TG && CN.reb != nullptr && CN.reb[k] != 0;      // block-uniform
 
     for (;;) {
         if (++iter > max_iter) { status = 1; break; }
         phase(1);
+        if (!reb_now) {
         // ---- A. cooperative parts: feasibility scan, phase-1 prices, fresh reduced costs
         if (need_check || infeasible) {
             int viol = 0;
@@ -1333,6 +1337,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
         if (infeasible) { status = 4; break; }
         // nothing moved since the last optimal solve of this block: x_k is still what B.x holds
         if (!s_changed && n_reb == 0 && !P.initial && !P.force_full) { status = 5; x_in_rowp = false; break; }
+        }   // !reb_now
         phase(8);
         // claimed optimal: x into rowp, auxiliary values into colq
         for (int j = tid; j < n; j += NT) {
@@ -1353,8 +1358,9 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
             worst = fmax(worst, fabs(s - c.colq[i]) / (1.0 + fabs(s)));
         }
         worst = block_max<NT>(worst, scr);
-        if (worst > 0.1 * tol_bnd && n_reb < 3) {          // n_reb is block-uniform
+        if ((worst > 0.1 * tol_bnd || reb_now) && n_reb < 3) {          // n_reb is block-uniform
             ++n_reb;
+            reb_now = false;
             phase(9);
             // rebuild T from A_k for the current basis
             for (int e = tid; e < m * ld; e += NT) c.T[e] = 0.0;

@@ -437,6 +437,17 @@ class Engine:
     def last_launch_count(self) -> int:
         return int(self._lib.dwgpu_last_launch_count(self._h))
 
+    def sparse_stats(self, reset: bool = False) -> dict:
+        """Path-5 diagnostics (packed shared-memory tableau): hand-overs, heap re-packs, probe outcomes, heap sizes."""
+        out = (C.c_ulonglong * 10)()
+        fn = self._lib.dwgpu_debug_sparse_stats
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]
+        if fn(self._h, out, 1 if reset else 0) != 0:
+            raise RuntimeError("dwgpu_debug_sparse_stats failed")
+        names = ["to_large_heap", "to_dense_heap", "to_dense_residual", "repacks", "batched_sweeps", "union_checks",
+                 "probe_finished", "probe_passed_on", "heap_small", "heap_large"]
+        return {k: int(v) for k, v in zip(names, out)}
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.dwgpu_destroy(self._h)

@@ -69,7 +69,10 @@ typedef struct dwgpu_options {
     int    clamp_lo_cols; /* 1: finite-lb/no-ub columns get ub = 3000 (dw_subprob.c:116-120) */
     int    force_path;    /* 0 auto; 1 shared-memory tableau; 2 legacy all-global kernel;
                              3 global-memory tableau + shared-memory vectors (one CTA per block);
-                             4 thread-block cluster per block, tableau striped over the CTAs in HBM */
+                             4 thread-block cluster per block, tableau striped over the CTAs in HBM;
+                             5 packed sparse tableau resident in shared memory (opt-in, also DWGPU_SPARSE=1: blocks of
+                               the path-3 class with m <= 1024, n <= 512 and a sparse A_k; hands a block that outgrows
+                               its heap over to path 3) */
     int    max_iter_mult; /* iteration limit = max_iter_mult*(m+n) + 1000 (default 50) */
     double tol_dj;        /* dual feasibility   (default 1e-9) */
     double tol_bnd;       /* primal feasibility, scaled by 1+|bound| (default 1e-9) */

@@ -147,7 +147,7 @@ def test_mcf_config_b_shape_global_tableau_kernel(threads, monkeypatch):
     from oracle import oracle as O
     monkeypatch.setenv("DWGPU_TG_THREADS", str(threads))
     prob = P.gen_mcf(48, 256, 512, 256, 8192001)
-    eng = engine(prob)
+    eng = engine(prob, force_path=3)
     assert set(eng.block_paths()) == {3}
     orc = O.OracleBlocks(prob)
     compare_round(prob, eng.initial(), orc.initial(8), None, False, initial=True)
@@ -688,3 +688,99 @@ def test_two_live_engines_of_different_shapes():
     assert got0 == want0 and got1 == want1             # same kernels, same inputs: bit-identical
     b.close()
     a.close()
+
+
+# ---- path 5: packed sparse tableau in shared memory (simplex_sparse.cuh) ---------------------------------------------
+
+def _traj_b_pis(L, rounds):
+    import os
+    tr = np.load(os.path.join(os.path.dirname(__file__), "golden", "traj_B.npz"))
+    assert tr["pis"].shape[1] == L
+    return [(tr["pis"][r], bool(tr["phase_one"][r])) for r in range(min(rounds, len(tr["pis"])))]
+
+
+@pytest.mark.parametrize("threads", [128, 256])
+def test_sparse_path_matches_oracle_on_config_b_blocks(threads, monkeypatch):
+    """256 x 512 network blocks on path 5 (opt-in: force_path = 5 or DWGPU_SPARSE=1): every round (cold solve, the recorded
+    dual trajectory of config B) matches the oracle at identical (k, pi, phase)."""
+    from oracle import oracle as O
+    monkeypatch.setenv("DWGPU_SPARSE_THREADS", str(threads))
+    prob = P.make_config("B", block_range=range(0, 48))
+    eng = engine(prob, force_path=5)
+    assert set(eng.block_paths()) == {5}
+    orc = O.OracleBlocks(prob)
+    compare_round(prob, eng.initial(), orc.initial(8), None, False, initial=True)
+    for pi, ph in _traj_b_pis(prob.L, 8):
+        compare_round(prob, eng.iterate(pi, ph), orc.iterate(pi, ph, 8), pi, ph)
+    c = eng.counters()
+    assert c["pivots"] > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("threads", [128, 256])
+def test_sparse_path_visits_the_same_vertices_as_path_3(threads, monkeypatch):
+    """Path 5 keeps path 3's pivoting rules, arithmetic and tie-breaks: x_k, the proposal columns, the statuses and the
+    pivot and flip counts agree bit for bit with the dense-tableau kernel, round after round."""
+    monkeypatch.setenv("DWGPU_SPARSE_THREADS", str(threads))
+    prob = P.make_config("B", block_range=range(64, 128))
+    e5, e3 = engine(prob, force_path=5), engine(prob, force_path=3)
+    assert set(e5.block_paths()) == {5} and set(e3.block_paths()) == {3}
+
+    def same(a, b):
+        for k in range(prob.K):
+            assert a[k]["status"] == b[k]["status"], k
+            assert np.array_equal(a[k]["x"], b[k]["x"]), k
+            assert np.array_equal(a[k]["ind"], b[k]["ind"]) and np.array_equal(a[k]["val"], b[k]["val"]), k
+            assert abs(a[k]["obj"] - b[k]["obj"]) <= 1e-12 * (1 + abs(b[k]["obj"])), k
+    same(e5.initial(), e3.initial())
+    for pi, ph in _traj_b_pis(prob.L, 12):
+        same(e5.iterate(pi, ph), e3.iterate(pi, ph))
+    c5, c3 = e5.counters(), e3.counters()
+    assert c5["pivots"] == c3["pivots"] and c5["flips"] == c3["flips"], (c5, c3)
+    e5.close(); e3.close()
+
+
+@pytest.mark.parametrize("h0,h1", [(2600, 0), (2600, 3200), (1200, 1400)])
+def test_sparse_path_hands_over_when_the_heap_fills_up(h0, h1, monkeypatch):
+    """A block whose packed tableau outgrows the small heap is re-packed, then continued by the launch with the large heap,
+    and from there by the dense path-3 kernel (which rebuilds its tableau from A_k for the basis reached).  Tiny heaps
+    (DWGPU_SPARSE_H0 / _H1, in doubles) force every stage; the results still match the oracle, and a block that went dense
+    stays on path 3 in later rounds."""
+    from oracle import oracle as O
+    monkeypatch.setenv("DWGPU_SPARSE_H0", str(h0))
+    if h1:
+        monkeypatch.setenv("DWGPU_SPARSE_H1", str(h1))
+    prob = P.make_config("B", block_range=range(200, 232))
+    eng = engine(prob, force_path=5)
+    assert set(eng.block_paths()) == {5}
+    orc = O.OracleBlocks(prob)
+    compare_round(prob, eng.initial(), orc.initial(8), None, False, initial=True)
+    for pi, ph in _traj_b_pis(prob.L, 6):
+        compare_round(prob, eng.iterate(pi, ph), orc.iterate(pi, ph, 8), pi, ph)
+    # a reset brings every block back to its packed image
+    eng.reset()
+    orc = O.OracleBlocks(prob)
+    compare_round(prob, eng.initial(), orc.initial(8), None, False, initial=True)
+    eng.close()
+
+
+def test_sparse_path_generic_shapes_and_rounds_without_pivots():
+    """shapes that are not 256 x 512 (n not a multiple of 32, m > n / 2), random duals, and a repeated dual vector: the
+    second round with the same duals is finished by the probe launch alone (no pivots, same proposals)."""
+    from oracle import oracle as O
+    for (K, m, n, L, seed) in [(12, 200, 450, 24, 77), (9, 300, 500, 16, 78)]:
+        prob = P.gen_mcf(K, m, n, L, seed)
+        eng = engine(prob, force_path=5)
+        assert set(eng.block_paths()) == {5}
+        orc = O.OracleBlocks(prob)
+        compare_round(prob, eng.initial(), orc.initial(8), None, False, initial=True)
+        rng = np.random.default_rng(seed)
+        for t in range(3):
+            pi = -rng.random(prob.L) * 12.0 * (t + 1)
+            compare_round(prob, eng.iterate(pi, t == 0), orc.iterate(pi, t == 0, 8), pi, t == 0)
+        before = eng.counters()
+        again = eng.iterate(pi, False)
+        compare_round(prob, again, orc.iterate(pi, False, 8), pi, False)
+        after = eng.counters()
+        assert after["pivots"] == before["pivots"] and after["flips"] == before["flips"]
+        eng.close()
