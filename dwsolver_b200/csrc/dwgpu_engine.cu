@@ -27,6 +27,7 @@
 #include "simplex_cta.cuh"
 #include "simplex_smem.cuh"
 #include "simplex_warp.cuh"
+#include "screen_tg.cuh"
 #include "simplex_sparse.cuh"
 #include "pack.cuh"
 #include "simplex_cluster.cuh"
@@ -69,6 +70,7 @@ constexpr int NT_GMEM = 1024;
 // waves of blocks; 128-thread CTAs at 4 per SM finish a single block ~25 % sooner, which is what bounds a
 // launch when the shard is only a wave or two deep (multi-GPU shards of config B: 1024 blocks at N = 8)
 constexpr int NT_TG = 64, NT_TG_WIDE = 128;
+constexpr int SCREEN_NW = 4;        // blocks (warps) per CTA of the screening launch
 
 template <typename T>
 struct DevBuf {
@@ -157,6 +159,21 @@ struct dwgpu_engine {
     int sp_H0 = 0, sp_H1 = 0;          // heap doubles of the two solve launches
     size_t sp_smem0 = 0, sp_smem1 = 0, sp_smem_probe = 0;
     bool sp_probe = true;              // DWGPU_SPARSE_PROBE=0: every round goes straight to the solve launch
+    // screening launch of a priced round on path 3 (screen_tg.cuh): one warp per block finishes the blocks that need no
+    // pivot; the solve launch then covers the device-side list of the others, most attractive columns first
+    bool screen = false;               // DWGPU_SCREEN=1 switches it on.  Measured on config B (profiles/r2o_*): the screening
+                                       // launch costs what a no-pivot round of the CTA kernel costs (0.19 ms: both are bound by the
+                                       // ~55 KB of per-block state a round reads, not by the 4 resident CTAs), so it only adds
+                                       // to the rounds that pivot; ordering the solve launch by attractive columns does not
+                                       // shorten its tail either
+    bool screen_sort = true;           // DWGPU_SCREEN_SORT=0: the solve launch keeps the (atomic) arrival order
+    bool screen_ok_b = false, screen_ok_g = false;
+    int screen_wb_b = 0, screen_wb_g = 0;      // shared memory per warp
+    DevBuf<int> scr_list, scr_count;   // 2 x K ids, 2 counters (list_b, list_g)
+    DevBuf<unsigned> scr_key;          // by block id
+    // staged rounds of the 256 x 512 kernel (simplex_smem.cuh, STG): per-block round data arrives by bulk copies
+    bool stage_b = false;              // DWGPU_STAGE=0 switches it off
+    size_t smem_stage_b = 0;           // dynamic shared memory of the staged instantiation
     int warp_bail_after = 0;           // test hook (DWGPU_WARP_BAIL_AFTER): hand over after this many basis changes
     bool reorder = true;
     bool have_proposals = false;       // a round has written every block's proposal since create / reset
@@ -186,6 +203,7 @@ struct dwgpu_engine {
     DevBuf<int> comm_flag;
     size_t smem_dyn = 0;
     int max_smem_optin = 0;
+    int max_smem_sm = 0;               // shared memory of one SM
     // device arenas
     DevBuf<double> T, bnd, dsave, cssave, a_v, dc_val, dr_val, c_file, c_master, x, ws;
     DevBuf<int> a_rp, a_ci, dc_ptr, dc_row, dr_ptr, dr_col;
@@ -472,6 +490,7 @@ void dwgpu_destroy(dwgpu_engine *e)
     e->r_dev.release();
     e->counters.release(); e->last_iters.release();
     e->redo_list.release(); e->redo_count.release(); e->redo_moved.release();
+    e->scr_list.release(); e->scr_count.release(); e->scr_key.release();
     e->d_list_s.release(); e->sp_lists.release(); e->sp_counts.release(); e->spflag.release(); e->sp_moved.release(); e->sp_reb.release(); e->sp_stats.release();
     if (e->h_pi) cudaFreeHost(e->h_pi);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -510,6 +529,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     double ts[8]; int nts = 0;
     ts[nts++] = stamp();
     CUE(cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, opt.device));
+    CUE(cudaDeviceGetAttribute(&e->max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, opt.device));
     CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     for (auto &ev : e->ev) CUE(cudaEventCreate(&ev));
     CUE(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
@@ -572,8 +592,10 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         v_off[k + 1] = v_off[k] + b.m + b.n;
         a_off[k + 1] = a_off[k] + nnz;
         arp_off[k + 1] = arp_off[k] + b.m + 1;
-        d_off[k + 1] = d_off[k] + b.d_nnz;
-        dcp_off[k + 1] = dcp_off[k] + b.n + 1;
+        // (every block's slices start on a 16-byte boundary and are padded to one: the staged path-3 prologue moves them
+        //  with bulk copies)
+        d_off[k + 1] = d_off[k] + ((b.d_nnz + 3) & ~3);
+        dcp_off[k + 1] = dcp_off[k] + ((b.n + 1 + 3) & ~3);
         drp_off[k + 1] = drp_off[k] + L + 1;
         if (path == 1 && b.m == 64 && b.n == 128) e->list_a.push_back(k);
         else if (path == 1) { e->list_smem.push_back(k); e->smem_dyn = std::max(e->smem_dyn, dwk::smem2_bytes(b.m, b.n)); }
@@ -783,6 +805,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         B.sparse = e->path[k] == 5 ? 1 : 0;
         B.spflag = e->path[k] == 5 ? e->spflag.p + k : nullptr;
         B.rwd = dwk::rmask_words(B.n);
+        B.dnnz = bd[k].d_nnz;
         B.xoff = e->xoff[k];
         B.Dt = dt_off[k] >= 0 ? e->Dt.p + dt_off[k] : nullptr;
     }
@@ -832,6 +855,34 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         e->tg_threads = (v == 256 || v == NT_TG_WIDE || v == NT_TG || v == 32) ? v : 0;
     }
     if (const char *ba = std::getenv("DWGPU_WARP_BAIL_AFTER")) e->warp_bail_after = std::max(0, std::atoi(ba));
+    if (const char *sv = std::getenv("DWGPU_SCREEN")) e->screen = std::atoi(sv) != 0;
+    if (const char *sv = std::getenv("DWGPU_SCREEN_SORT")) e->screen_sort = std::atoi(sv) != 0;
+    if (e->screen && (!e->list_g.empty() || !e->list_b.empty())) {
+        // the screening warp keeps a block's reduced costs in registers (4 items per lane: n <= 512) and 16-bit row ids
+        auto fits = [&](const std::vector<int> &l, int &wb) {
+            if (l.empty()) return false;
+            size_t mx = 0;
+            for (int k : l) {
+                if (e->n[k] > 512 || e->m[k] >= 65535) return false;
+                if ((e->n[k] & 3) || (e->xoff[k] & 1)) return false;       // 16-byte stores into the saved row
+                mx = std::max(mx, dwk::screen_warp_bytes(e->m[k], e->n[k]));
+            }
+            wb = (int)mx;
+            return mx * SCREEN_NW <= (size_t)smem_cap / 2;
+        };
+        e->screen_ok_b = fits(e->list_b, e->screen_wb_b);
+        e->screen_ok_g = fits(e->list_g, e->screen_wb_g);
+        if (e->screen_ok_b || e->screen_ok_g) {
+            CUE(e->scr_list.alloc(2 * (size_t)K)); CUE(e->scr_count.alloc(2)); CUE(e->scr_key.alloc(K));
+            CUE(cudaMemset(e->scr_count.p, 0, 2 * sizeof(int)));
+            CUE(cudaMemset(e->scr_key.p, 0, sizeof(unsigned) * (size_t)K));
+            const int wb = std::max(e->screen_wb_b, e->screen_wb_g) * SCREEN_NW;
+            CUE(allow_dynamic_smem(e->device, (const void *)dwk::screen_tg_kernel<SCREEN_NW, NT_TG>, wb));
+            CUE(allow_dynamic_smem(e->device, (const void *)dwk::screen_tg_kernel<SCREEN_NW, NT_TG_WIDE>, wb));
+            CUE(allow_dynamic_smem(e->device, (const void *)dwk::screen_tg_kernel<SCREEN_NW, NT_SMEM>, wb));
+            CUE(allow_dynamic_smem(e->device, (const void *)dwk::order_screened_kernel<1024>, (int)(8192 * sizeof(unsigned long long))));
+        }
+    }
     // warp kernel: 16-bit variable ids, at least 4 blocks per SM
     e->warp_ok_g = !e->list_g.empty() && e->smem_dyn_w <= smem_cap / 4;
     for (int k : e->list_g) if (e->m[k] + e->n[k] >= 65535) e->warp_ok_g = false;
@@ -850,6 +901,25 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG_WIDE, 0, 0, true>, (int)e->smem_dyn_g));
     }
     if (!e->list_b.empty()) {
+        {   // staged rounds: 16-byte aligned per-block slices, and still four CTAs per SM
+            bool ok = true;
+            int dmax = 0;
+            for (int k : e->list_b) { ok = ok && !(e->xoff[k] & 1); dmax = std::max(dmax, bd[k].d_nnz); }
+            const size_t sm = dwk::smem2_bytes(256, 512, true) + dwk::stage_bytes(512, dmax);
+            // opt-in (DWGPU_STAGE=1).  Measured on config B (profiles/r2q_*): a no-pivot launch 0.176 ms instead of 0.197 ms,
+            // but the launches that pivot lose 7 % (51 KB instead of 29 KB of shared memory per CTA leaves the L1 a quarter of
+            // its size): 34.4 ms per step against 31.7 ms.  ncu of the staged no-pivot launch: the same 365 MB of DRAM reads,
+            // 1 260 instructions per warp — the round is bound by the length of its instruction chain, not by its round trips.
+            const char *sv = std::getenv("DWGPU_STAGE");
+            ok = ok && sv != nullptr && std::atoi(sv) != 0;
+            if (ok && (sm + 1024 + 512) * DWK_TGW_OCC <= (size_t)e->max_smem_sm) {
+                e->stage_b = true; e->smem_stage_b = sm;
+                CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true, true>, (int)sm));
+                // four CTAs of ~51 KB need the largest shared-memory carve-out; the driver's default heuristic may pick less
+                CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true, true>,
+                                         cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            }
+        }
         CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_SMEM, 256, 512, true>, (int)dwk::smem2_bytes(256, 512, true)));
         CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG, 256, 512, true>, (int)dwk::smem2_bytes(256, 512, true)));
         CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true>, (int)dwk::smem2_bytes(256, 512, true)));
@@ -918,7 +988,10 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
             e->last_launches++;
             return cudaGetLastError();
         };
-        CU(order(e->d_list_b, e->list_b.size())); CU(order(e->d_list_g, e->list_g.size()));
+        // (lists that go through the screening launch are ordered by it)
+        const bool scr_any = !P.force_full && P.cs_pre == nullptr && e->tg_threads != 32;
+        if (!(scr_any && e->screen_ok_b && e->list_b.size() <= 8192)) CU(order(e->d_list_b, e->list_b.size()));
+        if (!(scr_any && e->screen_ok_g && e->list_g.size() <= 8192)) CU(order(e->d_list_g, e->list_g.size()));
         CU(order(e->d_list_s, e->list_s.size()));
         CU(order(e->d_list_a, e->list_a.size())); CU(order(e->d_list_smem, e->list_smem.size()));
     }
@@ -1002,6 +1075,7 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
             if (spec_b) {
                 if (nt == 256) dwk::solve_smem_kernel<NT_SMEM, 256, 512, true><<<nb, NT_SMEM, sm, st>>>(e->blocks.p, list, (int)nb, P, cn);
                 else if (nt == NT_TG) dwk::solve_smem_kernel<NT_TG, 256, 512, true><<<nb, NT_TG, sm, st>>>(e->blocks.p, list, (int)nb, P, cn);
+                else if (e->stage_b) dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true, true><<<nb, NT_TG_WIDE, e->smem_stage_b, st>>>(e->blocks.p, list, (int)nb, P, cn);
                 else dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true><<<nb, NT_TG_WIDE, sm, st>>>(e->blocks.p, list, (int)nb, P, cn);
             } else {
                 if (nt == 256) dwk::solve_smem_kernel<NT_SMEM, 0, 0, true><<<nb, NT_SMEM, sm, st>>>(e->blocks.p, list, (int)nb, P, cn);
@@ -1013,6 +1087,32 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         };
         auto run_list = [&](bool spec_b, const int *list, unsigned nb, bool warp_fits) -> cudaError_t {
             const bool warp = warp_fits && e->tg_threads == 32;
+            const bool scr = !warp && e->tg_threads != 32 && (spec_b ? e->screen_ok_b : e->screen_ok_g) && !initial &&
+                             !P.force_full && P.cs_pre == nullptr && nb <= 8192;
+            if (scr) {
+                // screening launch -> (sort) -> solve launch over the device-side list of the blocks that still need pivots
+                int *nl = e->scr_list.p + (spec_b ? 0 : e->K), *nc = e->scr_count.p + (spec_b ? 0 : 1);
+                cudaError_t rc = cudaMemsetAsync(nc, 0, sizeof(int), st);
+                if (rc != cudaSuccess) return rc;
+                const dwk::ScreenOut S{nl, nc, e->scr_key.p};
+                const int wb = spec_b ? e->screen_wb_b : e->screen_wb_g;
+                const unsigned gb = (nb + SCREEN_NW - 1) / SCREEN_NW;
+                const int nt = e->tg_threads ? e->tg_threads : NT_TG_WIDE;
+                if (nt == NT_SMEM) dwk::screen_tg_kernel<SCREEN_NW, NT_SMEM><<<gb, SCREEN_NW * 32, (size_t)wb * SCREEN_NW, st>>>(e->blocks.p, list, (int)nb, P, S, wb);
+                else if (nt == NT_TG) dwk::screen_tg_kernel<SCREEN_NW, NT_TG><<<gb, SCREEN_NW * 32, (size_t)wb * SCREEN_NW, st>>>(e->blocks.p, list, (int)nb, P, S, wb);
+                else dwk::screen_tg_kernel<SCREEN_NW, NT_TG_WIDE><<<gb, SCREEN_NW * 32, (size_t)wb * SCREEN_NW, st>>>(e->blocks.p, list, (int)nb, P, S, wb);
+                e->last_launches++;
+                rc = cudaGetLastError();
+                if (rc != cudaSuccess) return rc;
+                if (e->screen_sort) {
+                    dwk::order_screened_kernel<1024><<<1, 1024, 8192 * sizeof(unsigned long long), st>>>(nl, nc, e->scr_key.p, 8192);
+                    e->last_launches++;
+                    rc = cudaGetLastError();
+                    if (rc != cudaSuccess) return rc;
+                }
+                const dwk::Continuation cn{nc, nullptr, nullptr};
+                return cta_launch(spec_b, nl, nb, e->tg_threads, cn);
+            }
             if (!warp) return cta_launch(spec_b, list, nb, e->tg_threads == 32 ? 0 : e->tg_threads, none);
             cudaError_t rc = cudaMemsetAsync(e->redo_count.p, 0, sizeof(int), st);
             if (rc != cudaSuccess) return rc;

@@ -49,7 +49,7 @@ struct BlockDev {
     int *dflag;             // solves since dsave was last recomputed in full (0 = dsave invalid)
     unsigned *rmask;        // path 3: per row, one bit per 32-byte item of T that may be non-zero (nullptr: none)
     int rwd;                // 32-bit words per row of rmask
-    int pad2;
+    int dnnz;               // entries of D_k
     long long xoff;         // offset of this block's columns in the engine-wide column arrays (x, cs_pre)
     const double *Dt;       // dense D_k transposed, n x L row-major (blocks whose D_k is dense enough for the pricing GEMM; else nullptr)
     int *spflag;            // path 5: 0 = T holds the packed image, 1 = the block moved to the dense layout of path 3 (nullptr: not a path-5 block)

@@ -34,6 +34,22 @@
 #ifndef DWK_TG_FUSED
 #define DWK_TG_FUSED 1      // 1: sparse pivots fetch the pivot row inside the sweep's first batch (one HBM round trip less)
 #endif
+#ifndef DWK_DEAD_COLS
+#define DWK_DEAD_COLS 1     // 1: a fixed variable that leaves the basis can never come back (pricing skips ST_FIX), so the column
+                            // slot it moves into is written as exact zeros instead of the transformed column; nothing ever reads
+                            // it for a decision, and it drops out of the row masks, the item lists and all later sweeps
+                            // (equality-constrained blocks: every auxiliary variable the cold solve drives out, half the slots)
+#endif
+#ifndef DWK_TG_PREFETCH
+#define DWK_TG_PREFETCH 0    // 1: L2 prefetch of the active rows' items during the ratio test (experiment)
+#endif
+#ifndef DWK_TG_EARLYQ
+#define DWK_TG_EARLYQ 0      // 1: the sparse sweep prices the next entering column as soon as the pivot row is known and
+                            // prefetches that column into L2 while its own loads are in flight (experiment)
+#endif
+#ifndef DWK_FASTDIV
+#define DWK_FASTDIV 1
+#endif
 #ifndef DWK_TGW_OCC
 #define DWK_TGW_OCC 4       // CTAs per SM the 128- and 256-thread global-tableau kernels are compiled for
 #endif
@@ -118,6 +134,20 @@ __host__ __device__ inline size_t smem2_bytes(int m, int n, bool tg = false)
          + (tg ? rmask_bytes(m, n) : 0);                                        // row-item masks
 }
 
+// Staged rounds (STG): everything a priced round reads about a block besides its tableau — saved reduced costs and the
+// costs they belong to, the kept x_k, the master costs, D_k by column — arrives with the state image in ONE batch of bulk
+// copies, so the prologue, a no-pivot round and the "nothing moved" epilogue are shared-memory work behind a single HBM
+// round trip instead of a chain of ~11 dependent ones (29 of the 40 rounds of config B's trajectory move < 100 blocks).
+// Needs n even and the D_k arenas padded per block (dwgpu_create does that).
+__host__ __device__ inline int al4(int v) { return (v + 3) & ~3; }
+__host__ __device__ inline size_t stage_bytes(int n, int dnnz)
+{
+    return 4 * align16(sizeof(double) * (size_t)n)          // dsave | cssave | x | c_master (becomes cs in place)
+         + align16(sizeof(double) * (size_t)al4(dnnz))       // dc_val
+         + align16(sizeof(int) * (size_t)al4(n + 1))         // dc_ptr
+         + align16(sizeof(int) * (size_t)al4(dnnz));         // dc_row
+}
+
 enum { K_NONE = 0, K_PIVOT = 1, K_FAIL = 2, K_REDO = 3 };
 
 // Second launch of a round over the blocks the warp kernel (simplex_warp.cuh) handed over: the list length is read
@@ -140,6 +170,8 @@ struct Decision {
     int p, q, na, fail_status;
     int nc;          // active column items of the pivot row; -1: the row is dense, sweep whole rows
     int fused;       // 1: rowp has NOT been staged — the sparse sweep fetches row p (first in the list) with its first batch
+    int dead;        // 1: the leaving variable is fixed (lo == up), so it can never be priced in again: the column it moves
+                     //    into is written as zeros and drops out of the row masks, the item lists and every later sweep
     double inv;
 };
 
@@ -400,6 +432,7 @@ __device__ __forceinline__ int decide_warp0(Sm3 &c, const double *dd, bool d_liv
             c.colq[m] = with_d ? dq : 0.0;
             if (with_d) c.arow[na] = (unsigned short)m;      // the reduced-cost row rides along
             dec->p = p; dec->q = q; dec->inv = inv; dec->na = na + (with_d ? 1 : 0); dec->nc = nc; dec->fused = 0;
+            dec->dead = (DWK_DEAD_COLS && lov == upv) ? 1 : 0;
         }
         ++n_piv;
         n_rows += (unsigned long long)na;
@@ -426,11 +459,47 @@ struct DecShared {
 };
 enum { K_FLIPPED = 4 };
 
+// Entering column: largest |d_j| among the attractive nonbasic columns (Bland: lowest variable id); all threads take
+// part and all get the answer (-1: none).  One block barrier.
+template <int NT, int NC>
+__device__ __forceinline__ int price_block_tg(const Sm3 &c, const double *dd, bool bland, double tol_dj, DecShared *ds)
+{
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = NC ? NC : c.n;
+    double key = 0.0; int q = -1;
+#pragma unroll 8
+    for (int j = tid; j < n; j += NT) {
+        const double dj = dd[j];
+        const signed char st = c.cstat[j];
+        const bool ok = (st == ST_LO && dj < -tol_dj) || (st == ST_UP && dj > tol_dj) ||
+                        (st == ST_FREE && fabs(dj) > tol_dj);
+        const double kj = bland ? 2147483648.0 - (double)c.nbv[j] : fabs(dj);
+        if (ok && kj > key) { key = kj; q = j; }
+    }
+    {
+        const int src = warp_argmax_nonneg(key, q >= 0);
+        const int sl = src < 0 ? 0 : src;
+        const double kw = __shfl_sync(0xffffffffu, key, sl);
+        const int qw = __shfl_sync(0xffffffffu, q, sl);
+        if (lane == 0) { ds->key[warp] = kw; ds->q[warp] = src < 0 ? -1 : qw; }
+    }
+    __syncthreads();
+    q = -1; key = -1.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const double kw = ds->key[w];
+        const int qw = ds->q[w];
+        if (qw >= 0 && kw > key) { key = kw; q = qw; }
+    }
+    return q;
+}
+
 template <bool INF, int NT, int MC, int NC>
 __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_live, bool &bland, int &degen, int degen_limit,
                             double tol_dj, double tol_bnd, double tol_piv,
                             unsigned long long &n_piv, unsigned long long &n_flip, unsigned long long &n_rows,
-                            unsigned long long &n_cells, Decision *dec, DecShared *ds)
+                            unsigned long long &n_cells, Decision *dec, DecShared *ds, int &q_hint)
 {
     constexpr int NW = NT / 32;
     static_assert(NW <= 8, "DecShared holds 8 warp slots");
@@ -441,32 +510,11 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
     const int RW = ((m + NW - 1) / NW + 31) & ~31;          // rows of the column each warp fetches
     for (;;) {
         phase(3);
-        // ---- pricing, all threads
-        double key = 0.0; int q = -1;
-#pragma unroll 8
-        for (int j = tid; j < n; j += NT) {
-            const double dj = dd[j];
-            const signed char st = c.cstat[j];
-            const bool ok = (st == ST_LO && dj < -tol_dj) || (st == ST_UP && dj > tol_dj) ||
-                            (st == ST_FREE && fabs(dj) > tol_dj);
-            const double kj = bland ? 2147483648.0 - (double)c.nbv[j] : fabs(dj);
-            if (ok && kj > key) { key = kj; q = j; }
-        }
-        {
-            const int src = warp_argmax_nonneg(key, q >= 0);
-            const int sl = src < 0 ? 0 : src;
-            const double kw = __shfl_sync(0xffffffffu, key, sl);
-            const int qw = __shfl_sync(0xffffffffu, q, sl);
-            if (lane == 0) { ds->key[warp] = kw; ds->q[warp] = src < 0 ? -1 : qw; }
-        }
-        __syncthreads();
-        q = -1; key = -1.0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            const double kw = ds->key[w];
-            const int qw = ds->q[w];
-            if (qw >= 0 && kw > key) { key = kw; q = qw; }
-        }
+        // ---- pricing, all threads (or the column the previous sweep already chose and prefetched)
+        int q = -1;
+        if (DWK_TG_EARLYQ && q_hint >= 0) q = q_hint;            // block-uniform
+        else q = price_block_tg<NT, NC>(c, dd, bland, tol_dj, ds);
+        q_hint = -1;
         if (q < 0) return K_NONE;                                // block-uniform
         phase(4);
         const double dq = dd[q];
@@ -504,6 +552,18 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
                 }
             }
             if (lane == 0) ds->cnt[warp] = cnt;
+#if DWK_TG_PREFETCH
+            // While warp 0 runs the ratio test, pull the active rows' items towards L2: the sweep will read a subset of
+            // them (the items the pivot row carries) as soon as the leaving row is known.
+            __syncwarp();
+            for (int e = 0; e < cnt; ++e) {
+                const int i = c.arow2[rbeg + e];
+                const unsigned *mi = c.rmask + (size_t)i * rwd;
+                for (int w_ = 0; w_ < rwd; ++w_)
+                    if ((mi[w_] >> lane) & 1u)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(c.T + (size_t)i * ld + (size_t)(w_ * 32 + lane) * 4));
+            }
+#endif
         }
         __syncthreads();
         int na = 0;
@@ -613,6 +673,7 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
                     c.colq[m] = with_d ? dq : 0.0;
                     if (with_d) c.arow[na] = (unsigned short)m;      // the reduced-cost row rides along
                     dec->p = p; dec->q = q; dec->inv = inv; dec->na = na + (with_d ? 1 : 0);
+                    dec->dead = (DWK_DEAD_COLS && lov == upv) ? 1 : 0;
                 }
                 ++n_piv;
                 n_rows += (unsigned long long)na;
@@ -733,13 +794,43 @@ __device__ __forceinline__ double cost_delta(double cs_new, double cs_saved)
     return fabs(d) > 1e-11 * (1.0 + fabs(cs_new)) ? d : 0.0;
 }
 
+// the reduced-cost row's share of a sparse rank-1 sweep (it lives in shared memory): d'[j] = d[j] - d_q rowp[j] over the
+// pivot row's items, d'[q] = -d_q / pivot
+template <int NT, bool TG>
+__device__ __forceinline__ void sweep_drow(Sm3 &c, int q, double inv, int nc, bool dead)
+{
+    constexpr int IW = ItemW<TG>::D2;
+    const double2 *rowp2 = reinterpret_cast<const double2 *>(c.rowp);
+    double2 *d2 = reinterpret_cast<double2 *>(c.drow);
+    const double dq = c.colq[c.m];
+    const double cq = dead ? 0.0 : dq * inv;
+    for (int t = threadIdx.x; t < nc; t += NT) {
+        const int j = (int)c.acol[t] * IW;
+#pragma unroll
+        for (int u = 0; u < IW; ++u) {
+            const double2 ra = rowp2[j + u];
+            const int jq = q - 2 * (j + u);
+            double2 r = d2[j + u];
+            r.x = fma(-dq, ra.x, r.x);
+            r.y = fma(-dq, ra.y, r.y);
+            if (jq == 0) r.x = cq;
+            if (jq == 1) r.y = cq;
+            d2[j + u] = r;
+        }
+    }
+}
+
 // rank-1 sweep over (active rows) x (active column items): every load of a batch is issued before the
 // first dependent instruction, so a typical network pivot (13 rows x 30 items) is ONE memory round trip.
 // The reduced-cost row (last list entry when it rides along) lives in shared memory and is done apart,
 // so the tableau loop is pure global (TG) or pure shared traffic with 32-bit cell offsets.
 template <int NT, int NC, bool TG>
-__device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, int na, int nc, bool fused)
+__device__ __forceinline__ int sweep_sparse(Sm3 &c, int p, int q, double inv, int na, int nc, bool fused, bool dead,
+                                             bool bland, double tol_dj, DecShared *ds)
 {
+    int q_next = -1;                                       // DWK_TG_EARLYQ: the entering column of the next iteration
+    bool d_done = false;
+    const double invq = dead ? 0.0 : inv;                  // what column q receives: nothing when the leaving variable is fixed
     constexpr int IW = ItemW<TG>::D2;
     constexpr int SB = TG ? DWK_TG_SB : 2;                 // items per thread in flight
     const int nc2 = (NC ? tab_ld(NC, TG) : c.ld) >> 1;    // row pitch in double2
@@ -748,6 +839,9 @@ __device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, i
     const bool with_d = na > 0 && c.arow[na - 1] == c.m;
     const int nat = with_d ? na - 1 : na;
     const int total = nat * nc;
+    // e / nc by multiplication: ceil(2^32 / nc) is exact for e * nc < 2^32 (a generic 32-bit division costs ~25 instructions
+    // per element, a tenth of what a warp executes per basis change)
+    const unsigned nc_magic = nc > 1 ? 0xffffffffu / (unsigned)nc + 1u : 0u;
     for (int e0 = 0; e0 < total; e0 += NT * SB) {
         double2 v[SB][IW];
         int off[SB];                                       // double2 offset of the item; -1: none
@@ -757,7 +851,7 @@ __device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, i
             const int e = e0 + t * NT + threadIdx.x;
             off[t] = -1; had[t] = true;
             if (e < total) {
-                const int a = e / nc;
+                const int a = DWK_FASTDIV ? (nc > 1 ? (int)__umulhi((unsigned)e, nc_magic) : e) : e / nc;
                 const int i = c.arow[a], item = c.acol[e - a * nc];
                 off[t] = i * nc2 + item * IW;
                 if (TG) had[t] = (c.rmask[(size_t)i * c.rwd + (item >> 5)] >> (item & 31)) & 1u;
@@ -789,13 +883,30 @@ __device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, i
             }
             __syncthreads();
         }
+        if (TG && DWK_TG_EARLYQ && e0 == 0 && with_d) {
+            // The scaled pivot row is complete (staged before the call, or by the branch above) while this batch's loads
+            // are still in flight: finish the reduced-cost row now, choose the NEXT entering column and pull its
+            // sectors towards L2, so that the next iteration's column fetch does not wait for HBM.
+            sweep_drow<NT, TG>(c, q, inv, nc, dead);
+            d_done = true;
+            __syncthreads();
+            q_next = price_block_tg<NT, NC>(c, c.drow, bland, tol_dj, ds);
+            if (q_next >= 0) {
+                const int m_ = c.m, ld_ = NC ? tab_ld(NC, TG) : c.ld;
+                const unsigned *mq = c.rmask + (q_next >> 7);
+                const unsigned qbit = 1u << ((q_next >> 2) & 31);
+                for (int i = threadIdx.x; i < m_; i += NT)
+                    if (mq[(size_t)i * c.rwd] & qbit)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(c.T + (size_t)i * ld_ + q_next));
+            }
+        }
 #pragma unroll
         for (int t = 0; t < SB; ++t) {
             if (off[t] >= 0) {
                 const int i = off[t] / nc2;
                 const int j = off[t] - i * nc2;
                 const double ci = c.colq[i];
-                const double cq = ci * inv;
+                const double cq = dead ? 0.0 : ci * inv;
                 const bool is_p = i == p;
                 bool all_zero = true;
                 double2 res[IW];
@@ -806,8 +917,8 @@ __device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, i
                     double2 r;
                     r.x = is_p ? -ra.x : fma(-ci, ra.x, v[t][u].x);
                     r.y = is_p ? -ra.y : fma(-ci, ra.y, v[t][u].y);
-                    if (jq == 0) r.x = is_p ? inv : cq;
-                    if (jq == 1) r.y = is_p ? inv : cq;
+                    if (jq == 0) r.x = is_p ? invq : cq;
+                    if (jq == 1) r.y = is_p ? invq : cq;
                     all_zero = all_zero && r.x == 0.0 && r.y == 0.0;
                     res[u] = r;
                 }
@@ -826,31 +937,15 @@ __device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, i
             }
         }
     }
-    if (with_d) {
-        double2 *d2 = reinterpret_cast<double2 *>(c.drow);
-        const double dq = c.colq[c.m];
-        const double cq = dq * inv;
-        for (int t = threadIdx.x; t < nc; t += NT) {
-            const int j = (int)c.acol[t] * IW;
-#pragma unroll
-            for (int u = 0; u < IW; ++u) {
-                const double2 ra = rowp2[j + u];
-                const int jq = q - 2 * (j + u);
-                double2 r = d2[j + u];
-                r.x = fma(-dq, ra.x, r.x);
-                r.y = fma(-dq, ra.y, r.y);
-                if (jq == 0) r.x = cq;
-                if (jq == 1) r.y = cq;
-                d2[j + u] = r;
-            }
-        }
-    }
+    if (with_d && !d_done) sweep_drow<NT, TG>(c, q, inv, nc, dead);
+    return q_next;
 }
 
 // rank-1 sweep over the active rows only (row m = reduced costs when it is in the list)
 template <int NT, int NC, bool TG>
-__device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, int na)
+__device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, int na, bool dead)
 {
+    const double invq = dead ? 0.0 : inv;
     constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nc2 = (NC ? tab_ld(NC, TG) : c.ld) >> 1;    // row pitch in double2
@@ -861,7 +956,7 @@ __device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, i
     for (int a = warp; a < na; a += NW) {
         const int i = c.arow[a];
         const double ci = c.colq[i];
-        const double cq = ci * inv;
+        const double cq = dead ? 0.0 : ci * inv;
         double2 *row = (i == c.m) ? d2 : T2 + (size_t)i * nc2;
         const bool is_p = i == p;
         if (TG) {
@@ -894,8 +989,8 @@ __device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, i
                         double2 r;
                         r.x = is_p ? -ra.x : fma(-ci, ra.x, v[t].x);
                         r.y = is_p ? -ra.y : fma(-ci, ra.y, v[t].y);
-                        if (jq == 0) r.x = is_p ? inv : cq;
-                        if (jq == 1) r.y = is_p ? inv : cq;
+                        if (jq == 0) r.x = is_p ? invq : cq;
+                        if (jq == 1) r.y = is_p ? invq : cq;
                         nzv[t] = r.x != 0.0 || r.y != 0.0;
                         v[t] = r;
                     }
@@ -923,8 +1018,8 @@ __device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, i
                 double2 r;
                 r.x = is_p ? -ra.x : fma(-ci, ra.x, va.x);
                 r.y = is_p ? -ra.y : fma(-ci, ra.y, va.y);
-                if (jq == 0) r.x = is_p ? inv : cq;
-                if (jq == 1) r.y = is_p ? inv : cq;
+                if (jq == 0) r.x = is_p ? invq : cq;
+                if (jq == 1) r.y = is_p ? invq : cq;
                 row[ja] = r;
             }
             if (ob) {
@@ -932,8 +1027,8 @@ __device__ __forceinline__ void sweep_active(Sm3 &c, int p, int q, double inv, i
                 double2 r;
                 r.x = is_p ? -rb.x : fma(-ci, rb.x, vb.x);
                 r.y = is_p ? -rb.y : fma(-ci, rb.y, vb.y);
-                if (jq == 0) r.x = is_p ? inv : cq;
-                if (jq == 1) r.y = is_p ? inv : cq;
+                if (jq == 0) r.x = is_p ? invq : cq;
+                if (jq == 1) r.y = is_p ? invq : cq;
                 row[jb] = r;
             }
         }
@@ -1078,10 +1173,11 @@ __device__ __forceinline__ unsigned masked_cells(const Sm3 &c, int nl)
 // constants); MC = NC = 0: any shape that fits.
 // TG = true: the tableau stays in global memory (L2/HBM) and only the vectors live in shared memory
 // (blocks too large for one CTA's shared memory, config B class); the decision/sweep code is shared.
-template <int NT, int MC, int NC, bool TG>
+template <int NT, int MC, int NC, bool TG, bool STG = false>
 __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC) : 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
                                                           SolveParams P, Continuation CN)
 {
+    static_assert(!STG || TG, "staged rounds belong to the global-tableau kernel");
     extern __shared__ __align__(16) char smem_raw[];
     __shared__ Scratch<NT> scr;
     __shared__ Decision dec;
@@ -1126,23 +1222,102 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
     c.arow2 = (unsigned short *)sp; sp += TG ? align16(sizeof(unsigned short) * (size_t)(m + 32 * 8)) : 0;
     c.rmask = TG ? (unsigned *)sp : nullptr;
     c.rwd = rmask_words(n);
+    // staged round data (STG): [dsave | cssave | x | c_master -> cs | dc_val | dc_ptr | dc_row]
+    const int dnnz = STG ? B.dnnz : 0;
+    double *sg_dsave = nullptr, *sg_cssave = nullptr, *sg_x = nullptr, *sg_dcv = nullptr;
+    int *sg_dcp = nullptr, *sg_dcr = nullptr;
+    if (STG) {
+        sp += rmask_bytes(m, n);
+        const size_t nb = align16(sizeof(double) * (size_t)n);
+        sg_dsave = (double *)sp; sp += nb;
+        sg_cssave = (double *)sp; sp += nb;
+        sg_x = (double *)sp; sp += nb;
+        c.cs = (double *)sp; sp += nb;
+        sg_dcv = (double *)sp; sp += align16(sizeof(double) * (size_t)al4(dnnz));
+        sg_dcp = (int *)sp; sp += align16(sizeof(int) * (size_t)al4(n + 1));
+        sg_dcr = (int *)sp;
+    }
 
+    const int dflag_in = B.dflag[0];        // (loaded here: its latency hides behind the bulk copies)
     // ---- state in: bulk copies (tableau or row masks, state image), one mbarrier
     const uint32_t t_bytes = TG ? 0u : (uint32_t)(sizeof(double) * (size_t)m * ld);
     const uint32_t p_bytes = (uint32_t)pst_bytes(m, n);
     const uint32_t k_bytes = TG ? (uint32_t)rmask_bytes(m, n) : 0u;
     if (tid == 0) {
         mbar_init(&bar, 1);
-        mbar_expect_tx(&bar, t_bytes + p_bytes + k_bytes);
+        const uint32_t n_bytes = STG ? (uint32_t)align16(sizeof(double) * (size_t)n) : 0u;
+        const uint32_t dv_bytes = STG ? (uint32_t)align16(sizeof(double) * (size_t)dnnz) : 0u;
+        const uint32_t dp_bytes = STG ? (uint32_t)align16(sizeof(int) * (size_t)(n + 1)) : 0u;
+        const uint32_t dr_bytes = STG ? (uint32_t)align16(sizeof(int) * (size_t)dnnz) : 0u;
+        mbar_expect_tx(&bar, t_bytes + p_bytes + k_bytes + 4u * n_bytes + dv_bytes + dp_bytes + dr_bytes);
         if (t_bytes) bulk_g2s(c.T, B.T, t_bytes, &bar);
         if (k_bytes) bulk_g2s(c.rmask, B.rmask, k_bytes, &bar);
         bulk_g2s(pst, B.beta, p_bytes, &bar);
+        if (STG) {
+            bulk_g2s(sg_dsave, B.dsave, n_bytes, &bar);
+            bulk_g2s(sg_cssave, B.cssave, n_bytes, &bar);
+            bulk_g2s(sg_x, B.x, n_bytes, &bar);
+            bulk_g2s(c.cs, P.initial ? B.c_file : B.c_master, n_bytes, &bar);
+            if (dv_bytes) bulk_g2s(sg_dcv, B.dc_val, dv_bytes, &bar);
+            bulk_g2s(sg_dcp, B.dc_ptr, dp_bytes, &bar);
+            if (dr_bytes) bulk_g2s(sg_dcr, B.dc_row, dr_bytes, &bar);
+        }
         s_changed = (CN.moved != nullptr && CN.moved[k]) ? 1 : 0;
     }
     // priced objective while the copies fly (same arithmetic as the generic kernel / reference)
     // (four columns per thread at a time, every level of the CSC walk issued as one batch of read-only
     //  loads: a chain of 3 dependent loads per column otherwise, which dominated the no-pivot rounds)
-    if (P.initial) {
+    if (STG) {
+        // everything arrives with the bulk copies: the walk over D_k's columns reads shared memory, only the duals are
+        // gathered (L doubles shared by all blocks: L1/L2), and the row bounds are gathered while they fly
+        __syncthreads();            // mbarrier init visible
+        mbar_wait(&bar, 0);
+        // row bounds by basic variable: gathered now, consumed after the pricing walk (one round trip for both)
+        constexpr int RU = MC ? (MC + NT - 1) / NT : 1;
+        double blo[RU], bup[RU];
+        if (MC) {
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                const int i = tid + u * NT;
+                if (i < m) { const int v = c.head[i]; blo[u] = __ldg(c.glo + v); bup[u] = __ldg(c.gup + v); }
+            }
+        }
+        if (!P.initial) {
+            constexpr int U = (NC && NC / NT >= 8) ? 8 : 4;
+            for (int j0 = tid; j0 < n; j0 += NT * U) {
+                int pb[U], pe[U];
+                double p0[U], v0[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = j0 + u * NT;
+                    pb[u] = pe[u] = 0; p0[u] = 0.0; v0[u] = 0.0;
+                    if (j < n) { pb[u] = sg_dcp[j]; pe[u] = sg_dcp[j + 1]; }
+                    if (pb[u] < pe[u]) { p0[u] = __ldg(P.pi + sg_dcr[pb[u]]); v0[u] = sg_dcv[pb[u]]; }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = j0 + u * NT;
+                    if (j >= n) continue;
+                    double y = 0.0;
+                    if (pb[u] < pe[u]) {
+                        y = __dadd_rn(y, __dmul_rn(p0[u], v0[u]));
+                        for (int e = pb[u] + 1; e < pe[u]; ++e)
+                            y = __dadd_rn(y, __dmul_rn(__ldg(P.pi + sg_dcr[e]), sg_dcv[e]));
+                    }
+                    const double base = P.phase_one ? 0.0 : c.cs[j];       // the slot holds c_master[j]
+                    c.cs[j] = __dadd_rn(__dmul_rn(-1.0, y), base);
+                }
+            }
+        }
+        if (MC) {
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                const int i = tid + u * NT;
+                if (i < m) { c.rlo[i] = blo[u]; c.rup[i] = bup[u]; }
+            }
+            for (int j = tid; j < n; j += NT) c.cstat[j] = c.vstat[c.nbv[j]];
+        } else gather_bounds<NT, TG>(B, c);
+    } else if (P.initial) {
         const double *cf = B.c_file;
         for (int j = tid; j < n; j += NT) c.cs[j] = __ldg(cf + j);
     } else {
@@ -1181,9 +1356,11 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
             }
         }
     }
-    __syncthreads();            // mbarrier init + cs visible
-    mbar_wait(&bar, 0);
-    gather_bounds<NT, TG>(B, c);
+    if (!STG) {
+        __syncthreads();            // mbarrier init + cs visible
+        mbar_wait(&bar, 0);
+        gather_bounds<NT, TG>(B, c);
+    }
     __syncthreads();
 
     int status = 0;
@@ -1193,8 +1370,8 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
     unsigned long long n_price = 0;     // tableau doubles read to (re)compute price rows (block-uniform)
     bool need_check = true, infeasible = false, d_valid = false, bland = false, d_full = false, x_in_rowp = true;
     int degen = 0;
+    int q_hint = -1;            // TG: entering column chosen (and prefetched) by the previous sparse sweep
     const int degen_limit = 100 + (m + n) / 2;
-    const int dflag_in = B.dflag[0];
     const bool use_saved = dflag_in > 0 && dflag_in < 32;
     bool reb_now = TG && CN.reb != nullptr && CN.reb[k] != 0;      // block-uniform
 
@@ -1240,7 +1417,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
             // which only touches the rows of T whose basic cost changed (late rounds: a handful);
             // otherwise (and every 32nd solve, to stop drift) recompute d = c_N + T' c_B in full.
             const bool inc = use_saved && !s_changed && n_reb == 0;
-            const double *cssave = B.cssave, *dsave = B.dsave;     // only written in the epilogue: read-only here
+            const double *cssave = STG ? sg_cssave : B.cssave, *dsave = STG ? sg_dsave : B.dsave;     // only written in the epilogue: read-only here
             constexpr int U = (NC && NC / NT >= 8) ? 8 : 4;
             for (int i0 = tid; i0 < m; i0 += NT * U) {
                 double a[U], b[U];
@@ -1251,7 +1428,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
                     st[u] = false; a[u] = 0.0; b[u] = 0.0;
                     if (i < m) {
                         const int v = c.head[i];
-                        if (v >= m) { st[u] = true; a[u] = c.cs[v - m]; if (inc) b[u] = __ldg(cssave + v - m); }
+                        if (v >= m) { st[u] = true; a[u] = c.cs[v - m]; if (inc) b[u] = STG ? cssave[v - m] : __ldg(cssave + v - m); }
                     }
                 }
 #pragma unroll
@@ -1277,8 +1454,8 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
                     st[u] = false; a[u] = 0.0; b[u] = 0.0; dsv[u] = 0.0;
                     if (j < n) {
                         const int v = c.nbv[j];
-                        if (v >= m) { st[u] = true; a[u] = c.cs[v - m]; if (inc) b[u] = __ldg(cssave + v - m); }
-                        if (inc) dsv[u] = __ldg(dsave + j);
+                        if (v >= m) { st[u] = true; a[u] = c.cs[v - m]; if (inc) b[u] = STG ? cssave[v - m] : __ldg(cssave + v - m); }
+                        if (inc) dsv[u] = STG ? dsave[j] : __ldg(dsave + j);
                     }
                 }
 #pragma unroll
@@ -1307,10 +1484,10 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
             int kind;
             if (infeasible)
                 kind = decide_block_tg<true, NT, MC, NC>(c, c.rowp, false, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
-                                                         n_piv, n_flip, n_rows, n_cells, &dec, &dsh);
+                                                         n_piv, n_flip, n_rows, n_cells, &dec, &dsh, q_hint);
             else
                 kind = decide_block_tg<false, NT, MC, NC>(c, c.drow, true, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
-                                                          n_piv, n_flip, n_rows, n_cells, &dec, &dsh);
+                                                          n_piv, n_flip, n_rows, n_cells, &dec, &dsh, q_hint);
             if (tid == 0) { s_kind = kind; if (n_piv + n_flip) s_changed = 1; }
         } else if (warp == 0) {
             int kind;
@@ -1326,8 +1503,9 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
         const int kind = s_kind;
         if (kind == K_PIVOT) {
             phase(dec.nc >= 0 ? 7 : 11);
-            if (dec.nc >= 0) sweep_sparse<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na, dec.nc, TG && dec.fused != 0);
-            else sweep_active<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na);
+            if (dec.nc >= 0) q_hint = sweep_sparse<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na, dec.nc, TG && dec.fused != 0, dec.dead != 0,
+                                                               bland, tol_dj, &dsh);
+            else sweep_active<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na, dec.dead != 0);
             __syncthreads();
             continue;
         }
@@ -1395,7 +1573,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
                 for (int jj = tid; jj < ld; jj += NT) c.rowp[jj] = ld_t<TG>(c.T + (size_t)pr * ld + jj) * inv;
                 for (int i = tid; i < m; i += NT) c.arow[i] = (unsigned short)i;
                 __syncthreads();
-                sweep_active<NT, NC, TG>(c, pr, j, inv, m);
+                sweep_active<NT, NC, TG>(c, pr, j, inv, m, false);
                 if (tid == 0) { const int t = c.head[pr]; c.head[pr] = c.nbv[j]; c.nbv[j] = t; }
                 __syncthreads();
             }
@@ -1441,7 +1619,8 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
         // state in HBM are still those of the previous round; only the priced optimum moves
         double zo = 0.0;
         {
-            const double *xk = B.x;
+            const double *xk = STG ? sg_x : B.x;
+            const double *cssv = STG ? sg_cssave : B.cssave;
             double *dsave = B.dsave, *cssave = B.cssave;
             constexpr int U = (NC && NC / NT >= 8) ? 8 : 4;
             for (int j0 = tid; j0 < n; j0 += NT * U) {
@@ -1449,7 +1628,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int j = j0 + u * NT;
-                    if (j < n) { cv[u] = c.cs[j]; xv[u] = x_in_rowp ? c.rowp[j] : __ldcg(xk + j); sv[u] = __ldcg(cssave + j); }
+                    if (j < n) { cv[u] = c.cs[j]; xv[u] = x_in_rowp ? c.rowp[j] : (STG ? xk[j] : __ldcg(xk + j)); sv[u] = STG ? cssv[j] : __ldcg(cssv + j); }
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -1475,7 +1654,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
     if (status == 5 && d_valid) {
         for (int j = tid; j < n; j += NT) {
             B.dsave[j] = c.drow[j];
-            if (d_full || cost_delta(c.cs[j], B.cssave[j]) != 0.0) B.cssave[j] = c.cs[j];
+            if (d_full || cost_delta(c.cs[j], STG ? sg_cssave[j] : B.cssave[j]) != 0.0) B.cssave[j] = c.cs[j];
         }
         if (tid == 0) B.dflag[0] = d_full ? 1 : dflag_in + 1;
     } else if (tid == 0) B.dflag[0] = 0;

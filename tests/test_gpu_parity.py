@@ -740,6 +740,43 @@ def test_sparse_path_visits_the_same_vertices_as_path_3(threads, monkeypatch):
     e5.close(); e3.close()
 
 
+@pytest.mark.parametrize("threads", [64, 128, 256])
+def test_screening_launch_changes_nothing(threads, monkeypatch):
+    """Path 3 runs a priced round as screening launch (one warp per block: the blocks that need no pivot are finished
+    there) + solve launch over the rest.  With the screening switched off (DWGPU_SCREEN=0) every block goes through the
+    CTA kernel; both engines must agree bit for bit — priced optimum included — round after round of the recorded
+    config-B trajectory (late rounds move no block at all), also with repeated duals and after a reset."""
+    monkeypatch.setenv("DWGPU_TG_THREADS", str(threads))
+    prob = P.make_config("B", block_range=range(256, 352))
+    monkeypatch.setenv("DWGPU_SCREEN", "1")
+    e1 = engine(prob, force_path=3)
+    monkeypatch.setenv("DWGPU_SCREEN", "0")
+    e0 = engine(prob, force_path=3)
+    assert e1.last_launch_count() >= 0
+
+    def same(a, b):
+        for k in range(prob.K):
+            assert a[k]["status"] == b[k]["status"], k
+            assert a[k]["obj"] == b[k]["obj"] and a[k]["cost"] == b[k]["cost"], (k, a[k]["obj"], b[k]["obj"])
+            assert np.array_equal(a[k]["x"], b[k]["x"]), k
+            assert np.array_equal(a[k]["ind"], b[k]["ind"]) and np.array_equal(a[k]["val"], b[k]["val"]), k
+    same(e1.initial(), e0.initial())
+    pis = _traj_b_pis(prob.L, 39)
+    screened_launches = 0
+    for t, (pi, ph) in enumerate(pis):
+        same(e1.iterate(pi, ph), e0.iterate(pi, ph))
+        screened_launches = max(screened_launches, e1.last_launch_count())
+        if t in (5, 20):                                   # the same duals again: nothing may move
+            same(e1.iterate(pi, ph), e0.iterate(pi, ph))
+    assert screened_launches >= 2 and e0.last_launch_count() <= 2
+    c1, c0 = e1.counters(), e0.counters()
+    assert c1["pivots"] == c0["pivots"] and c1["flips"] == c0["flips"], (c1, c0)
+    e1.reset(); e0.reset()
+    same(e1.iterate(pis[3][0], False), e0.iterate(pis[3][0], False))     # first round after a reset: full proposals
+    same(e1.iterate(pis[9][0], False), e0.iterate(pis[9][0], False))
+    e1.close(); e0.close()
+
+
 @pytest.mark.parametrize("h0,h1", [(2600, 0), (2600, 3200), (1200, 1400)])
 def test_sparse_path_hands_over_when_the_heap_fills_up(h0, h1, monkeypatch):
     """A block whose packed tableau outgrows the small heap is re-packed, then continued by the launch with the large heap,
