@@ -28,6 +28,7 @@
 #include "simplex_smem.cuh"
 #include "simplex_warp.cuh"
 #include "screen_tg.cuh"
+#include "delta_tg.cuh"
 #include "simplex_sparse.cuh"
 #include "pack.cuh"
 #include "simplex_cluster.cuh"
@@ -171,6 +172,16 @@ struct dwgpu_engine {
     int screen_wb_b = 0, screen_wb_g = 0;      // shared memory per warp
     DevBuf<int> scr_list, scr_count;   // 2 x K ids, 2 counters (list_b, list_g)
     DevBuf<unsigned> scr_key;          // by block id
+    // delta rounds (delta_tg.cuh): rounds in which few duals moved are screened by one warp per block against the duals
+    // last applied per linking row; DWGPU_DELTA=0 switches it off (then the duals are used exactly as given)
+    bool delta = true;
+    bool delta_ok_b = false, delta_ok_g = false;
+    DevBuf<double> pi_ref;             // duals last applied, by linking row: the vector a round prices with
+    DevBuf<int> dl_rows, dl_meta;      // listed rows; DeltaMeta
+    DevBuf<int> dl_list;               // 2 x K: blocks left for the CTA kernel (list_b, list_g)
+    DevBuf<int> dl_pos;                // position of every variable of the blocks above (BlockDev::pos)
+    bool pi_ref_valid = false;         // false: the next round lists every row (after create, cold solve, reset)
+    int last_phase = -1;
     // staged rounds of the 256 x 512 kernel (simplex_smem.cuh, STG): per-block round data arrives by bulk copies
     bool stage_b = false;              // DWGPU_STAGE=0 switches it off
     size_t smem_stage_b = 0;           // dynamic shared memory of the staged instantiation
@@ -491,6 +502,7 @@ void dwgpu_destroy(dwgpu_engine *e)
     e->counters.release(); e->last_iters.release();
     e->redo_list.release(); e->redo_count.release(); e->redo_moved.release();
     e->scr_list.release(); e->scr_count.release(); e->scr_key.release();
+    e->pi_ref.release(); e->dl_rows.release(); e->dl_meta.release(); e->dl_list.release(); e->dl_pos.release();
     e->d_list_s.release(); e->sp_lists.release(); e->sp_counts.release(); e->spflag.release(); e->sp_moved.release(); e->sp_reb.release(); e->sp_stats.release();
     if (e->h_pi) cudaFreeHost(e->h_pi);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -784,6 +796,28 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         if (dt_tot > 0) { CUE(e->Dt.alloc((size_t)dt_tot)); CUE(e->d_list_dense.upload(e->list_dense)); }
     }
     ts[nts++] = stamp();
+    // delta rounds (delta_tg.cuh): which path-3 lists take part, and the variable-position map of their blocks
+    std::vector<long long> pos_off(K, -1);
+    {
+        if (const char *sv = std::getenv("DWGPU_DELTA")) e->delta = std::atoi(sv) != 0;
+        if (const char *tg = std::getenv("DWGPU_TG_THREADS")) if (std::atoi(tg) == 32) e->delta = false;   // the warp kernel keeps no map
+        auto fits = [&](const std::vector<int> &l) {
+            if (l.empty()) return false;
+            for (int k : l) if (e->n[k] > 512 || e->m[k] < 1) return false;       // 4 items per lane, 4 mask words per row
+            return true;
+        };
+        if (e->delta && L > 0) { e->delta_ok_b = fits(e->list_b); e->delta_ok_g = fits(e->list_g); }
+        long long tot = 0;
+        if (e->delta_ok_b) for (int k : e->list_b) { pos_off[k] = tot; tot += e->m[k] + e->n[k]; }
+        if (e->delta_ok_g) for (int k : e->list_g) { pos_off[k] = tot; tot += e->m[k] + e->n[k]; }
+        if (tot > 0) {
+            CUE(e->dl_pos.alloc((size_t)tot));
+            CUE(e->pi_ref.alloc(L)); CUE(cudaMemset(e->pi_ref.p, 0, sizeof(double) * (size_t)L));
+            CUE(e->dl_rows.alloc(dwk::DELTA_MAX_ROWS)); CUE(e->dl_meta.alloc(4)); CUE(e->dl_list.alloc(2 * (size_t)K));
+            CUE(cudaMemset(e->dl_rows.p, 0, sizeof(int) * dwk::DELTA_MAX_ROWS));
+            CUE(cudaMemset(e->dl_meta.p, 0, sizeof(int) * 4));
+        }
+    }
     std::vector<dwk::BlockDev> hb(K);
     for (int k = 0; k < K; ++k) {
         dwk::BlockDev &B = hb[k];
@@ -806,6 +840,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         B.spflag = e->path[k] == 5 ? e->spflag.p + k : nullptr;
         B.rwd = dwk::rmask_words(B.n);
         B.dnnz = bd[k].d_nnz;
+        B.pos = pos_off[k] >= 0 ? e->dl_pos.p + pos_off[k] : nullptr;
         B.xoff = e->xoff[k];
         B.Dt = dt_off[k] >= 0 ? e->Dt.p + dt_off[k] : nullptr;
     }
@@ -959,6 +994,7 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         if (!mail) e->mail_valid = false;
     }
     P.pi = d_pi; P.phase_one = phase_one; P.initial = initial;
+    bool delta_round = false;
     P.max_iter_mult = e->opt.max_iter_mult;
     P.no_dual_start = e->opt.no_dual_start;
     // the "nothing moved" exit of the kernels rewrites only obj/status and relies on the previous proposal of
@@ -971,6 +1007,20 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
     P.obj = e->obj.p; P.cost = e->cost.p; P.status = e->status.p; P.len = e->len.p;
     P.ind = e->ind.p; P.val = e->val.p; P.counters = e->counters.p; P.last_iters = e->last_iters.p;
     e->last_launches = 0;
+    if (initial) e->pi_ref_valid = false;
+    else if ((e->delta_ok_b || e->delta_ok_g) && e->tg_threads != 32 && d_pi != nullptr) {
+        if (P.cs_pre != nullptr) e->pi_ref_valid = false;       // (priced by the multi-vector GEMM with the duals as given)
+        else {
+            // duals down: list the rows that moved since they were last applied, snap the others; the round prices with pi_ref
+            const int force = (!e->pi_ref_valid || e->last_phase != phase_one || P.force_full) ? 1 : 0;
+            dwk::delta_rows_kernel<<<1, 256, 0, st>>>(d_pi, e->pi_ref.p, e->L, force, e->dl_rows.p, (dwk::DeltaMeta *)e->dl_meta.p);
+            CU(cudaGetLastError());
+            e->last_launches++;
+            e->pi_ref_valid = true; e->last_phase = phase_one;
+            P.pi = e->pi_ref.p;
+            delta_round = true;
+        }
+    }
     // longest-processing-time-first inside each list (DWGPU_NO_REORDER=1 keeps the natural order)
     if (!initial && e->reorder) {
         auto order = [&](DevBuf<int> &d, size_t n) -> cudaError_t {
@@ -1052,7 +1102,7 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         CU(solve(solve_list, solve_count, 0, l1, c1, 0, e->sp_H0, e->sp_smem0));
         CU(solve(l1, c1, 1, l2, c2, 1, e->sp_H1, e->sp_smem1));
         {
-            const dwk::Continuation cn{c2, e->sp_moved.p, e->sp_reb.p};
+            const dwk::Continuation cn{c2, e->sp_moved.p, e->sp_reb.p, nullptr, nullptr};
             dwk::solve_smem_kernel<NT_TG_WIDE, 0, 0, true><<<nb, NT_TG_WIDE, e->smem_dyn_g, st>>>(e->blocks.p, l2, (int)nb, P, cn);
             CU(cudaGetLastError());
             e->last_launches++;
@@ -1069,7 +1119,7 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         // (normally none: the second launch reads the list length on the device and its CTAs exit at once).  Measured on
         // config B (profiles/r2a_warp_kernel.md): the warp kernel needs 30 % fewer instructions per basis change but a
         // single warp's dependent chain is 3x longer, so 10 resident blocks do not beat 4 CTAs (40.1 vs 33.1 ms a step).
-        const dwk::Continuation none{nullptr, nullptr, nullptr};
+        const dwk::Continuation none{nullptr, nullptr, nullptr, nullptr, nullptr};
         auto cta_launch = [&](bool spec_b, const int *list, unsigned nb, int nt, const dwk::Continuation &cn) {
             const size_t sm = spec_b ? dwk::smem2_bytes(256, 512, true) : e->smem_dyn_g;
             if (spec_b) {
@@ -1089,6 +1139,21 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
             const bool warp = warp_fits && e->tg_threads == 32;
             const bool scr = !warp && e->tg_threads != 32 && (spec_b ? e->screen_ok_b : e->screen_ok_g) && !initial &&
                              !P.force_full && P.cs_pre == nullptr && nb <= 8192;
+            if (delta_round && !warp && (spec_b ? e->delta_ok_b : e->delta_ok_g)) {
+                // one warp per block finishes the blocks no listed dual can move; the CTA kernel takes the rest (or, when the
+                // device-side flag says so, its whole static list)
+                const dwk::DeltaMeta *meta = (const dwk::DeltaMeta *)e->dl_meta.p;
+                int *nl = e->dl_list.p + (spec_b ? 0 : e->K);
+                int *nc = e->dl_meta.p + (spec_b ? 2 : 3);
+                const dwk::DeltaIn D{e->dl_rows.p, meta, nl, nc};
+                constexpr int DNW = 4;
+                dwk::delta_round_kernel<DNW><<<(nb + DNW - 1) / DNW, DNW * 32, 0, st>>>(e->blocks.p, list, (int)nb, P, D);
+                e->last_launches++;
+                cudaError_t rc = cudaGetLastError();
+                if (rc != cudaSuccess) return rc;
+                const dwk::Continuation cn{nc, nullptr, nullptr, e->dl_meta.p + 1, list};
+                return cta_launch(spec_b, nl, nb, e->tg_threads, cn);
+            }
             if (scr) {
                 // screening launch -> (sort) -> solve launch over the device-side list of the blocks that still need pivots
                 int *nl = e->scr_list.p + (spec_b ? 0 : e->K), *nc = e->scr_count.p + (spec_b ? 0 : 1);
@@ -1110,7 +1175,7 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
                     rc = cudaGetLastError();
                     if (rc != cudaSuccess) return rc;
                 }
-                const dwk::Continuation cn{nc, nullptr, nullptr};
+                const dwk::Continuation cn{nc, nullptr, nullptr, nullptr, nullptr};
                 return cta_launch(spec_b, nl, nb, e->tg_threads, cn);
             }
             if (!warp) return cta_launch(spec_b, list, nb, e->tg_threads == 32 ? 0 : e->tg_threads, none);
@@ -1124,7 +1189,7 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
             e->last_launches++;
             rc = cudaGetLastError();
             if (rc != cudaSuccess) return rc;
-            const dwk::Continuation cn{e->redo_count.p, e->redo_moved.p, nullptr};
+            const dwk::Continuation cn{e->redo_count.p, e->redo_moved.p, nullptr, nullptr, nullptr};
             return cta_launch(spec_b, e->redo_list.p, nb, 0, cn);
         };
         if (!e->list_b.empty()) CU(run_list(true, e->d_list_b.p, (unsigned)e->list_b.size(), true));
@@ -1136,13 +1201,13 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         CU(cudaEventRecord(e->ev[2], st));
         if (!e->list_a.empty()) {
             dwk::solve_smem_kernel<NT_SMEM, 64, 128, false><<<(unsigned)e->list_a.size(), NT_SMEM, dwk::smem2_bytes(64, 128), st>>>(
-                e->blocks.p, e->d_list_a.p, (int)e->list_a.size(), P, dwk::Continuation{nullptr, nullptr, nullptr});
+                e->blocks.p, e->d_list_a.p, (int)e->list_a.size(), P, dwk::Continuation{nullptr, nullptr, nullptr, nullptr, nullptr});
             CU(cudaGetLastError());
             e->last_launches++;
         }
         if (!e->list_smem.empty()) {
             dwk::solve_smem_kernel<NT_SMEM, 0, 0, false><<<(unsigned)e->list_smem.size(), NT_SMEM, e->smem_dyn, st>>>(
-                e->blocks.p, e->d_list_smem.p, (int)e->list_smem.size(), P, dwk::Continuation{nullptr, nullptr, nullptr});
+                e->blocks.p, e->d_list_smem.p, (int)e->list_smem.size(), P, dwk::Continuation{nullptr, nullptr, nullptr, nullptr, nullptr});
             CU(cudaGetLastError());
             e->last_launches++;
         }
@@ -1387,6 +1452,7 @@ int dwgpu_reset(dwgpu_engine *e, void *stream)
     e->have_proposals = false;
     e->mail_valid = false;
     e->uplink_valid = false;
+    e->pi_ref_valid = false;
     if (st != e->stream && e->ev_done) { CU(cudaEventRecord(e->ev_done, st)); e->ev_done_pending = true; }
     return 0;
 }

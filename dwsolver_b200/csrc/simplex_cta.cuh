@@ -52,6 +52,8 @@ struct BlockDev {
     int dnnz;               // entries of D_k
     long long xoff;         // offset of this block's columns in the engine-wide column arrays (x, cs_pre)
     const double *Dt;       // dense D_k transposed, n x L row-major (blocks whose D_k is dense enough for the pricing GEMM; else nullptr)
+    int *pos;               // m+n, by variable id: tableau row of a basic variable / column slot of a nonbasic one (blocks that
+                            // take part in delta rounds, delta_tg.cuh; nullptr: not kept)
     int *spflag;            // path 5: 0 = T holds the packed image, 1 = the block moved to the dense layout of path 3 (nullptr: not a path-5 block)
 };
 
@@ -670,6 +672,10 @@ __global__ void __launch_bounds__(NT) init_kernel(const BlockDev *blocks, int K)
         __syncthreads();
     } else
     reset_tableau<NT>(B, c);
+    if (B.pos != nullptr) {          // all-logical basis: variable i sits in row i, structural j in slot j
+        for (int i = threadIdx.x; i < B.m; i += NT) B.pos[i] = i;
+        for (int j = threadIdx.x; j < B.n; j += NT) B.pos[B.m + j] = j;
+    }
     // beta = A_k x_N straight from the CSR rows (all structurals are nonbasic): no second pass over T
     for (int i = threadIdx.x; i < B.m; i += NT) {
         double s = 0.0;

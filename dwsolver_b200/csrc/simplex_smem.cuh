@@ -157,6 +157,8 @@ struct Continuation {
     const unsigned char *moved;     // by block id; nullptr: none
     const unsigned char *reb;       // by block id: the tableau in HBM is not valid, rebuild it from A_k for the basis of the
                                     // state image before anything else (blocks handed over by path 5); nullptr: none
+    const int *full_flag;           // delta rounds (delta_tg.cuh): non-zero on the device = this launch covers ALL `count`
+    const int *full_list;           // blocks of full_list instead of the first *dyn_count entries of `list`; nullptr: n/a
 };
 
 // tableau accessors: global-memory tableaux (TG) bypass L1 (.cg) — rows are streamed once per basis
@@ -1185,9 +1187,10 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
     __shared__ __align__(8) uint64_t bar;
     __shared__ int s_kind, s_changed;
     if ((int)blockIdx.x >= count) return;
-    if (CN.dyn_count != nullptr && (int)blockIdx.x >= *CN.dyn_count) return;
+    const bool whole = CN.full_flag != nullptr && *CN.full_flag != 0;
+    if (!whole && CN.dyn_count != nullptr && (int)blockIdx.x >= *CN.dyn_count) return;
     phase_init();
-    const int k = list[blockIdx.x];
+    const int k = (whole ? CN.full_list : list)[blockIdx.x];
     const BlockDev &B = blocks[k];      // fields are fetched where they are used (read-only, cached)
     const int m = MC ? MC : B.m, n = NC ? NC : B.n, L = B.L, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double tol_dj = P.tol_dj, tol_bnd = P.tol_bnd, tol_piv = P.tol_piv;
@@ -1658,6 +1661,11 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
         }
         if (tid == 0) B.dflag[0] = d_full ? 1 : dflag_in + 1;
     } else if (tid == 0) B.dflag[0] = 0;
+    if (TG && B.pos != nullptr) {       // where every variable sits now (delta rounds look it up instead of searching)
+        int *pos = B.pos;
+        for (int i = tid; i < m; i += NT) pos[c.head[i]] = i;
+        for (int j = tid; j < n; j += NT) pos[c.nbv[j]] = j;
+    }
     // state out first (async), then the proposal while the copies fly
     if (tid == 0) {
         const bool t_dirty = (n_piv + n_reb) != 0;        // thread 0 sits in warp 0, which owns n_piv

@@ -141,7 +141,16 @@ int  dwgpu_reset(dwgpu_engine *e, void *stream);
 int  dwgpu_initial_solve(dwgpu_engine *e, dwgpu_proposals *out);
 
 /* One round with HOST buffers: pi (L doubles) is copied to the device, every block is priced
- * and re-solved from its stored basis, and the proposals are copied back into *out. */
+ * and re-solved from its stored basis, and the proposals are copied back into *out.
+ *
+ * Duals as applied (all dwgpu_iterate* / dwgpu_round_comm calls, engines with blocks on the HBM-tableau path): the
+ * engine remembers per linking row the dual it last applied.  A dual that differs from that value by no more than
+ * 1e-13 (1 + |pi_r|) — the round-off level of the master's solve — is taken AT that value; the rows that moved further
+ * are applied as given.  Rounds in which at most 16 rows moved ("delta rounds", csrc/delta_tg.cuh) look only at the
+ * columns on those rows.  obj is therefore the block's optimum at a vector within 1e-13 relative of pi per row (its
+ * effect on obj and on the reduced costs is three to four orders below the 1e-9 / 1e-7 tolerances of the path).  The
+ * first round after a cold solve, dwgpu_reset() or a phase change applies every row as given; DWGPU_DELTA=0 in the
+ * environment of dwgpu_create() switches the mechanism off. */
 int  dwgpu_iterate(dwgpu_engine *e, const double *pi, int phase_one, dwgpu_proposals *out);
 
 /* The same two calls with the proposals returned as ONE packed record (a single device-written
