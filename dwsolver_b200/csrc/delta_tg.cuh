@@ -233,16 +233,7 @@ __global__ void __launch_bounds__(NW * 32, 6) delta_round_kernel(const BlockDev 
     }
     if (act) B.cssave[j] = cs_new;
     // priced optimum of the kept x_k from the standing proposal: c_k.x_k - pi'.(D_k x_k)
-    double zo = 0.0;
-    {
-        const int len = P.len[k];
-        const double *yv = P.val + (size_t)k * B.L;
-        const int *yi = P.ind + (size_t)k * B.L;
-        for (int t = lane; t < len; t += 32) zo = fma(__ldg(P.pi + (__ldcg(yi + t) - 1)), __ldcg(yv + t), zo);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) zo += __shfl_xor_sync(FULL, zo, o);
-        zo = (P.phase_one ? 0.0 : P.cost[k]) - zo;
-    }
+    const double zo = standing_optimum(P, k, B.L, lane);
 #pragma unroll
     for (int o = 16; o; o >>= 1) cells += __shfl_xor_sync(FULL, cells, o);
     if (lane == 0) {

@@ -175,6 +175,9 @@ struct dwgpu_engine {
     // delta rounds (delta_tg.cuh): rounds in which few duals moved are screened by one warp per block against the duals
     // last applied per linking row; DWGPU_DELTA=0 switches it off (then the duals are used exactly as given)
     bool delta = true;
+    int delta_min_blocks = 1536;       // lists shorter than this go through the CTA kernel alone (same duals, same results: below
+                                       // ~2.5 waves of CTAs one launch is shorter than delta launch + CTA launch — measured with
+                                       // profiles/scan_delta.py: 1024 blocks 37 vs 47 us, 2048 blocks 58 vs 49 us); DWGPU_DELTA_MIN_BLOCKS
     bool delta_ok_b = false, delta_ok_g = false;
     DevBuf<double> pi_ref;             // duals last applied, by linking row: the vector a round prices with
     DevBuf<int> dl_rows, dl_meta;      // listed rows; DeltaMeta
@@ -800,6 +803,7 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     std::vector<long long> pos_off(K, -1);
     {
         if (const char *sv = std::getenv("DWGPU_DELTA")) e->delta = std::atoi(sv) != 0;
+        if (const char *sv = std::getenv("DWGPU_DELTA_MIN_BLOCKS")) e->delta_min_blocks = std::max(0, std::atoi(sv));
         if (const char *tg = std::getenv("DWGPU_TG_THREADS")) if (std::atoi(tg) == 32) e->delta = false;   // the warp kernel keeps no map
         auto fits = [&](const std::vector<int> &l) {
             if (l.empty()) return false;
@@ -1139,7 +1143,7 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
             const bool warp = warp_fits && e->tg_threads == 32;
             const bool scr = !warp && e->tg_threads != 32 && (spec_b ? e->screen_ok_b : e->screen_ok_g) && !initial &&
                              !P.force_full && P.cs_pre == nullptr && nb <= 8192;
-            if (delta_round && !warp && (spec_b ? e->delta_ok_b : e->delta_ok_g)) {
+            if (delta_round && !warp && (spec_b ? e->delta_ok_b : e->delta_ok_g) && (int)nb >= e->delta_min_blocks) {
                 // one warp per block finishes the blocks no listed dual can move; the CTA kernel takes the rest (or, when the
                 // device-side flag says so, its whole static list)
                 const dwk::DeltaMeta *meta = (const dwk::DeltaMeta *)e->dl_meta.p;

@@ -31,8 +31,7 @@ __host__ __device__ inline size_t screen_warp_bytes(int m, int n)
          + align16(sizeof(unsigned short) * (size_t)(m + 2));        // listed rows
 }
 
-// VNT: thread count of the CTA kernel whose summation order the priced optimum follows (obj is bit-identical to what
-// solve_smem_kernel<VNT, ...> writes for an unchanged block).  Handles n <= 512 (<= 4 items per lane).
+// VNT: columns priced per batch of loads (the CTA kernel's thread count).  Handles n <= 512 (<= 4 items per lane).
 template <int NW, int VNT>
 __global__ void __launch_bounds__(NW * 32) screen_tg_kernel(const BlockDev *blocks, const int *list, int count, SolveParams P,
                                                             ScreenOut S, int warp_bytes)
@@ -91,17 +90,13 @@ __global__ void __launch_bounds__(NW * 32) screen_tg_kernel(const BlockDev *bloc
         }
     }
     // ---- priced costs cs = (phase_one ? 0 : c_master) - D_k' pi  -> B.ws (as the CTA kernel), cost changes -> dl,
-    //      and the priced value of the kept x_k in the CTA kernel's summation order
-    double z[VW];
-#pragma unroll
-    for (int w = 0; w < VW; ++w) z[w] = 0.0;
     {
         const int *dcp = B.dc_ptr, *dcr = B.dc_row;
-        const double *dcv = B.dc_val, *cm = B.c_master, *cssave = B.cssave, *xk = B.x;
+        const double *dcv = B.dc_val, *cm = B.c_master, *cssave = B.cssave;
         double *csw = B.ws;
         for (int base = 0; base < n; base += VNT) {
             int pb[VW], pe[VW], r0[VW];
-            double v0[VW], p0[VW], cb[VW], sv[VW], xv[VW];
+            double v0[VW], p0[VW], cb[VW], sv[VW];
 #pragma unroll
             for (int w = 0; w < VW; ++w) {
                 const int j = base + 32 * w + lane;
@@ -112,8 +107,8 @@ __global__ void __launch_bounds__(NW * 32) screen_tg_kernel(const BlockDev *bloc
             for (int w = 0; w < VW; ++w) {
                 const int j = base + 32 * w + lane;
                 cb[w] = (j < n && !P.phase_one) ? __ldg(cm + j) : 0.0;
-                sv[w] = 0.0; xv[w] = 0.0;
-                if (j < n) { sv[w] = __ldcg(cssave + j); xv[w] = __ldcg(xk + j); }
+                sv[w] = 0.0;
+                if (j < n) sv[w] = __ldcg(cssave + j);
                 r0[w] = 0; v0[w] = 0.0;
                 if (pb[w] < pe[w]) { r0[w] = __ldg(dcr + pb[w]); v0[w] = __ldg(dcv + pb[w]); }
             }
@@ -132,7 +127,6 @@ __global__ void __launch_bounds__(NW * 32) screen_tg_kernel(const BlockDev *bloc
                 const double c = __dadd_rn(__dmul_rn(-1.0, y), cb[w]);
                 csw[j] = c;
                 dl[j] = cost_delta(c, sv[w]);
-                z[w] = fma(c, xv[w], z[w]);
             }
         }
     }
@@ -252,20 +246,7 @@ __global__ void __launch_bounds__(NW * 32) screen_tg_kernel(const BlockDev *bloc
     __syncwarp();
     for (int j = lane; j < n; j += 32)
         if (dl[j] != 0.0) B.cssave[j] = B.ws[j];          // (written by this lane above)
-    double zo;
-    {
-#pragma unroll
-        for (int w = 0; w < VW; ++w) {
-#pragma unroll
-            for (int o = 16; o; o >>= 1) z[w] += __shfl_xor_sync(0xffffffffu, z[w], o);
-        }
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < VW; ++w) if (lane == w) v = z[w];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        zo = v;
-    }
+    const double zo = standing_optimum(P, k, B.L, lane);
 #pragma unroll
     for (int o = 16; o; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
     if (lane == 0) {

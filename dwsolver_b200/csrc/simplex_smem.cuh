@@ -507,7 +507,7 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
     static_assert(NW <= 8, "DecShared holds 8 warp slots");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int m = MC ? MC : c.m, n = NC ? NC : c.n, ld = NC ? tab_ld(NC, true) : c.ld;
+    const int m = MC ? MC : c.m, ld = NC ? tab_ld(NC, true) : c.ld;
     const double harris = 0.5 * tol_bnd;
     const int RW = ((m + NW - 1) / NW + 31) & ~31;          // rows of the column each warp fetches
     for (;;) {
@@ -1171,6 +1171,20 @@ __device__ __forceinline__ unsigned masked_cells(const Sm3 &c, int nl)
     return cnt * 4u;
 }
 
+// Priced optimum of a block that did not move, from its standing proposal in the result arrays (one warp; every lane
+// gets the value): (phase_one ? 0 : c_k.x_k) - sum_e pi[ind_e] val_e over the len non-zeros of D_k x_k.
+__device__ __forceinline__ double standing_optimum(const SolveParams &P, int k, int L, int lane)
+{
+    const int len = P.len[k];
+    const double *yv = P.val + (size_t)k * L;
+    const int *yi = P.ind + (size_t)k * L;
+    double z = 0.0;
+    for (int t = lane; t < len; t += 32) z = fma(__ldg(P.pi + (__ldcg(yi + t) - 1)), __ldcg(yv + t), z);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    return (P.phase_one ? 0.0 : __ldcg(P.cost + k)) - z;
+}
+
 // MC/NC != 0: block shape known at compile time (all shared-memory offsets and trip counts are
 // constants); MC = NC = 0: any shape that fits.
 // TG = true: the tableau stays in global memory (L2/HBM) and only the vectors live in shared memory
@@ -1620,31 +1634,31 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
     if (!changed) {
         // the block was already optimal under the new prices: x_k, D_k x_k, c_k.x_k and the whole
         // state in HBM are still those of the previous round; only the priced optimum moves
-        double zo = 0.0;
         {
-            const double *xk = STG ? sg_x : B.x;
             const double *cssv = STG ? sg_cssave : B.cssave;
             double *dsave = B.dsave, *cssave = B.cssave;
             constexpr int U = (NC && NC / NT >= 8) ? 8 : 4;
             for (int j0 = tid; j0 < n; j0 += NT * U) {
-                double cv[U], xv[U], sv[U];
+                double cv[U], sv[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int j = j0 + u * NT;
-                    if (j < n) { cv[u] = c.cs[j]; xv[u] = x_in_rowp ? c.rowp[j] : (STG ? xk[j] : __ldcg(xk + j)); sv[u] = STG ? cssv[j] : __ldcg(cssv + j); }
+                    if (j < n) { cv[u] = c.cs[j]; sv[u] = STG ? cssv[j] : __ldcg(cssv + j); }
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int j = j0 + u * NT;
                     if (j < n) {
-                        zo = fma(cv[u], xv[u], zo);
                         dsave[j] = c.drow[j];
                         if (d_full || cost_delta(cv[u], sv[u]) != 0.0) cssave[j] = cv[u];
                     }
                 }
             }
         }
-        zo = block_sum<NT>(zo, scr);
+        // priced optimum of the kept x_k from the block's standing proposal: c_k.x_k - pi.(D_k x_k) (= sum cs_j x_j); the
+        // same warp code as the delta rounds (delta_tg.cuh), so that both routes of an unmoved block agree bit for bit
+        double zo = 0.0;
+        if (warp == 0) zo = standing_optimum(P, k, L, lane);
         if (tid == 0) {
             P.obj[k] = zo; P.status[k] = 5; P.last_iters[k] = 0;
             if (P.m_obj != nullptr) { P.m_obj[k] = zo; P.m_status[k] = 5; P.counters[8 * (size_t)k + 7] += 12; }   // the rest of the mailbox still holds
