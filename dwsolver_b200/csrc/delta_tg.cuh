@@ -67,7 +67,7 @@ __host__ __device__ inline size_t delta_warp_bytes()
 }
 
 template <int NW>
-__global__ void __launch_bounds__(NW * 32, 6) delta_round_kernel(const BlockDev *blocks, const int *list, int count, SolveParams P, DeltaIn D)
+__global__ void __launch_bounds__(NW * 32, 8) delta_round_kernel(const BlockDev *blocks, const int *list, int count, SolveParams P, DeltaIn D)
 {
     __shared__ __align__(16) char smem_raw[NW * (32 * 2 * 8 + 32 * 4 * 4 + 32 * 2 * 4)];
     __shared__ double2 stash_all[NW][4 * 32 * 2];           // new reduced costs of the touched items until the block is decided
@@ -89,12 +89,14 @@ __global__ void __launch_bounds__(NW * 32, 6) delta_round_kernel(const BlockDev 
 
     auto handoff = [&]() { if (lane == 0) D.next_list[atomicAdd(D.next_count, 1)] = k; };
 
+    // (independent loads are issued side by side: the warp's time is its chain of dependent round trips)
     const int dflag_in = B.dflag[0];
-    if (!(dflag_in > 0 && dflag_in < 32)) { handoff(); return; }     // no valid saved row, or the periodic full recomputation
-    // ---- columns of D_k on the listed rows, one per lane
     const int nR = D.meta->nrows;
     int rb = 0, re = 0;
     if (lane < nR) { const int r = D.rows[lane]; rb = __ldg(B.dr_ptr + r); re = __ldg(B.dr_ptr + r + 1); }
+    const double zo = standing_optimum(P, k, B.L, lane);   // needed only if the block stays; three round trips hidden here
+    if (!(dflag_in > 0 && dflag_in < 32)) { handoff(); return; }     // no valid saved row, or the periodic full recomputation
+    // ---- columns of D_k on the listed rows, one per lane
     int cnt = re - rb, incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
@@ -117,25 +119,25 @@ __global__ void __launch_bounds__(NW * 32, 6) delta_round_kernel(const BlockDev 
     double dl = 0.0, cs_new = 0.0;
     bool basic = false;
     int var = -1;
+    int pos = -1;               // where the variable sits: tableau row of a basic one, column slot of a nonbasic one
     if (j >= 0) {
+        var = m + j;
         const int pb = __ldg(B.dc_ptr + j), pe = __ldg(B.dc_ptr + j + 1);
+        const double base = P.phase_one ? 0.0 : __ldg(B.c_master + j);
+        const double sv = __ldcg(B.cssave + j);
+        const signed char st = __ldcg(B.vstat + var);
+        const int ps = __ldcg(B.pos + var);
         double y = 0.0;
         for (int t = pb; t < pe; ++t) y = __dadd_rn(y, __dmul_rn(__ldg(P.pi + __ldg(B.dc_row + t)), __ldg(B.dc_val + t)));
-        const double base = P.phase_one ? 0.0 : __ldg(B.c_master + j);
+        basic = st == ST_BASIC;
+        const bool in_range = ps >= 0 && ps < (basic ? m : n);
+        const int owner = in_range ? __ldcg((basic ? B.head : B.nbv) + ps) : -1;
         cs_new = __dadd_rn(__dmul_rn(-1.0, y), base);
-        dl = cost_delta(cs_new, __ldcg(B.cssave + j));
-        var = m + j;
-        basic = __ldcg(B.vstat + var) == ST_BASIC;
+        dl = cost_delta(cs_new, sv);
+        pos = owner == var ? ps : -1;
     }
     const bool act = j >= 0 && dl != 0.0;
     const unsigned actB = __ballot_sync(FULL, act && basic), actN = __ballot_sync(FULL, act && !basic);
-    // ---- where those variables sit: tableau row of a basic one, column slot of a nonbasic one
-    int pos = -1;
-    if (act) {
-        pos = __ldcg(B.pos + var);
-        const bool ok = basic ? (pos >= 0 && pos < m && __ldcg(B.head + pos) == var) : (pos >= 0 && pos < n && __ldcg(B.nbv + pos) == var);
-        if (!ok) pos = -1;
-    }
     if (__any_sync(FULL, act && pos < 0)) { handoff(); return; }     // (inconsistent state image: let the CTA kernel look)
     // listed tableau rows in ascending order with their weights and masks; slots of the nonbasic columns
     const int nl = __popc(actB), nn = __popc(actN);
@@ -233,7 +235,6 @@ __global__ void __launch_bounds__(NW * 32, 6) delta_round_kernel(const BlockDev 
     }
     if (act) B.cssave[j] = cs_new;
     // priced optimum of the kept x_k from the standing proposal: c_k.x_k - pi'.(D_k x_k)
-    const double zo = standing_optimum(P, k, B.L, lane);
 #pragma unroll
     for (int o = 16; o; o >>= 1) cells += __shfl_xor_sync(FULL, cells, o);
     if (lane == 0) {

@@ -797,6 +797,50 @@ def test_delta_rounds_against_the_oracle_and_against_full_rounds(threads, monkey
     e1.close(); e2.close(); e0.close()
 
 
+@pytest.mark.parametrize("shape", [(40, 48, 100, 24), (24, 96, 203, 40), (16, 130, 512, 64)])
+def test_delta_rounds_generic_shapes(shape, monkeypatch):
+    """Delta rounds on the generic path-3 kernel (odd column counts, fewer than four mask words per row): a dual
+    sequence in which two or three components move per round, a round that repeats
+    its duals, one that moves every component, and a phase change.  Against the oracle every round, and bit for bit
+    against an engine that applies the same duals through the CTA kernel only."""
+    from oracle import oracle as O
+    K, nodes, cols, L = shape
+    prob = P.gen_mcf(K, nodes, cols, L, seed=77 + cols)
+    monkeypatch.setenv("DWGPU_DELTA_MIN_BLOCKS", "0")
+    e1 = engine(prob, force_path=3)
+    monkeypatch.setenv("DWGPU_DELTA_MIN_BLOCKS", "1000000")
+    e2 = engine(prob, force_path=3)
+    assert set(e1.block_paths()) == {3}
+    orc = O.OracleBlocks(prob)
+
+    def same(a, b):
+        for k in range(prob.K):
+            assert a[k]["status"] == b[k]["status"] and a[k]["obj"] == b[k]["obj"] and a[k]["cost"] == b[k]["cost"], k
+            assert np.array_equal(a[k]["x"], b[k]["x"]), k
+            assert np.array_equal(a[k]["ind"], b[k]["ind"]) and np.array_equal(a[k]["val"], b[k]["val"]), k
+    g1, g2 = e1.initial(), e2.initial()
+    same(g1, g2)
+    compare_round(prob, g1, orc.initial(8), None, False, initial=True)
+    rng = np.random.default_rng(5)
+    pi = -rng.random(prob.L) * 8.0
+    took_delta = 0
+    for t in range(24):
+        phase = t < 2
+        if t == 12:
+            pi = -rng.random(prob.L) * 8.0                  # every dual moves
+        elif t not in (0, 7):                               # (round 7 repeats round 6)
+            idx = rng.choice(prob.L, size=2 + t % 2, replace=False)
+            pi = pi.copy()
+            pi[idx] = -rng.random(len(idx)) * 8.0
+            pi[rng.integers(prob.L)] *= 1.0 + 1e-15         # master round-off: stays at the applied value
+        g1, g2 = e1.iterate(pi, phase), e2.iterate(pi, phase)
+        took_delta += e1.last_launch_count() > e2.last_launch_count()
+        same(g1, g2)
+        compare_round(prob, g1, orc.iterate(pi, phase, 8), pi, phase)
+    assert took_delta >= 20
+    e1.close(); e2.close()
+
+
 @pytest.mark.parametrize("threads", [64, 128, 256])
 def test_screening_launch_changes_nothing(threads, monkeypatch):
     """Path 3 runs a priced round as screening launch (one warp per block: the blocks that need no pivot are finished
