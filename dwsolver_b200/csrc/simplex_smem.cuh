@@ -40,16 +40,6 @@
                             // it for a decision, and it drops out of the row masks, the item lists and all later sweeps
                             // (equality-constrained blocks: every auxiliary variable the cold solve drives out, half the slots)
 #endif
-#ifndef DWK_TG_PREFETCH
-#define DWK_TG_PREFETCH 0    // 1: L2 prefetch of the active rows' items during the ratio test (experiment)
-#endif
-#ifndef DWK_TG_EARLYQ
-#define DWK_TG_EARLYQ 0      // 1: the sparse sweep prices the next entering column as soon as the pivot row is known and
-                            // prefetches that column into L2 while its own loads are in flight (experiment)
-#endif
-#ifndef DWK_FASTDIV
-#define DWK_FASTDIV 1
-#endif
 #ifndef DWK_TGW_OCC
 #define DWK_TGW_OCC 4       // CTAs per SM the 128- and 256-thread global-tableau kernels are compiled for
 #endif
@@ -501,7 +491,7 @@ template <bool INF, int NT, int MC, int NC>
 __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_live, bool &bland, int &degen, int degen_limit,
                             double tol_dj, double tol_bnd, double tol_piv,
                             unsigned long long &n_piv, unsigned long long &n_flip, unsigned long long &n_rows,
-                            unsigned long long &n_cells, Decision *dec, DecShared *ds, int &q_hint)
+                            unsigned long long &n_cells, Decision *dec, DecShared *ds)
 {
     constexpr int NW = NT / 32;
     static_assert(NW <= 8, "DecShared holds 8 warp slots");
@@ -512,11 +502,8 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
     const int RW = ((m + NW - 1) / NW + 31) & ~31;          // rows of the column each warp fetches
     for (;;) {
         phase(3);
-        // ---- pricing, all threads (or the column the previous sweep already chose and prefetched)
-        int q = -1;
-        if (DWK_TG_EARLYQ && q_hint >= 0) q = q_hint;            // block-uniform
-        else q = price_block_tg<NT, NC>(c, dd, bland, tol_dj, ds);
-        q_hint = -1;
+        // ---- pricing, all threads
+        const int q = price_block_tg<NT, NC>(c, dd, bland, tol_dj, ds);
         if (q < 0) return K_NONE;                                // block-uniform
         phase(4);
         const double dq = dd[q];
@@ -554,18 +541,6 @@ __device__ __forceinline__ int decide_block_tg(Sm3 &c, const double *dd, bool d_
                 }
             }
             if (lane == 0) ds->cnt[warp] = cnt;
-#if DWK_TG_PREFETCH
-            // While warp 0 runs the ratio test, pull the active rows' items towards L2: the sweep will read a subset of
-            // them (the items the pivot row carries) as soon as the leaving row is known.
-            __syncwarp();
-            for (int e = 0; e < cnt; ++e) {
-                const int i = c.arow2[rbeg + e];
-                const unsigned *mi = c.rmask + (size_t)i * rwd;
-                for (int w_ = 0; w_ < rwd; ++w_)
-                    if ((mi[w_] >> lane) & 1u)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(c.T + (size_t)i * ld + (size_t)(w_ * 32 + lane) * 4));
-            }
-#endif
         }
         __syncthreads();
         int na = 0;
@@ -827,11 +802,8 @@ __device__ __forceinline__ void sweep_drow(Sm3 &c, int q, double inv, int nc, bo
 // The reduced-cost row (last list entry when it rides along) lives in shared memory and is done apart,
 // so the tableau loop is pure global (TG) or pure shared traffic with 32-bit cell offsets.
 template <int NT, int NC, bool TG>
-__device__ __forceinline__ int sweep_sparse(Sm3 &c, int p, int q, double inv, int na, int nc, bool fused, bool dead,
-                                             bool bland, double tol_dj, DecShared *ds)
+__device__ __forceinline__ void sweep_sparse(Sm3 &c, int p, int q, double inv, int na, int nc, bool fused, bool dead)
 {
-    int q_next = -1;                                       // DWK_TG_EARLYQ: the entering column of the next iteration
-    bool d_done = false;
     const double invq = dead ? 0.0 : inv;                  // what column q receives: nothing when the leaving variable is fixed
     constexpr int IW = ItemW<TG>::D2;
     constexpr int SB = TG ? DWK_TG_SB : 2;                 // items per thread in flight
@@ -853,7 +825,7 @@ __device__ __forceinline__ int sweep_sparse(Sm3 &c, int p, int q, double inv, in
             const int e = e0 + t * NT + threadIdx.x;
             off[t] = -1; had[t] = true;
             if (e < total) {
-                const int a = DWK_FASTDIV ? (nc > 1 ? (int)__umulhi((unsigned)e, nc_magic) : e) : e / nc;
+                const int a = nc > 1 ? (int)__umulhi((unsigned)e, nc_magic) : e;
                 const int i = c.arow[a], item = c.acol[e - a * nc];
                 off[t] = i * nc2 + item * IW;
                 if (TG) had[t] = (c.rmask[(size_t)i * c.rwd + (item >> 5)] >> (item & 31)) & 1u;
@@ -884,23 +856,6 @@ __device__ __forceinline__ int sweep_sparse(Sm3 &c, int p, int q, double inv, in
                 }
             }
             __syncthreads();
-        }
-        if (TG && DWK_TG_EARLYQ && e0 == 0 && with_d) {
-            // The scaled pivot row is complete (staged before the call, or by the branch above) while this batch's loads
-            // are still in flight: finish the reduced-cost row now, choose the NEXT entering column and pull its
-            // sectors towards L2, so that the next iteration's column fetch does not wait for HBM.
-            sweep_drow<NT, TG>(c, q, inv, nc, dead);
-            d_done = true;
-            __syncthreads();
-            q_next = price_block_tg<NT, NC>(c, c.drow, bland, tol_dj, ds);
-            if (q_next >= 0) {
-                const int m_ = c.m, ld_ = NC ? tab_ld(NC, TG) : c.ld;
-                const unsigned *mq = c.rmask + (q_next >> 7);
-                const unsigned qbit = 1u << ((q_next >> 2) & 31);
-                for (int i = threadIdx.x; i < m_; i += NT)
-                    if (mq[(size_t)i * c.rwd] & qbit)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(c.T + (size_t)i * ld_ + q_next));
-            }
         }
 #pragma unroll
         for (int t = 0; t < SB; ++t) {
@@ -939,8 +894,7 @@ __device__ __forceinline__ int sweep_sparse(Sm3 &c, int p, int q, double inv, in
             }
         }
     }
-    if (with_d && !d_done) sweep_drow<NT, TG>(c, q, inv, nc, dead);
-    return q_next;
+    if (with_d) sweep_drow<NT, TG>(c, q, inv, nc, dead);
 }
 
 // rank-1 sweep over the active rows only (row m = reduced costs when it is in the list)
@@ -1387,7 +1341,6 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
     unsigned long long n_price = 0;     // tableau doubles read to (re)compute price rows (block-uniform)
     bool need_check = true, infeasible = false, d_valid = false, bland = false, d_full = false, x_in_rowp = true;
     int degen = 0;
-    int q_hint = -1;            // TG: entering column chosen (and prefetched) by the previous sparse sweep
     const int degen_limit = 100 + (m + n) / 2;
     const bool use_saved = dflag_in > 0 && dflag_in < 32;
     bool reb_now = TG && CN.reb != nullptr && CN.reb[k] != 0;      // block-uniform
@@ -1501,10 +1454,10 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
             int kind;
             if (infeasible)
                 kind = decide_block_tg<true, NT, MC, NC>(c, c.rowp, false, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
-                                                         n_piv, n_flip, n_rows, n_cells, &dec, &dsh, q_hint);
+                                                         n_piv, n_flip, n_rows, n_cells, &dec, &dsh);
             else
                 kind = decide_block_tg<false, NT, MC, NC>(c, c.drow, true, bland, degen, degen_limit, tol_dj, tol_bnd, tol_piv,
-                                                          n_piv, n_flip, n_rows, n_cells, &dec, &dsh, q_hint);
+                                                          n_piv, n_flip, n_rows, n_cells, &dec, &dsh);
             if (tid == 0) { s_kind = kind; if (n_piv + n_flip) s_changed = 1; }
         } else if (warp == 0) {
             int kind;
@@ -1520,8 +1473,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
         const int kind = s_kind;
         if (kind == K_PIVOT) {
             phase(dec.nc >= 0 ? 7 : 11);
-            if (dec.nc >= 0) q_hint = sweep_sparse<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na, dec.nc, TG && dec.fused != 0, dec.dead != 0,
-                                                               bland, tol_dj, &dsh);
+            if (dec.nc >= 0) sweep_sparse<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na, dec.nc, TG && dec.fused != 0, dec.dead != 0);
             else sweep_active<NT, NC, TG>(c, dec.p, dec.q, dec.inv, dec.na, dec.dead != 0);
             __syncthreads();
             continue;
