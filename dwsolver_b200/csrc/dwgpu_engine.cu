@@ -214,6 +214,11 @@ struct dwgpu_engine {
     size_t hp_cap = 0;
     ncclComm_t comm = nullptr;
     int comm_world = 0, comm_rank = 0;
+    // round hand-shakes over the control block at the end of the up-link buffer (pack.cuh: UplinkCtl) instead of NCCL
+    // collectives; DWGPU_COMM=nccl restores the broadcast + all-reduce
+    bool comm_p2p = true;
+    dwk::UplinkCtl *uplink_ctl = nullptr;
+    unsigned long long comm_seq = 0, comm_rounds = 0;
     DevBuf<int> comm_flag;
     size_t smem_dyn = 0;
     int max_smem_optin = 0;
@@ -343,6 +348,11 @@ int dwgpu_comm_init(dwgpu_engine *e, const void *id128, int world, int rank)
     return 0;
 }
 
+static size_t uplink_ctl_offset(size_t K, size_t KL)
+{
+    return (sizeof(double) * (2 * K + KL) + sizeof(int) * (2 * K + KL) + 64 + 255) & ~(size_t)255;
+}
+
 // Rank 0 allocates one mailbox per block of the whole instance in its HBM and publishes a CUDA IPC handle (64 bytes,
 // sent to the other ranks by whatever the host uses for its rendezvous).
 int dwgpu_uplink_create(dwgpu_engine *e, int K_total, void *ipc_handle64, dwgpu_proposals *dev_out)
@@ -350,7 +360,8 @@ int dwgpu_uplink_create(dwgpu_engine *e, int K_total, void *ipc_handle64, dwgpu_
     if (!e || K_total < e->K || !ipc_handle64) return fail(DWGPU_E_ARGS, "bad arguments");
     CU(cudaSetDevice(e->device));
     const size_t K = (size_t)K_total, KL = K * (size_t)e->L;
-    const size_t bytes = sizeof(double) * (2 * K + KL) + sizeof(int) * (2 * K + KL) + 64;
+    const size_t ctl_off = uplink_ctl_offset(K, KL);
+    const size_t bytes = ctl_off + sizeof(dwk::UplinkCtl) + sizeof(double) * (size_t)std::max(e->L, 1);
     CU(cudaMalloc((void **)&e->uplink_base, bytes));
     CU(cudaMemset(e->uplink_base, 0, bytes));
     e->uplink_owned = true;
@@ -392,6 +403,8 @@ int dwgpu_uplink_attach(dwgpu_engine *e, const void *ipc_handle64, int K_total, 
     e->uplink = dwk::MailDst{dd + f, dd + K + f, dd + 2 * K + f * e->L, ii + f, ii + K + f, ii + 2 * K + f * e->L};
     e->uplink_first = k_first;
     e->uplink_valid = false;
+    e->uplink_ctl = (dwk::UplinkCtl *)(e->uplink_base + uplink_ctl_offset(K, KL));
+    if (const char *cv = std::getenv("DWGPU_COMM")) e->comm_p2p = std::strcmp(cv, "nccl") != 0;
     return 0;
 }
 
@@ -407,7 +420,15 @@ int dwgpu_round_comm(dwgpu_engine *e, double *pi_dev, int phase_one, int initial
     if (!initial && e->L > 0 && !pi_dev) return fail(DWGPU_E_ARGS, "pi_dev is NULL");
     CU(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-    if (!initial && e->L > 0) NC(g_nccl.Broadcast(pi_dev, pi_dev, (size_t)e->L, ncclDouble, 0, e->comm, st));
+    const bool p2p = e->comm_p2p && e->uplink_ctl != nullptr;
+    if (!initial && e->L > 0) {
+        if (p2p) {          // duals down through the control block in rank 0's HBM
+            ++e->comm_seq;
+            if (e->comm_rank == 0) dwk::comm_publish_kernel<<<1, 256, 0, st>>>(e->uplink_ctl, pi_dev, e->L, e->comm_seq);
+            else dwk::comm_fetch_kernel<<<1, 256, 0, st>>>(e->uplink_ctl, pi_dev, e->L, e->comm_seq);
+            CU(cudaGetLastError());
+        } else NC(g_nccl.Broadcast(pi_dev, pi_dev, (size_t)e->L, ncclDouble, 0, e->comm, st));
+    }
     const bool direct = e->uplink_valid;
     int rc = launch_round(e, pi_dev, phase_one ? 1 : 0, initial ? 1 : 0, st, false, &e->uplink);
     if (rc) return rc;
@@ -425,7 +446,12 @@ int dwgpu_round_comm(dwgpu_engine *e, double *pi_dev, int phase_one, int initial
     if (!direct) CU(copy(nullptr, (size_t)e->K));
     else { CU(copy(e->d_list_gmem.p, e->list_gmem.size())); CU(copy(e->d_list_c.p, e->list_c.size())); }
     e->uplink_valid = true;
-    NC(g_nccl.AllReduce(e->comm_flag.p, e->comm_flag.p + 1, 1, ncclInt, ncclSum, e->comm, st));
+    if (p2p) {              // close: every rank counts itself in; rank 0 waits for all of them
+        ++e->comm_rounds;
+        dwk::comm_signal_kernel<<<1, 1, 0, st>>>(e->uplink_ctl);
+        if (e->comm_rank == 0) dwk::comm_wait_kernel<<<1, 1, 0, st>>>(e->uplink_ctl, e->comm_rounds * (unsigned long long)e->comm_world);
+        CU(cudaGetLastError());
+    } else NC(g_nccl.AllReduce(e->comm_flag.p, e->comm_flag.p + 1, 1, ncclInt, ncclSum, e->comm, st));
     return 0;
 }
 

@@ -150,6 +150,69 @@ __global__ void __launch_bounds__(NT) mailbox_copy_kernel(PackSrc s, const int *
     }
 }
 
+// ---- multi-GPU round control over peer memory ---------------------------------------------------------------------
+// The up-link buffer in rank 0's HBM (every rank maps it: CUDA IPC over NVLink) ends with a control block.  A round's two
+// hand-shakes — duals down, proposals complete — are a sequence number and a counter in that block instead of two NCCL
+// collectives (a 2 KB broadcast and a one-int all-reduce cost 20-30 us each on 8 GPUs; a flag costs one NVLink round trip):
+//   rank 0   comm_publish_kernel: copies pi into the block, fence, seq = s
+//   others   comm_fetch_kernel:   waits until seq >= s (system-scope acquire loads), copies pi into its own buffer
+//   all      comm_signal_kernel after the solve kernels: fence, done += 1 (their proposal stores into rank 0's HBM are
+//            ordered before it)
+//   rank 0   comm_wait_kernel: waits until done >= world x rounds; what follows on its stream may read the up-link buffer
+// A wait that lasts longer than 10 s traps (a peer died): the process fails instead of hanging.
+struct UplinkCtl {
+    unsigned long long seq, done, pad0, pad1;
+    double pi[1];                      // L doubles
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void spin_until(const unsigned long long *flag, unsigned long long want)
+{
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(flag) < want) {
+        if (global_ns() - t0 > 10000000000ull) __trap();
+        __nanosleep(100);
+    }
+}
+__global__ void __launch_bounds__(256) comm_publish_kernel(UplinkCtl *ctl, const double *pi, int L, unsigned long long seq)
+{
+    for (int r = threadIdx.x; r < L; r += 256) ctl->pi[r] = pi[r];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&ctl->seq), "l"(seq) : "memory");
+    }
+}
+__global__ void __launch_bounds__(256) comm_fetch_kernel(const UplinkCtl *ctl, double *pi, int L, unsigned long long seq)
+{
+    if (threadIdx.x == 0) spin_until(&ctl->seq, seq);
+    __syncthreads();
+    for (int r = threadIdx.x; r < L; r += 256) {
+        double v;
+        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(ctl->pi + r) : "memory");
+        pi[r] = v;
+    }
+}
+__global__ void comm_signal_kernel(UplinkCtl *ctl)
+{
+    __threadfence_system();
+    atomicAdd_system(&ctl->done, 1ull);
+}
+__global__ void comm_wait_kernel(const UplinkCtl *ctl, unsigned long long want)
+{
+    spin_until(&ctl->done, want);
+}
+
 // ---- longest-processing-time-first launch order -----------------------------------------------------
 // A round's kernel time is max(total work / resident CTAs, longest block).  Blocks differ by 100x in
 // pivots (most need none), and the blocks that pivoted a lot in the previous round tend to do so

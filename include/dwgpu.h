@@ -265,9 +265,14 @@ const char *dwgpu_version(void);
  *                                            status, len: K_total; ind, val: K_total x L, block-major) for
  *                                            dwgpu_pack_gathered();
  *   dwgpu_uplink_attach (every rank)         maps the buffer (NULL handle on rank 0) and selects this rank's window;
- *   dwgpu_round_comm                         ncclBroadcast of pi from rank 0 -> solve kernels whose epilogues store the
- *                                            proposals into rank 0's buffer over NVLink peer memory (only what moved)
- *                                            -> a one-int ncclAllReduce that closes the round; all on one stream. */
+ *   dwgpu_round_comm                         duals down from rank 0 -> solve kernels whose epilogues store the proposals
+ *                                            into rank 0's buffer over NVLink peer memory (only what moved) -> close;
+ *                                            all on one stream.  The two hand-shakes go through a control block at the
+ *                                            end of the up-link buffer (sequence number + completion counter, system-scope
+ *                                            loads / stores over NVLink; a wait of more than 10 s traps); with
+ *                                            DWGPU_COMM=nccl in the environment they are an ncclBroadcast of pi and a
+ *                                            one-int ncclAllReduce instead.  Every rank must make the same sequence of
+ *                                            dwgpu_round_comm calls. */
 int  dwgpu_comm_unique_id(void *id128);
 int  dwgpu_comm_init(dwgpu_engine *e, const void *id128, int world, int rank);
 void dwgpu_comm_release(dwgpu_engine *e);

@@ -808,10 +808,17 @@ def test_delta_rounds_generic_shapes(shape, monkeypatch):
     prob = P.gen_mcf(K, nodes, cols, L, seed=77 + cols)
     monkeypatch.setenv("DWGPU_DELTA_MIN_BLOCKS", "0")
     e1 = engine(prob, force_path=3)
+    e3 = engine(prob, force_path=3)                         # the same rounds through the host mailboxes
     monkeypatch.setenv("DWGPU_DELTA_MIN_BLOCKS", "1000000")
     e2 = engine(prob, force_path=3)
     assert set(e1.block_paths()) == {3}
     orc = O.OracleBlocks(prob)
+
+    def same_mail(a, mb):
+        for k in range(prob.K):
+            n_k = int(mb["len"][k])
+            assert int(mb["status"][k]) == a[k]["status"] and mb["obj"][k] == a[k]["obj"] and mb["cost"][k] == a[k]["cost"], k
+            assert np.array_equal(mb["ind"][k, :n_k], a[k]["ind"]) and np.array_equal(mb["val"][k, :n_k], a[k]["val"]), k
 
     def same(a, b):
         for k in range(prob.K):
@@ -820,6 +827,7 @@ def test_delta_rounds_generic_shapes(shape, monkeypatch):
             assert np.array_equal(a[k]["ind"], b[k]["ind"]) and np.array_equal(a[k]["val"], b[k]["val"]), k
     g1, g2 = e1.initial(), e2.initial()
     same(g1, g2)
+    same_mail(g1, e3.initial_solve_mailboxes())
     compare_round(prob, g1, orc.initial(8), None, False, initial=True)
     rng = np.random.default_rng(5)
     pi = -rng.random(prob.L) * 8.0
@@ -836,9 +844,10 @@ def test_delta_rounds_generic_shapes(shape, monkeypatch):
         g1, g2 = e1.iterate(pi, phase), e2.iterate(pi, phase)
         took_delta += e1.last_launch_count() > e2.last_launch_count()
         same(g1, g2)
+        same_mail(g1, e3.iterate_mailboxes(pi, phase))
         compare_round(prob, g1, orc.iterate(pi, phase, 8), pi, phase)
     assert took_delta >= 20
-    e1.close(); e2.close()
+    e1.close(); e2.close(); e3.close()
 
 
 @pytest.mark.parametrize("threads", [64, 128, 256])
