@@ -36,28 +36,8 @@ struct DeltaIn {
     int *next_count;
 };
 
-// One CTA: which duals moved since they were last applied.  pi_ref is updated in place and is the vector the round uses.
-__global__ void __launch_bounds__(256) delta_rows_kernel(const double *pi, double *pi_ref, int L, int force_full, int *rows, DeltaMeta *meta)
-{
-    __shared__ int s_n;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    for (int r = threadIdx.x; r < L; r += 256) {
-        const double p = pi[r], ref = pi_ref[r];
-        const bool moved = force_full || !(fabs(p - ref) <= 1e-13 * (1.0 + fabs(p)));
-        if (moved) {
-            pi_ref[r] = p;
-            const int pos = atomicAdd(&s_n, 1);
-            if (pos < DELTA_MAX_ROWS) rows[pos] = r;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        meta->nrows = s_n;
-        meta->full = (force_full || s_n > DELTA_MAX_ROWS) ? 1 : 0;
-        meta->count_b = 0; meta->count_g = 0;
-    }
-}
+// (delta_rows_kernel / round_prep: pack.cuh — the dual screening shares a launch with the launch-order kernel and, in
+//  multi-GPU rounds, with the duals' hand-shake)
 
 __host__ __device__ inline size_t delta_warp_bytes()
 {

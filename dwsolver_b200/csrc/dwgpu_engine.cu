@@ -219,6 +219,8 @@ struct dwgpu_engine {
     bool comm_p2p = true;
     dwk::UplinkCtl *uplink_ctl = nullptr;
     unsigned long long comm_seq = 0, comm_rounds = 0;
+    int prep_comm_mode = 0;            // set by dwgpu_round_comm for the launch_round that follows: 1 publish, 2 fetch the duals
+    unsigned long long prep_seq = 0;
     DevBuf<int> comm_flag;
     size_t smem_dyn = 0;
     int max_smem_optin = 0;
@@ -422,11 +424,10 @@ int dwgpu_round_comm(dwgpu_engine *e, double *pi_dev, int phase_one, int initial
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     const bool p2p = e->comm_p2p && e->uplink_ctl != nullptr;
     if (!initial && e->L > 0) {
-        if (p2p) {          // duals down through the control block in rank 0's HBM
+        if (p2p) {          // duals down through the control block in rank 0's HBM: part of the round's preparation launch
             ++e->comm_seq;
-            if (e->comm_rank == 0) dwk::comm_publish_kernel<<<1, 256, 0, st>>>(e->uplink_ctl, pi_dev, e->L, e->comm_seq);
-            else dwk::comm_fetch_kernel<<<1, 256, 0, st>>>(e->uplink_ctl, pi_dev, e->L, e->comm_seq);
-            CU(cudaGetLastError());
+            e->prep_comm_mode = e->comm_rank == 0 ? 1 : 2;
+            e->prep_seq = e->comm_seq;
         } else NC(g_nccl.Broadcast(pi_dev, pi_dev, (size_t)e->L, ncclDouble, 0, e->comm, st));
     }
     const bool direct = e->uplink_valid;
@@ -448,8 +449,8 @@ int dwgpu_round_comm(dwgpu_engine *e, double *pi_dev, int phase_one, int initial
     e->uplink_valid = true;
     if (p2p) {              // close: every rank counts itself in; rank 0 waits for all of them
         ++e->comm_rounds;
-        dwk::comm_signal_kernel<<<1, 1, 0, st>>>(e->uplink_ctl);
-        if (e->comm_rank == 0) dwk::comm_wait_kernel<<<1, 1, 0, st>>>(e->uplink_ctl, e->comm_rounds * (unsigned long long)e->comm_world);
+        if (e->comm_rank == 0) dwk::comm_signal_wait_kernel<<<1, 1, 0, st>>>(e->uplink_ctl, e->comm_rounds * (unsigned long long)e->comm_world);
+        else dwk::comm_signal_kernel<<<1, 1, 0, st>>>(e->uplink_ctl);
         CU(cudaGetLastError());
     } else NC(g_nccl.AllReduce(e->comm_flag.p, e->comm_flag.p + 1, 1, ncclInt, ncclSum, e->comm, st));
     return 0;
@@ -1037,34 +1038,42 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
     P.obj = e->obj.p; P.cost = e->cost.p; P.status = e->status.p; P.len = e->len.p;
     P.ind = e->ind.p; P.val = e->val.p; P.counters = e->counters.p; P.last_iters = e->last_iters.p;
     e->last_launches = 0;
+    // ---- the round's preparation (pack.cuh: prep_job): multi-GPU hand-shake of the duals + dual screening for the delta
+    // rounds.  It rides along as the second CTA of the first launch-order kernel of the round, or is its own small launch.
+    dwk::PrepJob J;
+    std::memset(&J, 0, sizeof(J));
+    J.pi = d_pi; J.L = e->L;
+    J.ctl = e->uplink_ctl; J.seq = e->prep_seq; J.comm_mode = (initial || d_pi == nullptr) ? 0 : e->prep_comm_mode;
+    e->prep_comm_mode = 0;
     if (initial) e->pi_ref_valid = false;
     else if ((e->delta_ok_b || e->delta_ok_g) && e->tg_threads != 32 && d_pi != nullptr) {
         if (P.cs_pre != nullptr) e->pi_ref_valid = false;       // (priced by the multi-vector GEMM with the duals as given)
         else {
             // duals down: list the rows that moved since they were last applied, snap the others; the round prices with pi_ref
-            const int force = (!e->pi_ref_valid || e->last_phase != phase_one || P.force_full) ? 1 : 0;
-            dwk::delta_rows_kernel<<<1, 256, 0, st>>>(d_pi, e->pi_ref.p, e->L, force, e->dl_rows.p, (dwk::DeltaMeta *)e->dl_meta.p);
-            CU(cudaGetLastError());
-            e->last_launches++;
+            J.force_full = (!e->pi_ref_valid || e->last_phase != phase_one || P.force_full) ? 1 : 0;
+            J.pi_ref = e->pi_ref.p; J.rows = e->dl_rows.p; J.meta = (dwk::DeltaMeta *)e->dl_meta.p;
             e->pi_ref_valid = true; e->last_phase = phase_one;
             P.pi = e->pi_ref.p;
             delta_round = true;
         }
     }
+    bool prep_pending = J.pi_ref != nullptr || J.comm_mode != 0;
     // longest-processing-time-first inside each list (DWGPU_NO_REORDER=1 keeps the natural order)
     if (!initial && e->reorder) {
         auto order = [&](DevBuf<int> &d, size_t n) -> cudaError_t {
             // pays off whenever a launch is more than one wave of CTAs deep (592 resident 128-thread CTAs): multi-GPU
             // shards of 1024 blocks are 1.7 waves, where the long poles of an unordered launch end up in the tail
             if (n < 600 || n > 8192) return cudaSuccess;
+            const unsigned grid = prep_pending ? 2u : 1u;
             if (n <= 1024)
-                dwk::order_by_last_iterations_kernel<1024, 1024><<<1, 1024, 1024 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p);
+                dwk::order_by_last_iterations_kernel<1024, 1024><<<grid, 1024, 1024 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p, J);
             else if (n <= 2048)
-                dwk::order_by_last_iterations_kernel<1024, 2048><<<1, 1024, 2048 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p);
+                dwk::order_by_last_iterations_kernel<1024, 2048><<<grid, 1024, 2048 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p, J);
             else if (n <= 4096)
-                dwk::order_by_last_iterations_kernel<1024, 4096><<<1, 1024, 4096 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p);
+                dwk::order_by_last_iterations_kernel<1024, 4096><<<grid, 1024, 4096 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p, J);
             else
-                dwk::order_by_last_iterations_kernel<1024, 8192><<<1, 1024, 8192 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p);
+                dwk::order_by_last_iterations_kernel<1024, 8192><<<grid, 1024, 8192 * sizeof(unsigned long long), st>>>(d.p, (int)n, e->last_iters.p, J);
+            prep_pending = false;
             e->last_launches++;
             return cudaGetLastError();
         };
@@ -1074,6 +1083,11 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
         if (!(scr_any && e->screen_ok_g && e->list_g.size() <= 8192)) CU(order(e->d_list_g, e->list_g.size()));
         CU(order(e->d_list_s, e->list_s.size()));
         CU(order(e->d_list_a, e->list_a.size())); CU(order(e->d_list_smem, e->list_smem.size()));
+    }
+    if (prep_pending) {
+        dwk::delta_rows_kernel<<<1, 256, 0, st>>>(J);
+        CU(cudaGetLastError());
+        e->last_launches++;
     }
     // large blocks first: they are the long poles
     e->ev_used[0] = e->ev_used[1] = false;

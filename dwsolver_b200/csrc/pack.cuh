@@ -154,11 +154,12 @@ __global__ void __launch_bounds__(NT) mailbox_copy_kernel(PackSrc s, const int *
 // The up-link buffer in rank 0's HBM (every rank maps it: CUDA IPC over NVLink) ends with a control block.  A round's two
 // hand-shakes — duals down, proposals complete — are a sequence number and a counter in that block instead of two NCCL
 // collectives (a 2 KB broadcast and a one-int all-reduce cost 20-30 us each on 8 GPUs; a flag costs one NVLink round trip):
-//   rank 0   comm_publish_kernel: copies pi into the block, fence, seq = s
-//   others   comm_fetch_kernel:   waits until seq >= s (system-scope acquire loads), copies pi into its own buffer
+//   rank 0   prep_job (comm_mode 1): copies pi into the block, fence, seq = s
+//   others   prep_job (comm_mode 2): waits until seq >= s (system-scope acquire loads), copies pi into its own buffer
 //   all      comm_signal_kernel after the solve kernels: fence, done += 1 (their proposal stores into rank 0's HBM are
 //            ordered before it)
-//   rank 0   comm_wait_kernel: waits until done >= world x rounds; what follows on its stream may read the up-link buffer
+//   rank 0   comm_signal_wait_kernel: counts itself in and waits until done >= world x rounds; what follows on its stream
+//            may read the up-link buffer
 // A wait that lasts longer than 10 s traps (a peer died): the process fails instead of hanging.
 struct UplinkCtl {
     unsigned long long seq, done, pad0, pad1;
@@ -184,34 +185,75 @@ __device__ __forceinline__ void spin_until(const unsigned long long *flag, unsig
         __nanosleep(100);
     }
 }
-__global__ void __launch_bounds__(256) comm_publish_kernel(UplinkCtl *ctl, const double *pi, int L, unsigned long long seq)
-{
-    for (int r = threadIdx.x; r < L; r += 256) ctl->pi[r] = pi[r];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&ctl->seq), "l"(seq) : "memory");
-    }
-}
-__global__ void __launch_bounds__(256) comm_fetch_kernel(const UplinkCtl *ctl, double *pi, int L, unsigned long long seq)
-{
-    if (threadIdx.x == 0) spin_until(&ctl->seq, seq);
-    __syncthreads();
-    for (int r = threadIdx.x; r < L; r += 256) {
-        double v;
-        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(ctl->pi + r) : "memory");
-        pi[r] = v;
-    }
-}
 __global__ void comm_signal_kernel(UplinkCtl *ctl)
 {
     __threadfence_system();
     atomicAdd_system(&ctl->done, 1ull);
 }
-__global__ void comm_wait_kernel(const UplinkCtl *ctl, unsigned long long want)
+__global__ void comm_signal_wait_kernel(UplinkCtl *ctl, unsigned long long want)       // rank 0: both in one launch
 {
+    __threadfence_system();
+    atomicAdd_system(&ctl->done, 1ull);
     spin_until(&ctl->done, want);
 }
+
+// ---- start of a priced round: one CTA's worth of work that rides along with another small launch ----------------------
+// (a) multi-GPU: the duals' hand-shake (publish on rank 0, fetch elsewhere), (b) delta rounds (delta_tg.cuh): which duals
+// moved since they were last applied — pi_ref is updated in place and is the vector the round prices with.  Launched as
+// its own kernel (delta_rows_kernel) or as the second CTA of the launch-order kernel below: every launch less is ~4 us of a
+// round that may only last 40.
+struct PrepJob {
+    const double *pi;           // this round's duals on the device (multi-GPU fetch: written first, see comm_mode)
+    double *pi_ref;             // nullptr: no dual screening
+    int L, force_full;
+    int *rows;
+    DeltaMeta *meta;
+    UplinkCtl *ctl;             // multi-GPU control block; comm_mode 0: none, 1: publish pi, 2: fetch pi
+    unsigned long long seq;
+    int comm_mode;
+};
+__device__ __forceinline__ void prep_job(const PrepJob &J)
+{
+    __shared__ int s_n;
+    const int nt = blockDim.x;
+    if (J.comm_mode == 1) {
+        for (int r = threadIdx.x; r < J.L; r += nt) J.ctl->pi[r] = J.pi[r];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&J.ctl->seq), "l"(J.seq) : "memory");
+        }
+    } else if (J.comm_mode == 2) {
+        if (threadIdx.x == 0) spin_until(&J.ctl->seq, J.seq);
+        __syncthreads();
+        double *dst = const_cast<double *>(J.pi);
+        for (int r = threadIdx.x; r < J.L; r += nt) {
+            double v;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(J.ctl->pi + r) : "memory");
+            dst[r] = v;
+        }
+        __syncthreads();        // (each thread screens below exactly the rows it has just written)
+    }
+    if (J.pi_ref == nullptr) return;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int r = threadIdx.x; r < J.L; r += nt) {
+        const double p = J.pi[r], ref = J.pi_ref[r];
+        const bool moved = J.force_full || !(fabs(p - ref) <= 1e-13 * (1.0 + fabs(p)));
+        if (moved) {
+            J.pi_ref[r] = p;
+            const int pos = atomicAdd(&s_n, 1);
+            if (pos < DELTA_MAX_ROWS) J.rows[pos] = r;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        J.meta->nrows = s_n;
+        J.meta->full = (J.force_full || s_n > DELTA_MAX_ROWS) ? 1 : 0;
+        J.meta->count_b = 0; J.meta->count_g = 0;
+    }
+}
+__global__ void __launch_bounds__(256) delta_rows_kernel(PrepJob J) { prep_job(J); }
 
 // ---- longest-processing-time-first launch order -----------------------------------------------------
 // A round's kernel time is max(total work / resident CTAs, longest block).  Blocks differ by 100x in
@@ -219,8 +261,9 @@ __global__ void comm_wait_kernel(const UplinkCtl *ctl, unsigned long long want)
 // again; dispatching them first keeps the long poles off the tail of the launch.  One CTA orders the
 // (<= 8192-entry) block list by last round's iteration count, descending (counting sort in shared memory).
 template <int NT, int CAP>
-__global__ void __launch_bounds__(NT) order_by_last_iterations_kernel(int *list, int count, const long long *last_iters)
+__global__ void __launch_bounds__(NT) order_by_last_iterations_kernel(int *list, int count, const long long *last_iters, PrepJob J)
 {
+    if (blockIdx.x == 1) { prep_job(J); return; }          // (grid of 2: the round's preparation rides along)
     // Counting sort by min(iterations, NB - 1), descending (the bitonic sort of 8192 64-bit keys this replaces took 80 us
     // in each of the rounds that pivot — 0.9 ms of a 30 ms step at config B).  Blocks with the same count keep no
     // particular order: the order of a launch list only decides when a block starts, never what it computes.
