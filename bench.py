@@ -715,14 +715,16 @@ def main():
                    "passes": "single pass: value = pivots / summed CUDA-event time of the solve kernels of the e2e pass" if single
                    else "separate e2e and device-resident passes",
                    "parallelism": f"blocks sharded over {world} GPU(s)" +
-                   ("; per round: ncclBroadcast of pi, kernels store proposals into rank 0's HBM over NVLink peer memory, one-int ncclAllReduce closes the round (dwgpu_round_comm)" if world > 1 else ""),
+                   ("; per round (dwgpu_round_comm): duals down and round close are hand-shakes over a control block in rank 0's HBM "
+                    "(NVLink peer memory; DWGPU_COMM=nccl: ncclBroadcast + one-int ncclAllReduce), kernels store proposals into rank 0's HBM "
+                    "over NVLink peer memory; comm = " + os.environ.get("DWGPU_COMM", "p2p") if world > 1 else ""),
                    "dw_objective_of_trajectory": dw_objective},
         "e2e": {"value": (e2e_cnt[0] + e2e_cnt[1]) / e2e_time if e2e_time > 0 else 0.0, "unit": UNIT,
                 "h2d_bytes_per_step": 8 * L * R,
                 "d2h_bytes_per_step": int(e2e_cnt[6] / max(S, 1)) if world == 1 else d2h[0],
                 "api": "dwgpu_initial_solve_mailboxes + dwgpu_iterate_mailboxes (host pi in; the kernels store every block's "
                        "proposal into pinned host mailboxes, d2h = bytes stored, device counter)"
-                       if world == 1 else "per rank dwgpu_round_comm (NCCL duals down, NVLink peer-memory up-link into rank 0's HBM); "
+                       if world == 1 else "per rank dwgpu_round_comm (duals down + NVLink peer-memory up-link into rank 0's HBM); "
                                           "rank 0: host pi in, dwgpu_pack_gathered into its pinned record every round",
                 "ms_per_step": 1e3 * e2e_time / S},
         "gpu_launches": launches[0] * S,
