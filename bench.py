@@ -248,9 +248,13 @@ def tto_child(tag):
     prob = P.make_config(tag)
     os.chdir(tempfile.mkdtemp())
     first = dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=0)["stats"]["seconds_total"]
-    r = dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=0)
+    # fastest of three warm calls (all listed), like the N = 1 leg: right after the ranks of the bench have let go of
+    # their GPUs the first warm call can still pay for their teardown (seen: 1.4 s against 0.37 s stand-alone)
+    runs = [dw_solve_blocks(prob, verbosity=-1, print_relaxed_sol=0) for _ in range(3)]
+    r = min(runs, key=lambda q: q["stats"]["seconds_total"])
     st = r["stats"]
     print(json.dumps({"seconds": st["seconds_total"], "first_call_seconds": first,
+                      "warm_call_seconds": [q["stats"]["seconds_total"] for q in runs],
                       "subproblem_seconds": st["seconds_subproblems"], "master_seconds": st["seconds_master"],
                       "dw_rounds": st["dw_iterations"], "status": r["status"], "objective": r["objective"],
                       "devices": os.environ.get("DWSOLVER_DEVICES", "")}))
@@ -752,7 +756,7 @@ def main():
                     tto["objective_of_recorded_run"] = dw_objective
                     tto["api"] = (f"dw_solve_blocks (include/dwsolver.h) in a child process, DWSOLVER_DEVICES={env['DWSOLVER_DEVICES']}: "
                                   "one engine per GPU over a contiguous block range, one host thread per shard and round, "
-                                  "this build's master LP (device interior point when K L >= 2^18, else host GUB simplex); second call of the process (first_call_seconds beside it)")
+                                  "this build's master LP (device interior point when K L >= 2^18, else host GUB simplex); fastest of three warm calls of the process (warm_call_seconds, first_call_seconds beside it)")
                 else:
                     tto = {"error": f"child exit {ch.returncode}: {(ch.stderr or ch.stdout)[-300:]}"}
             except Exception as exc:                 # the bench line must not die on the optional part
