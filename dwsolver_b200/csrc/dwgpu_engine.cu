@@ -185,9 +185,6 @@ struct dwgpu_engine {
     DevBuf<int> dl_pos;                // position of every variable of the blocks above (BlockDev::pos)
     bool pi_ref_valid = false;         // false: the next round lists every row (after create, cold solve, reset)
     int last_phase = -1;
-    // staged rounds of the 256 x 512 kernel (simplex_smem.cuh, STG): per-block round data arrives by bulk copies
-    bool stage_b = false;              // DWGPU_STAGE=0 switches it off
-    size_t smem_stage_b = 0;           // dynamic shared memory of the staged instantiation
     int warp_bail_after = 0;           // test hook (DWGPU_WARP_BAIL_AFTER): hand over after this many basis changes
     bool reorder = true;
     bool have_proposals = false;       // a round has written every block's proposal since create / reset
@@ -224,7 +221,6 @@ struct dwgpu_engine {
     DevBuf<int> comm_flag;
     size_t smem_dyn = 0;
     int max_smem_optin = 0;
-    int max_smem_sm = 0;               // shared memory of one SM
     // device arenas
     DevBuf<double> T, bnd, dsave, cssave, a_v, dc_val, dr_val, c_file, c_master, x, ws;
     DevBuf<int> a_rp, a_ci, dc_ptr, dc_row, dr_ptr, dr_col;
@@ -571,7 +567,6 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
     double ts[8]; int nts = 0;
     ts[nts++] = stamp();
     CUE(cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, opt.device));
-    CUE(cudaDeviceGetAttribute(&e->max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, opt.device));
     CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     for (auto &ev : e->ev) CUE(cudaEventCreate(&ev));
     CUE(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
@@ -634,8 +629,8 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         v_off[k + 1] = v_off[k] + b.m + b.n;
         a_off[k + 1] = a_off[k] + nnz;
         arp_off[k + 1] = arp_off[k] + b.m + 1;
-        // (every block's slices start on a 16-byte boundary and are padded to one: the staged path-3 prologue moves them
-        //  with bulk copies)
+        // (every block's slices start on a 16-byte boundary and are padded to one, so that they can be moved by bulk copies
+        //  or 16-byte loads)
         d_off[k + 1] = d_off[k] + ((b.d_nnz + 3) & ~3);
         dcp_off[k + 1] = dcp_off[k] + ((b.n + 1 + 3) & ~3);
         drp_off[k + 1] = drp_off[k] + L + 1;
@@ -967,25 +962,6 @@ int dwgpu_create(int K, int L, const dwgpu_block_desc *bd, const dwgpu_options *
         CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG_WIDE, 0, 0, true>, (int)e->smem_dyn_g));
     }
     if (!e->list_b.empty()) {
-        {   // staged rounds: 16-byte aligned per-block slices, and still four CTAs per SM
-            bool ok = true;
-            int dmax = 0;
-            for (int k : e->list_b) { ok = ok && !(e->xoff[k] & 1); dmax = std::max(dmax, bd[k].d_nnz); }
-            const size_t sm = dwk::smem2_bytes(256, 512, true) + dwk::stage_bytes(512, dmax);
-            // opt-in (DWGPU_STAGE=1).  Measured on config B (profiles/r2q_*): a no-pivot launch 0.176 ms instead of 0.197 ms,
-            // but the launches that pivot lose 7 % (51 KB instead of 29 KB of shared memory per CTA leaves the L1 a quarter of
-            // its size): 34.4 ms per step against 31.7 ms.  ncu of the staged no-pivot launch: the same 365 MB of DRAM reads,
-            // 1 260 instructions per warp — the round is bound by the length of its instruction chain, not by its round trips.
-            const char *sv = std::getenv("DWGPU_STAGE");
-            ok = ok && sv != nullptr && std::atoi(sv) != 0;
-            if (ok && (sm + 1024 + 512) * DWK_TGW_OCC <= (size_t)e->max_smem_sm) {
-                e->stage_b = true; e->smem_stage_b = sm;
-                CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true, true>, (int)sm));
-                // four CTAs of ~51 KB need the largest shared-memory carve-out; the driver's default heuristic may pick less
-                CUE(cudaFuncSetAttribute(dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true, true>,
-                                         cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-            }
-        }
         CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_SMEM, 256, 512, true>, (int)dwk::smem2_bytes(256, 512, true)));
         CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG, 256, 512, true>, (int)dwk::smem2_bytes(256, 512, true)));
         CUE(allow_dynamic_smem(e->device, (const void *)dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true>, (int)dwk::smem2_bytes(256, 512, true)));
@@ -1169,7 +1145,6 @@ static int launch_round(dwgpu_engine *e, const double *d_pi, int phase_one, int 
             if (spec_b) {
                 if (nt == 256) dwk::solve_smem_kernel<NT_SMEM, 256, 512, true><<<nb, NT_SMEM, sm, st>>>(e->blocks.p, list, (int)nb, P, cn);
                 else if (nt == NT_TG) dwk::solve_smem_kernel<NT_TG, 256, 512, true><<<nb, NT_TG, sm, st>>>(e->blocks.p, list, (int)nb, P, cn);
-                else if (e->stage_b) dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true, true><<<nb, NT_TG_WIDE, e->smem_stage_b, st>>>(e->blocks.p, list, (int)nb, P, cn);
                 else dwk::solve_smem_kernel<NT_TG_WIDE, 256, 512, true><<<nb, NT_TG_WIDE, sm, st>>>(e->blocks.p, list, (int)nb, P, cn);
             } else {
                 if (nt == 256) dwk::solve_smem_kernel<NT_SMEM, 0, 0, true><<<nb, NT_SMEM, sm, st>>>(e->blocks.p, list, (int)nb, P, cn);

@@ -124,20 +124,6 @@ __host__ __device__ inline size_t smem2_bytes(int m, int n, bool tg = false)
          + (tg ? rmask_bytes(m, n) : 0);                                        // row-item masks
 }
 
-// Staged rounds (STG): everything a priced round reads about a block besides its tableau — saved reduced costs and the
-// costs they belong to, the kept x_k, the master costs, D_k by column — arrives with the state image in ONE batch of bulk
-// copies, so the prologue, a no-pivot round and the "nothing moved" epilogue are shared-memory work behind a single HBM
-// round trip instead of a chain of ~11 dependent ones (29 of the 40 rounds of config B's trajectory move < 100 blocks).
-// Needs n even and the D_k arenas padded per block (dwgpu_create does that).
-__host__ __device__ inline int al4(int v) { return (v + 3) & ~3; }
-__host__ __device__ inline size_t stage_bytes(int n, int dnnz)
-{
-    return 4 * align16(sizeof(double) * (size_t)n)          // dsave | cssave | x | c_master (becomes cs in place)
-         + align16(sizeof(double) * (size_t)al4(dnnz))       // dc_val
-         + align16(sizeof(int) * (size_t)al4(n + 1))         // dc_ptr
-         + align16(sizeof(int) * (size_t)al4(dnnz));         // dc_row
-}
-
 enum { K_NONE = 0, K_PIVOT = 1, K_FAIL = 2, K_REDO = 3 };
 
 // Second launch of a round over the blocks the warp kernel (simplex_warp.cuh) handed over: the list length is read
@@ -1143,11 +1129,10 @@ __device__ __forceinline__ double standing_optimum(const SolveParams &P, int k, 
 // constants); MC = NC = 0: any shape that fits.
 // TG = true: the tableau stays in global memory (L2/HBM) and only the vectors live in shared memory
 // (blocks too large for one CTA's shared memory, config B class); the decision/sweep code is shared.
-template <int NT, int MC, int NC, bool TG, bool STG = false>
+template <int NT, int MC, int NC, bool TG>
 __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC) : 3) solve_smem_kernel(const BlockDev *blocks, const int *list, int count,
                                                           SolveParams P, Continuation CN)
 {
-    static_assert(!STG || TG, "staged rounds belong to the global-tableau kernel");
     extern __shared__ __align__(16) char smem_raw[];
     __shared__ Scratch<NT> scr;
     __shared__ Decision dec;
@@ -1193,22 +1178,6 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
     c.arow2 = (unsigned short *)sp; sp += TG ? align16(sizeof(unsigned short) * (size_t)(m + 32 * 8)) : 0;
     c.rmask = TG ? (unsigned *)sp : nullptr;
     c.rwd = rmask_words(n);
-    // staged round data (STG): [dsave | cssave | x | c_master -> cs | dc_val | dc_ptr | dc_row]
-    const int dnnz = STG ? B.dnnz : 0;
-    double *sg_dsave = nullptr, *sg_cssave = nullptr, *sg_x = nullptr, *sg_dcv = nullptr;
-    int *sg_dcp = nullptr, *sg_dcr = nullptr;
-    if (STG) {
-        sp += rmask_bytes(m, n);
-        const size_t nb = align16(sizeof(double) * (size_t)n);
-        sg_dsave = (double *)sp; sp += nb;
-        sg_cssave = (double *)sp; sp += nb;
-        sg_x = (double *)sp; sp += nb;
-        c.cs = (double *)sp; sp += nb;
-        sg_dcv = (double *)sp; sp += align16(sizeof(double) * (size_t)al4(dnnz));
-        sg_dcp = (int *)sp; sp += align16(sizeof(int) * (size_t)al4(n + 1));
-        sg_dcr = (int *)sp;
-    }
-
     const int dflag_in = B.dflag[0];        // (loaded here: its latency hides behind the bulk copies)
     // ---- state in: bulk copies (tableau or row masks, state image), one mbarrier
     const uint32_t t_bytes = TG ? 0u : (uint32_t)(sizeof(double) * (size_t)m * ld);
@@ -1216,79 +1185,16 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
     const uint32_t k_bytes = TG ? (uint32_t)rmask_bytes(m, n) : 0u;
     if (tid == 0) {
         mbar_init(&bar, 1);
-        const uint32_t n_bytes = STG ? (uint32_t)align16(sizeof(double) * (size_t)n) : 0u;
-        const uint32_t dv_bytes = STG ? (uint32_t)align16(sizeof(double) * (size_t)dnnz) : 0u;
-        const uint32_t dp_bytes = STG ? (uint32_t)align16(sizeof(int) * (size_t)(n + 1)) : 0u;
-        const uint32_t dr_bytes = STG ? (uint32_t)align16(sizeof(int) * (size_t)dnnz) : 0u;
-        mbar_expect_tx(&bar, t_bytes + p_bytes + k_bytes + 4u * n_bytes + dv_bytes + dp_bytes + dr_bytes);
+        mbar_expect_tx(&bar, t_bytes + p_bytes + k_bytes);
         if (t_bytes) bulk_g2s(c.T, B.T, t_bytes, &bar);
         if (k_bytes) bulk_g2s(c.rmask, B.rmask, k_bytes, &bar);
         bulk_g2s(pst, B.beta, p_bytes, &bar);
-        if (STG) {
-            bulk_g2s(sg_dsave, B.dsave, n_bytes, &bar);
-            bulk_g2s(sg_cssave, B.cssave, n_bytes, &bar);
-            bulk_g2s(sg_x, B.x, n_bytes, &bar);
-            bulk_g2s(c.cs, P.initial ? B.c_file : B.c_master, n_bytes, &bar);
-            if (dv_bytes) bulk_g2s(sg_dcv, B.dc_val, dv_bytes, &bar);
-            bulk_g2s(sg_dcp, B.dc_ptr, dp_bytes, &bar);
-            if (dr_bytes) bulk_g2s(sg_dcr, B.dc_row, dr_bytes, &bar);
-        }
         s_changed = (CN.moved != nullptr && CN.moved[k]) ? 1 : 0;
     }
     // priced objective while the copies fly (same arithmetic as the generic kernel / reference)
     // (four columns per thread at a time, every level of the CSC walk issued as one batch of read-only
     //  loads: a chain of 3 dependent loads per column otherwise, which dominated the no-pivot rounds)
-    if (STG) {
-        // everything arrives with the bulk copies: the walk over D_k's columns reads shared memory, only the duals are
-        // gathered (L doubles shared by all blocks: L1/L2), and the row bounds are gathered while they fly
-        __syncthreads();            // mbarrier init visible
-        mbar_wait(&bar, 0);
-        // row bounds by basic variable: gathered now, consumed after the pricing walk (one round trip for both)
-        constexpr int RU = MC ? (MC + NT - 1) / NT : 1;
-        double blo[RU], bup[RU];
-        if (MC) {
-#pragma unroll
-            for (int u = 0; u < RU; ++u) {
-                const int i = tid + u * NT;
-                if (i < m) { const int v = c.head[i]; blo[u] = __ldg(c.glo + v); bup[u] = __ldg(c.gup + v); }
-            }
-        }
-        if (!P.initial) {
-            constexpr int U = (NC && NC / NT >= 8) ? 8 : 4;
-            for (int j0 = tid; j0 < n; j0 += NT * U) {
-                int pb[U], pe[U];
-                double p0[U], v0[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int j = j0 + u * NT;
-                    pb[u] = pe[u] = 0; p0[u] = 0.0; v0[u] = 0.0;
-                    if (j < n) { pb[u] = sg_dcp[j]; pe[u] = sg_dcp[j + 1]; }
-                    if (pb[u] < pe[u]) { p0[u] = __ldg(P.pi + sg_dcr[pb[u]]); v0[u] = sg_dcv[pb[u]]; }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int j = j0 + u * NT;
-                    if (j >= n) continue;
-                    double y = 0.0;
-                    if (pb[u] < pe[u]) {
-                        y = __dadd_rn(y, __dmul_rn(p0[u], v0[u]));
-                        for (int e = pb[u] + 1; e < pe[u]; ++e)
-                            y = __dadd_rn(y, __dmul_rn(__ldg(P.pi + sg_dcr[e]), sg_dcv[e]));
-                    }
-                    const double base = P.phase_one ? 0.0 : c.cs[j];       // the slot holds c_master[j]
-                    c.cs[j] = __dadd_rn(__dmul_rn(-1.0, y), base);
-                }
-            }
-        }
-        if (MC) {
-#pragma unroll
-            for (int u = 0; u < RU; ++u) {
-                const int i = tid + u * NT;
-                if (i < m) { c.rlo[i] = blo[u]; c.rup[i] = bup[u]; }
-            }
-            for (int j = tid; j < n; j += NT) c.cstat[j] = c.vstat[c.nbv[j]];
-        } else gather_bounds<NT, TG>(B, c);
-    } else if (P.initial) {
+    if (P.initial) {
         const double *cf = B.c_file;
         for (int j = tid; j < n; j += NT) c.cs[j] = __ldg(cf + j);
     } else {
@@ -1327,11 +1233,9 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
             }
         }
     }
-    if (!STG) {
-        __syncthreads();            // mbarrier init + cs visible
-        mbar_wait(&bar, 0);
-        gather_bounds<NT, TG>(B, c);
-    }
+    __syncthreads();            // mbarrier init + cs visible
+    mbar_wait(&bar, 0);
+    gather_bounds<NT, TG>(B, c);
     __syncthreads();
 
     int status = 0;
@@ -1387,7 +1291,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
             // which only touches the rows of T whose basic cost changed (late rounds: a handful);
             // otherwise (and every 32nd solve, to stop drift) recompute d = c_N + T' c_B in full.
             const bool inc = use_saved && !s_changed && n_reb == 0;
-            const double *cssave = STG ? sg_cssave : B.cssave, *dsave = STG ? sg_dsave : B.dsave;     // only written in the epilogue: read-only here
+            const double *cssave = B.cssave, *dsave = B.dsave;     // only written in the epilogue: read-only here
             constexpr int U = (NC && NC / NT >= 8) ? 8 : 4;
             for (int i0 = tid; i0 < m; i0 += NT * U) {
                 double a[U], b[U];
@@ -1398,7 +1302,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
                     st[u] = false; a[u] = 0.0; b[u] = 0.0;
                     if (i < m) {
                         const int v = c.head[i];
-                        if (v >= m) { st[u] = true; a[u] = c.cs[v - m]; if (inc) b[u] = STG ? cssave[v - m] : __ldg(cssave + v - m); }
+                        if (v >= m) { st[u] = true; a[u] = c.cs[v - m]; if (inc) b[u] = __ldg(cssave + v - m); }
                     }
                 }
 #pragma unroll
@@ -1424,8 +1328,8 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
                     st[u] = false; a[u] = 0.0; b[u] = 0.0; dsv[u] = 0.0;
                     if (j < n) {
                         const int v = c.nbv[j];
-                        if (v >= m) { st[u] = true; a[u] = c.cs[v - m]; if (inc) b[u] = STG ? cssave[v - m] : __ldg(cssave + v - m); }
-                        if (inc) dsv[u] = STG ? dsave[j] : __ldg(dsave + j);
+                        if (v >= m) { st[u] = true; a[u] = c.cs[v - m]; if (inc) b[u] = __ldg(cssave + v - m); }
+                        if (inc) dsv[u] = __ldg(dsave + j);
                     }
                 }
 #pragma unroll
@@ -1587,7 +1491,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
         // the block was already optimal under the new prices: x_k, D_k x_k, c_k.x_k and the whole
         // state in HBM are still those of the previous round; only the priced optimum moves
         {
-            const double *cssv = STG ? sg_cssave : B.cssave;
+            const double *cssv = B.cssave;
             double *dsave = B.dsave, *cssave = B.cssave;
             constexpr int U = (NC && NC / NT >= 8) ? 8 : 4;
             for (int j0 = tid; j0 < n; j0 += NT * U) {
@@ -1595,7 +1499,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int j = j0 + u * NT;
-                    if (j < n) { cv[u] = c.cs[j]; sv[u] = STG ? cssv[j] : __ldcg(cssv + j); }
+                    if (j < n) { cv[u] = c.cs[j]; sv[u] = __ldcg(cssv + j); }
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -1623,7 +1527,7 @@ __global__ void __launch_bounds__(NT, TG ? (NT <= 64 ? DWK_TG_OCC : DWK_TGW_OCC)
     if (status == 5 && d_valid) {
         for (int j = tid; j < n; j += NT) {
             B.dsave[j] = c.drow[j];
-            if (d_full || cost_delta(c.cs[j], STG ? sg_cssave[j] : B.cssave[j]) != 0.0) B.cssave[j] = c.cs[j];
+            if (d_full || cost_delta(c.cs[j], B.cssave[j]) != 0.0) B.cssave[j] = c.cs[j];
         }
         if (tid == 0) B.dflag[0] = d_full ? 1 : dflag_in + 1;
     } else if (tid == 0) B.dflag[0] = 0;
